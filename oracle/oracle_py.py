@@ -1,0 +1,249 @@
+"""ctypes binding of the CPU oracle (oracle/libq3dr_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (quad3dr_b200/) never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libq3dr_oracle.so")
+
+
+class ScoreOpts(C.Structure):
+    _fields_ = [
+        ("voxel_sensor_size_ratio_threshold", C.c_float),
+        ("voxel_sensor_size_ratio_inv_falloff_factor", C.c_float),
+        ("incidence_angle_threshold_degrees", C.c_float),
+        ("incidence_angle_inv_falloff_factor_degrees", C.c_float),
+        ("incidence_ignore_dot_product_sign", C.c_int32),
+        ("ignore_voxels_with_zero_information", C.c_int32),
+        ("raycast_min_range", C.c_float),
+        ("raycast_max_range", C.c_float),
+    ]
+
+
+def default_opts(**kw) -> ScoreOpts:
+    o = ScoreOpts(0.002, 0.001, 30.0, 30.0, 0, 1, 0.0, 60.0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def build_library(force: bool = False) -> str:
+    src = os.path.join(_HERE, "q3dr_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-s", "libq3dr_oracle.so"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build_library()
+    L = C.CDLL(_LIB_PATH)
+    fp = C.POINTER(C.c_float)
+    u32p = C.POINTER(C.c_uint32)
+    i32p = C.POINTER(C.c_int32)
+    L.orc_tree_build.restype = C.c_void_p
+    L.orc_tree_build.argtypes = [fp, C.c_size_t]
+    L.orc_tree_free.argtypes = [C.c_void_p]
+    for f in ("orc_tree_num_leaves", "orc_tree_num_nodes", "orc_tree_depth"):
+        getattr(L, f).restype = C.c_size_t
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.orc_tree_dfs_order.argtypes = [C.c_void_p, u32p]
+    L.orc_tree_leaf_depths.argtypes = [C.c_void_p, u32p]
+    L.orc_tree_voxel_index.argtypes = [C.c_void_p, u32p]
+    L.orc_tree_root_box.argtypes = [C.c_void_p, fp]
+    L.orc_pose_to_rt.argtypes = [fp, fp, fp]
+    L.orc_raycast_window.restype = C.c_uint64
+    L.orc_raycast_window.argtypes = [C.c_void_p, fp, fp] + [C.c_uint32] * 4 + [C.c_float] * 2 + [i32p, fp, fp, u32p]
+    L.orc_raycast_window_brute.argtypes = [C.c_void_p, fp, fp] + [C.c_uint32] * 4 + [C.c_float] * 2 + [i32p, fp]
+    L.orc_intersect_rays.argtypes = [C.c_void_p, fp, fp, C.c_size_t, C.c_float, C.c_float, i32p, fp, fp, u32p]
+    L.orc_voxel_information.restype = C.c_float
+    L.orc_voxel_information.argtypes = [fp, C.c_float, fp, fp, C.c_float, C.c_uint32, C.POINTER(ScoreOpts)]
+    L.orc_score_viewpoint.restype = C.c_size_t
+    L.orc_score_viewpoint.argtypes = (
+        [C.c_void_p, fp, fp, fp, C.c_uint32, fp]
+        + [C.c_uint32] * 4
+        + [C.POINTER(ScoreOpts), C.c_size_t, i32p, fp, u32p, fp, u32p, fp, fp]
+    )
+    L.orc_score_batch.restype = C.c_uint64
+    L.orc_score_batch.argtypes = [
+        C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
+    ]
+    L.orc_max_threads.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        assert a.shape == shape, (a.shape, shape)
+    return a
+
+
+class OracleTree:
+    """The reference's bvh::Tree (splitMedian build + recursive closest-hit), on the CPU."""
+
+    def __init__(self, boxes: np.ndarray):
+        self.boxes = _f32(boxes)
+        assert self.boxes.ndim == 2 and self.boxes.shape[1] == 6
+        self.n = self.boxes.shape[0]
+        self._h = lib().orc_tree_build(_f(self.boxes), self.n)
+        if not self._h:
+            raise ValueError("orc_tree_build failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_tree_free(self._h)
+            self._h = None
+
+    @property
+    def num_nodes(self) -> int:
+        return lib().orc_tree_num_nodes(self._h)
+
+    @property
+    def depth(self) -> int:
+        return lib().orc_tree_depth(self._h)
+
+    def dfs_order(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.uint32)
+        lib().orc_tree_dfs_order(self._h, _u(out))
+        return out
+
+    def leaf_depths(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.uint32)
+        lib().orc_tree_leaf_depths(self._h, _u(out))
+        return out
+
+    def voxel_index(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.uint32)
+        lib().orc_tree_voxel_index(self._h, _u(out))
+        return out
+
+    def root_box(self) -> np.ndarray:
+        out = np.empty(6, dtype=np.float32)
+        lib().orc_tree_root_box(self._h, _f(out))
+        return out
+
+    def raycast_window(self, K, Rt, x0, x1, y0, y1, min_range=0.0, max_range=-1.0):
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        n = (x1 - x0) * (y1 - y0)
+        leaf = np.empty(n, dtype=np.int32)
+        dsq = np.empty(n, dtype=np.float32)
+        xyz = np.empty((n, 3), dtype=np.float32)
+        depth = np.empty(n, dtype=np.uint32)
+        visits = lib().orc_raycast_window(
+            self._h, _f(K), _f(Rt), x0, x1, y0, y1, min_range, max_range, _i(leaf), _f(dsq), _f(xyz), _u(depth)
+        )
+        return dict(leaf=leaf, dsq=dsq, xyz=xyz, depth=depth, visits=int(visits))
+
+    def raycast_window_brute(self, K, Rt, x0, x1, y0, y1, min_range=0.0, max_range=-1.0):
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        n = (x1 - x0) * (y1 - y0)
+        leaf = np.empty(n, dtype=np.int32)
+        dsq = np.empty(n, dtype=np.float32)
+        lib().orc_raycast_window_brute(self._h, _f(K), _f(Rt), x0, x1, y0, y1, min_range, max_range, _i(leaf), _f(dsq))
+        return dict(leaf=leaf, dsq=dsq)
+
+    def intersect_rays(self, origins, directions, min_range=0.0, max_range=-1.0):
+        o = _f32(origins)
+        d = _f32(directions)
+        n = o.shape[0]
+        leaf = np.empty(n, dtype=np.int32)
+        dsq = np.empty(n, dtype=np.float32)
+        xyz = np.empty((n, 3), dtype=np.float32)
+        depth = np.empty(n, dtype=np.uint32)
+        lib().orc_intersect_rays(self._h, _f(o), _f(d), n, min_range, max_range, _i(leaf), _f(dsq), _f(xyz), _u(depth))
+        return dict(leaf=leaf, dsq=dsq, xyz=xyz, depth=depth)
+
+    def score_viewpoint(self, weights, normals, K, width, Rt, window=None, height=None, opts: Optional[ScoreOpts] = None):
+        """getRaycastHitVoxelsWithInformationScore for one viewpoint (sorted by leaf index)."""
+        opts = opts or default_opts()
+        w = _f32(weights, (self.n,))
+        nr = _f32(normals, (self.n, 3))
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        if window is None:
+            assert height is not None
+            window = (0, width, 0, height)
+        x0, x1, y0, y1 = window
+        cap = (x1 - x0) * (y1 - y0)
+        leaf = np.empty(cap, dtype=np.int32)
+        info = np.empty(cap, dtype=np.float32)
+        pix = np.empty(cap, dtype=np.uint32)
+        dsq = np.empty(cap, dtype=np.float32)
+        hc = C.c_uint32(0)
+        tot = C.c_float(0)
+        tot32 = C.c_float(0)
+        k = lib().orc_score_viewpoint(
+            self._h, _f(w), _f(nr), _f(K), width, _f(Rt), x0, x1, y0, y1, C.byref(opts), cap,
+            _i(leaf), _f(info), _u(pix), _f(dsq), C.byref(hc), C.byref(tot), C.byref(tot32),
+        )
+        assert k != C.c_size_t(-1).value
+        return dict(
+            leaf=leaf[:k].copy(), info=info[:k].copy(), pixel=pix[:k].copy(), dsq=dsq[:k].copy(),
+            hit_count=int(hc.value), total=float(tot.value), total_f32=float(tot32.value),
+        )
+
+    def score_batch(self, weights, normals, K, width, height, Rt, opts: Optional[ScoreOpts] = None, threads: int = 1):
+        opts = opts or default_opts()
+        w = _f32(weights, (self.n,))
+        nr = _f32(normals, (self.n, 3))
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        n = Rt.shape[0]
+        kept = np.empty(n, dtype=np.uint32)
+        hit = np.empty(n, dtype=np.uint32)
+        tot = np.empty(n, dtype=np.float32)
+        rays = lib().orc_score_batch(
+            self._h, _f(w), _f(nr), _f(K), width, height, _f(Rt), n, C.byref(opts), threads, _u(kept), _u(hit), _f(tot)
+        )
+        return dict(kept_count=kept, hit_count=hit, total=tot, rays=int(rays))
+
+
+def voxel_information(box, weight, normal, cam, fx, width, opts: Optional[ScoreOpts] = None) -> float:
+    opts = opts or default_opts()
+    return float(
+        lib().orc_voxel_information(
+            _f(_f32(box, (6,))), float(weight), _f(_f32(normal, (3,))), _f(_f32(cam, (3,))), float(fx), int(width),
+            C.byref(opts),
+        )
+    )
+
+
+def pose_to_rt(quat_wxyz, trans) -> np.ndarray:
+    out = np.empty(12, dtype=np.float32)
+    lib().orc_pose_to_rt(_f(_f32(quat_wxyz, (4,))), _f(_f32(trans, (3,))), _f(out))
+    return out
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

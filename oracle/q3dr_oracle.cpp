@@ -1,0 +1,560 @@
+// q3dr_oracle.cpp -- CPU ORACLE (test infrastructure, not the product; see q3dr_oracle.h).
+//
+// Dependency-free restatement of the reference CPU raycast + score path in strict IEEE
+// binary32.  Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -fopenmp (oracle/Makefile).
+// Every function cites the reference file:line it follows (paths relative to the reference root).
+#include "q3dr_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stack>
+#include <unordered_map>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#if defined(__FAST_MATH__)
+#error "the oracle must not be built with fast-math"
+#endif
+
+namespace {
+
+// std::min / std::max semantics (ternaries), as used by geometry.h:336-343.
+inline float smin(float a, float b) { return (b < a) ? b : a; }
+inline float smax(float a, float b) { return (a < b) ? b : a; }
+
+struct Box {
+  float mn[3];
+  float mx[3];
+};
+
+// bvh.h:46-119: node = bounding box + left/right + object.  Stored in one array; `leaf` is the
+// input index of the object for leaves, -1 for inner nodes.
+struct Node {
+  Box box;
+  int32_t left;
+  int32_t right;
+  int32_t leaf;
+};
+
+struct Ray {  // geometry.h:57-110 (RayData)
+  float o[3];
+  float d[3];
+  float inv[3];
+};
+
+struct Hit {  // bvh.h:162-172 (IntersectionResult)
+  float p[3];
+  int32_t node;
+  uint32_t depth;
+  float dist_sq;
+};
+
+}  // namespace
+
+struct orc_tree {
+  std::vector<Node> nodes;
+  std::vector<Box> leaf_boxes;       // input order
+  std::vector<uint32_t> dfs_order;   // k -> input index
+  std::vector<uint32_t> dfs_rank;    // input index -> k
+  std::vector<uint32_t> leaf_depth;  // input index -> depth
+  size_t depth = 0;
+  int32_t root = -1;
+};
+
+namespace {
+
+// geometry.h:227-229  getCenter(i) = (min(i) + max(i)) / 2
+inline float center(const Box& b, int axis) { return (b.mn[axis] + b.mx[axis]) / 2.0f; }
+
+// bvh.h:764-788 splitMedian.  `idx` plays the role of the objects vector (it is permuted in place,
+// exactly like std::stable_sort permutes the ObjectWithBoundingBox range).
+int32_t splitMedian(orc_tree* t, std::vector<uint32_t>& idx, size_t begin, size_t end, int sort_axis,
+                    size_t cur_depth) {
+  const int32_t me = (int32_t)t->nodes.size();
+  t->nodes.emplace_back();
+  t->nodes[me].left = t->nodes[me].right = t->nodes[me].leaf = -1;
+  if (end - begin > 1) {
+    const std::vector<Box>& boxes = t->leaf_boxes;
+    std::stable_sort(idx.begin() + begin, idx.begin() + end, [&](uint32_t a, uint32_t b) -> bool {
+      return center(boxes[a], sort_axis) < center(boxes[b], sort_axis);
+    });
+    const int next_sort_axis = (sort_axis + 1) % 3;
+    const size_t mid = begin + (end - begin) / 2;
+    const int32_t l = splitMedian(t, idx, begin, mid, next_sort_axis, cur_depth + 1);
+    const int32_t r = splitMedian(t, idx, mid, end, next_sort_axis, cur_depth + 1);
+    Node& n = t->nodes[me];
+    n.left = l;
+    n.right = r;
+    // bvh.h:96-106 computeBoundingBox -> geometry.h:353-357 getUnion (cwiseMin / cwiseMax)
+    const Box& a = t->nodes[l].box;
+    const Box& b = t->nodes[r].box;
+    for (int i = 0; i < 3; ++i) {
+      n.box.mn[i] = smin(a.mn[i], b.mn[i]);
+      n.box.mx[i] = smax(a.mx[i], b.mx[i]);
+    }
+  } else {
+    Node& n = t->nodes[me];
+    n.box = t->leaf_boxes[idx[begin]];
+    n.leaf = (int32_t)idx[begin];
+    t->leaf_depth[idx[begin]] = (uint32_t)cur_depth;
+    if (cur_depth > t->depth) t->depth = cur_depth;
+  }
+  return me;
+}
+
+// geometry.h:235-238
+inline bool isOutside(const Box& b, const float* p) {
+  return (p[0] < b.mn[0]) || (p[1] < b.mn[1]) || (p[2] < b.mn[2]) || (p[0] > b.mx[0]) ||
+         (p[1] > b.mx[1]) || (p[2] > b.mx[2]);
+}
+
+// geometry.h:319-351 BoundingBox3D::intersects(RayData, Vector3*)
+inline bool boxIntersects(const Box& b, const Ray& r, float* intersection) {
+  float t_min = -std::numeric_limits<float>::max();
+  float t_max = std::numeric_limits<float>::max();
+  for (int i = 0; i < 3; ++i) {
+    float t0 = (b.mn[i] - r.o[i]) * r.inv[i];
+    float t1 = (b.mx[i] - r.o[i]) * r.inv[i];
+    t_min = smax(t_min, smin(t0, t1));
+    t_max = smin(t_max, smax(t0, t1));
+  }
+  bool intersect = t_max > smax(t_min, 0.0f);
+  if (intersect) {
+    t_min = smax(t_min, 0.0f);
+    for (int i = 0; i < 3; ++i) {
+      float s = r.d[i] * t_min;
+      intersection[i] = r.o[i] + s;
+    }
+  }
+  return intersect;
+}
+
+// (a - b).squaredNorm() with Eigen's fixed-size-3 reduction order a0 + (a1 + a2).
+inline float distSq(const float* a, const float* b) {
+  float e0 = a[0] - b[0], e1 = a[1] - b[1], e2 = a[2] - b[2];
+  float s0 = e0 * e0, s1 = e1 * e1, s2 = e2 * e2;
+  float s12 = s1 + s2;
+  return s0 + s12;
+}
+
+// bvh.h:842-909 intersectsRecursive
+bool intersectsRecursive(const orc_tree* t, const Ray& ray, int32_t cur, uint32_t cur_depth, Hit* result,
+                         uint64_t* visits) {
+  ++*visits;
+  const Node& n = t->nodes[cur];
+  const bool outside = isOutside(n.box, ray.o);
+  float isect[3] = {0, 0, 0};
+  float isect_dist_sq = 0;
+  if (outside) {
+    const bool hit = boxIntersects(n.box, ray, isect);
+    if (hit) {
+      isect_dist_sq = distSq(ray.o, isect);
+      if (isect_dist_sq > result->dist_sq) {
+        return false;
+      }
+    } else {
+      return false;
+    }
+  }
+  if (n.left < 0 && n.right < 0) {
+    if (!outside) {
+      isect[0] = ray.o[0];
+      isect[1] = ray.o[1];
+      isect[2] = ray.o[2];
+      isect_dist_sq = 0;
+    }
+    result->p[0] = isect[0];
+    result->p[1] = isect[1];
+    result->p[2] = isect[2];
+    result->node = cur;
+    result->depth = cur_depth;
+    result->dist_sq = isect_dist_sq;
+    return true;
+  }
+  bool l = false, r = false;
+  if (n.left >= 0) l = intersectsRecursive(t, ray, n.left, cur_depth + 1, result, visits);
+  if (n.right >= 0) r = intersectsRecursive(t, ray, n.right, cur_depth + 1, result, visits);
+  return l || r;
+}
+
+// bvh.h:376-391 Tree::intersects(ray, min_range, max_range).  min_range is stored, never read.
+inline bool treeIntersects(const orc_tree* t, const Ray& ray, float /*min_range*/, float max_range, Hit* result,
+                           uint64_t* visits) {
+  result->p[0] = result->p[1] = result->p[2] = 0;
+  result->node = -1;
+  result->depth = 0;
+  if (max_range > 0) {
+    result->dist_sq = max_range * max_range;
+  } else {
+    result->dist_sq = std::numeric_limits<float>::max();
+  }
+  return intersectsRecursive(t, ray, t->root, 0, result, visits);
+}
+
+// geometry.h:65-66 Ray(origin, direction): direction.normalized(); RayData: cwiseInverse (bvh.h:380)
+inline void makeRay(const float* origin, const float* direction, Ray* r) {
+  float s0 = direction[0] * direction[0], s1 = direction[1] * direction[1], s2 = direction[2] * direction[2];
+  float n2 = s0 + (s1 + s2);
+  for (int i = 0; i < 3; ++i) r->o[i] = origin[i];
+  if (n2 > 0) {
+    float n = std::sqrt(n2);
+    for (int i = 0; i < 3; ++i) r->d[i] = direction[i] / n;
+  } else {
+    for (int i = 0; i < 3; ++i) r->d[i] = direction[i];
+  }
+  for (int i = 0; i < 3; ++i) r->inv[i] = 1.0f / r->d[i];
+}
+
+// viewpoint.cpp:88-96 + sparse_reconstruction.cpp:148-154: camera ray for integer pixel (x, y).
+inline void cameraRay(const float K[4], const float Rt[12], uint32_t x, uint32_t y, Ray* r) {
+  const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  float c[3];
+  c[0] = ((float)x - cx) / fx;
+  c[1] = ((float)y - cy) / fy;
+  c[2] = 1.0f;
+  float origin[3] = {Rt[3], Rt[7], Rt[11]};
+  float d[3];
+  for (int i = 0; i < 3; ++i) {
+    // Eigen 3x3 * vec3 lazy product: row(i).cwiseProduct(v).sum() = p0 + (p1 + p2)
+    float p0 = Rt[4 * i + 0] * c[0];
+    float p1 = Rt[4 * i + 1] * c[1];
+    float p2 = Rt[4 * i + 2] * c[2];
+    float p12 = p1 + p2;
+    d[i] = p0 + p12;
+  }
+  makeRay(origin, d, r);
+}
+
+struct Derived {  // viewpoint_score.cpp:20-28, viewpoint_planner.cpp:107-109
+  float thr, kf, a_thr, ka;
+};
+
+inline Derived derive(const orc_score_opts* o) {
+  Derived d;
+  d.thr = o->voxel_sensor_size_ratio_threshold;
+  d.kf = 1 / o->voxel_sensor_size_ratio_inv_falloff_factor;
+  d.a_thr = o->incidence_angle_threshold_degrees * float(M_PI) / float(180);
+  d.ka = 1 / (o->incidence_angle_inv_falloff_factor_degrees * float(M_PI) / float(180));
+  return d;
+}
+
+// viewpoint_planner_scoring.cpp:11-24,67-73,116-122 ; viewpoint_score.cpp:45-68
+float voxelInformation(const Box& b, float weight, const float* nrm, const float* cam, float fx,
+                       uint32_t image_width, const orc_score_opts* opts, const Derived& dv) {
+  float g[3];
+  for (int i = 0; i < 3; ++i) {
+    float m = (b.mn[i] + b.mx[i]) / 2.0f;  // getCenter, geometry.h:223-225
+    g[i] = cam[i] - m;
+  }
+  float s0 = g[0] * g[0], s1 = g[1] * g[1], s2 = g[2] * g[2];
+  float n2 = s0 + (s1 + s2);
+  float distance = std::sqrt(n2);                  // .norm()
+  float size_x = b.mx[0] - b.mn[0];                // getExtent(0), geometry.h:203-205
+  float rel = fx * size_x / distance / (float)image_width;  // sparse_reconstruction.cpp:132-135
+  float res;
+  if (rel >= dv.thr) {
+    res = 1;
+  } else {
+    res = std::exp(-dv.kf * (dv.thr - rel));
+  }
+  float inc;
+  if (nrm[0] == 0 && nrm[1] == 0 && nrm[2] == 0) {
+    inc = 1;
+  } else {
+    float v[3];
+    if (n2 > 0) {
+      for (int i = 0; i < 3; ++i) v[i] = g[i] / distance;  // normalized()
+    } else {
+      for (int i = 0; i < 3; ++i) v[i] = g[i];
+    }
+    float p0 = v[0] * nrm[0], p1 = v[1] * nrm[1], p2 = v[2] * nrm[2];
+    float dot = p0 + (p1 + p2);
+    dot = smax(smin(dot, 1.0f), -1.0f);  // ait::clamp, include/ait/utilities.h:65-68
+    bool zero = false;
+    if (dot <= 0) {
+      if (opts->incidence_ignore_dot_product_sign) {
+        dot = std::fabs(dot);
+      } else {
+        zero = true;
+      }
+    }
+    if (zero) {
+      inc = 0;
+    } else {
+      float angle = std::acos(dot);
+      if (angle <= dv.a_thr) {
+        inc = 1;
+      } else {
+        inc = std::exp(-dv.ka * (angle - dv.a_thr));
+      }
+    }
+  }
+  float factor = res * inc;
+  return factor * weight;
+}
+
+struct Kept {
+  int32_t leaf;
+  uint32_t pixel;
+  float dsq;
+};
+
+// viewpoint_raycast.cpp:166-219 pixel loop + :321-335 first-writer dedup
+void castAndDedup(const orc_tree* t, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                  uint32_t y1, float min_range, float max_range, std::vector<Kept>* kept) {
+  const uint32_t w = x1 - x0;
+  std::unordered_map<int32_t, Kept> raycast_map;
+  uint64_t visits = 0;
+  for (uint32_t y = y0; y < y1; ++y) {
+    for (uint32_t x = x0; x < x1; ++x) {
+      Ray ray;
+      cameraRay(K, Rt, x, y, &ray);
+      Hit h;
+      if (treeIntersects(t, ray, min_range, max_range, &h, &visits)) {
+        Kept k;
+        k.leaf = t->nodes[h.node].leaf;
+        k.pixel = (y - y0) * w + (x - x0);
+        k.dsq = h.dist_sq;
+        raycast_map.emplace(k.leaf, k);  // emplace keeps the first pixel
+      }
+    }
+  }
+  kept->clear();
+  kept->reserve(raycast_map.size());
+  for (const auto& kv : raycast_map) kept->push_back(kv.second);
+  // The reference's output order is hash order (unspecified); pinned here: ascending leaf index.
+  std::sort(kept->begin(), kept->end(), [](const Kept& a, const Kept& b) { return a.leaf < b.leaf; });
+}
+
+}  // namespace
+
+extern "C" {
+
+orc_tree* orc_tree_build(const float* boxes, size_t n) {
+  if (n == 0) return nullptr;
+  orc_tree* t = new orc_tree;
+  t->leaf_boxes.resize(n);
+  std::memcpy(t->leaf_boxes.data(), boxes, n * sizeof(Box));
+  t->leaf_depth.assign(n, 0);
+  t->nodes.reserve(2 * n);
+  std::vector<uint32_t> idx(n);
+  for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+  t->root = splitMedian(t, idx, 0, n, 0, 0);
+  t->dfs_order = idx;  // after all the in-place sorts the range is in left-to-right leaf order
+  t->dfs_rank.resize(n);
+  for (size_t k = 0; k < n; ++k) t->dfs_rank[idx[k]] = (uint32_t)k;
+  return t;
+}
+
+void orc_tree_free(orc_tree* t) { delete t; }
+size_t orc_tree_num_leaves(const orc_tree* t) { return t->leaf_boxes.size(); }
+size_t orc_tree_num_nodes(const orc_tree* t) { return t->nodes.size(); }
+size_t orc_tree_depth(const orc_tree* t) { return t->depth; }
+
+void orc_tree_dfs_order(const orc_tree* t, uint32_t* order) {
+  std::memcpy(order, t->dfs_order.data(), t->dfs_order.size() * sizeof(uint32_t));
+}
+
+void orc_tree_leaf_depths(const orc_tree* t, uint32_t* depth_out) {
+  std::memcpy(depth_out, t->leaf_depth.data(), t->leaf_depth.size() * sizeof(uint32_t));
+}
+
+// bvh.h:203-246 all-node iterator: stack, push left then right => root, right subtree, left subtree.
+void orc_tree_voxel_index(const orc_tree* t, uint32_t* idx_out) {
+  std::stack<int32_t> st;
+  st.push(t->root);
+  uint32_t voxel_index = 0;
+  while (!st.empty()) {
+    int32_t n = st.top();
+    st.pop();
+    const Node& node = t->nodes[n];
+    if (node.leaf >= 0) idx_out[node.leaf] = voxel_index;
+    ++voxel_index;
+    if (node.left >= 0) st.push(node.left);
+    if (node.right >= 0) st.push(node.right);
+  }
+}
+
+void orc_tree_root_box(const orc_tree* t, float* box_out) {
+  std::memcpy(box_out, &t->nodes[t->root].box, sizeof(Box));
+}
+
+// Eigen QuaternionBase::toRotationMatrix (Eigen 3.3.1, Geometry/Quaternion.h), used by pose.h:122-127.
+void orc_pose_to_rt(const float q[4], const float trans[3], float rt[12]) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  rt[0] = 1.0f - (tyy + tzz);
+  rt[1] = txy - twz;
+  rt[2] = txz + twy;
+  rt[4] = txy + twz;
+  rt[5] = 1.0f - (txx + tzz);
+  rt[6] = tyz - twx;
+  rt[8] = txz - twy;
+  rt[9] = tyz + twx;
+  rt[10] = 1.0f - (txx + tyy);
+  rt[3] = trans[0];
+  rt[7] = trans[1];
+  rt[11] = trans[2];
+}
+
+uint64_t orc_raycast_window(const orc_tree* t, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1,
+                            uint32_t y0, uint32_t y1, float min_range, float max_range, int32_t* leaf, float* dsq,
+                            float* xyz, uint32_t* depth) {
+  const uint32_t w = x1 - x0;
+  uint64_t visits = 0;
+  for (uint32_t y = y0; y < y1; ++y) {
+    for (uint32_t x = x0; x < x1; ++x) {
+      Ray ray;
+      cameraRay(K, Rt, x, y, &ray);
+      Hit h;
+      const bool ok = treeIntersects(t, ray, min_range, max_range, &h, &visits);
+      const size_t i = (size_t)(y - y0) * w + (x - x0);
+      if (leaf) leaf[i] = ok ? t->nodes[h.node].leaf : -1;
+      if (dsq) dsq[i] = ok ? h.dist_sq : 0.0f;
+      if (xyz) {
+        xyz[3 * i + 0] = ok ? h.p[0] : 0.0f;
+        xyz[3 * i + 1] = ok ? h.p[1] : 0.0f;
+        xyz[3 * i + 2] = ok ? h.p[2] : 0.0f;
+      }
+      if (depth) depth[i] = ok ? h.depth : 0u;
+    }
+  }
+  return visits;
+}
+
+void orc_raycast_window_brute(const orc_tree* t, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1,
+                              uint32_t y0, uint32_t y1, float /*min_range*/, float max_range, int32_t* leaf,
+                              float* dsq) {
+  const uint32_t w = x1 - x0;
+  const size_t n = t->leaf_boxes.size();
+  for (uint32_t y = y0; y < y1; ++y) {
+    for (uint32_t x = x0; x < x1; ++x) {
+      Ray ray;
+      cameraRay(K, Rt, x, y, &ray);
+      float best = (max_range > 0) ? max_range * max_range : std::numeric_limits<float>::max();
+      int32_t best_leaf = -1;
+      // leaves in DFS order; "<=" so that a later leaf at equal distance overwrites (bvh.h:867,881-895)
+      for (size_t k = 0; k < n; ++k) {
+        const uint32_t li = t->dfs_order[k];
+        const Box& b = t->leaf_boxes[li];
+        float d2;
+        if (isOutside(b, ray.o)) {
+          float p[3];
+          if (!boxIntersects(b, ray, p)) continue;
+          d2 = distSq(ray.o, p);
+          if (d2 > best) continue;
+        } else {
+          d2 = 0;
+        }
+        best = d2;
+        best_leaf = (int32_t)li;
+      }
+      const size_t i = (size_t)(y - y0) * w + (x - x0);
+      leaf[i] = best_leaf;
+      if (dsq) dsq[i] = best_leaf >= 0 ? best : 0.0f;
+    }
+  }
+}
+
+void orc_intersect_rays(const orc_tree* t, const float* origins, const float* directions, size_t n,
+                        float min_range, float max_range, int32_t* leaf, float* dsq, float* xyz,
+                        uint32_t* depth) {
+  uint64_t visits = 0;
+  for (size_t i = 0; i < n; ++i) {
+    Ray ray;
+    makeRay(origins + 3 * i, directions + 3 * i, &ray);
+    Hit h;
+    const bool ok = treeIntersects(t, ray, min_range, max_range, &h, &visits);
+    if (leaf) leaf[i] = ok ? t->nodes[h.node].leaf : -1;
+    if (dsq) dsq[i] = ok ? h.dist_sq : 0.0f;
+    if (xyz) {
+      xyz[3 * i + 0] = ok ? h.p[0] : 0.0f;
+      xyz[3 * i + 1] = ok ? h.p[1] : 0.0f;
+      xyz[3 * i + 2] = ok ? h.p[2] : 0.0f;
+    }
+    if (depth) depth[i] = ok ? h.depth : 0u;
+  }
+}
+
+float orc_voxel_information(const float box[6], float weight, const float normal[3], const float cam[3],
+                            float fx, uint32_t image_width, const orc_score_opts* opts) {
+  Box b;
+  std::memcpy(&b, box, sizeof(Box));
+  return voxelInformation(b, weight, normal, cam, fx, image_width, opts, derive(opts));
+}
+
+size_t orc_score_viewpoint(const orc_tree* t, const float* weights, const float* normals, const float K[4],
+                           uint32_t image_width, const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                           uint32_t y1, const orc_score_opts* opts, size_t cap, int32_t* out_leaf,
+                           float* out_info, uint32_t* out_pixel, float* out_dsq, uint32_t* hit_count,
+                           float* total, float* total_f32) {
+  std::vector<Kept> kept;
+  castAndDedup(t, K, Rt, x0, x1, y0, y1, opts->raycast_min_range, opts->raycast_max_range, &kept);
+  const Derived dv = derive(opts);
+  const float cam[3] = {Rt[3], Rt[7], Rt[11]};
+  // viewpoint_planner_raycast.cpp:128-137
+  size_t n_out = 0;
+  double sum64 = 0.0;
+  float sum32 = 0.0f;
+  bool overflow = false;
+  const bool counting_only = !out_leaf && !out_info && !out_pixel && !out_dsq;
+  for (const Kept& k : kept) {
+    const float info = voxelInformation(t->leaf_boxes[k.leaf], weights[k.leaf], normals + 3 * (size_t)k.leaf, cam,
+                                        K[0], image_width, opts, dv);
+    if (!opts->ignore_voxels_with_zero_information || info > 0) {
+      if (n_out < cap) {
+        if (out_leaf) out_leaf[n_out] = k.leaf;
+        if (out_info) out_info[n_out] = info;
+        if (out_pixel) out_pixel[n_out] = k.pixel;
+        if (out_dsq) out_dsq[n_out] = k.dsq;
+      } else if (counting_only == false) {
+        overflow = true;
+      }
+      ++n_out;
+      sum64 += (double)info;
+      sum32 += info;
+    }
+  }
+  if (hit_count) *hit_count = (uint32_t)kept.size();
+  if (total) *total = (float)sum64;
+  if (total_f32) *total_f32 = sum32;
+  return overflow ? (size_t)-1 : n_out;
+}
+
+uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* normals, const float K[4],
+                         uint32_t width, uint32_t height, const float* Rt, size_t n_vp,
+                         const orc_score_opts* opts, int threads, uint32_t* kept_count, uint32_t* hit_count,
+                         float* total) {
+  if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (long v = 0; v < (long)n_vp; ++v) {
+    uint32_t hc = 0;
+    float tot = 0, tot32 = 0;
+    // all output arrays NULL => counting mode (no capacity check)
+    size_t kc = orc_score_viewpoint(t, weights, normals, K, width, Rt + 12 * v, 0, width, 0, height, opts, 0,
+                                    nullptr, nullptr, nullptr, nullptr, &hc, &tot, &tot32);
+    if (hit_count) hit_count[v] = hc;
+    if (total) total[v] = tot;
+    if (kept_count) kept_count[v] = (uint32_t)kc;
+  }
+  return (uint64_t)n_vp * width * height;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+/*
+ * q3dr_oracle.h -- CPU ORACLE for the Quad3DR viewpoint raycast + scoring path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.  The
+ * product (quad3dr_b200/, libq3dr_raycast.so) never links, imports or calls it.
+ *
+ * It restates, in dependency-free C++17 with strict IEEE-754 binary32 arithmetic
+ * (no FMA contraction, no reassociation: built with -ffp-contract=off, no fast-math),
+ * the reference's CPU algorithm.  Citations are relative to the reference checkout:
+ *   tree build      viewpoint_planner/src/bvh/bvh.h:361-373,764-788,96-106
+ *   ray query       viewpoint_planner/src/bvh/bvh.h:376-391,842-909
+ *   box / ray math  include/bh/math/geometry.h:65-66,159-160,223-238,319-351,357-361
+ *   camera ray      viewpoint_planner/src/planner/viewpoint.cpp:88-96,
+ *                   viewpoint_planner/src/reconstruction/sparse_reconstruction.cpp:132-135,148-154,
+ *                   include/bh/pose.h:122-127
+ *   pixel loop      viewpoint_planner/src/planner/viewpoint_raycast.cpp:166-219
+ *   dedup           viewpoint_planner/src/planner/viewpoint_raycast.cpp:321-335
+ *   scoring         viewpoint_planner/src/planner/viewpoint_planner_scoring.cpp:11-38,67-73,116-122,
+ *                   viewpoint_planner/src/planner/viewpoint_score.cpp:20-28,45-68,
+ *                   include/ait/utilities.h:65-68
+ *   aggregation     viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:116-148
+ *
+ * PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture
+ * for this path, and its CPU path cannot be compiled here (Eigen,
+ * Boost, octomap, OMPL, Qt5 are absent).  Third-party arithmetic on the path is Eigen
+ * (header-only, version unpinned in-tree; cmake.sh points at eigen-3.3.1): fixed-size-3
+ * reductions are restated as  a0 + (a1 + a2)  (Eigen 3.3 redux_novec_unroller halves the
+ * range), normalized() as componentwise division by sqrt(squaredNorm()) when that is > 0.
+ * The reference compiles this code under "#pragma GCC optimize(fast-math)"; its exact bits
+ * are therefore compiler dependent.  This oracle pins strict IEEE as THE definition.
+ */
+#ifndef Q3DR_ORACLE_H_
+#define Q3DR_ORACLE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_tree orc_tree;
+
+/* Scoring options, same meaning and defaults as ViewpointScore::Options
+ * (viewpoint_score.h:17-41) / ViewpointPlanner::Options (viewpoint_planner.h:320-329). */
+typedef struct orc_score_opts {
+  float voxel_sensor_size_ratio_threshold;          /* 0.002 */
+  float voxel_sensor_size_ratio_inv_falloff_factor; /* 0.001 */
+  float incidence_angle_threshold_degrees;          /* 30 */
+  float incidence_angle_inv_falloff_factor_degrees; /* 30 */
+  int32_t incidence_ignore_dot_product_sign;        /* 0 */
+  int32_t ignore_voxels_with_zero_information;      /* 1 at every graph-building call site */
+  float raycast_min_range;                          /* accepted, never read (bvh.h:381) */
+  float raycast_max_range;                          /* 60; <= 0 means unlimited */
+} orc_score_opts;
+
+/* boxes: n x 6 floats (min xyz, max xyz) in the order handed to Tree::build.  n >= 1. */
+orc_tree* orc_tree_build(const float* boxes, size_t n);
+void orc_tree_free(orc_tree* t);
+size_t orc_tree_num_leaves(const orc_tree* t);
+size_t orc_tree_num_nodes(const orc_tree* t);
+size_t orc_tree_depth(const orc_tree* t);
+/* order[k] = input index of the k-th leaf in left-to-right DFS order (the tie-break order). */
+void orc_tree_dfs_order(const orc_tree* t, uint32_t* order);
+/* depth_out[i] = BVH depth (root = 0) of the leaf built from input box i. */
+void orc_tree_leaf_depths(const orc_tree* t, uint32_t* depth_out);
+/* all-node iterator order (bvh.h:226-235): idx_out[i] = voxel index of input leaf i. */
+void orc_tree_voxel_index(const orc_tree* t, uint32_t* idx_out);
+/* root bounding box (6 floats) */
+void orc_tree_root_box(const orc_tree* t, float* box_out);
+
+/* Quaternion (w,x,y,z) + translation -> row-major 3x4 [R|t] as Eigen's
+ * QuaternionBase::toRotationMatrix (pose.h:122-127). */
+void orc_pose_to_rt(const float quat_wxyz[4], const float trans[3], float rt_out[12]);
+
+/* Per-pixel closest-hit query over the window [x0,x1) x [y0,y1), row-major.
+ * K = {fx, fy, cx, cy};  Rt = row-major 3x4 [R|t] (image-to-world).
+ * Outputs (any may be NULL), all of length (x1-x0)*(y1-y0):
+ *   leaf   input index of the hit leaf, -1 for a miss
+ *   dsq    squared distance (bits of the reference's dist_sq), 0 for a miss
+ *   xyz    intersection point (3 floats per pixel), 0 for a miss
+ *   depth  BVH depth of the hit leaf, 0 for a miss
+ * Returns the number of tree nodes visited (for the visits/ray statistic). */
+uint64_t orc_raycast_window(const orc_tree* t, const float K[4], const float Rt[12],
+                            uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                            float min_range, float max_range,
+                            int32_t* leaf, float* dsq, float* xyz, uint32_t* depth);
+
+/* Same query by brute force over all leaves (structure-independence check):
+ * argmin dist_sq, ties to the leaf latest in DFS order. */
+void orc_raycast_window_brute(const orc_tree* t, const float K[4], const float Rt[12],
+                              uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                              float min_range, float max_range, int32_t* leaf, float* dsq);
+
+/* Arbitrary ray list (bvh.h:512-541): origins/directions n x 3; directions are normalised
+ * like bh::Ray's constructor. */
+void orc_intersect_rays(const orc_tree* t, const float* origins, const float* directions, size_t n,
+                        float min_range, float max_range, int32_t* leaf, float* dsq, float* xyz,
+                        uint32_t* depth);
+
+/* observation score of one voxel seen from camera centre `cam` (scoring.cpp:116-122). */
+float orc_voxel_information(const float box[6], float weight, const float normal[3],
+                            const float cam[3], float fx, uint32_t image_width,
+                            const orc_score_opts* opts);
+
+/* getRaycastHitVoxelsWithInformationScore for one viewpoint over the window.
+ * weights: n floats; normals: n x 3 floats (input-leaf order).
+ * Outputs, capacity `cap` each (cap >= number of unique hit voxels, at most window size):
+ *   out_leaf   ascending input leaf index of every voxel kept in the voxel set
+ *   out_info   its information
+ *   out_pixel  row-major index (within the window) of the first pixel that hit it
+ *   out_dsq    dist_sq of that kept pixel
+ * hit_count   = unique voxels hit before the information>0 filter
+ * total       = (float) of the fp64 sum of kept informations in ascending leaf order
+ * total_f32   = fp32 running sum in ascending leaf order
+ * Returns the number of kept voxels (<= cap) or (size_t)-1 if cap is too small. */
+size_t orc_score_viewpoint(const orc_tree* t, const float* weights, const float* normals,
+                           const float K[4], uint32_t image_width, const float Rt[12],
+                           uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                           const orc_score_opts* opts, size_t cap,
+                           int32_t* out_leaf, float* out_info, uint32_t* out_pixel, float* out_dsq,
+                           uint32_t* hit_count, float* total, float* total_f32);
+
+/* Batch form used for the CPU baseline: n_vp viewpoints (Rt: n_vp x 12), OpenMP over
+ * viewpoints with `threads` threads (1 = the reference as shipped: serial pixel loop).
+ * Only counts and totals are returned.  Returns total rays cast. */
+uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* normals,
+                         const float K[4], uint32_t width, uint32_t height,
+                         const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,
+                         uint32_t* kept_count, uint32_t* hit_count, float* total);
+
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q3DR_ORACLE_H_ */
