@@ -1,0 +1,203 @@
+/*
+ * q3dr_raycast.h -- C ABI of the B200-native viewpoint raycast + scoring engine.
+ *
+ * Drop-in boundary for the one data-parallel hot path of Quad3DR.  Plain
+ * pointers and sizes only; every entry point returns an int status (Q3DR_OK == 0) and never throws.
+ * The library runs on sm_100a CUDA kernels only: there is no CPU fallback, and every compute entry
+ * point fails with Q3DR_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   q3dr_map_create / q3dr_map_destroy
+ *        bvh::Tree::ensureCudaTreeIsInitialized + CudaTree::createCopyFromHostTree, Tree::clear
+ *        viewpoint_planner/src/bvh/bvh.h:949-955,296-314 ; viewpoint_planner/src/bvh/bvh.cu:25-83
+ *   q3dr_map_update_weights
+ *        ViewpointPlannerData::updateWeights* writing NodeObject::weight
+ *        viewpoint_planner/src/planner/viewpoint_planner_data.cpp:476-482,573-577
+ *   q3dr_raycast_window
+ *        bvh::Tree::raycastCuda / raycastWithScreenCoordinatesCuda
+ *        viewpoint_planner/src/bvh/bvh.h:396-451,453-509 ; bvh.cu:583-689
+ *   q3dr_intersect_rays
+ *        bvh::Tree::intersectsCuda                         bvh.h:512-541 ; bvh.cu:546-579
+ *   q3dr_raycast_unique
+ *        ViewpointRaycast::getRaycastHitVoxels[WithScreenCoordinates]Cuda (+ removeDuplicateRaycastHitVoxels)
+ *        viewpoint_planner/src/planner/viewpoint_raycast.cpp:221-283,305-335
+ *   q3dr_score_viewpoints / q3dr_score_viewpoints_device
+ *        ViewpointPlanner::getRaycastHitVoxelsWithInformationScore, batched over viewpoints
+ *        viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:89-148,
+ *        viewpoint_planner/src/planner/viewpoint_planner_scoring.cpp:11-38,67-73,116-122,
+ *        viewpoint_planner/src/planner/viewpoint_score.cpp:45-68
+ *   q3dr_splitmedian_order
+ *        bvh::Tree::build -> splitMedian (defines the tie-break order)     bvh.h:361-373,764-788
+ *   q3dr_pose_to_rt
+ *        Pose::getTransformationImageToWorld                               include/bh/pose.h:122-127
+ *
+ * Numeric contract: strict IEEE-754 binary32 in the reference's operation
+ * order, no FMA contraction.  hit(ray) = leaf of least dist_sq among leaves the ray's slab test
+ * accepts (dist_sq <= max_range^2; origin inside a leaf => dist_sq 0); equal dist_sq => the leaf
+ * with the HIGHER INDEX wins.  Callers therefore pass leaves in the left-to-right leaf order of the
+ * reference's bvh::Tree (what a walk of the host tree yields, or q3dr_splitmedian_order computes),
+ * so that "higher index" == "visited later by the reference's depth-first recursion".
+ */
+#ifndef Q3DR_RAYCAST_H_
+#define Q3DR_RAYCAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3DR_ABI_VERSION 1
+
+enum q3dr_status {
+  Q3DR_OK = 0,
+  Q3DR_ERR_INVALID_ARG = 1, /* null pointer, empty map, bad window ... (BH_EXCEPTION class) */
+  Q3DR_ERR_CUDA = 2,        /* a CUDA call or kernel failed (bh::CudaError / Tree::CudaError class) */
+  Q3DR_ERR_NO_DEVICE = 3,   /* no usable CUDA device: the engine has no CPU path */
+  Q3DR_ERR_OUT_OF_MEMORY = 4,
+  Q3DR_ERR_INTERNAL = 5
+};
+
+typedef struct q3dr_map q3dr_map;
+
+/* Same fields, meaning and defaults as ViewpointScore::Options (viewpoint_score.h:17-41) plus the
+ * raycast ranges of ViewpointPlanner::Options (viewpoint_planner.h:201-202). */
+typedef struct q3dr_score_opts {
+  float voxel_sensor_size_ratio_threshold;          /* 0.002 */
+  float voxel_sensor_size_ratio_inv_falloff_factor; /* 0.001 */
+  float incidence_angle_threshold_degrees;          /* 30 */
+  float incidence_angle_inv_falloff_factor_degrees; /* 30 */
+  int32_t incidence_ignore_dot_product_sign;        /* 0 */
+  int32_t ignore_voxels_with_zero_information;      /* 1 */
+  float raycast_min_range;                          /* 0; accepted and ignored like the reference */
+  float raycast_max_range;                          /* 60; <= 0 means unlimited */
+} q3dr_score_opts;
+
+/* One pixel of raycast*Cuda (bvh::Tree::IntersectionResultWithScreenCoordinates, bvh.h:162-182). */
+typedef struct q3dr_pixel_hit {
+  float intersection[3]; /* hit point; 0 for a miss */
+  int32_t leaf;          /* leaf index, -1 for a miss (reference: node == nullptr) */
+  uint32_t depth;        /* depth of the leaf in the reference's bvh::Tree; 0 for a miss */
+  float dist_sq;         /* 0 for a miss */
+  float screen_x;        /* pixel x, y as floats (viewpoint_raycast.cpp:203) */
+  float screen_y;
+} q3dr_pixel_hit;
+
+/* Per-viewpoint hit lists + scores in CSR form.  Viewpoint v owns entries [offsets[v], offsets[v+1]).
+ * Entries are sorted by ascending leaf index.  Host arrays are owned by the map and stay valid until
+ * the next scoring call on the same map or q3dr_map_destroy. */
+typedef struct q3dr_result {
+  uint64_t n_viewpoints;
+  uint64_t n_entries;          /* == offsets[n_viewpoints] */
+  const uint64_t* offsets;     /* n_viewpoints + 1 */
+  const int32_t* leaf;         /* voxel (leaf index) */
+  const float* information;    /* its observation score */
+  const uint32_t* first_pixel; /* row-major index inside the window of the first pixel that hit it */
+  const float* dist_sq;        /* dist_sq of that kept pixel */
+  const float* total;          /* n_viewpoints: sum of information (fp64 accumulate, rounded once) */
+  const uint32_t* hit_count;   /* n_viewpoints: unique voxels hit before the information > 0 filter */
+} q3dr_result;
+
+typedef struct q3dr_map_info {
+  uint64_t n_leaves;
+  uint64_t n_nodes;       /* 4-wide nodes in the flattened tree */
+  uint32_t tree_depth;    /* depth of the flattened 4-wide tree */
+  uint32_t ref_depth;     /* depth of the reference's splitMedian tree, ceil(log2(n)) */
+  uint64_t node_bytes;    /* bytes of the node array in HBM */
+  uint64_t device_bytes;  /* all device memory currently held by the map */
+  int32_t device;
+  int32_t sm_count;
+} q3dr_map_info;
+
+/* Kernel statistics of the last scoring / raycast call on a map. */
+typedef struct q3dr_stats {
+  uint64_t rays;             /* rays cast */
+  uint64_t kernel_launches;  /* kernels of this library launched */
+  float raycast_ms;          /* device time of the traversal kernel(s), CUDA events on the launch stream */
+  float score_ms;            /* device time of the dedup/score/compaction kernels */
+  float total_ms;            /* device time of the whole call (first launch to last) */
+  uint32_t chunks;
+  uint32_t viewpoints_per_chunk;
+} q3dr_stats;
+
+int q3dr_abi_version(void);
+const char* q3dr_status_string(int status);
+/* Message of the last failing call on this thread (empty string if none). */
+const char* q3dr_last_error(void);
+int q3dr_device_count(int* count);
+
+void q3dr_score_opts_default(q3dr_score_opts* opts);
+
+/* ---- host-side helpers (no device work) ---- */
+
+/* Leaf order of the reference's Tree::build for boxes (n x 6: min xyz, max xyz) given in the order
+ * they would be handed to build(): order[k] = input index of the k-th leaf, left to right.
+ * depth (nullable): depth[k] = depth of that leaf in the reference tree. */
+int q3dr_splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* depth);
+
+/* Quaternion (w, x, y, z) + translation -> row-major 3x4 [R|t], image-to-world. */
+int q3dr_pose_to_rt(const float quat_wxyz[4], const float trans[3], float rt_out[12]);
+
+/* Host-only diagnostic (no device): flattens the leaves like q3dr_map_create and verifies the tree's
+ * invariants; reports its size.  Any out pointer may be NULL. */
+int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t* n_nodes, uint32_t* depth,
+                         uint32_t* max_stack, uint32_t* top_nodes);
+
+/* ---- occupancy map: flatten + upload ---- */
+
+/* boxes   n x 6 floats, leaf k has tie-break priority k (see header comment).
+ * weights n floats or NULL (=> 1).   normals n x 3 floats or NULL (=> zero vectors).
+ * depth   n uint32 (depth of each leaf in the reference tree, only echoed in q3dr_pixel_hit.depth)
+ *         or NULL (=> the splitMedian depth implied by n and k). */
+int q3dr_map_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth,
+                    size_t n, int device, q3dr_map** out);
+int q3dr_map_update_weights(q3dr_map* map, const float* weights);
+int q3dr_map_update_normals(q3dr_map* map, const float* normals);
+int q3dr_map_get_info(const q3dr_map* map, q3dr_map_info* info);
+int q3dr_map_last_stats(const q3dr_map* map, q3dr_stats* stats);
+/* Frees and re-uploads all device state (the reference's recovery after a CUDA error, bvh.h:443-449). */
+int q3dr_map_reset(q3dr_map* map);
+int q3dr_map_destroy(q3dr_map* map);
+
+/* ---- compat layer: one viewpoint, per-pixel results ---- */
+
+/* K = {fx, fy, cx, cy}; Rt = row-major 3x4 [R|t]; window [x0,x1) x [y0,y1) in pixels.
+ * out: (x1-x0)*(y1-y0) records, row-major, HOST memory. */
+int q3dr_raycast_window(q3dr_map* map, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                        uint32_t y1, float min_range, float max_range, q3dr_pixel_hit* out);
+
+/* origins, directions: n x 3 floats (directions are normalised like bh::Ray).  out: n records;
+ * screen_x / screen_y are 0. */
+int q3dr_intersect_rays(q3dr_map* map, const float* origins, const float* directions, size_t n, float min_range,
+                        float max_range, q3dr_pixel_hit* out);
+
+/* getRaycastHitVoxelsWithScreenCoordinates(remove_duplicates = true): one record per unique voxel,
+ * the data of the first pixel (row-major) that hit it, ascending leaf index.  out capacity `cap`
+ * records; *count receives the number of unique voxels (call fails with INVALID_ARG if > cap). */
+int q3dr_raycast_unique(q3dr_map* map, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                        uint32_t y1, float min_range, float max_range, q3dr_pixel_hit* out, size_t cap,
+                        size_t* count);
+
+/* ---- the hot path: batched viewpoint scoring ---- */
+
+/* Rt: n x 12 floats in HOST memory.  image_width is the camera width used by the resolution factor
+ * (computeRelativeSizeOnSensorHorizontal); the window is [x0,x1) x [y0,y1).  result: filled in. */
+int q3dr_score_viewpoints(q3dr_map* map, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                          uint32_t y0, uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts,
+                          q3dr_result* result);
+
+/* Same with poses already resident in device memory (d_Rt) and results left in device memory
+ * (pointers in `result` are DEVICE pointers owned by the map).  stream: a cudaStream_t (0 = default). */
+int q3dr_score_viewpoints_device(q3dr_map* map, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                 uint32_t y0, uint32_t y1, const float* d_Rt, size_t n,
+                                 const q3dr_score_opts* opts, void* stream, q3dr_result* result);
+
+/* Copies the device-resident result of the last q3dr_score_viewpoints_device call to host memory
+ * owned by the map. */
+int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q3DR_RAYCAST_H_ */

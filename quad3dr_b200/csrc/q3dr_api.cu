@@ -1,0 +1,885 @@
+// q3dr_api.cu -- the C ABI (include/q3dr_raycast.h) over the sm_100a kernels.
+//
+// No CPU compute path exists in this library: without a usable CUDA device every compute entry point
+// returns Q3DR_ERR_NO_DEVICE.  Host code here only flattens the map (bvh_build.cpp), moves buffers and
+// launches kernels.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "raycast_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const std::string& msg) {
+  g_last_error = msg;
+  return status;
+}
+
+#define Q3DR_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      int st__ = (err__ == cudaErrorMemoryAllocation) ? Q3DR_ERR_OUT_OF_MEMORY : Q3DR_ERR_CUDA;  \
+      if (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver) st__ = Q3DR_ERR_NO_DEVICE; \
+      return fail(st__, std::string(#call) + ": " + cudaGetErrorString(err__));                  \
+    }                                                                                            \
+  } while (0)
+
+#define Q3DR_TRY(expr)             \
+  do {                             \
+    int st__ = (expr);             \
+    if (st__ != Q3DR_OK) return st__; \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    Q3DR_CUDA(cudaMalloc(&q, want * sizeof(T)));
+    if (keep && p && cap) {
+      cudaError_t e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return fail(Q3DR_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(e));
+      }
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return Q3DR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    Q3DR_CUDA(cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+    return Q3DR_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Derived {
+  float thr, kf, a_thr, ka;
+};
+
+// viewpoint_score.cpp:20-28 / viewpoint_planner.cpp:107-109 of the reference (fp32, same order)
+Derived derive(const q3dr_score_opts& o) {
+  Derived d;
+  d.thr = o.voxel_sensor_size_ratio_threshold;
+  d.kf = 1.0f / o.voxel_sensor_size_ratio_inv_falloff_factor;
+  d.a_thr = o.incidence_angle_threshold_degrees * float(M_PI) / float(180);
+  d.ka = 1.0f / (o.incidence_angle_inv_falloff_factor_degrees * float(M_PI) / float(180));
+  return d;
+}
+
+}  // namespace
+
+struct q3dr_map {
+  int device = 0;
+  int sm_count = 0;
+  size_t n = 0;
+  uint32_t ref_depth = 0;
+  // host copies (kept for q3dr_map_reset)
+  std::vector<float> h_boxes, h_weight, h_normal;
+  std::vector<uint8_t> h_depth;
+  q3dr::FlatTree tree;
+  // device: the map
+  DevBuf<float4> d_nodes;
+  DevBuf<float> d_boxes, d_weight, d_normal;
+  DevBuf<uint8_t> d_depth;
+  DevBuf<uint32_t> d_counter;
+  // device: per-chunk scratch
+  DevBuf<uint32_t> d_first_pix, d_bitmap, d_kept;
+  size_t slots = 0;
+  uint64_t leaf_stride = 0, word_stride = 0;
+  DevBuf<int32_t> t_leaf;
+  DevBuf<float> t_info, t_dsq;
+  DevBuf<uint32_t> t_pix;
+  uint64_t tmp_cap = 0;
+  // device: results of the last scoring call
+  DevBuf<uint64_t> d_offsets;
+  DevBuf<float> d_total;
+  DevBuf<uint32_t> d_hit_count;
+  DevBuf<int32_t> r_leaf;
+  DevBuf<float> r_info, r_dsq;
+  DevBuf<uint32_t> r_pix;
+  uint64_t last_n_vp = 0, last_n_entries = 0;
+  // staging
+  DevBuf<float> d_rt, d_ray_o, d_ray_d;
+  DevBuf<q3dr_pixel_hit> d_pixels;
+  PinnedBuf<uint64_t> h_scalar;
+  PinnedBuf<uint64_t> h_offsets;
+  PinnedBuf<float> h_total, h_info, h_dsq;
+  PinnedBuf<uint32_t> h_hit_count, h_pix;
+  PinnedBuf<int32_t> h_leaf;
+  PinnedBuf<float> h_rt;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int grid_ctas[3] = {0, 0, 0};
+  size_t smem_bytes = 0;
+  q3dr_stats stats{};
+
+  uint64_t device_bytes() const {
+    return d_nodes.bytes() + d_boxes.bytes() + d_weight.bytes() + d_normal.bytes() + d_depth.bytes() +
+           d_counter.bytes() + d_first_pix.bytes() + d_bitmap.bytes() + d_kept.bytes() + t_leaf.bytes() +
+           t_info.bytes() + t_dsq.bytes() + t_pix.bytes() + d_offsets.bytes() + d_total.bytes() +
+           d_hit_count.bytes() + r_leaf.bytes() + r_info.bytes() + r_dsq.bytes() + r_pix.bytes() + d_rt.bytes() +
+           d_ray_o.bytes() + d_ray_d.bytes() + d_pixels.bytes();
+  }
+};
+
+namespace {
+
+void release_device(q3dr_map* m) {
+  m->d_nodes.release();
+  m->d_boxes.release();
+  m->d_weight.release();
+  m->d_normal.release();
+  m->d_depth.release();
+  m->d_counter.release();
+  m->d_first_pix.release();
+  m->d_bitmap.release();
+  m->d_kept.release();
+  m->slots = 0;
+  m->t_leaf.release();
+  m->t_info.release();
+  m->t_dsq.release();
+  m->t_pix.release();
+  m->tmp_cap = 0;
+  m->d_offsets.release();
+  m->d_total.release();
+  m->d_hit_count.release();
+  m->r_leaf.release();
+  m->r_info.release();
+  m->r_dsq.release();
+  m->r_pix.release();
+  m->d_rt.release();
+  m->d_ray_o.release();
+  m->d_ray_d.release();
+  m->d_pixels.release();
+  m->last_n_vp = m->last_n_entries = 0;
+}
+
+template <int MODE>
+int configure_kernel(q3dr_map* m) {
+  if (m->smem_bytes > 48 * 1024) {
+    Q3DR_CUDA(cudaFuncSetAttribute(q3dr::raycast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)m->smem_bytes));
+  }
+  int per_sm = 0;
+  Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3dr::raycast_kernel<MODE>, q3dr::kThreadsPerCta,
+                                                          m->smem_bytes));
+  if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast kernel does not fit on an SM");
+  m->grid_ctas[MODE] = per_sm * m->sm_count;
+  return Q3DR_OK;
+}
+
+int upload_map(q3dr_map* m) {
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  const size_t n = m->n;
+  const size_t nn = m->tree.nodes.size();
+  Q3DR_TRY(m->d_nodes.ensure(nn * 8));
+  Q3DR_CUDA(cudaMemcpy(m->d_nodes.p, m->tree.nodes.data(), nn * sizeof(q3dr::Node4), cudaMemcpyHostToDevice));
+  Q3DR_TRY(m->d_boxes.ensure(n * 6));
+  Q3DR_CUDA(cudaMemcpy(m->d_boxes.p, m->h_boxes.data(), n * 6 * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_TRY(m->d_weight.ensure(n));
+  Q3DR_CUDA(cudaMemcpy(m->d_weight.p, m->h_weight.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_TRY(m->d_normal.ensure(n * 3));
+  Q3DR_CUDA(cudaMemcpy(m->d_normal.p, m->h_normal.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_TRY(m->d_depth.ensure(n));
+  Q3DR_CUDA(cudaMemcpy(m->d_depth.p, m->h_depth.data(), n, cudaMemcpyHostToDevice));
+  Q3DR_TRY(m->d_counter.ensure(4));
+  Q3DR_CUDA(cudaMemset(m->d_counter.p, 0, 4 * sizeof(uint32_t)));
+  Q3DR_TRY(m->h_scalar.ensure(8));
+  m->smem_bytes = (size_t)m->tree.top_nodes * sizeof(q3dr::Node4);
+  Q3DR_TRY(configure_kernel<q3dr::kModeScore>(m));
+  Q3DR_TRY(configure_kernel<q3dr::kModePixels>(m));
+  Q3DR_TRY(configure_kernel<q3dr::kModeRays>(m));
+  return Q3DR_OK;
+}
+
+// scratch for `slots` viewpoints in flight, `cap` result entries per viewpoint
+int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
+  const uint64_t leaf_stride = (m->n + 31) / 32 * 32;
+  const uint64_t word_stride = leaf_stride / 32;
+  if (slots > m->slots) {
+    m->d_first_pix.release();
+    m->d_bitmap.release();
+    Q3DR_TRY(m->d_first_pix.ensure(slots * leaf_stride));
+    Q3DR_TRY(m->d_bitmap.ensure(slots * word_stride));
+    Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), m->stream));
+    Q3DR_CUDA(cudaMemsetAsync(m->d_bitmap.p, 0, m->d_bitmap.bytes(), m->stream));
+    Q3DR_TRY(m->d_kept.ensure(slots));
+    m->slots = slots;
+    m->leaf_stride = leaf_stride;
+    m->word_stride = word_stride;
+  }
+  const size_t need = std::max<size_t>(slots, m->slots) * cap;
+  if (need > m->t_leaf.cap || cap != m->tmp_cap) {
+    Q3DR_TRY(m->t_leaf.ensure(need));
+    Q3DR_TRY(m->t_info.ensure(need));
+    Q3DR_TRY(m->t_dsq.ensure(need));
+    Q3DR_TRY(m->t_pix.ensure(need));
+    m->tmp_cap = cap;
+  }
+  return Q3DR_OK;
+}
+
+size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint64_t cap) {
+  // enough packets in flight that the persistent grid's tail is small ...
+  const size_t resident_warps = (size_t)m->grid_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
+  size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;
+  if (const char* e = std::getenv("Q3DR_CHUNK")) want = (size_t)std::max(1, atoi(e));
+  // ... bounded by scratch memory (first-pixel tables + temporary lists)
+  const uint64_t per_slot = ((m->n + 31) / 32 * 32) * 4 + cap * 16;
+  const uint64_t budget = 8ull << 30;
+  const size_t by_mem = (size_t)std::max<uint64_t>(1, budget / std::max<uint64_t>(per_slot, 1));
+  size_t b = std::min(want, by_mem);
+  b = std::min(b, n_vp);
+  b = std::min<size_t>(b, 4096);
+  return std::max<size_t>(b, 1);
+}
+
+float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return 0.f;
+  return ms;
+}
+
+void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                         float max_range, q3dr::RaycastParams* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->nodes = m->d_nodes.p;
+  p->n_top = m->tree.top_nodes;
+  p->fx = K[0];
+  p->fy = K[1];
+  p->cx = K[2];
+  p->cy = K[3];
+  p->x0 = x0;
+  p->y0 = y0;
+  p->w = x1 - x0;
+  p->h = y1 - y0;
+  p->tiles_x = (p->w + q3dr::kTileW - 1) / q3dr::kTileW;
+  const uint32_t tiles_y = (p->h + q3dr::kTileH - 1) / q3dr::kTileH;
+  p->tiles_per_vp = p->tiles_x * tiles_y;
+  p->max_range = max_range;
+  p->leaf_depth = m->d_depth.p;
+  p->tile_counter = m->d_counter.p;
+}
+
+int check_map(const q3dr_map* m) {
+  if (!m) return fail(Q3DR_ERR_INVALID_ARG, "map is NULL");
+  if (!m->d_nodes.p) return fail(Q3DR_ERR_INVALID_ARG, "map holds no device tree (failed reset?)");
+  return Q3DR_OK;
+}
+
+int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
+  if (x1 <= x0 || y1 <= y0) return fail(Q3DR_ERR_INVALID_ARG, "empty pixel window");
+  if ((uint64_t)(x1 - x0) * (uint64_t)(y1 - y0) >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "window too large");
+  return Q3DR_OK;
+}
+
+int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
+                      uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
+                      q3dr_result* result) {
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  m->stream = stream;
+  q3dr::RaycastParams rp;
+  fill_raycast_params(m, K, x0, x1, y0, y1, opts->raycast_max_range, &rp);
+  const uint64_t cap = std::min<uint64_t>((uint64_t)rp.w * rp.h, m->n);
+  const size_t B = choose_chunk(m, rp.tiles_per_vp, n_vp, cap);
+  if ((uint64_t)B * rp.tiles_per_vp >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "chunk too large");
+  Q3DR_TRY(ensure_scratch(m, B, cap));
+  Q3DR_TRY(m->d_offsets.ensure(n_vp + 1));
+  Q3DR_TRY(m->d_total.ensure(std::max<size_t>(n_vp, 1)));
+  Q3DR_TRY(m->d_hit_count.ensure(std::max<size_t>(n_vp, 1)));
+  Q3DR_CUDA(cudaMemsetAsync(m->d_offsets.p, 0, sizeof(uint64_t), stream));
+
+  const Derived dv = derive(*opts);
+  q3dr::ScoreParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.leaf_box = m->d_boxes.p;
+  sp.weight = m->d_weight.p;
+  sp.normal = m->d_normal.p;
+  sp.fx = K[0];
+  sp.fy = K[1];
+  sp.cx = K[2];
+  sp.cy = K[3];
+  sp.image_width_f = (float)image_width;
+  sp.x0 = x0;
+  sp.y0 = y0;
+  sp.w = rp.w;
+  sp.thr = dv.thr;
+  sp.kf = dv.kf;
+  sp.a_thr = dv.a_thr;
+  sp.ka = dv.ka;
+  sp.ignore_sign = opts->incidence_ignore_dot_product_sign;
+  sp.ignore_zero = opts->ignore_voxels_with_zero_information;
+  sp.n_words = (uint32_t)m->word_stride;
+  sp.first_pix = m->d_first_pix.p;
+  sp.bitmap = m->d_bitmap.p;
+  sp.leaf_stride = m->leaf_stride;
+  sp.word_stride = m->word_stride;
+  sp.cap = cap;
+  sp.kept_count = m->d_kept.p;
+
+  rp.first_pix = m->d_first_pix.p;
+  rp.bitmap = m->d_bitmap.p;
+  rp.leaf_stride = m->leaf_stride;
+  rp.word_stride = m->word_stride;
+
+  q3dr_stats st{};
+  st.viewpoints_per_chunk = (uint32_t)B;
+  Q3DR_CUDA(cudaEventRecord(m->ev[3], stream));
+  uint64_t total_entries = 0;
+  for (size_t v0 = 0; v0 < n_vp; v0 += B) {
+    const size_t nb = std::min(B, n_vp - v0);
+    rp.rt = d_Rt + 12 * v0;
+    rp.total_tiles = (uint32_t)(nb * rp.tiles_per_vp);
+    Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), stream));
+    Q3DR_CUDA(cudaEventRecord(m->ev[0], stream));
+    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeScore],
+                                            ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+    q3dr::raycast_kernel<q3dr::kModeScore><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, stream>>>(rp);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaEventRecord(m->ev[1], stream));
+    sp.rt = d_Rt + 12 * v0;
+    sp.tmp_leaf = m->t_leaf.p;
+    sp.tmp_info = m->t_info.p;
+    sp.tmp_pix = m->t_pix.p;
+    sp.tmp_dsq = m->t_dsq.p;
+    sp.hit_count = m->d_hit_count.p + v0;
+    sp.total = m->d_total.p + v0;
+    q3dr::score_compact_kernel<<<(unsigned)nb, q3dr::kScoreThreads, 0, stream>>>(sp);
+    Q3DR_CUDA(cudaGetLastError());
+    q3dr::scan_counts_kernel<<<1, 32, 0, stream>>>(m->d_kept.p, (uint32_t)nb, m->d_offsets.p + v0);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_scalar.p, m->d_offsets.p + v0 + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    Q3DR_CUDA(cudaStreamSynchronize(stream));
+    total_entries = m->h_scalar.p[0];
+    const size_t want = std::max<uint64_t>(total_entries, 1);
+    Q3DR_TRY(m->r_leaf.ensure(want, true, stream));
+    Q3DR_TRY(m->r_info.ensure(want, true, stream));
+    Q3DR_TRY(m->r_pix.ensure(want, true, stream));
+    Q3DR_TRY(m->r_dsq.ensure(want, true, stream));
+    q3dr::PackParams pp;
+    pp.offsets = m->d_offsets.p + v0;
+    pp.kept = m->d_kept.p;
+    pp.cap = cap;
+    pp.tmp_leaf = m->t_leaf.p;
+    pp.tmp_info = m->t_info.p;
+    pp.tmp_pix = m->t_pix.p;
+    pp.tmp_dsq = m->t_dsq.p;
+    pp.out_leaf = m->r_leaf.p;
+    pp.out_info = m->r_info.p;
+    pp.out_pix = m->r_pix.p;
+    pp.out_dsq = m->r_dsq.p;
+    const unsigned bx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(64, (cap + 255) / 256));
+    q3dr::pack_results_kernel<<<dim3(bx, (unsigned)nb), 256, 0, stream>>>(pp);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaEventRecord(m->ev[2], stream));
+    Q3DR_CUDA(cudaEventSynchronize(m->ev[2]));
+    st.raycast_ms += elapsed_ms(m->ev[0], m->ev[1]);
+    st.score_ms += elapsed_ms(m->ev[1], m->ev[2]);
+    st.kernel_launches += 4;
+    st.chunks += 1;
+  }
+  Q3DR_CUDA(cudaStreamSynchronize(stream));
+  if (n_vp > 0) st.total_ms = elapsed_ms(m->ev[3], m->ev[2]);
+  st.rays = (uint64_t)n_vp * rp.w * rp.h;
+  m->stats = st;
+  m->last_n_vp = n_vp;
+  m->last_n_entries = total_entries;
+  if (result) {
+    result->n_viewpoints = n_vp;
+    result->n_entries = total_entries;
+    result->offsets = m->d_offsets.p;
+    result->leaf = m->r_leaf.p;
+    result->information = m->r_info.p;
+    result->first_pixel = m->r_pix.p;
+    result->dist_sq = m->r_dsq.p;
+    result->total = m->d_total.p;
+    result->hit_count = m->d_hit_count.p;
+  }
+  return Q3DR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int q3dr_abi_version(void) { return Q3DR_ABI_VERSION; }
+
+const char* q3dr_status_string(int status) {
+  switch (status) {
+    case Q3DR_OK: return "ok";
+    case Q3DR_ERR_INVALID_ARG: return "invalid argument";
+    case Q3DR_ERR_CUDA: return "CUDA error";
+    case Q3DR_ERR_NO_DEVICE: return "no usable CUDA device (the engine has no CPU path)";
+    case Q3DR_ERR_OUT_OF_MEMORY: return "out of memory";
+    case Q3DR_ERR_INTERNAL: return "internal error";
+    default: return "unknown status";
+  }
+}
+
+const char* q3dr_last_error(void) { return g_last_error.c_str(); }
+
+int q3dr_device_count(int* count) {
+  if (!count) return fail(Q3DR_ERR_INVALID_ARG, "count is NULL");
+  *count = 0;
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(Q3DR_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  }
+  *count = c;
+  return Q3DR_OK;
+}
+
+void q3dr_score_opts_default(q3dr_score_opts* o) {
+  if (!o) return;
+  o->voxel_sensor_size_ratio_threshold = 0.002f;
+  o->voxel_sensor_size_ratio_inv_falloff_factor = 0.001f;
+  o->incidence_angle_threshold_degrees = 30.0f;
+  o->incidence_angle_inv_falloff_factor_degrees = 30.0f;
+  o->incidence_ignore_dot_product_sign = 0;
+  o->ignore_voxels_with_zero_information = 1;
+  o->raycast_min_range = 0.0f;
+  o->raycast_max_range = 60.0f;
+}
+
+int q3dr_splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* depth) {
+  if (!boxes || !order) return fail(Q3DR_ERR_INVALID_ARG, "boxes/order is NULL");
+  if (n == 0 || n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "leaf count out of range");
+  try {
+    q3dr::splitmedian_order(boxes, n, order, depth);
+  } catch (const std::bad_alloc&) {
+    return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  }
+  return Q3DR_OK;
+}
+
+// Eigen's QuaternionBase::toRotationMatrix in binary32, as Pose::getTransformationImageToWorld uses it.
+int q3dr_pose_to_rt(const float q[4], const float trans[3], float rt[12]) {
+  if (!q || !trans || !rt) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  rt[0] = 1.0f - (tyy + tzz);
+  rt[1] = txy - twz;
+  rt[2] = txz + twy;
+  rt[3] = trans[0];
+  rt[4] = txy + twz;
+  rt[5] = 1.0f - (txx + tzz);
+  rt[6] = tyz - twx;
+  rt[7] = trans[1];
+  rt[8] = txz - twy;
+  rt[9] = tyz + twx;
+  rt[10] = 1.0f - (txx + tyy);
+  rt[11] = trans[2];
+  return Q3DR_OK;
+}
+
+// Host-only diagnostic: flattens `boxes` exactly like q3dr_map_create and checks the invariants the
+// traversal relies on (every leaf referenced once; every child box contains the boxes of all leaves
+// below it, bit for bit as a union).  No device needed.
+int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t* n_nodes, uint32_t* depth,
+                         uint32_t* max_stack, uint32_t* top_nodes) {
+  if (!boxes || n == 0) return fail(Q3DR_ERR_INVALID_ARG, "boxes is NULL or empty");
+  q3dr::FlatTree t;
+  try {
+    q3dr::build_flat_tree(boxes, n, top_levels, &t);
+  } catch (const std::bad_alloc&) {
+    return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  }
+  if (n_nodes) *n_nodes = t.nodes.size();
+  if (depth) *depth = t.depth;
+  if (max_stack) *max_stack = t.max_stack;
+  if (top_nodes) *top_nodes = t.top_nodes;
+  // bottom-up check: nodes are laid out parents-before-children, so walk the array backwards
+  const size_t nn = t.nodes.size();
+  std::vector<float> nb(6 * nn);
+  std::vector<uint8_t> seen(n, 0);
+  std::vector<uint8_t> referenced(nn, 0);
+  for (size_t i = nn; i-- > 0;) {
+    const q3dr::Node4& nd = t.nodes[i];
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int s = 0; s < 4; ++s) {
+      const uint32_t c = nd.child[s];
+      if (c == q3dr::kEmptyChild) continue;
+      const float* ref;
+      if (c & q3dr::kLeafFlag) {
+        const uint32_t li = c & ~q3dr::kLeafFlag;
+        if (li >= n || seen[li]) return fail(Q3DR_ERR_INTERNAL, "leaf referenced twice or out of range");
+        seen[li] = 1;
+        ref = boxes + 6 * (size_t)li;
+      } else {
+        if (c <= i || c >= nn || referenced[c]) return fail(Q3DR_ERR_INTERNAL, "bad inner child reference");
+        referenced[c] = 1;
+        ref = nb.data() + 6 * (size_t)c;
+      }
+      for (int a = 0; a < 3; ++a) {
+        if (nd.mn[a][s] != ref[a] || nd.mx[a][s] != ref[3 + a]) return fail(Q3DR_ERR_INTERNAL, "child box mismatch");
+        mn[a] = std::min(mn[a], ref[a]);
+        mx[a] = std::max(mx[a], ref[3 + a]);
+      }
+    }
+    for (int a = 0; a < 3; ++a) {
+      nb[6 * i + a] = mn[a];
+      nb[6 * i + 3 + a] = mx[a];
+    }
+  }
+  for (size_t k = 0; k < n; ++k) {
+    if (!seen[k]) return fail(Q3DR_ERR_INTERNAL, "leaf missing from the flattened tree");
+  }
+  for (size_t i = 1; i < nn; ++i) {
+    if (!referenced[i]) return fail(Q3DR_ERR_INTERNAL, "unreferenced node");
+  }
+  return Q3DR_OK;
+}
+
+int q3dr_map_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                    int device, q3dr_map** out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (!boxes) return fail(Q3DR_ERR_INVALID_ARG, "boxes is NULL");
+  if (n == 0 || n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "leaf count out of range");
+  int count = 0;
+  Q3DR_TRY(q3dr_device_count(&count));
+  if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  if (device < 0 || device >= count) return fail(Q3DR_ERR_INVALID_ARG, "device index out of range");
+  q3dr_map* m = new (std::nothrow) q3dr_map;
+  if (!m) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  int st = Q3DR_OK;
+  try {
+    m->device = device;
+    m->n = n;
+    m->h_boxes.assign(boxes, boxes + 6 * n);
+    if (weights) {
+      m->h_weight.assign(weights, weights + n);
+    } else {
+      m->h_weight.assign(n, 1.0f);
+    }
+    if (normals) {
+      m->h_normal.assign(normals, normals + 3 * n);
+    } else {
+      m->h_normal.assign(3 * n, 0.0f);
+    }
+    m->h_depth.resize(n);
+    uint32_t ref_depth = 0;
+    for (size_t k = 0; k < n; ++k) {
+      const uint32_t d = depth ? depth[k] : q3dr::splitmedian_leaf_depth(n, k);
+      m->h_depth[k] = (uint8_t)std::min<uint32_t>(d, 255u);
+      ref_depth = std::max(ref_depth, d);
+    }
+    m->ref_depth = ref_depth;
+    int top_levels = 4;
+    if (const char* e = std::getenv("Q3DR_TOP_LEVELS")) top_levels = std::max(1, std::min(6, atoi(e)));
+    q3dr::build_flat_tree(m->h_boxes.data(), n, top_levels, &m->tree);
+    if (m->tree.max_stack > (uint32_t)q3dr::kStackEntries) {
+      st = fail(Q3DR_ERR_INTERNAL, "flattened tree too deep for the traversal stack");
+    }
+  } catch (const std::bad_alloc&) {
+    st = fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  }
+  if (st == Q3DR_OK) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+      st = fail(Q3DR_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    } else if (prop.major < 10) {
+      st = fail(Q3DR_ERR_NO_DEVICE, "device is not sm_100-class; this library carries sm_100a code only");
+    } else {
+      m->sm_count = prop.multiProcessorCount;
+    }
+  }
+  if (st == Q3DR_OK) {
+    cudaError_t e = cudaSetDevice(device);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev[i]);
+    if (e != cudaSuccess) st = fail(Q3DR_ERR_CUDA, std::string("event setup: ") + cudaGetErrorString(e));
+  }
+  if (st == Q3DR_OK) st = upload_map(m);
+  if (st != Q3DR_OK) {
+    q3dr_map_destroy(m);
+    return st;
+  }
+  *out = m;
+  return Q3DR_OK;
+}
+
+int q3dr_map_update_weights(q3dr_map* m, const float* weights) {
+  Q3DR_TRY(check_map(m));
+  if (!weights) return fail(Q3DR_ERR_INVALID_ARG, "weights is NULL");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  m->h_weight.assign(weights, weights + m->n);
+  Q3DR_CUDA(cudaMemcpy(m->d_weight.p, weights, m->n * sizeof(float), cudaMemcpyHostToDevice));
+  return Q3DR_OK;
+}
+
+int q3dr_map_update_normals(q3dr_map* m, const float* normals) {
+  Q3DR_TRY(check_map(m));
+  if (!normals) return fail(Q3DR_ERR_INVALID_ARG, "normals is NULL");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  m->h_normal.assign(normals, normals + 3 * m->n);
+  Q3DR_CUDA(cudaMemcpy(m->d_normal.p, normals, 3 * m->n * sizeof(float), cudaMemcpyHostToDevice));
+  return Q3DR_OK;
+}
+
+int q3dr_map_get_info(const q3dr_map* m, q3dr_map_info* info) {
+  if (!m || !info) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  info->n_leaves = m->n;
+  info->n_nodes = m->tree.nodes.size();
+  info->tree_depth = m->tree.depth;
+  info->ref_depth = m->ref_depth;
+  info->node_bytes = m->tree.nodes.size() * sizeof(q3dr::Node4);
+  info->device_bytes = m->device_bytes();
+  info->device = m->device;
+  info->sm_count = m->sm_count;
+  return Q3DR_OK;
+}
+
+int q3dr_map_last_stats(const q3dr_map* m, q3dr_stats* stats) {
+  if (!m || !stats) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  *stats = m->stats;
+  return Q3DR_OK;
+}
+
+int q3dr_map_reset(q3dr_map* m) {
+  if (!m) return fail(Q3DR_ERR_INVALID_ARG, "map is NULL");
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  cudaGetLastError();
+  release_device(m);
+  return upload_map(m);
+}
+
+int q3dr_map_destroy(q3dr_map* m) {
+  if (!m) return Q3DR_OK;
+  cudaSetDevice(m->device);
+  release_device(m);
+  m->h_scalar.release();
+  m->h_offsets.release();
+  m->h_total.release();
+  m->h_info.release();
+  m->h_dsq.release();
+  m->h_hit_count.release();
+  m->h_pix.release();
+  m->h_leaf.release();
+  m->h_rt.release();
+  for (int i = 0; i < 4; ++i) {
+    if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  }
+  cudaGetLastError();
+  delete m;
+  return Q3DR_OK;
+}
+
+int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                        uint32_t y1, float /*min_range*/, float max_range, q3dr_pixel_hit* out) {
+  Q3DR_TRY(check_map(m));
+  if (!K || !Rt || !out) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = nullptr;
+  q3dr::RaycastParams rp;
+  fill_raycast_params(m, K, x0, x1, y0, y1, max_range, &rp);
+  const size_t npix = (size_t)rp.w * rp.h;
+  Q3DR_TRY(m->d_rt.ensure(12));
+  Q3DR_TRY(m->d_pixels.ensure(npix));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), s));
+  rp.rt = m->d_rt.p;
+  rp.total_tiles = rp.tiles_per_vp;
+  rp.pixels = m->d_pixels.p;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModePixels],
+                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+  Q3DR_CUDA(cudaEventRecord(m->ev[0], s));
+  q3dr::raycast_kernel<q3dr::kModePixels><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaEventRecord(m->ev[1], s));
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, npix * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  q3dr_stats st{};
+  st.rays = npix;
+  st.kernel_launches = 1;
+  st.raycast_ms = elapsed_ms(m->ev[0], m->ev[1]);
+  st.total_ms = st.raycast_ms;
+  st.chunks = 1;
+  st.viewpoints_per_chunk = 1;
+  m->stats = st;
+  return Q3DR_OK;
+}
+
+int q3dr_intersect_rays(q3dr_map* m, const float* origins, const float* directions, size_t n, float /*min_range*/,
+                        float max_range, q3dr_pixel_hit* out) {
+  Q3DR_TRY(check_map(m));
+  if (!origins || !directions || !out) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n == 0) return Q3DR_OK;
+  if (n >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many rays for one call");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = nullptr;
+  Q3DR_TRY(m->d_ray_o.ensure(3 * n));
+  Q3DR_TRY(m->d_ray_d.ensure(3 * n));
+  Q3DR_TRY(m->d_pixels.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_ray_o.p, origins, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_ray_d.p, directions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), s));
+  q3dr::RaycastParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.nodes = m->d_nodes.p;
+  rp.n_top = m->tree.top_nodes;
+  rp.max_range = max_range;
+  rp.leaf_depth = m->d_depth.p;
+  rp.tile_counter = m->d_counter.p;
+  rp.ray_o = m->d_ray_o.p;
+  rp.ray_d = m->d_ray_d.p;
+  rp.n_rays = (uint32_t)n;
+  rp.total_tiles = (uint32_t)((n + 31) / 32);
+  rp.pixels = m->d_pixels.p;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeRays],
+                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+  q3dr::raycast_kernel<q3dr::kModeRays><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, n * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+int q3dr_score_viewpoints_device(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                 uint32_t y0, uint32_t y1, const float* d_Rt, size_t n, const q3dr_score_opts* opts,
+                                 void* stream, q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!K || (!d_Rt && n) || !opts) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  if (image_width == 0) return fail(Q3DR_ERR_INVALID_ARG, "image_width is 0");
+  return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result);
+}
+
+int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!result) return fail(Q3DR_ERR_INVALID_ARG, "result is NULL");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t nv = m->last_n_vp, ne = m->last_n_entries;
+  Q3DR_TRY(m->h_offsets.ensure(nv + 1));
+  Q3DR_TRY(m->h_total.ensure(std::max<size_t>(nv, 1)));
+  Q3DR_TRY(m->h_hit_count.ensure(std::max<size_t>(nv, 1)));
+  Q3DR_TRY(m->h_leaf.ensure(std::max<size_t>(ne, 1)));
+  Q3DR_TRY(m->h_info.ensure(std::max<size_t>(ne, 1)));
+  Q3DR_TRY(m->h_pix.ensure(std::max<size_t>(ne, 1)));
+  Q3DR_TRY(m->h_dsq.ensure(std::max<size_t>(ne, 1)));
+  Q3DR_CUDA(cudaMemcpyAsync(m->h_offsets.p, m->d_offsets.p, (nv + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+  if (nv) {
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_total.p, m->d_total.p, nv * sizeof(float), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_hit_count.p, m->d_hit_count.p, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  }
+  if (ne) {
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_leaf.p, m->r_leaf.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_info.p, m->r_info.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p, m->r_pix.p, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p, m->r_dsq.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  result->n_viewpoints = nv;
+  result->n_entries = ne;
+  result->offsets = m->h_offsets.p;
+  result->leaf = m->h_leaf.p;
+  result->information = m->h_info.p;
+  result->first_pixel = m->h_pix.p;
+  result->dist_sq = m->h_dsq.p;
+  result->total = m->h_total.p;
+  result->hit_count = m->h_hit_count.p;
+  return Q3DR_OK;
+}
+
+int q3dr_score_viewpoints(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
+                          uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts, q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!K || (!Rt && n) || !opts || !result) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  if (image_width == 0) return fail(Q3DR_ERR_INVALID_ARG, "image_width is 0");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = nullptr;
+  Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
+  if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr));
+  return q3dr_result_to_host(m, result);
+}
+
+int q3dr_raycast_unique(q3dr_map* m, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
+                        uint32_t y1, float min_range, float max_range, q3dr_pixel_hit* out, size_t cap,
+                        size_t* count) {
+  Q3DR_TRY(check_map(m));
+  if (!K || !Rt || !count || (!out && cap)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  q3dr_score_opts o;
+  q3dr_score_opts_default(&o);
+  o.ignore_voxels_with_zero_information = 0;
+  o.raycast_min_range = min_range;
+  o.raycast_max_range = max_range;
+  q3dr_result r;
+  Q3DR_TRY(q3dr_score_viewpoints(m, K, x1 > x0 ? x1 - x0 : 1, x0, x1, y0, y1, Rt, 1, &o, &r));
+  *count = (size_t)r.n_entries;
+  if (r.n_entries > cap) return fail(Q3DR_ERR_INVALID_ARG, "output capacity too small");
+  if (r.n_entries == 0) return Q3DR_OK;
+  // Full records of the kept pixels: re-cast exactly those pixels (device pixel list = first_pixel of the
+  // result still resident in HBM).  A kept pixel's ray hits its voxel by construction.
+  const size_t ne = (size_t)r.n_entries;
+  cudaStream_t s = nullptr;
+  Q3DR_TRY(m->d_pixels.ensure(ne));
+  Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), s));
+  q3dr::RaycastParams rp;
+  fill_raycast_params(m, K, x0, x1, y0, y1, max_range, &rp);
+  rp.rt = m->d_rt.p;  // the pose uploaded by q3dr_score_viewpoints above
+  rp.pix_list = m->r_pix.p;
+  rp.n_rays = (uint32_t)ne;
+  rp.total_tiles = (uint32_t)((ne + 31) / 32);
+  rp.pixels = m->d_pixels.p;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeRays],
+                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+  q3dr::raycast_kernel<q3dr::kModeRays><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, ne * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < ne; ++i) {
+    if (out[i].leaf != r.leaf[i]) return fail(Q3DR_ERR_INTERNAL, "kept pixel does not re-hit its voxel");
+  }
+  return Q3DR_OK;
+}
+
+}  // extern "C"

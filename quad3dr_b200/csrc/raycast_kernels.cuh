@@ -1,0 +1,572 @@
+// raycast_kernels.cuh -- sm_100a kernels of the viewpoint raycast + scoring engine.
+//
+// Numeric contract: every operation that feeds a hit decision is a single
+// correctly rounded binary32 operation in the reference's order (explicit __f*_rn intrinsics, the
+// translation unit is also compiled with -fmad=false, no fast-math, no FTZ).
+//
+// Kernel 1  raycast_kernel<MODE>      one warp = one 8x4 pixel packet of one viewpoint, persistent
+//                                     grid, packet traversal of the 4-wide node array.
+// Kernel 2  score_compact_kernel      one CTA per viewpoint: bitmap scan -> score -> ordered list.
+// Kernel 3  scan_counts_kernel        CSR offsets of the chunk.
+// Kernel 4  pack_results_kernel       per-viewpoint lists -> dense CSR pool.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/q3dr_raycast.h"
+#include "bvh_build.h"
+
+namespace q3dr {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kStackEntries = 64;
+constexpr uint32_t kEmptyPixel = 0xFFFFFFFFu;
+constexpr int kTileW = 8;
+constexpr int kTileH = 4;
+constexpr int kScoreThreads = 256;
+
+enum RaycastMode : int {
+  kModeScore = 0,   // dedup into the per-viewpoint first-pixel table + bitmap
+  kModePixels = 1,  // per-pixel q3dr_pixel_hit records (raycastCuda compat)
+  kModeRays = 2     // arbitrary ray list (intersectsCuda compat)
+};
+
+struct RaycastParams {
+  const float4* __restrict__ nodes;  // Node4 = 8 x float4
+  uint32_t n_top;                    // nodes staged in shared memory
+  const float* __restrict__ rt;      // [n_vp][12] row-major [R|t]
+  float fx, fy, cx, cy;
+  uint32_t x0, y0, w, h;  // window
+  uint32_t tiles_x, tiles_per_vp;
+  uint32_t total_tiles;
+  float max_range;
+  // kModeScore
+  uint32_t* first_pix;  // [slot][leaf_stride]
+  uint32_t* bitmap;     // [slot][word_stride]
+  uint64_t leaf_stride;
+  uint64_t word_stride;
+  // kModePixels / kModeRays
+  q3dr_pixel_hit* pixels;
+  const uint8_t* __restrict__ leaf_depth;
+  const float* __restrict__ ray_o;  // kModeRays: [n][3]
+  const float* __restrict__ ray_d;
+  const uint32_t* __restrict__ pix_list;  // kModeRays alternative: window pixel indices of one viewpoint
+  uint32_t n_rays;
+  uint32_t* tile_counter;
+};
+
+// std::min / std::max semantics of the reference (geometry.h:336-343), NaN behaviour included.
+__device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
+
+struct Ray {
+  float ox, oy, oz;
+  float dx, dy, dz;
+  float ix, iy, iz;
+};
+
+// Box test of intersectsRecursive (bvh.h:842-895) for one box:
+//   outside -> slab test (geometry.h:319-351), dist_sq = |o - (o + d t)|^2 ; inside -> dist_sq = 0.
+// Returns whether the box passes the slab test (or contains the origin); dsq and t are valid then.
+__device__ __forceinline__ bool box_test(const Ray& r, float mnx, float mny, float mnz, float mxx, float mxy,
+                                         float mxz, float& dsq, float& t) {
+  const float ax = __fsub_rn(mnx, r.ox), bx = __fsub_rn(mxx, r.ox);
+  const float ay = __fsub_rn(mny, r.oy), by = __fsub_rn(mxy, r.oy);
+  const float az = __fsub_rn(mnz, r.oz), bz = __fsub_rn(mxz, r.oz);
+  // isOutside: o < mn  <=>  mn - o > 0 exactly (gradual underflow keeps the sign of a difference)
+  const bool outside = (ax > 0.0f) | (ay > 0.0f) | (az > 0.0f) | (bx < 0.0f) | (by < 0.0f) | (bz < 0.0f);
+  const float t0x = __fmul_rn(ax, r.ix), t1x = __fmul_rn(bx, r.ix);
+  const float t0y = __fmul_rn(ay, r.iy), t1y = __fmul_rn(by, r.iy);
+  const float t0z = __fmul_rn(az, r.iz), t1z = __fmul_rn(bz, r.iz);
+  float tmin = -FLT_MAX, tmax = FLT_MAX;
+  tmin = smax(tmin, smin(t0x, t1x));
+  tmax = smin(tmax, smax(t0x, t1x));
+  tmin = smax(tmin, smin(t0y, t1y));
+  tmax = smin(tmax, smax(t0y, t1y));
+  tmin = smax(tmin, smin(t0z, t1z));
+  tmax = smin(tmax, smax(t0z, t1z));
+  const float tt = smax(tmin, 0.0f);
+  const bool slab = tmax > tt;
+  const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, tt));
+  const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, tt));
+  const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, tt));
+  const float ex = __fsub_rn(r.ox, px), ey = __fsub_rn(r.oy, py), ez = __fsub_rn(r.oz, pz);
+  const float d = __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+  dsq = outside ? d : 0.0f;
+  t = outside ? tt : 0.0f;
+  return outside ? slab : true;
+}
+
+// Camera ray of integer pixel (x, y): viewpoint.cpp:88-96, sparse_reconstruction.cpp:148-154,
+// bh::Ray normalisation geometry.h:65-66, inverse direction bvh.h:380.
+__device__ __forceinline__ void camera_ray(const float* __restrict__ rt, float fx, float fy, float cx, float cy,
+                                           uint32_t x, uint32_t y, Ray& r) {
+  const float c0 = __fdiv_rn(__fsub_rn((float)x, cx), fx);
+  const float c1 = __fdiv_rn(__fsub_rn((float)y, cy), fy);
+  const float r00 = __ldg(rt + 0), r01 = __ldg(rt + 1), r02 = __ldg(rt + 2), tx = __ldg(rt + 3);
+  const float r10 = __ldg(rt + 4), r11 = __ldg(rt + 5), r12 = __ldg(rt + 6), ty = __ldg(rt + 7);
+  const float r20 = __ldg(rt + 8), r21 = __ldg(rt + 9), r22 = __ldg(rt + 10), tz = __ldg(rt + 11);
+  const float d0 = __fadd_rn(__fmul_rn(r00, c0), __fadd_rn(__fmul_rn(r01, c1), r02));
+  const float d1 = __fadd_rn(__fmul_rn(r10, c0), __fadd_rn(__fmul_rn(r11, c1), r12));
+  const float d2 = __fadd_rn(__fmul_rn(r20, c0), __fadd_rn(__fmul_rn(r21, c1), r22));
+  const float n2 = __fadd_rn(__fmul_rn(d0, d0), __fadd_rn(__fmul_rn(d1, d1), __fmul_rn(d2, d2)));
+  r.ox = tx;
+  r.oy = ty;
+  r.oz = tz;
+  if (n2 > 0.0f) {
+    const float n = __fsqrt_rn(n2);
+    r.dx = __fdiv_rn(d0, n);
+    r.dy = __fdiv_rn(d1, n);
+    r.dz = __fdiv_rn(d2, n);
+  } else {
+    r.dx = d0;
+    r.dy = d1;
+    r.dz = d2;
+  }
+  r.ix = __fdiv_rn(1.0f, r.dx);
+  r.iy = __fdiv_rn(1.0f, r.dy);
+  r.iz = __fdiv_rn(1.0f, r.dz);
+}
+
+__device__ __forceinline__ void make_ray(float ox, float oy, float oz, float d0, float d1, float d2, Ray& r) {
+  const float n2 = __fadd_rn(__fmul_rn(d0, d0), __fadd_rn(__fmul_rn(d1, d1), __fmul_rn(d2, d2)));
+  r.ox = ox;
+  r.oy = oy;
+  r.oz = oz;
+  if (n2 > 0.0f) {
+    const float n = __fsqrt_rn(n2);
+    r.dx = __fdiv_rn(d0, n);
+    r.dy = __fdiv_rn(d1, n);
+    r.dz = __fdiv_rn(d2, n);
+  } else {
+    r.dx = d0;
+    r.dy = d1;
+    r.dz = d2;
+  }
+  r.ix = __fdiv_rn(1.0f, r.dx);
+  r.iy = __fdiv_rn(1.0f, r.dy);
+  r.iz = __fdiv_rn(1.0f, r.dz);
+}
+
+struct PacketHit {
+  float dsq;     // best dist_sq (the range bound while nothing is hit)
+  float t;       // ray parameter of the best hit
+  int32_t leaf;  // best leaf index, -1 = none
+};
+
+#define Q3DR_FULL_MASK 0xFFFFFFFFu
+
+// Conditional swap of two (key, node, per-lane dsq) candidates; key and node are warp-uniform.
+__device__ __forceinline__ void cswap(uint32_t& ka, uint32_t& na, float& da, uint32_t& kb, uint32_t& nb, float& db) {
+  if (kb < ka) {
+    uint32_t tk = ka; ka = kb; kb = tk;
+    uint32_t tn = na; na = nb; nb = tn;
+    float td = da; da = db; db = td;
+  }
+}
+
+// Packet traversal: the warp walks the 4-wide tree as one unit with a shared control flow; each lane
+// keeps its own ray, its own best hit and its own pruning distance.  A node is visited while at least
+// one lane can still improve below it (warp vote), children are visited nearest first (warp min of the
+// entry dist_sq), far children go on a short stack together with every lane's entry dist_sq so that a
+// popped entry no lane needs any more is dropped without touching memory.
+//
+// Correctness does not depend on the tree: a child is skipped by a lane only if its box fails the
+// reference's own test (miss, or dist_sq > best), and rounding is monotone, so the box of an ancestor
+// never fails when a descendant leaf would pass.  Equal dist_sq: higher leaf
+// index wins (= later in the reference's depth-first order).
+__device__ __forceinline__ void traverse_packet(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
+                                                const float4* smem_top, uint32_t n_top) {
+  float stack_d[kStackEntries];
+  uint32_t stack_n[kStackEntries];
+  int sp = 0;
+  uint32_t node = 0;
+  while (true) {
+    const float4* np = (node < n_top) ? (smem_top + (size_t)node * 8) : (nodes + (size_t)node * 8);
+    const float4 mnx = np[0], mny = np[1], mnz = np[2];
+    const float4 mxx = np[3], mxy = np[4], mxz = np[5];
+    const uint4 ch = *reinterpret_cast<const uint4*>(np + 6);
+
+    float d0, d1, d2, d3, t0, t1, t2, t3;
+    const bool h0 = box_test(ray, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, d0, t0);
+    const bool h1 = box_test(ray, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, d1, t1);
+    const bool h2 = box_test(ray, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, d2, t2);
+    const bool h3 = box_test(ray, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, d3, t3);
+
+    // leaves first: they tighten `best` before the inner children are judged
+#define Q3DR_LEAF(CH, H, D, T)                                                         \
+    if ((CH) & kLeafFlag) {                                                             \
+      if ((CH) != kEmptyChild) {                                                        \
+        const int32_t li = (int32_t)((CH) & ~kLeafFlag);                                \
+        const bool acc = (H) && ((D) < best.dsq || ((D) == best.dsq && li > best.leaf)); \
+        if (acc) {                                                                      \
+          best.dsq = (D);                                                               \
+          best.t = (T);                                                                 \
+          best.leaf = li;                                                               \
+        }                                                                               \
+      }                                                                                 \
+    }
+    Q3DR_LEAF(ch.x, h0, d0, t0)
+    Q3DR_LEAF(ch.y, h1, d1, t1)
+    Q3DR_LEAF(ch.z, h2, d2, t2)
+    Q3DR_LEAF(ch.w, h3, d3, t3)
+#undef Q3DR_LEAF
+
+    // inner children: warp-uniform key = least entry dist_sq over the lanes that still need the child
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+    float e0 = __int_as_float(0x7F800000), e1 = e0, e2 = e0, e3 = e0;  // +inf = "this lane does not need it"
+#define Q3DR_INNER(CH, H, D, K, E)                                                      \
+    if (!((CH) & kLeafFlag)) {                                                          \
+      const bool ok = (H) && !((D) > best.dsq);                                         \
+      if (ok) (E) = (D);                                                                \
+      (K) = __reduce_min_sync(Q3DR_FULL_MASK, ok ? __float_as_uint(D) : 0xFFFFFFFFu);   \
+    }
+    Q3DR_INNER(ch.x, h0, d0, k0, e0)
+    Q3DR_INNER(ch.y, h1, d1, k1, e1)
+    Q3DR_INNER(ch.z, h2, d2, k2, e2)
+    Q3DR_INNER(ch.w, h3, d3, k3, e3)
+#undef Q3DR_INNER
+
+    uint32_t n0 = ch.x, n1 = ch.y, n2 = ch.z, n3 = ch.w;
+    // 5-comparator sorting network on warp-uniform keys
+    cswap(k0, n0, e0, k1, n1, e1);
+    cswap(k2, n2, e2, k3, n3, e3);
+    cswap(k0, n0, e0, k2, n2, e2);
+    cswap(k1, n1, e1, k3, n3, e3);
+    cswap(k1, n1, e1, k2, n2, e2);
+    // push far ones first so that the nearest is on top
+    if (k3 != 0xFFFFFFFFu) { stack_d[sp] = e3; stack_n[sp] = n3; ++sp; }
+    if (k2 != 0xFFFFFFFFu) { stack_d[sp] = e2; stack_n[sp] = n2; ++sp; }
+    if (k1 != 0xFFFFFFFFu) { stack_d[sp] = e1; stack_n[sp] = n1; ++sp; }
+    if (k0 != 0xFFFFFFFFu) {
+      node = n0;  // nearest child: descend directly
+      continue;
+    }
+    // pop until an entry some lane still needs
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      const float d = stack_d[sp];
+      const uint32_t n = stack_n[sp];
+      if (__any_sync(Q3DR_FULL_MASK, !(d > best.dsq))) {
+        node = n;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsPerCta, 2) raycast_kernel(const RaycastParams p) {
+  extern __shared__ float4 smem_top[];
+  __shared__ uint32_t s_tile[kWarpsPerCta];
+  for (uint32_t i = threadIdx.x; i < p.n_top * 8; i += blockDim.x) smem_top[i] = p.nodes[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
+
+  while (true) {
+    if (lane == 0) s_tile[warp] = atomicAdd(p.tile_counter, 1u);
+    __syncwarp();
+    const uint32_t tile = s_tile[warp];
+    __syncwarp();
+    if (tile >= p.total_tiles) break;
+
+    Ray ray;
+    PacketHit best;
+    best.leaf = -1;
+    best.t = 0.0f;
+    bool live;
+    uint32_t vp = 0, pix = 0, px = 0, py = 0;
+    if (MODE == kModeRays) {
+      const uint32_t i = tile * 32u + lane;
+      live = i < p.n_rays;
+      pix = i;
+      if (live && p.pix_list != nullptr) {
+        const uint32_t wp = __ldg(p.pix_list + i);
+        py = wp / p.w;
+        px = wp - py * p.w;
+        camera_ray(p.rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+      } else if (live) {
+        make_ray(__ldg(p.ray_o + 3 * (size_t)i), __ldg(p.ray_o + 3 * (size_t)i + 1), __ldg(p.ray_o + 3 * (size_t)i + 2),
+                 __ldg(p.ray_d + 3 * (size_t)i), __ldg(p.ray_d + 3 * (size_t)i + 1), __ldg(p.ray_d + 3 * (size_t)i + 2),
+                 ray);
+      }
+    } else {
+      vp = tile / p.tiles_per_vp;
+      const uint32_t rem = tile - vp * p.tiles_per_vp;
+      const uint32_t ty = rem / p.tiles_x;
+      const uint32_t tx = rem - ty * p.tiles_x;
+      px = tx * kTileW + (lane & (kTileW - 1));
+      py = ty * kTileH + (lane >> 3);
+      live = (px < p.w) && (py < p.h);
+      pix = py * p.w + px;
+      camera_ray(p.rt + 12 * (size_t)vp, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+    }
+    if (!live) {
+      // a dead lane never accepts anything: dist_sq >= 0 > -1
+      ray.ox = ray.oy = ray.oz = 0.0f;
+      ray.dx = ray.dy = ray.dz = 1.0f;
+      ray.ix = ray.iy = ray.iz = 1.0f;
+    }
+    best.dsq = live ? range_sq : -1.0f;
+
+    traverse_packet(ray, best, p.nodes, smem_top, p.n_top);
+
+    if (MODE == kModeScore) {
+      // warp-aggregated dedup: lanes are in row-major pixel order inside the tile, so the lowest lane of
+      // each equal-leaf group owns the group's first pixel; only group leaders touch the tables.
+      const uint32_t grp = __match_any_sync(Q3DR_FULL_MASK, best.leaf);
+      const bool leader = (best.leaf >= 0) && ((__ffs(grp) - 1) == lane);
+      if (leader) {
+        uint32_t* fp = p.first_pix + (size_t)vp * p.leaf_stride + (uint32_t)best.leaf;
+        const uint32_t old = atomicMin(fp, pix);
+        if (old == kEmptyPixel) {
+          atomicOr(p.bitmap + (size_t)vp * p.word_stride + ((uint32_t)best.leaf >> 5), 1u << (best.leaf & 31));
+        }
+      }
+    } else {
+      if (live) {
+        q3dr_pixel_hit out;
+        const bool hit = best.leaf >= 0;
+        // intersection = origin + direction * t  (geometry.h:345-348); t = 0 when the origin is inside
+        out.intersection[0] = hit ? __fadd_rn(ray.ox, __fmul_rn(ray.dx, best.t)) : 0.0f;
+        out.intersection[1] = hit ? __fadd_rn(ray.oy, __fmul_rn(ray.dy, best.t)) : 0.0f;
+        out.intersection[2] = hit ? __fadd_rn(ray.oz, __fmul_rn(ray.dz, best.t)) : 0.0f;
+        out.leaf = best.leaf;
+        out.depth = hit ? (uint32_t)__ldg(p.leaf_depth + best.leaf) : 0u;
+        out.dist_sq = hit ? best.dsq : 0.0f;
+        const bool has_xy = (MODE == kModePixels) || (p.pix_list != nullptr);
+        out.screen_x = has_xy ? (float)(p.x0 + px) : 0.0f;
+        out.screen_y = has_xy ? (float)(p.y0 + py) : 0.0f;
+        const size_t oi = (MODE == kModePixels) ? ((size_t)vp * p.w * p.h + pix) : (size_t)pix;
+        float4* dst = reinterpret_cast<float4*>(p.pixels + oi);
+        dst[0] = make_float4(out.intersection[0], out.intersection[1], out.intersection[2], __int_as_float(out.leaf));
+        dst[1] = make_float4(__uint_as_float(out.depth), out.dist_sq, out.screen_x, out.screen_y);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+
+struct ScoreParams {
+  const float* __restrict__ leaf_box;  // [n][6]
+  const float* __restrict__ weight;    // [n]
+  const float* __restrict__ normal;    // [n][3]
+  const float* __restrict__ rt;        // [n_vp][12] (chunk)
+  float fx, fy, cx, cy;
+  float image_width_f;
+  uint32_t x0, y0, w;
+  float thr, kf, a_thr, ka;  // derived constants (viewpoint_score.cpp:20-28)
+  int32_t ignore_sign;
+  int32_t ignore_zero;
+  uint32_t n_words;
+  uint32_t* first_pix;
+  uint32_t* bitmap;
+  uint64_t leaf_stride, word_stride;
+  // per-viewpoint temporary lists, capacity `cap` entries per slot
+  uint64_t cap;
+  int32_t* tmp_leaf;
+  float* tmp_info;
+  uint32_t* tmp_pix;
+  float* tmp_dsq;
+  uint32_t* kept_count;  // [slots]
+  uint32_t* hit_count;   // [n_vp_total] (already offset to the chunk)
+  float* total;          // [n_vp_total] (already offset to the chunk)
+};
+
+// computeViewpointObservationScore (viewpoint_planner_scoring.cpp:11-24,67-73,116-122;
+// viewpoint_score.cpp:45-68) for one voxel.
+__device__ __forceinline__ float voxel_information(const ScoreParams& p, uint32_t leaf, float camx, float camy,
+                                                   float camz) {
+  const float* b = p.leaf_box + 6 * (size_t)leaf;
+  const float mnx = __ldg(b + 0), mny = __ldg(b + 1), mnz = __ldg(b + 2);
+  const float mxx = __ldg(b + 3), mxy = __ldg(b + 4), mxz = __ldg(b + 5);
+  const float gx = __fsub_rn(camx, __fdiv_rn(__fadd_rn(mnx, mxx), 2.0f));
+  const float gy = __fsub_rn(camy, __fdiv_rn(__fadd_rn(mny, mxy), 2.0f));
+  const float gz = __fsub_rn(camz, __fdiv_rn(__fadd_rn(mnz, mxz), 2.0f));
+  const float n2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+  const float dist = __fsqrt_rn(n2);
+  const float size_x = __fsub_rn(mxx, mnx);
+  const float rel = __fdiv_rn(__fdiv_rn(__fmul_rn(p.fx, size_x), dist), p.image_width_f);
+  float res;
+  if (rel >= p.thr) {
+    res = 1.0f;
+  } else {
+    res = expf(__fmul_rn(-p.kf, __fsub_rn(p.thr, rel)));
+  }
+  const float nx = __ldg(p.normal + 3 * (size_t)leaf), ny = __ldg(p.normal + 3 * (size_t)leaf + 1),
+              nz = __ldg(p.normal + 3 * (size_t)leaf + 2);
+  float inc;
+  if (nx == 0.0f && ny == 0.0f && nz == 0.0f) {
+    inc = 1.0f;
+  } else {
+    float vx = gx, vy = gy, vz = gz;
+    if (n2 > 0.0f) {
+      vx = __fdiv_rn(gx, dist);
+      vy = __fdiv_rn(gy, dist);
+      vz = __fdiv_rn(gz, dist);
+    }
+    float dot = __fadd_rn(__fmul_rn(vx, nx), __fadd_rn(__fmul_rn(vy, ny), __fmul_rn(vz, nz)));
+    dot = smax(smin(dot, 1.0f), -1.0f);
+    bool zero = false;
+    if (dot <= 0.0f) {
+      if (p.ignore_sign) {
+        dot = fabsf(dot);
+      } else {
+        zero = true;
+      }
+    }
+    if (zero) {
+      inc = 0.0f;
+    } else {
+      const float angle = acosf(dot);
+      if (angle <= p.a_thr) {
+        inc = 1.0f;
+      } else {
+        inc = expf(__fmul_rn(-p.ka, __fsub_rn(angle, p.a_thr)));
+      }
+    }
+  }
+  return __fmul_rn(__fmul_rn(res, inc), __ldg(p.weight + leaf));
+}
+
+// One CTA per viewpoint of the chunk.  Thread t owns a contiguous run of bitmap words, so a plain
+// exclusive scan over the threads' counts yields every entry's position in ascending leaf order.
+__global__ void __launch_bounds__(kScoreThreads) score_compact_kernel(const ScoreParams p) {
+  __shared__ uint32_t s_cnt[kScoreThreads];
+  __shared__ uint32_t s_hit[kScoreThreads];
+  __shared__ double s_sum[kScoreThreads];
+  const uint32_t slot = blockIdx.x;
+  const uint32_t tid = threadIdx.x;
+  const float* rt = p.rt + 12 * (size_t)slot;
+  const float camx = __ldg(rt + 3), camy = __ldg(rt + 7), camz = __ldg(rt + 11);
+  uint32_t* bitmap = p.bitmap + (size_t)slot * p.word_stride;
+  uint32_t* first_pix = p.first_pix + (size_t)slot * p.leaf_stride;
+
+  const uint32_t per = (p.n_words + kScoreThreads - 1) / kScoreThreads;
+  const uint32_t w_begin = min(tid * per, p.n_words);
+  const uint32_t w_end = min(w_begin + per, p.n_words);
+
+  // pass 1: count + ordered partial sum
+  uint32_t kept = 0, hits = 0;
+  double sum = 0.0;
+  for (uint32_t w = w_begin; w < w_end; ++w) {
+    uint32_t bits = bitmap[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const uint32_t leaf = w * 32u + b;
+      const float info = voxel_information(p, leaf, camx, camy, camz);
+      ++hits;
+      if (!p.ignore_zero || info > 0.0f) {
+        ++kept;
+        sum += (double)info;
+      }
+    }
+  }
+  s_cnt[tid] = kept;
+  s_hit[tid] = hits;
+  s_sum[tid] = sum;
+  __syncthreads();
+  // fixed-order block scan / reduction (deterministic)
+  if (tid == 0) {
+    uint32_t run = 0, hrun = 0;
+    double total = 0.0;
+    for (int i = 0; i < kScoreThreads; ++i) {
+      const uint32_t c = s_cnt[i];
+      s_cnt[i] = run;
+      run += c;
+      hrun += s_hit[i];
+      total += s_sum[i];
+    }
+    p.kept_count[slot] = run;
+    p.hit_count[slot] = hrun;
+    p.total[slot] = (float)total;
+  }
+  __syncthreads();
+
+  // pass 2: emit in ascending leaf order and reset the tables for the next chunk
+  size_t o = (size_t)slot * p.cap + s_cnt[tid];
+  for (uint32_t w = w_begin; w < w_end; ++w) {
+    uint32_t bits = bitmap[w];
+    if (!bits) continue;
+    bitmap[w] = 0u;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const uint32_t leaf = w * 32u + b;
+      const float info = voxel_information(p, leaf, camx, camy, camz);
+      const uint32_t pix = first_pix[leaf];
+      first_pix[leaf] = kEmptyPixel;
+      if (!p.ignore_zero || info > 0.0f) {
+        // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
+        const uint32_t py = pix / p.w, px = pix - py * p.w;
+        Ray ray;
+        camera_ray(rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+        const float* bx = p.leaf_box + 6 * (size_t)leaf;
+        float dsq, t;
+        box_test(ray, __ldg(bx + 0), __ldg(bx + 1), __ldg(bx + 2), __ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5), dsq, t);
+        p.tmp_leaf[o] = (int32_t)leaf;
+        p.tmp_info[o] = info;
+        p.tmp_pix[o] = pix;
+        p.tmp_dsq[o] = dsq;
+        ++o;
+      }
+    }
+  }
+}
+
+// offsets[v0 + i + 1] = offsets[v0] + inclusive_scan(kept)[i]; one block, n <= a few thousand.
+__global__ void scan_counts_kernel(const uint32_t* __restrict__ kept, uint32_t n, uint64_t* offsets /* at v0 */) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t run = offsets[0];
+    for (uint32_t i = 0; i < n; ++i) {
+      run += kept[i];
+      offsets[i + 1] = run;
+    }
+  }
+}
+
+struct PackParams {
+  const uint64_t* __restrict__ offsets;  // at v0
+  const uint32_t* __restrict__ kept;
+  uint64_t cap;
+  const int32_t* __restrict__ tmp_leaf;
+  const float* __restrict__ tmp_info;
+  const uint32_t* __restrict__ tmp_pix;
+  const float* __restrict__ tmp_dsq;
+  int32_t* out_leaf;
+  float* out_info;
+  uint32_t* out_pix;
+  float* out_dsq;
+};
+
+__global__ void pack_results_kernel(const PackParams p) {
+  const uint32_t slot = blockIdx.y;
+  const uint32_t n = p.kept[slot];
+  const uint64_t dst = p.offsets[slot];
+  const size_t src = (size_t)slot * p.cap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    p.out_leaf[dst + i] = p.tmp_leaf[src + i];
+    p.out_info[dst + i] = p.tmp_info[src + i];
+    p.out_pix[dst + i] = p.tmp_pix[src + i];
+    p.out_dsq[dst + i] = p.tmp_dsq[src + i];
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace q3dr

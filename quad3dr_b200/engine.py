@@ -1,0 +1,382 @@
+"""ctypes plumbing over the C ABI (include/q3dr_raycast.h -> quad3dr_b200/libq3dr_raycast.so).
+
+This module holds no arithmetic of the hot path: it marshals numpy buffers into the C entry points and
+raises when the CUDA library is missing or reports an error.  There is deliberately no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libq3dr_raycast.so")
+
+Q3DR_OK = 0
+Q3DR_ERR_INVALID_ARG = 1
+Q3DR_ERR_CUDA = 2
+Q3DR_ERR_NO_DEVICE = 3
+Q3DR_ERR_OUT_OF_MEMORY = 4
+Q3DR_ERR_INTERNAL = 5
+
+
+class Q3drError(RuntimeError):
+    """Non-zero status of a C-ABI call (the shim's equivalent of OccupiedTreeType::Error)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"q3dr status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class ScoreOpts(C.Structure):
+    _fields_ = [
+        ("voxel_sensor_size_ratio_threshold", C.c_float),
+        ("voxel_sensor_size_ratio_inv_falloff_factor", C.c_float),
+        ("incidence_angle_threshold_degrees", C.c_float),
+        ("incidence_angle_inv_falloff_factor_degrees", C.c_float),
+        ("incidence_ignore_dot_product_sign", C.c_int32),
+        ("ignore_voxels_with_zero_information", C.c_int32),
+        ("raycast_min_range", C.c_float),
+        ("raycast_max_range", C.c_float),
+    ]
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("n_viewpoints", C.c_uint64),
+        ("n_entries", C.c_uint64),
+        ("offsets", C.c_void_p),
+        ("leaf", C.c_void_p),
+        ("information", C.c_void_p),
+        ("first_pixel", C.c_void_p),
+        ("dist_sq", C.c_void_p),
+        ("total", C.c_void_p),
+        ("hit_count", C.c_void_p),
+    ]
+
+
+class MapInfo(C.Structure):
+    _fields_ = [
+        ("n_leaves", C.c_uint64),
+        ("n_nodes", C.c_uint64),
+        ("tree_depth", C.c_uint32),
+        ("ref_depth", C.c_uint32),
+        ("node_bytes", C.c_uint64),
+        ("device_bytes", C.c_uint64),
+        ("device", C.c_int32),
+        ("sm_count", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("raycast_ms", C.c_float),
+        ("score_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("chunks", C.c_uint32),
+        ("viewpoints_per_chunk", C.c_uint32),
+    ]
+
+
+PIXEL_HIT_DTYPE = np.dtype(
+    [
+        ("intersection", np.float32, (3,)),
+        ("leaf", np.int32),
+        ("depth", np.uint32),
+        ("dist_sq", np.float32),
+        ("screen_x", np.float32),
+        ("screen_y", np.float32),
+    ]
+)
+assert PIXEL_HIT_DTYPE.itemsize == 32
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sm_100a extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C quad3dr_b200/csrc`). "
+            "quad3dr_b200 has no CPU or PyTorch fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    fp = C.POINTER(C.c_float)
+    u32p = C.POINTER(C.c_uint32)
+    vp = C.c_void_p
+    L.q3dr_abi_version.restype = C.c_int
+    L.q3dr_status_string.restype = C.c_char_p
+    L.q3dr_status_string.argtypes = [C.c_int]
+    L.q3dr_last_error.restype = C.c_char_p
+    L.q3dr_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.q3dr_score_opts_default.argtypes = [C.POINTER(ScoreOpts)]
+    L.q3dr_score_opts_default.restype = None
+    L.q3dr_splitmedian_order.argtypes = [fp, C.c_size_t, u32p, u32p]
+    L.q3dr_pose_to_rt.argtypes = [fp, fp, fp]
+    L.q3dr_debug_flat_tree.argtypes = [fp, C.c_size_t, C.c_int, C.POINTER(C.c_uint64), u32p, u32p, u32p]
+    L.q3dr_map_create.argtypes = [fp, fp, fp, u32p, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.q3dr_map_update_weights.argtypes = [vp, fp]
+    L.q3dr_map_update_normals.argtypes = [vp, fp]
+    L.q3dr_map_get_info.argtypes = [vp, C.POINTER(MapInfo)]
+    L.q3dr_map_last_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.q3dr_map_reset.argtypes = [vp]
+    L.q3dr_map_destroy.argtypes = [vp]
+    L.q3dr_raycast_window.argtypes = [vp, fp, fp] + [C.c_uint32] * 4 + [C.c_float, C.c_float, vp]
+    L.q3dr_intersect_rays.argtypes = [vp, fp, fp, C.c_size_t, C.c_float, C.c_float, vp]
+    L.q3dr_raycast_unique.argtypes = (
+        [vp, fp, fp] + [C.c_uint32] * 4 + [C.c_float, C.c_float, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    )
+    L.q3dr_score_viewpoints.argtypes = (
+        [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_Result)]
+    )
+    L.q3dr_score_viewpoints_device.argtypes = (
+        [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [vp, C.c_size_t, C.POINTER(ScoreOpts), vp, C.POINTER(_Result)]
+    )
+    L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
+    for name in dir(L):
+        pass
+    _lib = L
+    return L
+
+
+def _check(status: int):
+    if status != Q3DR_OK:
+        L = load_library()
+        msg = L.q3dr_last_error().decode() or L.q3dr_status_string(status).decode()
+        raise Q3drError(status, msg)
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_opts(**kw) -> ScoreOpts:
+    o = ScoreOpts()
+    load_library().q3dr_score_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    st = load_library().q3dr_device_count(C.byref(n))
+    return int(n.value) if st == Q3DR_OK else 0
+
+
+def splitmedian_order(boxes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """(order, depth): order[k] = input index of the k-th leaf of the reference's Tree::build."""
+    b = _f32(boxes)
+    n = b.shape[0]
+    order = np.empty(n, dtype=np.uint32)
+    depth = np.empty(n, dtype=np.uint32)
+    _check(
+        load_library().q3dr_splitmedian_order(
+            _fp(b), n, order.ctypes.data_as(C.POINTER(C.c_uint32)), depth.ctypes.data_as(C.POINTER(C.c_uint32))
+        )
+    )
+    return order, depth
+
+
+def pose_to_rt(quat_wxyz, trans) -> np.ndarray:
+    out = np.empty(12, dtype=np.float32)
+    _check(load_library().q3dr_pose_to_rt(_fp(_f32(quat_wxyz, (4,))), _fp(_f32(trans, (3,))), _fp(out)))
+    return out
+
+
+def debug_flat_tree(boxes: np.ndarray, top_levels: int = 4) -> dict:
+    b = _f32(boxes)
+    nn = C.c_uint64(0)
+    d = C.c_uint32(0)
+    ms = C.c_uint32(0)
+    tn = C.c_uint32(0)
+    _check(load_library().q3dr_debug_flat_tree(_fp(b), b.shape[0], top_levels, C.byref(nn), C.byref(d), C.byref(ms), C.byref(tn)))
+    return dict(n_nodes=int(nn.value), depth=int(d.value), max_stack=int(ms.value), top_nodes=int(tn.value))
+
+
+class ScoreResult:
+    """CSR result of a batched scoring call, copied out of the map-owned host buffers."""
+
+    def __init__(self, r: _Result, copy: bool = True):
+        nv, ne = int(r.n_viewpoints), int(r.n_entries)
+
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.empty(0, dtype=dt)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt)
+            return a.copy() if copy else a
+
+        self.n_viewpoints = nv
+        self.n_entries = ne
+        self.offsets = arr(r.offsets, nv + 1, np.uint64)
+        self.leaf = arr(r.leaf, ne, np.int32)
+        self.information = arr(r.information, ne, np.float32)
+        self.first_pixel = arr(r.first_pixel, ne, np.uint32)
+        self.dist_sq = arr(r.dist_sq, ne, np.float32)
+        self.total = arr(r.total, nv, np.float32)
+        self.hit_count = arr(r.hit_count, nv, np.uint32)
+
+    def viewpoint(self, v: int) -> dict:
+        a, b = int(self.offsets[v]), int(self.offsets[v + 1])
+        return dict(
+            leaf=self.leaf[a:b], info=self.information[a:b], pixel=self.first_pixel[a:b], dsq=self.dist_sq[a:b],
+            total=float(self.total[v]), hit_count=int(self.hit_count[v]),
+        )
+
+
+class DeviceResult:
+    """Device pointers (ints) of a device-resident scoring result, owned by the map."""
+
+    def __init__(self, r: _Result):
+        self.n_viewpoints = int(r.n_viewpoints)
+        self.n_entries = int(r.n_entries)
+        self.offsets = r.offsets
+        self.leaf = r.leaf
+        self.information = r.information
+        self.first_pixel = r.first_pixel
+        self.dist_sq = r.dist_sq
+        self.total = r.total
+        self.hit_count = r.hit_count
+
+
+class OccupancyMap:
+    """Device-resident flattened occupancy map (q3dr_map).  Leaves must be in tie-break order
+    (see splitmedian_order); leaf k is reported as index k."""
+
+    def __init__(self, boxes, weights=None, normals=None, depth=None, device: int = 0):
+        L = load_library()
+        b = _f32(boxes)
+        if b.ndim != 2 or b.shape[1] != 6:
+            raise ValueError("boxes must be (n, 6)")
+        n = b.shape[0]
+        w = _f32(weights, (n,)) if weights is not None else None
+        nr = _f32(normals, (n, 3)) if normals is not None else None
+        dp = np.ascontiguousarray(depth, dtype=np.uint32) if depth is not None else None
+        h = C.c_void_p(None)
+        _check(
+            L.q3dr_map_create(
+                _fp(b), _fp(w) if w is not None else None, _fp(nr) if nr is not None else None,
+                dp.ctypes.data_as(C.POINTER(C.c_uint32)) if dp is not None else None, n, device, C.byref(h),
+            )
+        )
+        self._h = h
+        self.n = n
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().q3dr_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> MapInfo:
+        i = MapInfo()
+        _check(load_library().q3dr_map_get_info(self._h, C.byref(i)))
+        return i
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(load_library().q3dr_map_last_stats(self._h, C.byref(s)))
+        return s
+
+    def update_weights(self, weights):
+        _check(load_library().q3dr_map_update_weights(self._h, _fp(_f32(weights, (self.n,)))))
+
+    def update_normals(self, normals):
+        _check(load_library().q3dr_map_update_normals(self._h, _fp(_f32(normals, (self.n, 3)))))
+
+    def reset(self):
+        _check(load_library().q3dr_map_reset(self._h))
+
+    def raycast_window(self, K, Rt, x0, x1, y0, y1, min_range=0.0, max_range=-1.0) -> np.ndarray:
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        out = np.empty((y1 - y0) * (x1 - x0), dtype=PIXEL_HIT_DTYPE)
+        _check(
+            load_library().q3dr_raycast_window(
+                self._h, _fp(K), _fp(Rt), x0, x1, y0, y1, min_range, max_range, out.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return out
+
+    def intersect_rays(self, origins, directions, min_range=0.0, max_range=-1.0) -> np.ndarray:
+        o = _f32(origins)
+        d = _f32(directions)
+        if o.shape != d.shape or o.ndim != 2 or o.shape[1] != 3:
+            raise ValueError("origins/directions must both be (n, 3)")
+        out = np.empty(o.shape[0], dtype=PIXEL_HIT_DTYPE)
+        _check(
+            load_library().q3dr_intersect_rays(
+                self._h, _fp(o), _fp(d), o.shape[0], min_range, max_range, out.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return out
+
+    def raycast_unique(self, K, Rt, x0, x1, y0, y1, min_range=0.0, max_range=-1.0) -> np.ndarray:
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        cap = min((y1 - y0) * (x1 - x0), self.n)
+        out = np.empty(cap, dtype=PIXEL_HIT_DTYPE)
+        cnt = C.c_size_t(0)
+        _check(
+            load_library().q3dr_raycast_unique(
+                self._h, _fp(K), _fp(Rt), x0, x1, y0, y1, min_range, max_range, out.ctypes.data_as(C.c_void_p), cap,
+                C.byref(cnt),
+            )
+        )
+        return out[: cnt.value].copy()
+
+    def score_viewpoints(self, K, image_width: int, window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None,
+                         copy: bool = True) -> ScoreResult:
+        """Host poses in, host CSR result out (H2D + kernels + D2H inside the call)."""
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        opts = opts or default_opts()
+        x0, x1, y0, y1 = window
+        r = _Result()
+        _check(
+            load_library().q3dr_score_viewpoints(
+                self._h, _fp(K), image_width, x0, x1, y0, y1, _fp(Rt), Rt.shape[0], C.byref(opts), C.byref(r)
+            )
+        )
+        return ScoreResult(r, copy=copy)
+
+    def score_viewpoints_device(self, K, image_width: int, window: Sequence[int], d_rt_ptr: int, n: int,
+                                opts: Optional[ScoreOpts] = None, stream: int = 0) -> DeviceResult:
+        """Poses already in HBM (raw device pointer), results stay in HBM."""
+        K = _f32(K, (4,))
+        opts = opts or default_opts()
+        x0, x1, y0, y1 = window
+        r = _Result()
+        _check(
+            load_library().q3dr_score_viewpoints_device(
+                self._h, _fp(K), image_width, x0, x1, y0, y1, C.c_void_p(d_rt_ptr), n, C.byref(opts),
+                C.c_void_p(stream), C.byref(r),
+            )
+        )
+        return DeviceResult(r)
+
+    def result_to_host(self, copy: bool = True) -> ScoreResult:
+        r = _Result()
+        _check(load_library().q3dr_result_to_host(self._h, C.byref(r)))
+        return ScoreResult(r, copy=copy)
