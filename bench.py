@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of the viewpoint raycast + scoring path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a engine through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic viewpoints: every pixel ray of every
+viewpoint of the workload is cast through the occupancy map, hit voxels are de-duplicated per viewpoint and
+scored.  At N = 1 the workload is BASELINE.json configs[1] ("C2": ~1 M-leaf box-building map, 1000 viewpoints at
+640x480).  At N > 1 every rank scores its own 1000-viewpoint slice of an N x 1000 candidate set on a replicated
+map (weak scaling) and the per-viewpoint scores / hit lists are gathered over NCCL inside the timed step.
+
+One JSON line is printed by rank 0.  `value` = device-resident throughput (poses already in HBM, results left
+in HBM, CUDA events on the launch stream, max over ranks).  `e2e` = the same metric through the host-buffer
+C-ABI call (pinned host poses -> H2D -> kernels -> D2H of the CSR result inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "rays_per_sec"
+UNIT = "rays/s"
+WORKLOADS = {
+    # name: (synth config, viewpoints per rank, width, height)
+    "C1": ("C1", 100, 320, 240),
+    "C2": ("C2", 1000, 640, 480),
+    "C3": ("C3", 1250, 640, 480),
+    "C4": ("C4", 500, 1280, 960),
+    "small": ("small", 16, 160, 120),
+}
+
+
+def algorithmic_bytes_per_ray(n_leaves: int) -> int:
+    """(2 D + 1) * 32 B + 4 B with D = ceil(log2 N_leaf)."""
+    d = int(math.ceil(math.log2(max(n_leaves, 2))))
+    return (2 * d + 1) * 32 + 4
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def committed_traffic(workload: str):
+    """dram bytes per raycast launch from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append((time.time(), line.strip()))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(workload: str, rank: int, world: int):
+    from quad3dr_b200 import engine as E
+    from quad3dr_b200 import synth
+
+    cfg, nvp, w, h = WORKLOADS[workload]
+    leaves = synth.CONFIGS[cfg][0]()
+    order, depth = E.splitmedian_order(leaves.boxes)  # tie-break order of the reference's Tree::build
+    leaves = leaves.permuted(order)
+    cam = synth.make_camera(w, h)
+    # one global candidate set of world*nvp viewpoints, rank r scores the contiguous slice [r*nvp, (r+1)*nvp)
+    all_vps = synth.make_viewpoints(leaves, nvp * world, config_id=2)
+    vps = np.ascontiguousarray(all_vps[rank * nvp:(rank + 1) * nvp])
+    return leaves, depth, cam, vps
+
+
+def cpu_baseline(leaves, cam, vps, budget_s: float, threads=None):
+    """The oracle (CPU restatement of the reference algorithm) on host cores, bounded sample."""
+    from oracle import oracle_py as O
+
+    tree = O.OracleTree(leaves.boxes)
+    threads = threads or O.max_threads()
+    # calibrate on two viewpoints, single thread
+    t = time.perf_counter()
+    tree.score_batch(leaves.weight, leaves.normal, cam.K, cam.width, cam.height, vps[:2], threads=1)
+    per_vp = (time.perf_counter() - t) / 2
+    n = int(max(threads, min(vps.shape[0], math.ceil(budget_s * threads / max(per_vp, 1e-6)))))
+    n = min(n, vps.shape[0])
+    t = time.perf_counter()
+    r = tree.score_batch(leaves.weight, leaves.normal, cam.K, cam.width, cam.height, vps[:n], threads=threads)
+    dt = time.perf_counter() - t
+    rays = n * cam.width * cam.height
+    return {
+        "value": rays / dt, "unit": UNIT, "cores": int(threads), "kind": "port",
+        "sample": f"first {n} of {vps.shape[0]} viewpoints at {cam.width}x{cam.height} ({rays} rays), "
+                  f"OpenMP over viewpoints, {dt:.2f} s; single-thread rate {cam.width * cam.height / per_vp:.3e} rays/s",
+        "_n": n, "_dt": dt, "_result": r, "_tree": tree,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself needs Eigen/Boost, absent
+    here) with all host threads; each step a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+
+    leaves, depth, cam, vps = build_inputs(args.workload, 0, 1)
+    tree = O.OracleTree(leaves.boxes)
+    threads = O.max_threads()
+    t = time.perf_counter()
+    tree.score_batch(leaves.weight, leaves.normal, cam.K, cam.width, cam.height, vps[:2], threads=1)
+    per_vp = (time.perf_counter() - t) / 2
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)  # whole run within a few minutes
+    n = int(min(vps.shape[0], max(threads, math.floor(budget * threads / max(per_vp, 1e-6)))))
+    n = max(1, min(n, vps.shape[0]))
+    times = []
+    for s in range(total_steps):
+        t = time.perf_counter()
+        tree.score_batch(leaves.weight, leaves.normal, cam.K, cam.width, cam.height, vps[:n], threads=threads)
+        dt = time.perf_counter() - t
+        if s >= args.warmup:
+            times.append(dt)
+    rays = n * cam.width * cam.height
+    ms = 1e3 * sum(times) / len(times)
+    value = rays / (ms * 1e-3)
+    sample = (f"each step = first {n} of {vps.shape[0]} viewpoints at {cam.width}x{cam.height} ({rays} rays), "
+              f"OpenMP over viewpoints on {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, leaves, cam, vps.shape[0], 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(threads), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, leaves, cam, nvp_per_rank, world):
+    return {
+        "workload": f"{workload}: synthetic box-building occupancy map, {leaves.n} BVH leaves (r={leaves.resolution} m), "
+                    f"{nvp_per_rank * world} viewpoints at {cam.width}x{cam.height}, raycast_max_range 60 m, "
+                    f"dedup + distance/incidence score, ignore_zero=1",
+        "n_leaves": int(leaves.n), "viewpoints": int(nvp_per_rank * world), "viewpoints_per_gpu": int(nvp_per_rank),
+        "width": cam.width, "height": cam.height,
+        "parallelism": f"viewpoint-sharded x{world}, map replicated",
+        "l2": "flushed between timed steps (256 MiB device write); map node array is smaller than L2",
+        "timing": "CUDA events on the launch stream around each step (flush excluded), summed over steps, max over ranks",
+    }
+
+
+class _CAI:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def run_ours(args):
+    import torch
+
+    from quad3dr_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    leaves, depth, cam, vps = build_inputs(args.workload, rank, world)
+    nvp, w, h = vps.shape[0], cam.width, cam.height
+    gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=local_rank)
+    opts = E.default_opts()
+    window = (0, w, 0, h)
+    stream = torch.cuda.current_stream()
+    d_rt = torch.from_numpy(vps).to(dev)
+    h_rt = torch.from_numpy(vps).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rays_rank = nvp * w * h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(res):
+        """rank slices -> every rank (NCCL all_gather over NVLink): counts + totals, then the hit lists."""
+        if dist is None:
+            return
+        off = torch.as_tensor(_CAI(res.offsets, nvp + 1, "<u8"), device=dev).view(torch.int64)
+        tot = torch.as_tensor(_CAI(res.total, nvp, "<f4"), device=dev)
+        head = torch.empty(2 * nvp + 2, dtype=torch.float64, device=dev)
+        head[:nvp + 1] = off.to(torch.float64)
+        head[nvp + 1:2 * nvp + 1] = tot.to(torch.float64)
+        head[2 * nvp + 1] = float(res.n_entries)
+        heads = torch.empty(world * head.numel(), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(heads, head)
+        counts = heads.view(world, -1)[:, -1]
+        max_e = int(counts.max().item())
+        send = torch.empty(2 * max_e, dtype=torch.int32, device=dev)
+        ne = res.n_entries
+        if ne:
+            send[:ne] = torch.as_tensor(_CAI(res.leaf, ne, "<i4"), device=dev)
+            send[max_e:max_e + ne] = torch.as_tensor(_CAI(res.information, ne, "<f4"), device=dev).view(torch.int32)
+        recv = torch.empty(world * 2 * max_e, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(recv, send)
+        return heads, recv
+
+    def step_device():
+        res = gmap.score_viewpoints_device(cam.K, w, window, d_rt.data_ptr(), nvp, opts, stream=stream.cuda_stream)
+        gather(res)
+        return res
+
+    def step_host():
+        res = gmap.score_viewpoints(cam.K, w, window, h_rt.numpy(), opts, copy=False)
+        return res
+
+    # ---- device-resident arm ----
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step_device()
+    launches = 0
+    raycast_ms = 0.0
+    raycast_launches = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    t_wall0 = time.time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        ev[s][0].record(stream)
+        res = step_device()
+        ev[s][1].record(stream)
+        st = gmap.stats()
+        launches += int(st.kernel_launches)
+        raycast_ms += float(st.raycast_ms)
+        raycast_launches += int(st.chunks)
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    n_entries = res.n_entries
+
+    # ---- end-to-end arm (host buffers through the C ABI) ----
+    for _ in range(max(1, args.warmup - 1)):
+        step_host()
+    barrier()
+    e2e_ms = 0.0
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hres = step_host()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    h2d = nvp * 48
+    d2h = (nvp + 1) * 8 + nvp * 8 + hres.n_entries * 16
+
+    t = torch.tensor([dev_ms, e2e_ms, raycast_ms], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, raycast_ms_max = [float(x) for x in t.tolist()]
+    launches_all, h2d_all, d2h_all = [float(x) for x in agg.tolist()]
+
+    if rank == 0:
+        total_rays = rays_rank * world
+        ms_per_step = dev_ms / args.steps
+        value = total_rays / (ms_per_step * 1e-3)
+        e2e_value = total_rays / (e2e_ms / args.steps * 1e-3)
+        b_ray = algorithmic_bytes_per_ray(leaves.n)
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel: raycast_kernel<kModeScore>; per-launch figures on this rank
+        rays_per_launch = rays_rank * args.steps / max(raycast_launches, 1)
+        launch_ms = raycast_ms / max(raycast_launches, 1)
+        achieved = b_ray * rays_per_launch / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, leaves, cam, nvp, world),
+            "viewpoints_per_sec": nvp * world / (ms_per_step * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "note": "q3dr_score_viewpoints: pinned host poses -> H2D -> kernels -> D2H of the CSR hit lists + scores"},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "kernel": "raycast_kernel<kModeScore>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": committed_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rays_per_launch, "launch_ms": launch_ms,
+                "launches_timed": raycast_launches,
+                "kernel_share_of_step": raycast_ms_max / max(dev_ms, 1e-9),
+            },
+            "result_entries": int(n_entries),
+        }
+        if args.cpu_baseline:
+            cb = cpu_baseline(leaves, cam, vps, args.cpu_budget)
+            # parity spot check of the bench inputs themselves: counts + totals of the sampled viewpoints
+            n = cb.pop("_n")
+            r = cb.pop("_result")
+            cb.pop("_dt")
+            cb.pop("_tree")
+            hr = hres
+            kept = (hr.offsets[1:n + 1] - hr.offsets[:n]).astype(np.int64)
+            same_counts = bool(np.array_equal(kept, r["kept_count"].astype(np.int64)))
+            rel = np.abs(hr.total[:n] - r["total"]) / np.maximum(np.abs(r["total"]), 1e-30)
+            cb["parity_on_sample"] = {"viewpoints": int(n), "hit_list_sizes_equal": same_counts,
+                                      "max_rel_score_err": float(rel.max()) if n else 0.0}
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of wall time for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if world > 1:
+        args.cpu_baseline = False  # rank 0 at N = 1 only
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ constexpr int kStackEntries = 64;
 constexpr uint32_t kEmptyPixel = 0xFFFFFFFFu;
 constexpr int kTileW = 8;
 constexpr int kTileH = 4;
-constexpr int kScoreThreads = 256;
+constexpr int kScoreThreads = 512;
 
 enum RaycastMode : int {
   kModeScore = 0,   // dedup into the per-viewpoint first-pixel table + bitmap
@@ -441,89 +441,131 @@ __device__ __forceinline__ float voxel_information(const ScoreParams& p, uint32_
   return __fmul_rn(__fmul_rn(res, inc), __ldg(p.weight + leaf));
 }
 
-// One CTA per viewpoint of the chunk.  Thread t owns a contiguous run of bitmap words, so a plain
-// exclusive scan over the threads' counts yields every entry's position in ascending leaf order.
+// Block-wide exclusive scan of one uint per thread (fixed order => deterministic); returns the exclusive
+// prefix of `v` and the block total.  s_warp: kScoreThreads / 32 + 1 words of shared memory.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(Q3DR_FULL_MASK, inc, o);
+    if (lane >= o) inc += y;
+  }
+  __syncthreads();  // s_warp may still be read by the previous call
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < kScoreThreads / 32) ? s_warp[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(Q3DR_FULL_MASK, winc, o);
+      if (lane >= o) winc += y;
+    }
+    if (lane < kScoreThreads / 32) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[kScoreThreads / 32] = winc;
+  }
+  __syncthreads();
+  total = s_warp[kScoreThreads / 32];
+  return s_warp[warp] + inc - v;
+}
+
+// Fixed-tree block sum of one double per thread (deterministic for a given block size).
+__device__ __forceinline__ double block_sum_ordered(double v, double* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(Q3DR_FULL_MASK, v, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kScoreThreads / 32; ++i) t += s_warp[i];
+  }
+  return t;  // valid in thread 0
+}
+
+// One CTA per viewpoint of the chunk.
+//   phase A  bitmap -> ordered list of hit leaves (coalesced word reads, block scan of popcounts);
+//            the bitmap is cleared on the way.
+//   phase B  the list is scored blockDim entries at a time (balanced), entries that survive the
+//            information > 0 filter are compacted in place in ascending leaf order, the first-pixel
+//            table is reset, the total is accumulated in fp64 in a fixed order.
 __global__ void __launch_bounds__(kScoreThreads) score_compact_kernel(const ScoreParams p) {
-  __shared__ uint32_t s_cnt[kScoreThreads];
-  __shared__ uint32_t s_hit[kScoreThreads];
-  __shared__ double s_sum[kScoreThreads];
+  __shared__ uint32_t s_scan[kScoreThreads / 32 + 1];
+  __shared__ double s_dsum[kScoreThreads / 32];
   const uint32_t slot = blockIdx.x;
   const uint32_t tid = threadIdx.x;
   const float* rt = p.rt + 12 * (size_t)slot;
   const float camx = __ldg(rt + 3), camy = __ldg(rt + 7), camz = __ldg(rt + 11);
   uint32_t* bitmap = p.bitmap + (size_t)slot * p.word_stride;
   uint32_t* first_pix = p.first_pix + (size_t)slot * p.leaf_stride;
+  int32_t* list = p.tmp_leaf + (size_t)slot * p.cap;
+  float* o_info = p.tmp_info + (size_t)slot * p.cap;
+  uint32_t* o_pix = p.tmp_pix + (size_t)slot * p.cap;
+  float* o_dsq = p.tmp_dsq + (size_t)slot * p.cap;
 
-  const uint32_t per = (p.n_words + kScoreThreads - 1) / kScoreThreads;
-  const uint32_t w_begin = min(tid * per, p.n_words);
-  const uint32_t w_end = min(w_begin + per, p.n_words);
-
-  // pass 1: count + ordered partial sum
-  uint32_t kept = 0, hits = 0;
-  double sum = 0.0;
-  for (uint32_t w = w_begin; w < w_end; ++w) {
-    uint32_t bits = bitmap[w];
+  // phase A
+  uint32_t n_hit = 0;
+  for (uint32_t w0 = 0; w0 < p.n_words; w0 += kScoreThreads) {
+    const uint32_t w = w0 + tid;
+    uint32_t bits = (w < p.n_words) ? bitmap[w] : 0u;
+    if (!__syncthreads_or(bits != 0u)) continue;
+    uint32_t chunk_total;
+    uint32_t pos = n_hit + block_exclusive_scan(__popc(bits), s_scan, chunk_total);
+    if (bits) bitmap[w] = 0u;
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
-      const uint32_t leaf = w * 32u + b;
-      const float info = voxel_information(p, leaf, camx, camy, camz);
-      ++hits;
-      if (!p.ignore_zero || info > 0.0f) {
-        ++kept;
-        sum += (double)info;
-      }
+      list[pos++] = (int32_t)(w * 32u + b);
     }
-  }
-  s_cnt[tid] = kept;
-  s_hit[tid] = hits;
-  s_sum[tid] = sum;
-  __syncthreads();
-  // fixed-order block scan / reduction (deterministic)
-  if (tid == 0) {
-    uint32_t run = 0, hrun = 0;
-    double total = 0.0;
-    for (int i = 0; i < kScoreThreads; ++i) {
-      const uint32_t c = s_cnt[i];
-      s_cnt[i] = run;
-      run += c;
-      hrun += s_hit[i];
-      total += s_sum[i];
-    }
-    p.kept_count[slot] = run;
-    p.hit_count[slot] = hrun;
-    p.total[slot] = (float)total;
+    n_hit += chunk_total;
   }
   __syncthreads();
 
-  // pass 2: emit in ascending leaf order and reset the tables for the next chunk
-  size_t o = (size_t)slot * p.cap + s_cnt[tid];
-  for (uint32_t w = w_begin; w < w_end; ++w) {
-    uint32_t bits = bitmap[w];
-    if (!bits) continue;
-    bitmap[w] = 0u;
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const uint32_t leaf = w * 32u + b;
-      const float info = voxel_information(p, leaf, camx, camy, camz);
-      const uint32_t pix = first_pix[leaf];
+  // phase B
+  uint32_t n_kept = 0;
+  double total = 0.0;
+  for (uint32_t i0 = 0; i0 < n_hit; i0 += kScoreThreads) {
+    const uint32_t i = i0 + tid;
+    const bool valid = i < n_hit;
+    int32_t leaf = 0;
+    float info = 0.0f, dsq = 0.0f;
+    uint32_t pix = 0;
+    bool keep = false;
+    if (valid) {
+      leaf = list[i];
+      info = voxel_information(p, (uint32_t)leaf, camx, camy, camz);
+      pix = first_pix[leaf];
       first_pix[leaf] = kEmptyPixel;
-      if (!p.ignore_zero || info > 0.0f) {
+      keep = !p.ignore_zero || info > 0.0f;
+      if (keep) {
         // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
         const uint32_t py = pix / p.w, px = pix - py * p.w;
         Ray ray;
         camera_ray(rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
         const float* bx = p.leaf_box + 6 * (size_t)leaf;
-        float dsq, t;
+        float t;
         box_test(ray, __ldg(bx + 0), __ldg(bx + 1), __ldg(bx + 2), __ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5), dsq, t);
-        p.tmp_leaf[o] = (int32_t)leaf;
-        p.tmp_info[o] = info;
-        p.tmp_pix[o] = pix;
-        p.tmp_dsq[o] = dsq;
-        ++o;
       }
     }
+    uint32_t chunk_kept;
+    const uint32_t dst = n_kept + block_exclusive_scan(keep ? 1u : 0u, s_scan, chunk_kept);
+    // every thread of the chunk has read list[i] before the scan's barriers; dst <= i, so in place is safe
+    if (keep) {
+      list[dst] = leaf;
+      o_info[dst] = info;
+      o_pix[dst] = pix;
+      o_dsq[dst] = dsq;
+    }
+    const double part = block_sum_ordered(keep ? (double)info : 0.0, s_dsum);
+    if (tid == 0) total += part;
+    n_kept += chunk_kept;
+  }
+  if (tid == 0) {
+    p.kept_count[slot] = n_kept;
+    p.hit_count[slot] = n_hit;
+    p.total[slot] = (float)total;
   }
 }
 

@@ -230,8 +230,9 @@ _B1M = [
 
 
 def map_1m(unknown_interior: bool = False) -> OccupancyLeaves:
-    """C1/C2 (and C4 with unknown_interior=True): 800x800 ground + 4 buildings, ~1.1 M leaves."""
-    return make_box_building_map(400, _B1M, unknown_interior=unknown_interior)
+    """C1/C2 (and C4 with unknown_interior=True): 720x720 ground + 4 buildings, 1,028,168 leaves
+    (< 2^20, so the reference tree has depth 20 as in SURVEY.md section 8d)."""
+    return make_box_building_map(360, _B1M, unknown_interior=unknown_interior)
 
 
 def map_10m() -> OccupancyLeaves:
