@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
         except Exception:
@@ -220,11 +220,6 @@ def workload_config(workload, leaves, cam, nvp_per_rank, world):
     }
 
 
-class _CAI:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def run_ours(args):
     import torch
 
@@ -263,27 +258,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def gather(res):
-        """rank slices -> every rank (NCCL all_gather over NVLink): counts + totals, then the hit lists."""
+        """rank slices -> every rank (NCCL all_gather over NVLink): per-viewpoint headers, then the hit lists."""
         if dist is None:
-            return
-        off = torch.as_tensor(_CAI(res.offsets, nvp + 1, "<u8"), device=dev).view(torch.int64)
-        tot = torch.as_tensor(_CAI(res.total, nvp, "<f4"), device=dev)
-        head = torch.empty(2 * nvp + 2, dtype=torch.float64, device=dev)
-        head[:nvp + 1] = off.to(torch.float64)
-        head[nvp + 1:2 * nvp + 1] = tot.to(torch.float64)
-        head[2 * nvp + 1] = float(res.n_entries)
-        heads = torch.empty(world * head.numel(), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(heads, head)
-        counts = heads.view(world, -1)[:, -1]
-        max_e = int(counts.max().item())
-        send = torch.empty(2 * max_e, dtype=torch.int32, device=dev)
-        ne = res.n_entries
-        if ne:
-            send[:ne] = torch.as_tensor(_CAI(res.leaf, ne, "<i4"), device=dev)
-            send[max_e:max_e + ne] = torch.as_tensor(_CAI(res.information, ne, "<f4"), device=dev).view(torch.int32)
-        recv = torch.empty(world * 2 * max_e, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(recv, send)
-        return heads, recv
+            return None
+        from quad3dr_b200 import dist as qdist
+
+        off, tot, leaf, info = qdist.device_result_tensors(res, dev)
+        return qdist.gather_results(off, tot, leaf, info, nvp)
 
     def step_device():
         res = gmap.score_viewpoints_device(cam.K, w, window, d_rt.data_ptr(), nvp, opts, stream=stream.cuda_stream)

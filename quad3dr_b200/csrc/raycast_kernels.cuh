@@ -154,8 +154,35 @@ __device__ __forceinline__ void make_ray(float ox, float oy, float oz, float d0,
 struct PacketHit {
   float dsq;     // best dist_sq (the range bound while nothing is hit)
   float t;       // ray parameter of the best hit
+  float tU;      // fast path only: a ray parameter with dist_sq_at(tU) > dsq, verified by evaluation
   int32_t leaf;  // best leaf index, -1 = none
 };
+
+// dist_sq of the point at ray parameter t, in the reference's arithmetic (geometry.h:345-348, bvh.h:859):
+// |o - (o + d t)|^2.  Every operation is monotone in t >= 0, so the computed value is non-decreasing in t.
+__device__ __forceinline__ float dist_sq_at(const Ray& r, float t) {
+  const float px = __fadd_rn(r.ox, __fmul_rn(r.dx, t));
+  const float py = __fadd_rn(r.oy, __fmul_rn(r.dy, t));
+  const float pz = __fadd_rn(r.oz, __fmul_rn(r.dz, t));
+  const float ex = __fsub_rn(r.ox, px), ey = __fsub_rn(r.oy, py), ez = __fsub_rn(r.oz, pz);
+  return __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+}
+
+// A ray parameter u > t whose dist_sq is strictly greater than `dsq` -- checked by evaluating the
+// reference formula at u, not by error analysis.  Because dist_sq_at is non-decreasing, every box
+// entered at t' >= u has dist_sq > dsq and may be skipped without computing it; boxes in (t, u) are
+// simply visited.  +inf when no small margin separates (pruning by t is then off for this lane).
+__device__ __forceinline__ float prune_bound(const Ray& r, float t, float dsq) {
+  float rel = 1.0f / 2048.0f, ab = 1.0f / 8192.0f;
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    const float u = fmaf(t, rel, t) + ab;
+    if (dist_sq_at(r, u) > dsq) return u;
+    rel *= 16.0f;
+    ab *= 16.0f;
+  }
+  return __int_as_float(0x7F800000);
+}
 
 #define Q3DR_FULL_MASK 0xFFFFFFFFu
 
@@ -178,8 +205,8 @@ __device__ __forceinline__ void cswap(uint32_t& ka, uint32_t& na, float& da, uin
 // reference's own test (miss, or dist_sq > best), and rounding is monotone, so the box of an ancestor
 // never fails when a descendant leaf would pass.  Equal dist_sq: higher leaf
 // index wins (= later in the reference's depth-first order).
-__device__ __forceinline__ void traverse_packet(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
-                                                const float4* smem_top, uint32_t n_top) {
+__device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
+                                                   const float4* smem_top, uint32_t n_top) {
   float stack_d[kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
@@ -261,8 +288,127 @@ __device__ __forceinline__ void traverse_packet(const Ray& ray, PacketHit& best,
   }
 }
 
+
+// Fast variant of the same traversal for packets whose rays (a) have finite inverse directions (no NaN can
+// arise, so fminf/fmaxf equal the reference's ternaries) and (b) share one direction octant (the near / far
+// plane of every slab is then known per packet and loaded directly: lo = (near - o) * inv is bit-identical
+// to min(t0, t1)).  Results are bit-identical to traverse_packet_exact:
+//   * origin inside a box: the slab test then yields t = 0 and dist_sq = 0 like the reference's inside
+//     branch, except when tmax == 0 (origin on an exit face) -- those nodes are redone with box_test;
+//   * inner children are judged on the entry parameter t against best.tU (see prune_bound): skipping needs
+//     dist_sq > best, which t >= tU implies; visiting more than the reference never changes the result;
+//   * leaves compute dist_sq exactly whenever some lane could still accept them.
+__device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
+                                                     const float4* smem_top, uint32_t n_top, int nx, int ny, int nz) {
+  float stack_t[kStackEntries];
+  uint32_t stack_n[kStackEntries];
+  int sp = 0;
+  uint32_t node = 0;
+  const int fx = 3 - nx, fy = 5 - ny, fz = 7 - nz;  // far plane index: {0,3} {1,4} {2,5}
+  const float kInf = __int_as_float(0x7F800000);
+  while (true) {
+    const float4* np = (node < n_top) ? (smem_top + (size_t)node * 8) : (nodes + (size_t)node * 8);
+    const float4 nrx = np[nx], nry = np[ny], nrz = np[nz];
+    const float4 frx = np[fx], fry = np[fy], frz = np[fz];
+    const uint4 ch = *reinterpret_cast<const uint4*>(np + 6);
+
+    float t0, t1, t2, t3;
+    bool h0, h1, h2, h3, c0, c1, c2, c3;
+#define Q3DR_SLAB(NX, NY, NZ, FX, FY, FZ, T, H, C)                                                        \
+    {                                                                                                       \
+      const float lx = __fmul_rn(__fsub_rn(NX, ray.ox), ray.ix), hx = __fmul_rn(__fsub_rn(FX, ray.ox), ray.ix); \
+      const float ly = __fmul_rn(__fsub_rn(NY, ray.oy), ray.iy), hy = __fmul_rn(__fsub_rn(FY, ray.oy), ray.iy); \
+      const float lz = __fmul_rn(__fsub_rn(NZ, ray.oz), ray.iz), hz = __fmul_rn(__fsub_rn(FZ, ray.oz), ray.iz); \
+      const float tmax = fminf(fminf(fminf(hx, hy), hz), FLT_MAX);                                          \
+      (T) = fmaxf(fmaxf(fmaxf(lx, ly), lz), 0.0f);                                                          \
+      (H) = tmax > (T);                                                                                     \
+      (C) = tmax == 0.0f;                                                                                   \
+    }
+    Q3DR_SLAB(nrx.x, nry.x, nrz.x, frx.x, fry.x, frz.x, t0, h0, c0)
+    Q3DR_SLAB(nrx.y, nry.y, nrz.y, frx.y, fry.y, frz.y, t1, h1, c1)
+    Q3DR_SLAB(nrx.z, nry.z, nrz.z, frx.z, fry.z, frz.z, t2, h2, c2)
+    Q3DR_SLAB(nrx.w, nry.w, nrz.w, frx.w, fry.w, frz.w, t3, h3, c3)
+#undef Q3DR_SLAB
+    if (__any_sync(Q3DR_FULL_MASK, c0 | c1 | c2 | c3)) {
+      // rare: some lane's origin lies on a face plane of a child box -> the reference's inside / outside
+      // distinction matters; redo this node with the reference's full box test
+      const float4 mnx = np[0], mny = np[1], mnz = np[2], mxx = np[3], mxy = np[4], mxz = np[5];
+      float dd;
+      h0 = box_test(ray, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t0);
+      h1 = box_test(ray, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t1);
+      h2 = box_test(ray, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t2);
+      h3 = box_test(ray, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t3);
+    }
+
+    // leaves first: they tighten the bound before the inner children are judged
+#define Q3DR_LEAF(CH, H, T)                                                                \
+    if ((CH) & kLeafFlag) {                                                                 \
+      const bool cand = (H) && ((T) < best.tU);                                             \
+      if (__any_sync(Q3DR_FULL_MASK, cand)) {                                               \
+        const float d = dist_sq_at(ray, (T));                                               \
+        const int32_t li = (int32_t)((CH) & ~kLeafFlag);                                    \
+        const bool acc = cand && (d < best.dsq || (d == best.dsq && li > best.leaf));       \
+        if (__any_sync(Q3DR_FULL_MASK, acc)) {                                              \
+          const float u = prune_bound(ray, (T), d);                                         \
+          if (acc) {                                                                        \
+            best.dsq = d;                                                                   \
+            best.t = (T);                                                                   \
+            best.leaf = li;                                                                 \
+            best.tU = u;                                                                    \
+          }                                                                                 \
+        }                                                                                   \
+      }                                                                                     \
+    }
+    Q3DR_LEAF(ch.x, h0, t0)
+    Q3DR_LEAF(ch.y, h1, t1)
+    Q3DR_LEAF(ch.z, h2, t2)
+    Q3DR_LEAF(ch.w, h3, t3)
+#undef Q3DR_LEAF
+
+    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
+    float e0 = kInf, e1 = kInf, e2 = kInf, e3 = kInf;
+#define Q3DR_INNER(CH, H, T, K, E)                                                      \
+    if (!((CH) & kLeafFlag)) {                                                          \
+      const bool ok = (H) && ((T) < best.tU);                                           \
+      if (ok) (E) = (T);                                                                \
+      (K) = __reduce_min_sync(Q3DR_FULL_MASK, ok ? __float_as_uint(T) : 0xFFFFFFFFu);   \
+    }
+    Q3DR_INNER(ch.x, h0, t0, k0, e0)
+    Q3DR_INNER(ch.y, h1, t1, k1, e1)
+    Q3DR_INNER(ch.z, h2, t2, k2, e2)
+    Q3DR_INNER(ch.w, h3, t3, k3, e3)
+#undef Q3DR_INNER
+
+    uint32_t n0 = ch.x, n1 = ch.y, n2 = ch.z, n3 = ch.w;
+    cswap(k0, n0, e0, k1, n1, e1);
+    cswap(k2, n2, e2, k3, n3, e3);
+    cswap(k0, n0, e0, k2, n2, e2);
+    cswap(k1, n1, e1, k3, n3, e3);
+    cswap(k1, n1, e1, k2, n2, e2);
+    if (k3 != 0xFFFFFFFFu) { stack_t[sp] = e3; stack_n[sp] = n3; ++sp; }
+    if (k2 != 0xFFFFFFFFu) { stack_t[sp] = e2; stack_n[sp] = n2; ++sp; }
+    if (k1 != 0xFFFFFFFFu) { stack_t[sp] = e1; stack_n[sp] = n1; ++sp; }
+    if (k0 != 0xFFFFFFFFu) {
+      node = n0;
+      continue;
+    }
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      const float d = stack_t[sp];
+      const uint32_t n = stack_n[sp];
+      if (__any_sync(Q3DR_FULL_MASK, d < best.tU)) {
+        node = n;
+        found = true;
+        break;
+      }
+    }
+    if (!found) break;
+  }
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerCta, 2) raycast_kernel(const RaycastParams p) {
+__global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const RaycastParams p) {
   extern __shared__ float4 smem_top[];
   __shared__ uint32_t s_tile[kWarpsPerCta];
   for (uint32_t i = threadIdx.x; i < p.n_top * 8; i += blockDim.x) smem_top[i] = p.nodes[i];
@@ -283,6 +429,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2) raycast_kernel(const Raycas
     PacketHit best;
     best.leaf = -1;
     best.t = 0.0f;
+    best.tU = 0.0f;
     bool live;
     uint32_t vp = 0, pix = 0, px = 0, py = 0;
     if (MODE == kModeRays) {
@@ -310,15 +457,41 @@ __global__ void __launch_bounds__(kThreadsPerCta, 2) raycast_kernel(const Raycas
       pix = py * p.w + px;
       camera_ray(p.rt + 12 * (size_t)vp, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
     }
-    if (!live) {
-      // a dead lane never accepts anything: dist_sq >= 0 > -1
-      ray.ox = ray.oy = ray.oz = 0.0f;
-      ray.dx = ray.dy = ray.dz = 1.0f;
-      ray.ix = ray.iy = ray.iz = 1.0f;
+    const uint32_t live_mask = __ballot_sync(Q3DR_FULL_MASK, live);
+    if (live_mask == 0u) continue;
+    {
+      // a dead lane rides along with a copy of a live lane's ray and never accepts anything
+      // (dist_sq >= 0 > -1, t >= 0 > -1)
+      const int src = __ffs(live_mask) - 1;
+      const float ox = __shfl_sync(Q3DR_FULL_MASK, ray.ox, src), oy = __shfl_sync(Q3DR_FULL_MASK, ray.oy, src),
+                  oz = __shfl_sync(Q3DR_FULL_MASK, ray.oz, src);
+      const float dx = __shfl_sync(Q3DR_FULL_MASK, ray.dx, src), dy = __shfl_sync(Q3DR_FULL_MASK, ray.dy, src),
+                  dz = __shfl_sync(Q3DR_FULL_MASK, ray.dz, src);
+      const float ix = __shfl_sync(Q3DR_FULL_MASK, ray.ix, src), iy = __shfl_sync(Q3DR_FULL_MASK, ray.iy, src),
+                  iz = __shfl_sync(Q3DR_FULL_MASK, ray.iz, src);
+      if (!live) {
+        ray.ox = ox; ray.oy = oy; ray.oz = oz;
+        ray.dx = dx; ray.dy = dy; ray.dz = dz;
+        ray.ix = ix; ray.iy = iy; ray.iz = iz;
+      }
     }
     best.dsq = live ? range_sq : -1.0f;
 
-    traverse_packet(ray, best, p.nodes, smem_top, p.n_top);
+    // fast path: every inverse direction finite (no 0 * inf, so no NaN anywhere) and one octant per packet
+    const bool finite = (fabsf(ray.ix) <= FLT_MAX) && (fabsf(ray.iy) <= FLT_MAX) && (fabsf(ray.iz) <= FLT_MAX);
+    const uint32_t bx = __ballot_sync(Q3DR_FULL_MASK, ray.ix < 0.0f);
+    const uint32_t by = __ballot_sync(Q3DR_FULL_MASK, ray.iy < 0.0f);
+    const uint32_t bz = __ballot_sync(Q3DR_FULL_MASK, ray.iz < 0.0f);
+    const bool uniform_octant = (bx == 0u || bx == Q3DR_FULL_MASK) && (by == 0u || by == Q3DR_FULL_MASK) &&
+                                (bz == 0u || bz == Q3DR_FULL_MASK);
+    if (__all_sync(Q3DR_FULL_MASK, finite) && uniform_octant) {
+      const float kInf = __int_as_float(0x7F800000);
+      best.tU = live ? ((p.max_range > 0.0f) ? prune_bound(ray, p.max_range, range_sq) : kInf) : -1.0f;
+      traverse_packet_fast(ray, best, p.nodes, smem_top, p.n_top, bx ? 3 : 0, by ? 4 : 1, bz ? 5 : 2);
+    } else {
+      best.tU = 0.0f;
+      traverse_packet_exact(ray, best, p.nodes, smem_top, p.n_top);
+    }
 
     if (MODE == kModeScore) {
       // warp-aggregated dedup: lanes are in row-major pixel order inside the tile, so the lowest lane of

@@ -71,3 +71,252 @@ def test_score_viewpoints_matches_oracle(name, w, h, nvp, ignore_zero):
         assert got["hit_count"] == ref["hit_count"]
         np.testing.assert_allclose(got["info"], ref["info"], rtol=REL_TOL, atol=0)
         assert abs(got["total"] - ref["total"]) <= REL_TOL * abs(ref["total"])
+
+
+# ----------------------------------------------------------------------------------------------------
+# golden fixtures (inputs + oracle outputs committed under tests/golden/)
+# ----------------------------------------------------------------------------------------------------
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_gpu_reproduces_golden(path):
+    g = np.load(path)
+    m = E.OccupancyMap(g["boxes"], g["weight"], g["normal"], g["depth"])
+    w, h, mr = int(g["width"]), int(g["height"]), float(g["max_range"])
+    for v in range(g["Rt"].shape[0]):
+        px = m.raycast_window(g["K"], g["Rt"][v], 0, w, 0, h, 0.0, mr)
+        assert np.array_equal(px["leaf"], g["px_leaf"][v])
+        assert np.array_equal(bits(px["dist_sq"]), g["px_dsq_bits"][v])
+        assert np.array_equal(px["depth"], g["px_depth"][v])
+        assert np.array_equal(px["intersection"], g["px_xyz"][v])
+    res = m.score_viewpoints(g["K"], w, (0, w, 0, h), g["Rt"], E.default_opts(raycast_max_range=mr))
+    assert np.array_equal(res.offsets, g["offsets"])
+    assert np.array_equal(res.leaf, g["leaf"])
+    assert np.array_equal(res.first_pixel, g["pixel"])
+    assert np.array_equal(bits(res.dist_sq), g["dsq_bits"])
+    assert np.array_equal(res.hit_count, g["hit_count"])
+    np.testing.assert_allclose(res.information, g["info"], rtol=REL_TOL)
+    np.testing.assert_allclose(res.total, g["total"], rtol=REL_TOL)
+    m.close()
+
+
+# ----------------------------------------------------------------------------------------------------
+# edge cases the domain has: axis-parallel rays (0 * inf = NaN hazard), origins on voxel faces / grid planes,
+# origins inside leaves, duplicated boxes (exact ties), ranges, far-from-origin coordinates (coarser rounding
+# => many equal dist_sq), degenerate maps
+# ----------------------------------------------------------------------------------------------------
+
+def _compare_rays(sc_or_boxes, origins, dirs, max_range=-1.0, gmap=None, oracle=None):
+    ref = oracle.intersect_rays(origins, dirs, 0.0, max_range)
+    got = gmap.intersect_rays(origins, dirs, 0.0, max_range)
+    assert np.array_equal(got["leaf"], ref["leaf"])
+    assert np.array_equal(bits(got["dist_sq"]), bits(ref["dsq"]))
+    assert np.array_equal(got["depth"], ref["depth"])
+    assert np.array_equal(got["intersection"], ref["xyz"])
+    return ref
+
+
+def test_arbitrary_rays_including_axis_parallel_and_on_grid_origins():
+    sc = scene("tiny_unknown")
+    rng = np.random.default_rng(5)
+    n = 4096
+    o = rng.uniform(-9, 9, size=(n, 3)).astype(np.float32)
+    o[:, 2] = rng.uniform(0.1, 6, size=n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    # axis-parallel and plane-parallel directions: exact zeros in the direction
+    d[0:256] = [1, 0, 0]
+    d[256:512] = [0, -1, 0]
+    d[512:768] = [0, 0, -1]
+    d[768:1024, 2] = 0.0
+    d[1024:1280, 0] = 0.0
+    # origins exactly on grid planes / voxel faces (multiples of the resolution)
+    o[128:256] = np.round(o[128:256] * 4) / 4
+    o[384:512] = np.round(o[384:512] * 4) / 4
+    o[640:768] = np.round(o[640:768] * 4) / 4
+    o[1280:2048] = np.round(o[1280:2048] * 4) / 4
+    o[2048:2304, 2] = 0.0  # exactly on the ground top face
+    ref = _compare_rays(None, o, d, -1.0, sc.gpu_map, sc.oracle)
+    assert (ref["leaf"] >= 0).sum() > n // 4
+    _compare_rays(None, o, d, 3.0, sc.gpu_map, sc.oracle)
+
+
+def test_origin_inside_leaves_and_on_faces():
+    sc = scene("tiny_unknown")
+    b = sc.leaves.boxes
+    big = np.where((b[:, 3] - b[:, 0]) >= 1.0)[0][:64]  # unknown-space cubes
+    assert len(big) > 0
+    rng = np.random.default_rng(6)
+    c = (b[big, :3] + b[big, 3:]) / 2
+    inside = c + rng.uniform(-0.2, 0.2, size=c.shape).astype(np.float32)
+    on_face = c.copy()
+    on_face[:, 0] = b[big, 3]  # exactly on the +x face: inclusive bounds => still "inside"
+    corner = b[big, 3:].copy()
+    o = np.concatenate([inside, on_face, corner]).astype(np.float32)
+    d = rng.normal(size=o.shape).astype(np.float32)
+    ref = _compare_rays(None, o, d, -1.0, sc.gpu_map, sc.oracle)
+    assert np.all(ref["dsq"][: len(big)] == 0)
+    # cameras placed on grid points / inside unknown space: window API + scoring
+    cam = synth.make_camera(64, 48)
+    vps = synth.make_viewpoints(sc.leaves, 6, config_id=31)
+    vps[:, [3, 7, 11]] = np.round(vps[:, [3, 7, 11]] * 4) / 4  # origins exactly on voxel face planes
+    vps[4, [3, 7, 11]] = inside[0]
+    vps[5, [3, 7, 11]] = on_face[1]
+    for v in range(6):
+        ref = sc.oracle.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, 60.0)
+        got = sc.gpu_map.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, 60.0)
+        _assert_pixels_equal(got, ref)
+    res = sc.gpu_map.score_viewpoints(cam.K, 64, (0, 64, 0, 48), vps)
+    for v in range(6):
+        ref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, cam.K, 64, vps[v], height=48)
+        got = res.viewpoint(v)
+        assert np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(got["pixel"], ref["pixel"])
+
+
+def test_axis_aligned_camera_poses():
+    """Identity-like rotations put exact zeros into many ray directions (centre row / column)."""
+    sc = scene("tiny")
+    cam = synth.make_camera(64, 48)
+    poses = []
+    for R in (np.eye(3), np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]]), np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]]),
+              np.array([[1, 0, 0], [0, -1, 0], [0, 0, -1]])):
+        for t in ([0.5, -6.0, 2.0], [1.0, 2.0, 9.0]):
+            poses.append(np.concatenate([np.asarray(R, np.float32), np.asarray(t, np.float32)[:, None]], axis=1).reshape(12))
+    for Rt in poses:
+        ref = sc.oracle.raycast_window(cam.K, Rt, 0, 64, 0, 48, 0.0, 60.0)
+        got = sc.gpu_map.raycast_window(cam.K, Rt, 0, 64, 0, 48, 0.0, 60.0)
+        _assert_pixels_equal(got, ref)
+
+
+def test_duplicate_and_overlapping_boxes_tie_break():
+    rng = np.random.default_rng(8)
+    c = rng.integers(-6, 6, size=(400, 3)).astype(np.float32)
+    s = rng.choice([0.5, 1.0, 2.0], size=(400, 1)).astype(np.float32)
+    boxes = np.concatenate([c - s / 2, c + s / 2], axis=1).astype(np.float32)
+    boxes = np.concatenate([boxes, boxes[:150], boxes[:50]])  # exact duplicates => exact dist_sq ties
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    assert np.array_equal(oracle.dfs_order(), np.arange(len(boxes)))
+    gmap = E.OccupancyMap(boxes, None, None, depth)
+    o = rng.uniform(-12, 12, size=(8192, 3)).astype(np.float32)
+    d = rng.normal(size=(8192, 3)).astype(np.float32)
+    ref = _compare_rays(None, o, d, -1.0, gmap, oracle)
+    assert (ref["leaf"] >= 0).mean() > 0.3
+    brute = oracle.raycast_window_brute  # noqa: F841
+    gmap.close()
+
+
+def test_far_from_origin_coordinates():
+    """Map and cameras translated by kilometres: fp32 rounding gets coarse, equal dist_sq become common."""
+    leaves = synth.map_tiny()
+    shift = np.array([4096.0, -2048.0, 1024.0], np.float32)
+    boxes = (leaves.boxes + np.concatenate([shift, shift])).astype(np.float32)
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    gmap = E.OccupancyMap(boxes, leaves.weight[order], leaves.normal[order], depth)
+    cam = synth.make_camera(96, 72)
+    vps = synth.make_viewpoints(leaves, 6, config_id=41)
+    vps[:, [3, 7, 11]] += shift
+    for v in range(6):
+        ref = oracle.raycast_window(cam.K, vps[v], 0, 96, 0, 72, 0.0, 60.0)
+        got = gmap.raycast_window(cam.K, vps[v], 0, 96, 0, 72, 0.0, 60.0)
+        _assert_pixels_equal(got, ref)
+    gmap.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9])
+def test_tiny_maps(n):
+    rng = np.random.default_rng(n)
+    c = rng.uniform(-3, 3, size=(n, 3)).astype(np.float32)
+    boxes = np.concatenate([c - 0.5, c + 0.5], axis=1).astype(np.float32)
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    gmap = E.OccupancyMap(boxes, None, None, depth)
+    o = rng.uniform(-8, 8, size=(512, 3)).astype(np.float32)
+    d = (c[rng.integers(0, n, size=512)] - o + rng.normal(scale=0.3, size=(512, 3))).astype(np.float32)
+    _compare_rays(None, o, d, -1.0, gmap, oracle)
+    gmap.close()
+
+
+def test_empty_inputs_and_bad_arguments():
+    sc = scene("tiny")
+    cam = synth.make_camera(64, 48)
+    res = sc.gpu_map.score_viewpoints(cam.K, 64, (0, 64, 0, 48), np.zeros((0, 12), np.float32))
+    assert res.n_viewpoints == 0 and res.n_entries == 0 and np.array_equal(res.offsets, [0])
+    assert len(sc.gpu_map.intersect_rays(np.zeros((0, 3)), np.zeros((0, 3)))) == 0
+    with pytest.raises(E.Q3drError) as ei:
+        sc.gpu_map.raycast_window(cam.K, np.zeros(12, np.float32), 5, 5, 0, 48)
+    assert ei.value.status == E.Q3DR_ERR_INVALID_ARG
+    # a camera looking at the sky: all misses, empty hit list, zero score
+    up = np.array([1, 0, 0, 0.3, 0, -1, 0, 0.3, 0, 0, 1, 30.0], np.float32)
+    px = sc.gpu_map.raycast_window(cam.K, up, 0, 64, 0, 48, 0.0, 60.0)
+    assert np.all(px["leaf"] == -1) and np.all(px["dist_sq"] == 0) and np.all(px["intersection"] == 0)
+    res = sc.gpu_map.score_viewpoints(cam.K, 64, (0, 64, 0, 48), up[None])
+    assert res.n_entries == 0 and res.total[0] == 0 and res.hit_count[0] == 0
+
+
+def test_raycast_unique_matches_first_pixel_dedup():
+    sc = scene("tiny")
+    cam = synth.make_camera(64, 48)
+    vps = synth.make_viewpoints(sc.leaves, 3, config_id=13)
+    for v in range(3):
+        ref = sc.oracle.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, 60.0)
+        uniq, first = np.unique(ref["leaf"], return_index=True)
+        first, uniq = first[uniq >= 0], uniq[uniq >= 0]
+        got = sc.gpu_map.raycast_unique(cam.K, vps[v], 0, 64, 0, 48, 0.0, 60.0)
+        assert np.array_equal(got["leaf"], uniq)
+        assert np.array_equal(got["screen_x"], (first % 64).astype(np.float32))
+        assert np.array_equal(got["screen_y"], (first // 64).astype(np.float32))
+        assert np.array_equal(bits(got["dist_sq"]), bits(ref["dsq"][first]))
+        assert np.array_equal(got["intersection"], ref["xyz"][first])
+        assert np.array_equal(got["depth"], ref["depth"][first])
+
+
+def test_update_weights_and_options():
+    sc = scene("tiny")
+    cam = synth.make_camera(64, 48)
+    vps = synth.make_viewpoints(sc.leaves, 2, config_id=17)
+    w2 = (sc.leaves.weight * 0.5 + 0.125).astype(np.float32)
+    w2[::7] = 0.0  # zero-weight voxels drop out of the voxel set when ignore_zero = 1
+    gmap = E.OccupancyMap(sc.leaves.boxes, sc.leaves.weight, sc.leaves.normal, sc.depth)
+    gmap.update_weights(w2)
+    for kw in (dict(), dict(incidence_ignore_dot_product_sign=1), dict(incidence_angle_threshold_degrees=10.0,
+               incidence_angle_inv_falloff_factor_degrees=45.0, voxel_sensor_size_ratio_threshold=0.02,
+               voxel_sensor_size_ratio_inv_falloff_factor=0.01), dict(raycast_max_range=9.0)):
+        res = gmap.score_viewpoints(cam.K, 64, (0, 64, 0, 48), vps, E.default_opts(**kw))
+        for v in range(2):
+            ref = sc.oracle.score_viewpoint(w2, sc.leaves.normal, cam.K, 64, vps[v], height=48, opts=O.default_opts(**kw))
+            got = res.viewpoint(v)
+            assert np.array_equal(got["leaf"], ref["leaf"])
+            assert got["hit_count"] == ref["hit_count"]
+            np.testing.assert_allclose(got["info"], ref["info"], rtol=REL_TOL)
+            assert abs(got["total"] - ref["total"]) <= REL_TOL * max(abs(ref["total"]), 1e-30)
+    gmap.reset()
+    res2 = gmap.score_viewpoints(cam.K, 64, (0, 64, 0, 48), vps, E.default_opts(raycast_max_range=9.0))
+    assert np.array_equal(res2.leaf, res.leaf) and np.array_equal(bits(res2.information), bits(res.information))
+    gmap.close()
+
+
+def test_full_size_map_full_resolution_against_oracle():
+    """C2's map (1,028,168 leaves) at 640x480 for a few viewpoints: per-pixel and per-viewpoint parity."""
+    sc = scene("1m")
+    cam = synth.make_camera(640, 480)
+    vps = synth.make_viewpoints(sc.leaves, 4, config_id=2)
+    res = sc.gpu_map.score_viewpoints(cam.K, 640, (0, 640, 0, 480), vps)
+    for v in range(4):
+        ref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, cam.K, 640, vps[v], height=480)
+        got = res.viewpoint(v)
+        assert np.array_equal(got["leaf"], ref["leaf"])
+        assert np.array_equal(got["pixel"], ref["pixel"])
+        assert np.array_equal(bits(got["dsq"]), bits(ref["dsq"]))
+        np.testing.assert_allclose(got["info"], ref["info"], rtol=REL_TOL)
+        assert abs(got["total"] - ref["total"]) <= REL_TOL * abs(ref["total"])
+    refpx = sc.oracle.raycast_window(cam.K, vps[0], 0, 640, 0, 480, 0.0, 60.0)
+    gotpx = sc.gpu_map.raycast_window(cam.K, vps[0], 0, 640, 0, 480, 0.0, 60.0)
+    _assert_pixels_equal(gotpx, refpx)
