@@ -1,0 +1,397 @@
+// occupied_tree_cuda.hpp -- header-only C++ host side above the C ABI (q3dr_raycast.h).
+//
+// Mirrors, name for name, the CUDA bridge of the reference's bvh::Tree and the raycast / scoring calls
+// layered on it, so that the reference's callers keep compiling unchanged (INTEGRATION.md shows the
+// three-line patch).  Paths below are relative to the reference checkout.
+//
+//   q3dr::OccupiedTreeCuda<NodeT>            <- bvh::Tree<...>::{raycastCuda, raycastWithScreenCoordinatesCuda,
+//                                               intersectsCuda, ensureCudaTreeIsInitialized, clear}
+//                                               viewpoint_planner/src/bvh/bvh.h:396-542,949-955,296-314
+//   ...::IntersectionResult[WithScreenCoordinates]   <- bvh.h:162-182
+//   ...::Error / CudaError                   <- bvh.h:137-155 (callers catch OccupiedTreeType::Error)
+//   q3dr::ViewpointRaycastCuda<NodeT>        <- viewpoint_planner::ViewpointRaycast (enable_cuda path)
+//                                               viewpoint_planner/src/planner/viewpoint_raycast.h:19-143,
+//                                               viewpoint_raycast.cpp:94-113,221-283,305-335
+//   ...::getRaycastHitVoxelsWithInformationScore[Batch]
+//                                            <- ViewpointPlanner::getRaycastHitVoxelsWithInformationScore
+//                                               viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:89-148
+//   q3dr::VoxelWithInformation / VoxelWithInformationSet  <- planner/occupied_tree.h:62-92
+//
+// Matrices are taken as templates that only need operator()(row, col): Eigen::Matrix4f / Matrix<float,3,4> in the
+// reference tree, any small POD matrix elsewhere.  No Eigen, Boost or CUDA headers are needed to include this file.
+#ifndef Q3DR_OCCUPIED_TREE_CUDA_HPP_
+#define Q3DR_OCCUPIED_TREE_CUDA_HPP_
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <utility>
+#include <vector>
+
+#include "../q3dr_raycast.h"
+
+namespace q3dr {
+
+/// Voxel node and its information (planner/occupied_tree.h:62-92): hashed and compared by voxel pointer.
+template <typename NodeT>
+struct VoxelWithInformation {
+  VoxelWithInformation(const NodeT* voxel, float information) : voxel(voxel), information(information) {}
+  const NodeT* voxel;
+  float information;
+  bool operator==(const VoxelWithInformation& other) const {
+    return voxel == other.voxel && information == other.information;
+  }
+  struct VoxelHash {
+    std::size_t operator()(const VoxelWithInformation& v) const { return std::hash<const NodeT*>()(v.voxel); }
+  };
+};
+
+template <typename NodeT>
+using VoxelWithInformationSet =
+    std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash>;
+
+/// One BVH leaf as generateBVHTree emits it (viewpoint_planner_data.cpp:820-897) plus its host node.
+template <typename NodeT>
+struct LeafRecord {
+  float bbox_min[3];
+  float bbox_max[3];
+  float weight;      // NodeObject::weight
+  float normal[3];   // NodeObject::normal (zero vector: no normal)
+  NodeT* node;       // host bvh::Node, echoed back in results (the reference's CudaNode::ptr_)
+  std::uint32_t depth;  // depth of the leaf in the host tree (IntersectionResult::depth)
+};
+
+/// Walks a reference-style host tree left to right (the order of the recursion in bvh.h:899-905) and emits its
+/// leaves.  NodeT needs getLeftChild(), getRightChild(), isLeaf(), getBoundingBox().getMinimum(i)/getMaximum(i),
+/// getObject()->weight / ->normal(i).
+template <typename NodeT>
+void collectLeaves(NodeT* node, std::uint32_t depth, std::vector<LeafRecord<NodeT>>* out) {
+  if (node == nullptr) return;
+  if (node->isLeaf()) {
+    LeafRecord<NodeT> r;
+    for (int i = 0; i < 3; ++i) {
+      r.bbox_min[i] = node->getBoundingBox().getMinimum(i);
+      r.bbox_max[i] = node->getBoundingBox().getMaximum(i);
+      r.normal[i] = node->getObject()->normal(i);
+    }
+    r.weight = node->getObject()->weight;
+    r.node = node;
+    r.depth = depth;
+    out->push_back(r);
+    return;
+  }
+  collectLeaves(node->getLeftChild(), depth + 1, out);
+  collectLeaves(node->getRightChild(), depth + 1, out);
+}
+
+template <typename NodeT>
+class OccupiedTreeCuda {
+ public:
+  using NodeType = NodeT;
+
+  /// bvh::Tree::Error / CudaError (bvh.h:137-155); the planner catches Error and drops the candidate.
+  class Error : public std::runtime_error {
+   public:
+    Error(int status, const std::string& msg) : std::runtime_error(msg), status_(status) {}
+    int status() const { return status_; }
+   private:
+    int status_;
+  };
+  class CudaError : public Error {
+   public:
+    using Error::Error;
+  };
+
+  struct IntersectionResult {  // bvh.h:162-172
+    IntersectionResult() : intersection{0, 0, 0}, node(nullptr), depth(0), dist_sq(0) {}
+    float intersection[3];
+    NodeT* node;
+    std::size_t depth;
+    float dist_sq;
+  };
+  struct IntersectionResultWithScreenCoordinates {  // bvh.h:174-182
+    IntersectionResultWithScreenCoordinates() : screen_coordinates{0, 0} {}
+    IntersectionResult intersection_result;
+    float screen_coordinates[2];
+  };
+  struct Ray {  // bh::Ray: origin + direction (normalised by the engine like bh::Ray's constructor)
+    float origin[3];
+    float direction[3];
+  };
+
+  OccupiedTreeCuda() = default;
+  OccupiedTreeCuda(const OccupiedTreeCuda&) = delete;
+  OccupiedTreeCuda& operator=(const OccupiedTreeCuda&) = delete;
+  ~OccupiedTreeCuda() { clear(); }
+
+  /// ensureCudaTreeIsInitialized (bvh.h:949-955): flatten + upload.  `leaves` in left-to-right order of the host tree.
+  void ensureCudaTreeIsInitialized(const std::vector<LeafRecord<NodeT>>& leaves, int cuda_gpu_id = 0) {
+    if (map_ != nullptr) return;
+    const std::size_t n = leaves.size();
+    std::vector<float> boxes(6 * n), weights(n), normals(3 * n);
+    std::vector<std::uint32_t> depth(n);
+    nodes_.resize(n);
+    for (std::size_t k = 0; k < n; ++k) {
+      for (int i = 0; i < 3; ++i) {
+        boxes[6 * k + i] = leaves[k].bbox_min[i];
+        boxes[6 * k + 3 + i] = leaves[k].bbox_max[i];
+        normals[3 * k + i] = leaves[k].normal[i];
+      }
+      weights[k] = leaves[k].weight;
+      depth[k] = leaves[k].depth;
+      nodes_[k] = leaves[k].node;
+    }
+    check(q3dr_map_create(boxes.data(), weights.data(), normals.data(), depth.data(), n, cuda_gpu_id, &map_));
+  }
+
+  template <typename RootT>
+  void ensureCudaTreeIsInitialized(RootT* host_root, int cuda_gpu_id = 0) {
+    if (map_ != nullptr) return;
+    std::vector<LeafRecord<NodeT>> leaves;
+    collectLeaves<NodeT>(host_root, 0, &leaves);
+    ensureCudaTreeIsInitialized(leaves, cuda_gpu_id);
+  }
+
+  bool isInitialized() const { return map_ != nullptr; }
+
+  /// Tree::clear() frees the device tree (bvh.h:296-314).
+  void clear() {
+    if (map_ != nullptr) q3dr_map_destroy(map_);
+    map_ = nullptr;
+    nodes_.clear();
+  }
+
+  /// ViewpointPlannerData::updateWeights*: NodeObject::weight changed on the host, refresh the device copy.
+  void updateWeights(const std::vector<float>& weights_left_to_right) {
+    check(q3dr_map_update_weights(map_, weights_left_to_right.data()));
+  }
+
+  std::size_t getNumOfLeafNodes() const { return nodes_.size(); }
+  NodeT* leafNode(std::int32_t leaf) const { return leaf < 0 ? nullptr : nodes_[static_cast<std::size_t>(leaf)]; }
+  q3dr_map* handle() const { return map_; }
+
+  /// bvh.h:396-451.  intrinsics: 4x4 (fx, fy, cx, cy are read, bvh.cu:329-330); extrinsics: 3x4 [R|t] image-to-world.
+  template <typename Matrix4x4, typename Matrix3x4>
+  std::vector<IntersectionResult> raycastCuda(const Matrix4x4& intrinsics, const Matrix3x4& extrinsics,
+                                              std::size_t x_start, std::size_t x_end, std::size_t y_start,
+                                              std::size_t y_end, float min_range = 0, float max_range = -1,
+                                              bool fail_on_error = false) {
+    std::vector<q3dr_pixel_hit> px = castWindow(intrinsics, extrinsics, x_start, x_end, y_start, y_end, min_range,
+                                                max_range, fail_on_error);
+    std::vector<IntersectionResult> out(px.size());
+    for (std::size_t i = 0; i < px.size(); ++i) out[i] = convert(px[i]);
+    return out;
+  }
+
+  /// bvh.h:453-509
+  template <typename Matrix4x4, typename Matrix3x4>
+  std::vector<IntersectionResultWithScreenCoordinates> raycastWithScreenCoordinatesCuda(
+      const Matrix4x4& intrinsics, const Matrix3x4& extrinsics, std::size_t x_start, std::size_t x_end,
+      std::size_t y_start, std::size_t y_end, float min_range = 0, float max_range = -1, bool fail_on_error = false) {
+    std::vector<q3dr_pixel_hit> px = castWindow(intrinsics, extrinsics, x_start, x_end, y_start, y_end, min_range,
+                                                max_range, fail_on_error);
+    std::vector<IntersectionResultWithScreenCoordinates> out(px.size());
+    for (std::size_t i = 0; i < px.size(); ++i) {
+      out[i].intersection_result = convert(px[i]);
+      out[i].screen_coordinates[0] = px[i].screen_x;
+      out[i].screen_coordinates[1] = px[i].screen_y;
+    }
+    return out;
+  }
+
+  /// bvh.h:512-541: pair.first = hit?
+  std::vector<std::pair<bool, IntersectionResult>> intersectsCuda(const std::vector<Ray>& rays, float min_range = 0,
+                                                                  float max_range = -1) {
+    requireMap();
+    std::vector<float> o(3 * rays.size()), d(3 * rays.size());
+    for (std::size_t i = 0; i < rays.size(); ++i) {
+      for (int k = 0; k < 3; ++k) {
+        o[3 * i + k] = rays[i].origin[k];
+        d[3 * i + k] = rays[i].direction[k];
+      }
+    }
+    std::vector<q3dr_pixel_hit> px(rays.size());
+    check(q3dr_intersect_rays(map_, o.data(), d.data(), rays.size(), min_range, max_range, px.data()));
+    std::vector<std::pair<bool, IntersectionResult>> out(rays.size());
+    for (std::size_t i = 0; i < px.size(); ++i) out[i] = std::make_pair(px[i].leaf >= 0, convert(px[i]));
+    return out;
+  }
+
+  IntersectionResult convert(const q3dr_pixel_hit& h) const {
+    IntersectionResult r;
+    r.intersection[0] = h.intersection[0];
+    r.intersection[1] = h.intersection[1];
+    r.intersection[2] = h.intersection[2];
+    r.node = leafNode(h.leaf);
+    r.depth = h.depth;
+    r.dist_sq = h.dist_sq;
+    return r;
+  }
+
+  void check(int status) const {
+    if (status == Q3DR_OK) return;
+    const std::string msg = std::string(q3dr_status_string(status)) + ": " + q3dr_last_error();
+    if (status == Q3DR_ERR_CUDA || status == Q3DR_ERR_NO_DEVICE || status == Q3DR_ERR_OUT_OF_MEMORY) {
+      // the reference frees and re-uploads the device tree before rethrowing (bvh.h:443-449)
+      if (map_ != nullptr && status == Q3DR_ERR_CUDA) q3dr_map_reset(map_);
+      throw CudaError(status, msg);
+    }
+    throw Error(status, msg);
+  }
+
+  void requireMap() const {
+    if (map_ == nullptr) throw Error(Q3DR_ERR_INVALID_ARG, "device tree not initialised");
+  }
+
+ private:
+  template <typename Matrix4x4, typename Matrix3x4>
+  std::vector<q3dr_pixel_hit> castWindow(const Matrix4x4& intrinsics, const Matrix3x4& extrinsics, std::size_t x_start,
+                                         std::size_t x_end, std::size_t y_start, std::size_t y_end, float min_range,
+                                         float max_range, bool /*fail_on_error*/) {
+    requireMap();
+    float K[4], Rt[12];
+    packCamera(intrinsics, extrinsics, K, Rt);
+    std::vector<q3dr_pixel_hit> px((x_end - x_start) * (y_end - y_start));
+    check(q3dr_raycast_window(map_, K, Rt, static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
+                              static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end), min_range,
+                              max_range, px.data()));
+    return px;
+  }
+
+ public:
+  template <typename Matrix4x4, typename Matrix3x4>
+  static void packCamera(const Matrix4x4& intrinsics, const Matrix3x4& extrinsics, float K[4], float Rt[12]) {
+    K[0] = intrinsics(0, 0);
+    K[1] = intrinsics(1, 1);
+    K[2] = intrinsics(0, 2);
+    K[3] = intrinsics(1, 2);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 4; ++c) Rt[4 * r + c] = extrinsics(r, c);
+    }
+  }
+
+ private:
+  q3dr_map* map_ = nullptr;
+  std::vector<NodeT*> nodes_;  // leaf index -> host node
+};
+
+/// viewpoint_planner::ViewpointRaycast with enable_cuda = true, plus the planner's scoring facade.
+/// ViewpointT needs camera().intrinsics() (4x4), camera().width(), camera().height() and
+/// pose().getTransformationImageToWorld() (3x4).
+template <typename NodeT>
+class ViewpointRaycastCuda {
+ public:
+  using TreeType = OccupiedTreeCuda<NodeT>;
+  using IntersectionResult = typename TreeType::IntersectionResult;
+  using IntersectionResultWithScreenCoordinates = typename TreeType::IntersectionResultWithScreenCoordinates;
+  using VoxelSet = VoxelWithInformationSet<NodeT>;
+
+  /// viewpoint_raycast.h:28-31 (min_range is accepted and, like in the reference, never used by the query)
+  ViewpointRaycastCuda(TreeType* bvh_tree, float min_range = 0, float max_range = 60)
+      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range) {
+    q3dr_score_opts_default(&opts_);
+    opts_.raycast_min_range = min_range;
+    opts_.raycast_max_range = max_range;
+  }
+
+  q3dr_score_opts& scoreOptions() { return opts_; }
+
+  /// viewpoint_raycast.cpp:94-113,254-283,321-335
+  template <typename ViewpointT>
+  std::vector<IntersectionResultWithScreenCoordinates> getRaycastHitVoxelsWithScreenCoordinates(
+      const ViewpointT& viewpoint, std::size_t x_start, std::size_t x_end, std::size_t y_start, std::size_t y_end,
+      bool remove_duplicates = true, bool fail_on_error = false) const {
+    if (!remove_duplicates) {
+      // every hit pixel, misses dropped (the reference's removeInvalidRaycastHitVoxels erases a single element
+      // only -- viewpoint_raycast.cpp:287-303; this returns the properly compacted list)
+      auto all = bvh_tree_->raycastWithScreenCoordinatesCuda(viewpoint.camera().intrinsics(),
+                                                             viewpoint.pose().getTransformationImageToWorld(), x_start,
+                                                             x_end, y_start, y_end, min_range_, max_range_, fail_on_error);
+      std::vector<IntersectionResultWithScreenCoordinates> out;
+      for (const auto& r : all) {
+        if (r.intersection_result.node != nullptr) out.push_back(r);
+      }
+      return out;
+    }
+    bvh_tree_->requireMap();
+    float K[4], Rt[12];
+    TreeType::packCamera(viewpoint.camera().intrinsics(), viewpoint.pose().getTransformationImageToWorld(), K, Rt);
+    std::vector<q3dr_pixel_hit> px((x_end - x_start) * (y_end - y_start));
+    std::size_t count = 0;
+    bvh_tree_->check(q3dr_raycast_unique(bvh_tree_->handle(), K, Rt, static_cast<std::uint32_t>(x_start),
+                                         static_cast<std::uint32_t>(x_end), static_cast<std::uint32_t>(y_start),
+                                         static_cast<std::uint32_t>(y_end), min_range_, max_range_, px.data(), px.size(),
+                                         &count));
+    std::vector<IntersectionResultWithScreenCoordinates> out(count);
+    for (std::size_t i = 0; i < count; ++i) {
+      out[i].intersection_result = bvh_tree_->convert(px[i]);
+      out[i].screen_coordinates[0] = px[i].screen_x;
+      out[i].screen_coordinates[1] = px[i].screen_y;
+    }
+    return out;
+  }
+
+  /// ViewpointPlanner::getRaycastHitVoxelsWithInformationScore (viewpoint_planner_raycast.cpp:116-148)
+  template <typename ViewpointT>
+  std::pair<VoxelSet, float> getRaycastHitVoxelsWithInformationScore(
+      const ViewpointT& viewpoint, std::size_t x_start, std::size_t x_end, std::size_t y_start, std::size_t y_end,
+      bool ignore_voxels_with_zero_information = false) const {
+    std::vector<const ViewpointT*> one(1, &viewpoint);
+    auto all = getRaycastHitVoxelsWithInformationScoreBatch(one, x_start, x_end, y_start, y_end,
+                                                            ignore_voxels_with_zero_information);
+    return std::move(all[0]);
+  }
+
+  /// Same, whole image (viewpoint_planner_raycast.cpp:89-101)
+  template <typename ViewpointT>
+  std::pair<VoxelSet, float> getRaycastHitVoxelsWithInformationScore(
+      const ViewpointT& viewpoint, bool ignore_voxels_with_zero_information = false) const {
+    return getRaycastHitVoxelsWithInformationScore(viewpoint, 0, viewpoint.camera().width(), 0,
+                                                   viewpoint.camera().height(), ignore_voxels_with_zero_information);
+  }
+
+  /// Batched form: all candidates of one graph-building round in one call (one camera for all viewpoints).
+  template <typename ViewpointT>
+  std::vector<std::pair<VoxelSet, float>> getRaycastHitVoxelsWithInformationScoreBatch(
+      const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end, std::size_t y_start,
+      std::size_t y_end, bool ignore_voxels_with_zero_information = false) const {
+    std::vector<std::pair<VoxelSet, float>> out(viewpoints.size());
+    if (viewpoints.empty()) return out;
+    bvh_tree_->requireMap();
+    float K[4];
+    std::vector<float> Rt(12 * viewpoints.size());
+    for (std::size_t v = 0; v < viewpoints.size(); ++v) {
+      TreeType::packCamera(viewpoints[v]->camera().intrinsics(), viewpoints[v]->pose().getTransformationImageToWorld(),
+                           K, Rt.data() + 12 * v);
+    }
+    q3dr_score_opts o = opts_;
+    o.ignore_voxels_with_zero_information = ignore_voxels_with_zero_information ? 1 : 0;
+    q3dr_result r;
+    bvh_tree_->check(q3dr_score_viewpoints(bvh_tree_->handle(), K,
+                                           static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
+                                           static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
+                                           static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
+                                           Rt.data(), viewpoints.size(), &o, &r));
+    for (std::size_t v = 0; v < viewpoints.size(); ++v) {
+      VoxelSet& set = out[v].first;
+      set.reserve(static_cast<std::size_t>(r.offsets[v + 1] - r.offsets[v]));
+      for (std::uint64_t i = r.offsets[v]; i < r.offsets[v + 1]; ++i) {
+        set.insert(VoxelWithInformation<NodeT>(bvh_tree_->leafNode(r.leaf[i]), r.information[i]));
+      }
+      out[v].second = r.total[v];
+    }
+    return out;
+  }
+
+ private:
+  TreeType* bvh_tree_;
+  float min_range_;
+  float max_range_;
+  q3dr_score_opts opts_;
+};
+
+}  // namespace q3dr
+
+#endif  // Q3DR_OCCUPIED_TREE_CUDA_HPP_

@@ -262,6 +262,8 @@ size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint6
   // enough packets in flight that the persistent grid's tail is small ...
   const size_t resident_warps = (size_t)m->grid_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
   size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;
+  // ... and enough viewpoints per chunk that the one-CTA-per-viewpoint scoring kernel fills the machine
+  want = std::max<size_t>(want, 2 * (size_t)m->sm_count);
   if (const char* e = std::getenv("Q3DR_CHUNK")) want = (size_t)std::max(1, atoi(e));
   // ... bounded by scratch memory (first-pixel tables + temporary lists)
   const uint64_t per_slot = ((m->n + 31) / 32 * 32) * 4 + cap * 16;

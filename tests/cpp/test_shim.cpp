@@ -1,0 +1,322 @@
+// test_shim.cpp -- exercises include/q3dr/occupied_tree_cuda.hpp the way the reference's callers use bvh::Tree,
+// ViewpointRaycast and ViewpointPlanner::getRaycastHitVoxelsWithInformationScore, and checks every result against
+// the CPU oracle (test infrastructure, linked only here).
+//
+// A mock host tree with the reference's accessor names (getLeftChild / getRightChild / isLeaf / getBoundingBox /
+// getObject) is built by median splits with std::stable_sort, like bvh::Tree::build would; the shim walks it.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <vector>
+
+#include "../../include/q3dr/occupied_tree_cuda.hpp"
+#include "../../oracle/q3dr_oracle.h"
+
+namespace mock {
+
+struct Vec3 {
+  float v[3];
+  float operator()(int i) const { return v[i]; }
+};
+struct BBox {
+  float mn[3], mx[3];
+  float getMinimum(int i) const { return mn[i]; }
+  float getMaximum(int i) const { return mx[i]; }
+  float getCenter(int i) const { return (mn[i] + mx[i]) / 2; }
+};
+struct NodeObject {  // planner/occupied_tree.h:17-35
+  float occupancy;
+  uint16_t observation_count;
+  float weight;
+  Vec3 normal;
+};
+struct Node {
+  BBox box;
+  Node* left = nullptr;
+  Node* right = nullptr;
+  NodeObject* object = nullptr;
+  const BBox& getBoundingBox() const { return box; }
+  Node* getLeftChild() { return left; }
+  Node* getRightChild() { return right; }
+  bool isLeaf() const { return left == nullptr && right == nullptr; }
+  NodeObject* getObject() { return object; }
+};
+struct Obj {
+  BBox box;
+  NodeObject* object;
+};
+
+struct Tree {
+  std::vector<std::unique_ptr<Node>> pool;
+  std::vector<std::unique_ptr<NodeObject>> objects;
+  Node* root = nullptr;
+  Node* alloc() {
+    pool.emplace_back(new Node);
+    return pool.back().get();
+  }
+  void split(Node* node, std::vector<Obj>::iterator b, std::vector<Obj>::iterator e, int axis) {
+    if (e - b > 1) {
+      std::stable_sort(b, e, [axis](const Obj& x, const Obj& y) { return x.box.getCenter(axis) < y.box.getCenter(axis); });
+      node->left = alloc();
+      node->right = alloc();
+      split(node->left, b, b + (e - b) / 2, (axis + 1) % 3);
+      split(node->right, b + (e - b) / 2, e, (axis + 1) % 3);
+      for (int i = 0; i < 3; ++i) {
+        node->box.mn[i] = std::min(node->left->box.mn[i], node->right->box.mn[i]);
+        node->box.mx[i] = std::max(node->left->box.mx[i], node->right->box.mx[i]);
+      }
+    } else {
+      node->box = b->box;
+      node->object = b->object;
+    }
+  }
+  void build(std::vector<Obj> objs) {
+    root = alloc();
+    split(root, objs.begin(), objs.end(), 0);
+  }
+};
+
+struct Mat44 {
+  float m[4][4] = {};
+  float operator()(int r, int c) const { return m[r][c]; }
+};
+struct Mat34 {
+  float m[3][4] = {};
+  float operator()(int r, int c) const { return m[r][c]; }
+};
+struct Camera {
+  Mat44 K;
+  std::size_t w, h;
+  const Mat44& intrinsics() const { return K; }
+  std::size_t width() const { return w; }
+  std::size_t height() const { return h; }
+};
+struct Pose {
+  Mat34 T;
+  Mat34 getTransformationImageToWorld() const { return T; }
+};
+struct Viewpoint {
+  const Camera* cam;
+  Pose p;
+  const Camera& camera() const { return *cam; }
+  const Pose& pose() const { return p; }
+};
+
+}  // namespace mock
+
+#define CHECK(cond)                                                              \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      std::fprintf(stderr, "CHECK failed at line %d: %s\n", __LINE__, #cond);    \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+
+int main(int argc, char** argv) {
+  const bool compile_only = argc > 1 && std::string(argv[1]) == "--no-run";
+  if (compile_only) {
+    std::puts("shim compiled and linked");
+    return 0;
+  }
+  // --- scene: ground plate + two walls of 0.25 m voxels, one big "unknown" cube -------------------------------
+  mock::Tree host;
+  std::vector<mock::Obj> objs;
+  auto add = [&](float x, float y, float z, float s, float nx, float ny, float nz, int count) {
+    host.objects.emplace_back(new mock::NodeObject);
+    mock::NodeObject* o = host.objects.back().get();
+    o->occupancy = count ? 0.97f : 0.5f;
+    o->observation_count = (uint16_t)count;
+    o->weight = std::exp(-0.1f * count);
+    o->normal = mock::Vec3{{nx, ny, nz}};
+    mock::Obj ob;
+    ob.box = mock::BBox{{x, y, z}, {x + s, y + s, z + s}};
+    ob.object = o;
+    objs.push_back(ob);
+  };
+  for (int i = -24; i < 24; ++i)
+    for (int j = -24; j < 24; ++j) add(0.25f * i, 0.25f * j, -0.25f, 0.25f, 0, 0, 1, 1 + (i * 7 + j * 3 + 100) % 9);
+  for (int i = -10; i < 10; ++i)
+    for (int k = 0; k < 12; ++k) {
+      add(0.25f * i, 2.0f, 0.25f * k, 0.25f, 0, -1, 0, 2 + (i + k + 40) % 5);
+      add(-3.0f, 0.25f * i, 0.25f * k, 0.25f, 1, 0, 0, 3);
+    }
+  add(0.0f, 2.25f, 0.0f, 2.0f, 0, 0, 0, 0);  // unknown space behind the wall
+  const std::size_t n = objs.size();
+  host.build(objs);
+
+  // --- the shim: walk the host tree, upload --------------------------------------------------------------------
+  using Tree = q3dr::OccupiedTreeCuda<mock::Node>;
+  Tree tree;
+  try {
+    tree.ensureCudaTreeIsInitialized(host.root, 0);
+  } catch (const Tree::Error& e) {
+    std::fprintf(stderr, "upload failed: %s\n", e.what());
+    return 2;
+  }
+  CHECK(tree.getNumOfLeafNodes() == n);
+
+  // --- the oracle over the same leaves, in the same (left-to-right) order --------------------------------------
+  std::vector<q3dr::LeafRecord<mock::Node>> leaves;
+  q3dr::collectLeaves<mock::Node>(host.root, 0, &leaves);
+  std::vector<float> boxes(6 * n), weights(n), normals(3 * n);
+  for (std::size_t k = 0; k < n; ++k) {
+    for (int i = 0; i < 3; ++i) {
+      boxes[6 * k + i] = leaves[k].bbox_min[i];
+      boxes[6 * k + 3 + i] = leaves[k].bbox_max[i];
+      normals[3 * k + i] = leaves[k].normal[i];
+    }
+    weights[k] = leaves[k].weight;
+  }
+  orc_tree* oracle = orc_tree_build(boxes.data(), n);
+  std::vector<uint32_t> order(n), odepth(n);
+  orc_tree_dfs_order(oracle, order.data());
+  orc_tree_leaf_depths(oracle, odepth.data());
+  for (std::size_t k = 0; k < n; ++k) {
+    CHECK(order[k] == k);                      // the host tree's leaf order is the oracle's
+    CHECK(odepth[k] == leaves[k].depth);
+  }
+
+  // --- cameras --------------------------------------------------------------------------------------------------
+  mock::Camera cam;
+  cam.w = 96;
+  cam.h = 72;
+  cam.K.m[0][0] = cam.K.m[1][1] = 0.85f * 96;
+  cam.K.m[0][2] = 48;
+  cam.K.m[1][2] = 36;
+  cam.K.m[2][2] = cam.K.m[3][3] = 1;
+  const float Kf[4] = {cam.K.m[0][0], cam.K.m[1][1], cam.K.m[0][2], cam.K.m[1][2]};
+  std::vector<mock::Viewpoint> vps;
+  const float quats[3][4] = {{0.6532815f, -0.6532815f, 0.2705981f, -0.2705981f}, {0.5f, -0.5f, 0.5f, -0.5f}, {0.70710678f, -0.70710678f, 0.0f, 0.0f}};
+  const float pos[3][3] = {{1.3f, -4.1f, 2.2f}, {3.7f, 0.4f, 1.1f}, {-0.6f, -3.3f, 0.9f}};
+  for (int v = 0; v < 3; ++v) {
+    float rt[12];
+    CHECK(q3dr_pose_to_rt(quats[v], pos[v], rt) == Q3DR_OK);
+    mock::Viewpoint vp;
+    vp.cam = &cam;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) vp.p.T.m[r][c] = rt[4 * r + c];
+    vps.push_back(vp);
+  }
+
+  q3dr::ViewpointRaycastCuda<mock::Node> raycaster(&tree, 0.0f, 60.0f);
+  orc_score_opts oo = {0.002f, 0.001f, 30.0f, 30.0f, 0, 1, 0.0f, 60.0f};
+  std::size_t total_hits = 0;
+  for (const mock::Viewpoint& vp : vps) {
+    float Rt[12];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) Rt[4 * r + c] = vp.p.T.m[r][c];
+    const std::size_t np = cam.w * cam.h;
+    std::vector<int32_t> leaf(np);
+    std::vector<float> dsq(np), xyz(3 * np);
+    std::vector<uint32_t> depth(np);
+    orc_raycast_window(oracle, Kf, Rt, 0, cam.w, 0, cam.h, 0.0f, 60.0f, leaf.data(), dsq.data(), xyz.data(), depth.data());
+
+    // bvh::Tree::raycastWithScreenCoordinatesCuda
+    auto px = tree.raycastWithScreenCoordinatesCuda(cam.intrinsics(), vp.pose().getTransformationImageToWorld(), 0, cam.w, 0,
+                                                    cam.h, 0.0f, 60.0f);
+    CHECK(px.size() == np);
+    for (std::size_t i = 0; i < np; ++i) {
+      const auto& r = px[i].intersection_result;
+      CHECK(r.node == (leaf[i] < 0 ? nullptr : leaves[leaf[i]].node));
+      CHECK(r.dist_sq == dsq[i]);
+      CHECK(r.depth == depth[i]);
+      CHECK(r.intersection[0] == xyz[3 * i] && r.intersection[1] == xyz[3 * i + 1] && r.intersection[2] == xyz[3 * i + 2]);
+      CHECK(px[i].screen_coordinates[0] == (float)(i % cam.w) && px[i].screen_coordinates[1] == (float)(i / cam.w));
+      total_hits += r.node != nullptr;
+    }
+    auto px2 = tree.raycastCuda(cam.intrinsics(), vp.pose().getTransformationImageToWorld(), 8, 40, 4, 20, 0.0f, 60.0f);
+    CHECK(px2.size() == 32 * 16);
+    for (std::size_t y = 0; y < 16; ++y)
+      for (std::size_t x = 0; x < 32; ++x) CHECK(px2[y * 32 + x].node == px[(y + 4) * cam.w + x + 8].intersection_result.node);
+
+    // ViewpointRaycast::getRaycastHitVoxelsWithScreenCoordinates(remove_duplicates = true)
+    auto uniq = raycaster.getRaycastHitVoxelsWithScreenCoordinates(vp, 0, cam.w, 0, cam.h, true);
+    std::vector<int32_t> o_leaf(np);
+    std::vector<float> o_info(np), o_dsq(np);
+    std::vector<uint32_t> o_pix(np);
+    uint32_t hc = 0;
+    float tot = 0, tot32 = 0;
+    orc_score_opts all = oo;
+    all.ignore_voxels_with_zero_information = 0;
+    size_t k = orc_score_viewpoint(oracle, weights.data(), normals.data(), Kf, (uint32_t)cam.w, Rt, 0, cam.w, 0, cam.h, &all, np,
+                                   o_leaf.data(), o_info.data(), o_pix.data(), o_dsq.data(), &hc, &tot, &tot32);
+    CHECK(uniq.size() == k && k == hc);
+    for (size_t i = 0; i < k; ++i) {
+      CHECK(uniq[i].intersection_result.node == leaves[o_leaf[i]].node);
+      CHECK(uniq[i].intersection_result.dist_sq == o_dsq[i]);
+      CHECK(uniq[i].screen_coordinates[0] == (float)(o_pix[i] % cam.w));
+      CHECK(uniq[i].screen_coordinates[1] == (float)(o_pix[i] / cam.w));
+    }
+    auto nodup = raycaster.getRaycastHitVoxelsWithScreenCoordinates(vp, 0, cam.w, 0, cam.h, false);
+    std::size_t nh = 0;
+    for (std::size_t i = 0; i < np; ++i) nh += leaf[i] >= 0;
+    CHECK(nodup.size() == nh);
+
+    // ViewpointPlanner::getRaycastHitVoxelsWithInformationScore(viewpoint, ignore_zero = true)
+    auto scored = raycaster.getRaycastHitVoxelsWithInformationScore(vp, true);
+    k = orc_score_viewpoint(oracle, weights.data(), normals.data(), Kf, (uint32_t)cam.w, Rt, 0, cam.w, 0, cam.h, &oo, np,
+                            o_leaf.data(), o_info.data(), o_pix.data(), o_dsq.data(), &hc, &tot, &tot32);
+    CHECK(scored.first.size() == k);
+    for (size_t i = 0; i < k; ++i) {
+      auto it = scored.first.find(q3dr::VoxelWithInformation<mock::Node>(leaves[o_leaf[i]].node, 0.0f));
+      CHECK(it != scored.first.end());
+      CHECK(std::fabs(it->information - o_info[i]) <= 1e-5f * std::fabs(o_info[i]));
+    }
+    CHECK(std::fabs(scored.second - tot) <= 1e-5f * std::fabs(tot));
+  }
+  CHECK(total_hits > 5000);
+
+  // bvh::Tree::intersectsCuda
+  std::vector<Tree::Ray> rays;
+  for (int i = 0; i < 257; ++i) {
+    Tree::Ray r;
+    r.origin[0] = 0.11f * (i % 17) - 1.0f;
+    r.origin[1] = -4.0f + 0.05f * (i % 5);
+    r.origin[2] = 0.3f + 0.01f * i;
+    r.direction[0] = 0.02f * (i % 11) - 0.1f;
+    r.direction[1] = 1.0f;
+    r.direction[2] = -0.002f * i;
+    rays.push_back(r);
+  }
+  auto hits = tree.intersectsCuda(rays, 0.0f, -1.0f);
+  {
+    std::vector<float> o(3 * rays.size()), d(3 * rays.size()), dsq(rays.size()), xyz(3 * rays.size());
+    std::vector<int32_t> leaf(rays.size());
+    std::vector<uint32_t> depth(rays.size());
+    for (size_t i = 0; i < rays.size(); ++i)
+      for (int k = 0; k < 3; ++k) {
+        o[3 * i + k] = rays[i].origin[k];
+        d[3 * i + k] = rays[i].direction[k];
+      }
+    orc_intersect_rays(oracle, o.data(), d.data(), rays.size(), 0.0f, -1.0f, leaf.data(), dsq.data(), xyz.data(), depth.data());
+    for (size_t i = 0; i < rays.size(); ++i) {
+      CHECK(hits[i].first == (leaf[i] >= 0));
+      CHECK(hits[i].second.node == (leaf[i] < 0 ? nullptr : leaves[leaf[i]].node));
+      CHECK(hits[i].second.dist_sq == dsq[i]);
+    }
+  }
+
+  // error convention: callers catch OccupiedTreeType::Error
+  bool threw = false;
+  try {
+    tree.raycastCuda(cam.intrinsics(), vps[0].pose().getTransformationImageToWorld(), 10, 10, 0, 5);
+  } catch (const Tree::Error& e) {
+    threw = true;
+  }
+  CHECK(threw);
+  tree.clear();
+  CHECK(!tree.isInitialized());
+  threw = false;
+  try {
+    tree.intersectsCuda(rays);
+  } catch (const Tree::Error&) {
+    threw = true;
+  }
+  CHECK(threw);
+
+  orc_tree_free(oracle);
+  std::printf("shim parity OK: %zu leaves, %zu pixel hits checked\n", n, total_hits);
+  return 0;
+}
