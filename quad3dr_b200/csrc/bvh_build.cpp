@@ -296,8 +296,39 @@ int gather_children(const std::vector<BinNode>& bn, int64_t node, int64_t out[4]
   return cnt;
 }
 
+// Sorts the gathered children by box centre along the axis on which the centres spread most; returns it.
+int order_children(const std::vector<BinNode>& bn, int64_t ch[4], int cnt) {
+  float c[4][3];
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int s = 0; s < cnt; ++s) {
+    for (int a = 0; a < 3; ++a) {
+      c[s][a] = 0.5f * bn[ch[s]].box.mn[a] + 0.5f * bn[ch[s]].box.mx[a];
+      lo[a] = std::min(lo[a], c[s][a]);
+      hi[a] = std::max(hi[a], c[s][a]);
+    }
+  }
+  int axis = 0;
+  for (int a = 1; a < 3; ++a) {
+    if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+  }
+  for (int i = 1; i < cnt; ++i) {  // insertion sort, stable
+    const int64_t n = ch[i];
+    const float key = c[i][axis];
+    float keys[3] = {c[i][0], c[i][1], c[i][2]};
+    int j = i - 1;
+    while (j >= 0 && c[j][axis] > key) {
+      ch[j + 1] = ch[j];
+      for (int a = 0; a < 3; ++a) c[j + 1][a] = c[j][a];
+      --j;
+    }
+    ch[j + 1] = n;
+    for (int a = 0; a < 3; ++a) c[j + 1][a] = keys[a];
+  }
+  return axis;
+}
+
 void fill_node(const std::vector<BinNode>& bn, const int64_t ch[4], int cnt, uint32_t depth, uint32_t leaves,
-               Node4* n4) {
+               uint32_t axis, Node4* n4) {
   for (int s = 0; s < 4; ++s) {
     if (s < cnt) {
       const BinNode& c = bn[ch[s]];
@@ -318,7 +349,7 @@ void fill_node(const std::vector<BinNode>& bn, const int64_t ch[4], int cnt, uin
   n4->meta[0] = (uint32_t)cnt;
   n4->meta[1] = leaves;
   n4->meta[2] = depth;
-  n4->meta[3] = 0;
+  n4->meta[3] = axis;
 }
 
 struct Pending {
@@ -370,6 +401,7 @@ void splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* 
 void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out) {
   out->nodes.clear();
   out->top_nodes = 0;
+  out->root_axis = 0;
   out->depth = 0;
   out->max_stack = 4;
   if (n == 0) return;
@@ -426,10 +458,15 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
     const Pending p = queue[head++];
     const uint32_t me = (uint32_t)flat.size();
     flat.emplace_back();
-    if (p.parent != ~0u) flat[p.parent].child[p.slot] = me;
     int64_t ch[4];
     const int cnt = gather_children(bn, p.bin, ch);
-    fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, &flat[me]);
+    const uint32_t axis = (uint32_t)order_children(bn, ch, cnt);
+    if (p.parent != ~0u) {
+      flat[p.parent].child[p.slot] = me | (axis << kAxisShift);
+    } else {
+      out->root_axis = axis;
+    }
+    fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
     max_depth = std::max(max_depth, p.depth);
     for (int s = 0; s < cnt; ++s) {
       if (bn[ch[s]].left < 0) continue;
@@ -452,10 +489,11 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
       stack.pop_back();
       const uint32_t me = (uint32_t)flat.size();
       flat.emplace_back();
-      flat[p.parent].child[p.slot] = me;
       int64_t ch[4];
       const int cnt = gather_children(bn, p.bin, ch);
-      fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, &flat[me]);
+      const uint32_t axis = (uint32_t)order_children(bn, ch, cnt);
+      flat[p.parent].child[p.slot] = me | (axis << kAxisShift);
+      fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
       max_depth = std::max(max_depth, p.depth);
       for (int s = cnt - 1; s >= 0; --s) {  // reversed so that slot 0's subtree follows its parent
         if (bn[ch[s]].left < 0) continue;

@@ -21,10 +21,16 @@ static_assert(sizeof(Node4) == 128, "Node4 must be one 128-byte line");
 
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kEmptyChild = 0xFFFFFFFFu;
+// An inner child reference also carries, in bits 29..30, the ORDER AXIS of the node it points to: that node's
+// four children are stored sorted by box centre along this axis, so a packet travelling in +axis direction
+// meets them in slot order 0,1,2,3 and one travelling in -axis direction in order 3,2,1,0.
+constexpr uint32_t kAxisShift = 29;
+constexpr uint32_t kNodeIndexMask = (1u << kAxisShift) - 1u;
 
 struct FlatTree {
   std::vector<Node4> nodes;  // nodes[0] is the root; the first `top_nodes` are the top levels in BFS order
   uint32_t top_nodes = 0;
+  uint32_t root_axis = 0;    // order axis of nodes[0]
   uint32_t depth = 0;        // depth of the 4-wide tree (root = 0, deepest internal node)
   uint32_t max_stack = 0;    // upper bound of traversal-stack entries a packet can hold
 };

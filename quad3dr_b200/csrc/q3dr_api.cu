@@ -286,6 +286,7 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   std::memset(p, 0, sizeof(*p));
   p->nodes = m->d_nodes.p;
   p->n_top = m->tree.top_nodes;
+  p->root_ref = m->tree.root_axis << q3dr::kAxisShift;
   p->fx = K[0];
   p->fy = K[1];
   p->cx = K[2];
@@ -552,9 +553,11 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
         seen[li] = 1;
         ref = boxes + 6 * (size_t)li;
       } else {
-        if (c <= i || c >= nn || referenced[c]) return fail(Q3DR_ERR_INTERNAL, "bad inner child reference");
-        referenced[c] = 1;
-        ref = nb.data() + 6 * (size_t)c;
+        const uint32_t ci = c & q3dr::kNodeIndexMask;
+        if (ci <= i || ci >= nn || referenced[ci]) return fail(Q3DR_ERR_INTERNAL, "bad inner child reference");
+        if ((c >> q3dr::kAxisShift) != t.nodes[ci].meta[3]) return fail(Q3DR_ERR_INTERNAL, "order axis mismatch");
+        referenced[ci] = 1;
+        ref = nb.data() + 6 * (size_t)ci;
       }
       for (int a = 0; a < 3; ++a) {
         if (nd.mn[a][s] != ref[a] || nd.mx[a][s] != ref[3 + a]) return fail(Q3DR_ERR_INTERNAL, "child box mismatch");
@@ -617,6 +620,7 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
     if (m->tree.max_stack > (uint32_t)q3dr::kStackEntries) {
       st = fail(Q3DR_ERR_INTERNAL, "flattened tree too deep for the traversal stack");
     }
+    if (m->tree.nodes.size() > (size_t)q3dr::kNodeIndexMask) st = fail(Q3DR_ERR_INVALID_ARG, "too many nodes");
   } catch (const std::bad_alloc&) {
     st = fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
   }
@@ -766,6 +770,7 @@ int q3dr_intersect_rays(q3dr_map* m, const float* origins, const float* directio
   std::memset(&rp, 0, sizeof(rp));
   rp.nodes = m->d_nodes.p;
   rp.n_top = m->tree.top_nodes;
+  rp.root_ref = m->tree.root_axis << q3dr::kAxisShift;
   rp.max_range = max_range;
   rp.leaf_depth = m->d_depth.p;
   rp.tile_counter = m->d_counter.p;

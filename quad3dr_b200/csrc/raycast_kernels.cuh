@@ -27,6 +27,10 @@ constexpr uint32_t kEmptyPixel = 0xFFFFFFFFu;
 constexpr int kTileW = 8;
 constexpr int kTileH = 4;
 constexpr int kScoreThreads = 512;
+#ifndef Q3DR_SMEM_TOP
+#define Q3DR_SMEM_TOP 1
+#endif
+constexpr bool kSmemTopLevels = (Q3DR_SMEM_TOP != 0);
 
 enum RaycastMode : int {
   kModeScore = 0,   // dedup into the per-viewpoint first-pixel table + bitmap
@@ -37,6 +41,7 @@ enum RaycastMode : int {
 struct RaycastParams {
   const float4* __restrict__ nodes;  // Node4 = 8 x float4
   uint32_t n_top;                    // nodes staged in shared memory
+  uint32_t root_ref;                 // reference of the root node (index 0 | order axis << kAxisShift)
   const float* __restrict__ rt;      // [n_vp][12] row-major [R|t]
   float fx, fy, cx, cy;
   uint32_t x0, y0, w, h;  // window
@@ -210,8 +215,9 @@ __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& be
   float stack_d[kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
-  uint32_t node = 0;
+  uint32_t node = 0;  // inner references carry the order axis in their top bits; this path ignores it
   while (true) {
+    node &= kNodeIndexMask;
     const float4* np = (node < n_top) ? (smem_top + (size_t)node * 8) : (nodes + (size_t)node * 8);
     const float4 mnx = np[0], mny = np[1], mnz = np[2];
     const float4 mxx = np[3], mxy = np[4], mxz = np[5];
@@ -298,19 +304,36 @@ __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& be
 //   * inner children are judged on the entry parameter t against best.tU (see prune_bound): skipping needs
 //     dist_sq > best, which t >= tU implies; visiting more than the reference never changes the result;
 //   * leaves compute dist_sq exactly whenever some lane could still accept them.
+// Visit order: a node's children are stored sorted along the node's order axis (bvh_build.cpp), so the
+// packet's octant alone says whether slot order 0..3 or 3..0 is front to back -- no per-node sorting.
+// Far candidates go on the stack with every lane's entry parameter; a popped entry that no lane can still
+// improve under (warp vote against tU) is dropped without touching memory.
+template <bool kSmemTop>
 __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
-                                                     const float4* smem_top, uint32_t n_top, int nx, int ny, int nz) {
+                                                     const float4* smem_top, uint32_t n_top, uint32_t root_ref,
+                                                     uint32_t octant /* bit a set: direction negative on axis a */) {
   float stack_t[kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
-  uint32_t node = 0;
-  const int fx = 3 - nx, fy = 5 - ny, fz = 7 - nz;  // far plane index: {0,3} {1,4} {2,5}
+  uint32_t ref = root_ref;
+  // plane indices inside a node: mn x,y,z = 0,1,2 ; mx x,y,z = 3,4,5
+  const uint32_t nx = (octant & 1u) ? 3u : 0u, ny = (octant & 2u) ? 4u : 1u, nz = (octant & 4u) ? 5u : 2u;
+  const uint32_t fx = 3u - nx, fy = 5u - ny, fz = 7u - nz;
   const float kInf = __int_as_float(0x7F800000);
   while (true) {
-    const float4* np = (node < n_top) ? (smem_top + (size_t)node * 8) : (nodes + (size_t)node * 8);
-    const float4 nrx = np[nx], nry = np[ny], nrz = np[nz];
-    const float4 frx = np[fx], fry = np[fy], frz = np[fz];
-    const uint4 ch = *reinterpret_cast<const uint4*>(np + 6);
+    const uint32_t base = (ref & kNodeIndexMask) * 8u;
+    const bool reverse = (octant >> (ref >> kAxisShift)) & 1u;
+    float4 nrx, nry, nrz, frx, fry, frz;
+    uint4 ch;
+    if (kSmemTop && base < n_top * 8u) {
+      nrx = smem_top[base + nx]; nry = smem_top[base + ny]; nrz = smem_top[base + nz];
+      frx = smem_top[base + fx]; fry = smem_top[base + fy]; frz = smem_top[base + fz];
+      ch = *reinterpret_cast<const uint4*>(smem_top + base + 6u);
+    } else {
+      nrx = __ldg(nodes + (base + nx)); nry = __ldg(nodes + (base + ny)); nrz = __ldg(nodes + (base + nz));
+      frx = __ldg(nodes + (base + fx)); fry = __ldg(nodes + (base + fy)); frz = __ldg(nodes + (base + fz));
+      ch = __ldg(reinterpret_cast<const uint4*>(nodes + (base + 6u)));
+    }
 
     float t0, t1, t2, t3;
     bool h0, h1, h2, h3, c0, c1, c2, c3;
@@ -332,6 +355,7 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
     if (__any_sync(Q3DR_FULL_MASK, c0 | c1 | c2 | c3)) {
       // rare: some lane's origin lies on a face plane of a child box -> the reference's inside / outside
       // distinction matters; redo this node with the reference's full box test
+      const float4* np = nodes + base;
       const float4 mnx = np[0], mny = np[1], mnz = np[2], mxx = np[3], mxy = np[4], mxz = np[5];
       float dd;
       h0 = box_test(ray, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t0);
@@ -365,31 +389,36 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
     Q3DR_LEAF(ch.w, h3, t3)
 #undef Q3DR_LEAF
 
-    uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu, k3 = 0xFFFFFFFFu;
-    float e0 = kInf, e1 = kInf, e2 = kInf, e3 = kInf;
-#define Q3DR_INNER(CH, H, T, K, E)                                                      \
+    // inner children, far to near: each new candidate pushes the previous (farther) one
+    uint32_t next = kEmptyChild;
+    float next_t = kInf;
+#define Q3DR_INNER(CH, H, T)                                                            \
     if (!((CH) & kLeafFlag)) {                                                          \
       const bool ok = (H) && ((T) < best.tU);                                           \
-      if (ok) (E) = (T);                                                                \
-      (K) = __reduce_min_sync(Q3DR_FULL_MASK, ok ? __float_as_uint(T) : 0xFFFFFFFFu);   \
+      if (__any_sync(Q3DR_FULL_MASK, ok)) {                                             \
+        if (next != kEmptyChild) {                                                      \
+          stack_t[sp] = next_t;                                                         \
+          stack_n[sp] = next;                                                           \
+          ++sp;                                                                         \
+        }                                                                               \
+        next = (CH);                                                                    \
+        next_t = ok ? (T) : kInf;                                                       \
+      }                                                                                 \
     }
-    Q3DR_INNER(ch.x, h0, t0, k0, e0)
-    Q3DR_INNER(ch.y, h1, t1, k1, e1)
-    Q3DR_INNER(ch.z, h2, t2, k2, e2)
-    Q3DR_INNER(ch.w, h3, t3, k3, e3)
+    if (reverse) {
+      Q3DR_INNER(ch.x, h0, t0)
+      Q3DR_INNER(ch.y, h1, t1)
+      Q3DR_INNER(ch.z, h2, t2)
+      Q3DR_INNER(ch.w, h3, t3)
+    } else {
+      Q3DR_INNER(ch.w, h3, t3)
+      Q3DR_INNER(ch.z, h2, t2)
+      Q3DR_INNER(ch.y, h1, t1)
+      Q3DR_INNER(ch.x, h0, t0)
+    }
 #undef Q3DR_INNER
-
-    uint32_t n0 = ch.x, n1 = ch.y, n2 = ch.z, n3 = ch.w;
-    cswap(k0, n0, e0, k1, n1, e1);
-    cswap(k2, n2, e2, k3, n3, e3);
-    cswap(k0, n0, e0, k2, n2, e2);
-    cswap(k1, n1, e1, k3, n3, e3);
-    cswap(k1, n1, e1, k2, n2, e2);
-    if (k3 != 0xFFFFFFFFu) { stack_t[sp] = e3; stack_n[sp] = n3; ++sp; }
-    if (k2 != 0xFFFFFFFFu) { stack_t[sp] = e2; stack_n[sp] = n2; ++sp; }
-    if (k1 != 0xFFFFFFFFu) { stack_t[sp] = e1; stack_n[sp] = n1; ++sp; }
-    if (k0 != 0xFFFFFFFFu) {
-      node = n0;
+    if (next != kEmptyChild) {
+      ref = next;
       continue;
     }
     bool found = false;
@@ -398,7 +427,7 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
       const float d = stack_t[sp];
       const uint32_t n = stack_n[sp];
       if (__any_sync(Q3DR_FULL_MASK, d < best.tU)) {
-        node = n;
+        ref = n;
         found = true;
         break;
       }
@@ -487,7 +516,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const Raycas
     if (__all_sync(Q3DR_FULL_MASK, finite) && uniform_octant) {
       const float kInf = __int_as_float(0x7F800000);
       best.tU = live ? ((p.max_range > 0.0f) ? prune_bound(ray, p.max_range, range_sq) : kInf) : -1.0f;
-      traverse_packet_fast(ray, best, p.nodes, smem_top, p.n_top, bx ? 3 : 0, by ? 4 : 1, bz ? 5 : 2);
+      const uint32_t octant = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
+      traverse_packet_fast<kSmemTopLevels>(ray, best, p.nodes, smem_top, p.n_top, p.root_ref, octant);
     } else {
       best.tU = 0.0f;
       traverse_packet_exact(ray, best, p.nodes, smem_top, p.n_top);

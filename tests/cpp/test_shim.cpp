@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/q3dr/occupied_tree_cuda.hpp"
@@ -259,10 +261,16 @@ int main(int argc, char** argv) {
     k = orc_score_viewpoint(oracle, weights.data(), normals.data(), Kf, (uint32_t)cam.w, Rt, 0, cam.w, 0, cam.h, &oo, np,
                             o_leaf.data(), o_info.data(), o_pix.data(), o_dsq.data(), &hc, &tot, &tot32);
     CHECK(scored.first.size() == k);
-    for (size_t i = 0; i < k; ++i) {
-      auto it = scored.first.find(q3dr::VoxelWithInformation<mock::Node>(leaves[o_leaf[i]].node, 0.0f));
-      CHECK(it != scored.first.end());
-      CHECK(std::fabs(it->information - o_info[i]) <= 1e-5f * std::fabs(o_info[i]));
+    {
+      // the set is hashed by voxel pointer but compares (voxel, information), like planner/occupied_tree.h:62-92
+      std::unordered_map<const mock::Node*, float> by_voxel;
+      for (const auto& vi : scored.first) by_voxel[vi.voxel] = vi.information;
+      CHECK(by_voxel.size() == k);
+      for (size_t i = 0; i < k; ++i) {
+        auto it = by_voxel.find(leaves[o_leaf[i]].node);
+        CHECK(it != by_voxel.end());
+        CHECK(std::fabs(it->second - o_info[i]) <= 1e-5f * std::fabs(o_info[i]));
+      }
     }
     CHECK(std::fabs(scored.second - tot) <= 1e-5f * std::fabs(tot));
   }
