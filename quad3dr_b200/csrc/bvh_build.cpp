@@ -134,16 +134,18 @@ struct Box3 {
   }
 };
 
+// Binary build node.  Terminal nodes (left < 0) are GROUPS of 1..4 leaves idx[first, first + count): the
+// bottom of the tree is built in fours so that the 4-wide nodes over the leaves are full.
 struct BinNode {
   Box3 box;
-  int64_t left = -1, right = -1;  // binary node slots; -1 for a leaf
-  uint32_t leaf = 0;              // leaf index when left < 0
-  uint32_t count = 1;             // leaves below
+  int64_t left = -1, right = -1;
+  uint32_t first = 0;
+  uint32_t count = 1;  // leaves below
 };
 
 struct BuildCtx {
   const float* boxes;     // n x 6
-  std::vector<float> cx;  // centroids (double precision is not needed: they only steer the split)
+  std::vector<float> cx;  // centroids (they only steer the split; the boxes themselves stay exact)
   std::vector<float> cy;
   std::vector<float> cz;
   std::vector<uint32_t> idx;
@@ -152,37 +154,75 @@ struct BuildCtx {
 };
 
 constexpr int kBins = 16;
+constexpr size_t kSmallRange = 64;
+
+// Exact SAH sweep for a small range with the cut restricted to multiples of 4 leaves.
+size_t split_small(BuildCtx& c, size_t b, size_t e) {
+  const size_t n = e - b;
+  uint32_t sorted[3][kSmallRange];
+  double best_cost = DBL_MAX;
+  int best_axis = 0;
+  size_t best_k = 4;
+  for (int a = 0; a < 3; ++a) {
+    const float* cen = c.cen(a);
+    uint32_t* s = sorted[a];
+    for (size_t i = 0; i < n; ++i) s[i] = c.idx[b + i];
+    std::stable_sort(s, s + n, [cen](uint32_t x, uint32_t y) { return cen[x] < cen[y]; });
+    double right_area[kSmallRange];
+    Box3 acc;
+    acc.reset();
+    for (size_t i = n; i-- > 1;) {
+      acc.grow(c.boxes + 6 * (size_t)s[i]);
+      right_area[i] = acc.half_area();
+    }
+    acc.reset();
+    for (size_t k = 1; k < n; ++k) {
+      acc.grow(c.boxes + 6 * (size_t)s[k - 1]);
+      if (k % 4 != 0) continue;
+      const double cost = acc.half_area() * (double)k + right_area[k] * (double)(n - k);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_axis = a;
+        best_k = k;
+      }
+    }
+  }
+  for (size_t i = 0; i < n; ++i) c.idx[b + i] = sorted[best_axis][i];
+  return b + best_k;
+}
 
 // Builds the subtree over idx[b,e) into slots [base, base + 2(e-b) - 1); returns the root slot.
 int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
   const size_t n = e - b;
   const int64_t me = base + 2 * (int64_t)n - 2;
   BinNode& node = c.nodes[me];
-  if (n == 1) {
-    const uint32_t li = c.idx[b];
+  if (n <= 4) {
     node.box.reset();
-    node.box.grow(c.boxes + 6 * (size_t)li);
+    for (size_t i = b; i < e; ++i) node.box.grow(c.boxes + 6 * (size_t)c.idx[i]);
     node.left = node.right = -1;
-    node.leaf = li;
-    node.count = 1;
+    node.first = (uint32_t)b;
+    node.count = (uint32_t)n;
     return me;
   }
-  // centroid bounds
-  float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (size_t i = b; i < e; ++i) {
-    const uint32_t li = c.idx[i];
-    const float p[3] = {c.cx[li], c.cy[li], c.cz[li]};
-    for (int a = 0; a < 3; ++a) {
-      cmn[a] = std::min(cmn[a], p[a]);
-      cmx[a] = std::max(cmx[a], p[a]);
+  size_t mid;
+  if (n <= kSmallRange) {
+    mid = split_small(c, b, e);
+  } else {
+    // centroid bounds
+    float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (size_t i = b; i < e; ++i) {
+      const uint32_t li = c.idx[i];
+      const float p[3] = {c.cx[li], c.cy[li], c.cz[li]};
+      for (int a = 0; a < 3; ++a) {
+        cmn[a] = std::min(cmn[a], p[a]);
+        cmx[a] = std::max(cmx[a], p[a]);
+      }
     }
-  }
-  size_t mid = b + n / 2;
-  int best_axis = -1;
-  int best_split = -1;
-  double best_cost = DBL_MAX;
-  float best_scale = 0;
-  if (n > 2) {
+    mid = b + n / 2;
+    int best_axis = -1;
+    int best_split = -1;
+    double best_cost = DBL_MAX;
+    float best_scale = 0;
     for (int a = 0; a < 3; ++a) {
       const float ext = cmx[a] - cmn[a];
       if (!(ext > 0)) continue;
@@ -201,7 +241,6 @@ int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
         bin_box[k].grow(c.boxes + 6 * (size_t)li);
         ++bin_cnt[k];
       }
-      // sweep
       double right_area[kBins];
       uint32_t right_cnt[kBins];
       Box3 acc;
@@ -228,24 +267,23 @@ int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
         }
       }
     }
-  }
-  if (best_axis >= 0) {
-    const float* cen = c.cen(best_axis);
-    const float lo = cmn[best_axis];
-    uint32_t* first = c.idx.data() + b;
-    uint32_t* last = c.idx.data() + e;
-    uint32_t* p = std::partition(first, last, [&](uint32_t li) {
-      int k = (int)((cen[li] - lo) * best_scale);
-      k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-      return k <= best_split;
-    });
-    mid = b + (size_t)(p - first);
-    if (mid == b || mid == e) mid = b + n / 2;  // cannot happen; keep the build total anyway
-  } else if (n == 2) {
-    mid = b + 1;
-  } else {
-    // all centroids identical (or n == 2 handled above): split by position
-    mid = b + n / 2;
+    if (best_axis >= 0) {
+      const float* cen = c.cen(best_axis);
+      const float lo = cmn[best_axis];
+      uint32_t* first = c.idx.data() + b;
+      uint32_t* last = c.idx.data() + e;
+      uint32_t* p = std::partition(first, last, [&](uint32_t li) {
+        int k = (int)((cen[li] - lo) * best_scale);
+        k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+        return k <= best_split;
+      });
+      mid = b + (size_t)(p - first);
+      if (mid == b || mid == e) mid = b + n / 2;  // cannot happen; keep the build total anyway
+    } else {
+      // all centroids identical: split by position, on a multiple of four
+      mid = b + ((n / 2 + 3) / 4) * 4;
+      if (mid >= e) mid = b + n / 2;
+    }
   }
   const int64_t lbase = base;
   const int64_t rbase = base + 2 * (int64_t)(mid - b) - 1;
@@ -273,38 +311,78 @@ int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
 // collapse to 4-wide nodes + layout
 // ------------------------------------------------------------------------------------------
 
-int gather_children(const std::vector<BinNode>& bn, int64_t node, int64_t out[4]) {
+struct Child {
+  int64_t bin;   // binary node that becomes a 4-wide node of its own, or -1
+  int64_t leaf;  // leaf index referenced directly, or -1
+};
+
+// Up to four children of the 4-wide node made from binary node `node`.
+int gather_children(const BuildCtx& c, int64_t node, Child out[4]) {
+  const std::vector<BinNode>& bn = c.nodes;
   int cnt = 0;
-  out[cnt++] = bn[node].left;
-  out[cnt++] = bn[node].right;
+  if (bn[node].left < 0) {  // a group: its leaves
+    for (uint32_t i = 0; i < bn[node].count; ++i) out[cnt++] = Child{-1, (int64_t)c.idx[bn[node].first + i]};
+    return cnt;
+  }
+  out[cnt++] = Child{bn[node].left, -1};
+  out[cnt++] = Child{bn[node].right, -1};
+  // pull grandchildren up, largest box first
   while (cnt < 4) {
     int pick = -1;
     double best = -1.0;
     for (int i = 0; i < cnt; ++i) {
-      if (bn[out[i]].left < 0) continue;
-      const double a = bn[out[i]].box.half_area();
+      if (out[i].bin < 0 || bn[out[i].bin].left < 0) continue;
+      const double a = bn[out[i].bin].box.half_area();
       if (a > best) {
         best = a;
         pick = i;
       }
     }
     if (pick < 0) break;
-    const int64_t p = out[pick];
-    out[pick] = bn[p].left;
-    out[cnt++] = bn[p].right;
+    const int64_t p = out[pick].bin;
+    out[pick] = Child{bn[p].left, -1};
+    out[cnt++] = Child{bn[p].right, -1};
+  }
+  // inline groups that fit into the free slots (smallest first): saves a node visit
+  while (true) {
+    int pick = -1;
+    uint32_t best = 5;
+    for (int i = 0; i < cnt; ++i) {
+      if (out[i].bin < 0 || bn[out[i].bin].left >= 0) continue;
+      const uint32_t k = bn[out[i].bin].count;
+      if (k <= (uint32_t)(4 - cnt) + 1u && k < best) {
+        best = k;
+        pick = i;
+      }
+    }
+    if (pick < 0) break;
+    const BinNode& g = bn[out[pick].bin];
+    out[pick] = Child{-1, (int64_t)c.idx[g.first]};
+    for (uint32_t i = 1; i < g.count; ++i) out[cnt++] = Child{-1, (int64_t)c.idx[g.first + i]};
   }
   return cnt;
 }
 
+void child_box(const BuildCtx& c, const Child& ch, Box3* b) {
+  if (ch.bin >= 0) {
+    *b = c.nodes[ch.bin].box;
+  } else {
+    b->reset();
+    b->grow(c.boxes + 6 * (size_t)ch.leaf);
+  }
+}
+
 // Sorts the gathered children by box centre along the axis on which the centres spread most; returns it.
-int order_children(const std::vector<BinNode>& bn, int64_t ch[4], int cnt) {
-  float c[4][3];
+int order_children(const BuildCtx& c, Child ch[4], int cnt) {
+  float ctr[4][3];
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int s = 0; s < cnt; ++s) {
+    Box3 b;
+    child_box(c, ch[s], &b);
     for (int a = 0; a < 3; ++a) {
-      c[s][a] = 0.5f * bn[ch[s]].box.mn[a] + 0.5f * bn[ch[s]].box.mx[a];
-      lo[a] = std::min(lo[a], c[s][a]);
-      hi[a] = std::max(hi[a], c[s][a]);
+      ctr[s][a] = 0.5f * b.mn[a] + 0.5f * b.mx[a];
+      lo[a] = std::min(lo[a], ctr[s][a]);
+      hi[a] = std::max(hi[a], ctr[s][a]);
     }
   }
   int axis = 0;
@@ -312,31 +390,31 @@ int order_children(const std::vector<BinNode>& bn, int64_t ch[4], int cnt) {
     if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
   }
   for (int i = 1; i < cnt; ++i) {  // insertion sort, stable
-    const int64_t n = ch[i];
-    const float key = c[i][axis];
-    float keys[3] = {c[i][0], c[i][1], c[i][2]};
+    const Child n = ch[i];
+    const float keys[3] = {ctr[i][0], ctr[i][1], ctr[i][2]};
     int j = i - 1;
-    while (j >= 0 && c[j][axis] > key) {
+    while (j >= 0 && ctr[j][axis] > keys[axis]) {
       ch[j + 1] = ch[j];
-      for (int a = 0; a < 3; ++a) c[j + 1][a] = c[j][a];
+      for (int a = 0; a < 3; ++a) ctr[j + 1][a] = ctr[j][a];
       --j;
     }
     ch[j + 1] = n;
-    for (int a = 0; a < 3; ++a) c[j + 1][a] = keys[a];
+    for (int a = 0; a < 3; ++a) ctr[j + 1][a] = keys[a];
   }
   return axis;
 }
 
-void fill_node(const std::vector<BinNode>& bn, const int64_t ch[4], int cnt, uint32_t depth, uint32_t leaves,
-               uint32_t axis, Node4* n4) {
+void fill_node(const BuildCtx& c, const Child ch[4], int cnt, uint32_t depth, uint32_t leaves, uint32_t axis,
+               Node4* n4) {
   for (int s = 0; s < 4; ++s) {
     if (s < cnt) {
-      const BinNode& c = bn[ch[s]];
+      Box3 b;
+      child_box(c, ch[s], &b);
       for (int a = 0; a < 3; ++a) {
-        n4->mn[a][s] = c.box.mn[a];
-        n4->mx[a][s] = c.box.mx[a];
+        n4->mn[a][s] = b.mn[a];
+        n4->mx[a][s] = b.mx[a];
       }
-      n4->child[s] = (c.left < 0) ? (kLeafFlag | c.leaf) : 0u;  // internal refs are patched later
+      n4->child[s] = (ch[s].bin < 0) ? (kLeafFlag | (uint32_t)ch[s].leaf) : 0u;  // inner refs are patched later
     } else {
       // a point far away: tmax > max(tmin, 0) can never hold for a degenerate box seen from outside
       for (int a = 0; a < 3; ++a) {
@@ -405,24 +483,6 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
   out->depth = 0;
   out->max_stack = 4;
   if (n == 0) return;
-  if (n == 1) {
-    // a single leaf: one node with one used slot
-    out->nodes.resize(1);
-    Node4& r = out->nodes[0];
-    for (int s = 0; s < 4; ++s) {
-      for (int a = 0; a < 3; ++a) {
-        r.mn[a][s] = (s == 0) ? boxes[a] : FLT_MAX;
-        r.mx[a][s] = (s == 0) ? boxes[3 + a] : FLT_MAX;
-      }
-      r.child[s] = (s == 0) ? (kLeafFlag | 0u) : kEmptyChild;
-    }
-    r.meta[0] = 1;
-    r.meta[1] = 1;
-    r.meta[2] = 0;
-    r.meta[3] = 0;
-    out->top_nodes = 1;
-    return;
-  }
 
   BuildCtx c;
   c.boxes = boxes;
@@ -441,12 +501,10 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
 #pragma omp parallel
 #pragma omp single nowait
   root = build_binary(c, 0, n, 0);
-  c.idx.clear();
-  c.idx.shrink_to_fit();
 
   const std::vector<BinNode>& bn = c.nodes;
   std::vector<Node4>& flat = out->nodes;
-  flat.reserve((n + 1) / 2 + 16);
+  flat.reserve(n / 3 + 16);
 
   // phase 1: breadth-first over the top levels
   std::vector<Pending> queue;
@@ -454,29 +512,33 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
   queue.push_back(Pending{root, ~0u, 0u, 0u});
   size_t head = 0;
   uint32_t max_depth = 0;
-  while (head < queue.size()) {
-    const Pending p = queue[head++];
+  auto emit = [&](const Pending& p, std::vector<Pending>* same_phase, std::vector<Pending>* next_phase, bool reversed) {
     const uint32_t me = (uint32_t)flat.size();
     flat.emplace_back();
-    int64_t ch[4];
-    const int cnt = gather_children(bn, p.bin, ch);
-    const uint32_t axis = (uint32_t)order_children(bn, ch, cnt);
+    Child ch[4];
+    const int cnt = gather_children(c, p.bin, ch);
+    const uint32_t axis = (uint32_t)order_children(c, ch, cnt);
     if (p.parent != ~0u) {
       flat[p.parent].child[p.slot] = me | (axis << kAxisShift);
     } else {
       out->root_axis = axis;
     }
-    fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
+    fill_node(c, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
     max_depth = std::max(max_depth, p.depth);
-    for (int s = 0; s < cnt; ++s) {
-      if (bn[ch[s]].left < 0) continue;
-      Pending q{ch[s], me, (uint32_t)s, p.depth + 1};
-      if ((int)(p.depth + 1) < top_levels) {
-        queue.push_back(q);
+    for (int k = 0; k < cnt; ++k) {
+      const int s = reversed ? cnt - 1 - k : k;
+      if (ch[s].bin < 0) continue;
+      Pending q{ch[s].bin, me, (uint32_t)s, p.depth + 1};
+      if (same_phase != nullptr && (int)(p.depth + 1) < top_levels) {
+        same_phase->push_back(q);
       } else {
-        dfs_roots.push_back(q);
+        next_phase->push_back(q);
       }
     }
+  };
+  while (head < queue.size()) {
+    const Pending p = queue[head++];
+    emit(p, &queue, &dfs_roots, false);
   }
   out->top_nodes = (uint32_t)flat.size();
 
@@ -487,18 +549,7 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
     while (!stack.empty()) {
       const Pending p = stack.back();
       stack.pop_back();
-      const uint32_t me = (uint32_t)flat.size();
-      flat.emplace_back();
-      int64_t ch[4];
-      const int cnt = gather_children(bn, p.bin, ch);
-      const uint32_t axis = (uint32_t)order_children(bn, ch, cnt);
-      flat[p.parent].child[p.slot] = me | (axis << kAxisShift);
-      fill_node(bn, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
-      max_depth = std::max(max_depth, p.depth);
-      for (int s = cnt - 1; s >= 0; --s) {  // reversed so that slot 0's subtree follows its parent
-        if (bn[ch[s]].left < 0) continue;
-        stack.push_back(Pending{ch[s], me, (uint32_t)s, p.depth + 1});
-      }
+      emit(p, nullptr, &stack, true);  // reversed so that slot 0's subtree follows its parent
     }
   }
   out->depth = max_depth;

@@ -389,36 +389,47 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
     Q3DR_LEAF(ch.w, h3, t3)
 #undef Q3DR_LEAF
 
-    // inner children, far to near: each new candidate pushes the previous (farther) one
-    uint32_t next = kEmptyChild;
-    float next_t = kInf;
-#define Q3DR_INNER(CH, H, T)                                                            \
-    if (!((CH) & kLeafFlag)) {                                                          \
-      const bool ok = (H) && ((T) < best.tU);                                           \
-      if (__any_sync(Q3DR_FULL_MASK, ok)) {                                             \
-        if (next != kEmptyChild) {                                                      \
-          stack_t[sp] = next_t;                                                         \
-          stack_n[sp] = next;                                                           \
-          ++sp;                                                                         \
-        }                                                                               \
-        next = (CH);                                                                    \
-        next_t = ok ? (T) : kInf;                                                       \
-      }                                                                                 \
+    // inner children: a child is a candidate while some lane may still improve below it (warp vote)
+    const bool ok0 = h0 && (t0 < best.tU), ok1 = h1 && (t1 < best.tU);
+    const bool ok2 = h2 && (t2 < best.tU), ok3 = h3 && (t3 < best.tU);
+    const bool a0 = !(ch.x & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok0);
+    const bool a1 = !(ch.y & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok1);
+    const bool a2 = !(ch.z & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok2);
+    const bool a3 = !(ch.w & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok3);
+    const int ncand = (int)a0 + (int)a1 + (int)a2 + (int)a3;
+    if (ncand == 1) {
+      ref = a0 ? ch.x : (a1 ? ch.y : (a2 ? ch.z : ch.w));
+      continue;
     }
-    if (reverse) {
-      Q3DR_INNER(ch.x, h0, t0)
-      Q3DR_INNER(ch.y, h1, t1)
-      Q3DR_INNER(ch.z, h2, t2)
-      Q3DR_INNER(ch.w, h3, t3)
-    } else {
-      Q3DR_INNER(ch.w, h3, t3)
-      Q3DR_INNER(ch.z, h2, t2)
-      Q3DR_INNER(ch.y, h1, t1)
-      Q3DR_INNER(ch.x, h0, t0)
-    }
-#undef Q3DR_INNER
-    if (next != kEmptyChild) {
-      ref = next;
+    if (ncand > 1) {
+      // nearest candidate (least entry parameter over the lanes that need it) is entered directly; the
+      // others go on the stack in far-to-near slot order along the node's order axis, each with every
+      // lane's own entry parameter
+      const uint32_t k0 = a0 ? __reduce_min_sync(Q3DR_FULL_MASK, ok0 ? __float_as_uint(t0) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+      const uint32_t k1 = a1 ? __reduce_min_sync(Q3DR_FULL_MASK, ok1 ? __float_as_uint(t1) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+      const uint32_t k2 = a2 ? __reduce_min_sync(Q3DR_FULL_MASK, ok2 ? __float_as_uint(t2) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+      const uint32_t k3 = a3 ? __reduce_min_sync(Q3DR_FULL_MASK, ok3 ? __float_as_uint(t3) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+      const uint32_t kmin = min(min(k0, k1), min(k2, k3));
+      const int nearest = (k0 == kmin) ? 0 : ((k1 == kmin) ? 1 : ((k2 == kmin) ? 2 : 3));
+#define Q3DR_PUSH(IDX, A, OK, T, CH)                \
+      if ((A) && nearest != (IDX)) {                \
+        stack_t[sp] = (OK) ? (T) : kInf;            \
+        stack_n[sp] = (CH);                         \
+        ++sp;                                       \
+      }
+      if (reverse) {
+        Q3DR_PUSH(0, a0, ok0, t0, ch.x)
+        Q3DR_PUSH(1, a1, ok1, t1, ch.y)
+        Q3DR_PUSH(2, a2, ok2, t2, ch.z)
+        Q3DR_PUSH(3, a3, ok3, t3, ch.w)
+      } else {
+        Q3DR_PUSH(3, a3, ok3, t3, ch.w)
+        Q3DR_PUSH(2, a2, ok2, t2, ch.z)
+        Q3DR_PUSH(1, a1, ok1, t1, ch.y)
+        Q3DR_PUSH(0, a0, ok0, t0, ch.x)
+      }
+#undef Q3DR_PUSH
+      ref = (nearest == 0) ? ch.x : ((nearest == 1) ? ch.y : ((nearest == 2) ? ch.z : ch.w));
       continue;
     }
     bool found = false;
