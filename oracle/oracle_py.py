@@ -71,6 +71,10 @@ def lib():
     L.orc_raycast_window.argtypes = [C.c_void_p, fp, fp] + [C.c_uint32] * 4 + [C.c_float] * 2 + [i32p, fp, fp, u32p]
     L.orc_raycast_window_brute.argtypes = [C.c_void_p, fp, fp] + [C.c_uint32] * 4 + [C.c_float] * 2 + [i32p, fp]
     L.orc_intersect_rays.argtypes = [C.c_void_p, fp, fp, C.c_size_t, C.c_float, C.c_float, i32p, fp, fp, u32p]
+    L.orc_intersect_rays_raw.argtypes = [C.c_void_p, fp, fp, C.c_size_t, C.c_float, C.c_float, i32p, fp, fp, u32p]
+    L.orc_camera_rays.argtypes = [fp, fp] + [C.c_uint32] * 4 + [fp, fp]
+    L.orc_set_sqnorm_sequential.argtypes = [C.c_int]
+    L.orc_tree_export_nodes.argtypes = [C.c_void_p, fp, i32p, i32p, i32p, i32p]
     L.orc_voxel_information.restype = C.c_float
     L.orc_voxel_information.argtypes = [fp, C.c_float, fp, fp, C.c_float, C.c_uint32, C.POINTER(ScoreOpts)]
     L.orc_score_viewpoint.restype = C.c_size_t
@@ -184,6 +188,29 @@ class OracleTree:
         lib().orc_intersect_rays(self._h, _f(o), _f(d), n, min_range, max_range, _i(leaf), _f(dsq), _f(xyz), _u(depth))
         return dict(leaf=leaf, dsq=dsq, xyz=xyz, depth=depth)
 
+    def intersect_rays_raw(self, origins, directions, min_range=0.0, max_range=-1.0):
+        """Rays used as given (no normalisation), the form of the reference's CudaTree::intersectsRecursive."""
+        o = _f32(origins)
+        d = _f32(directions)
+        n = o.shape[0]
+        leaf = np.empty(n, dtype=np.int32)
+        dsq = np.empty(n, dtype=np.float32)
+        xyz = np.empty((n, 3), dtype=np.float32)
+        depth = np.empty(n, dtype=np.uint32)
+        lib().orc_intersect_rays_raw(self._h, _f(o), _f(d), n, min_range, max_range, _i(leaf), _f(dsq), _f(xyz), _u(depth))
+        return dict(leaf=leaf, dsq=dsq, xyz=xyz, depth=depth)
+
+    def export_nodes(self):
+        """The binary splitMedian tree: (boxes nn x 6, left, right, leaf, root)."""
+        nn = self.num_nodes
+        boxes = np.empty((nn, 6), dtype=np.float32)
+        left = np.empty(nn, dtype=np.int32)
+        right = np.empty(nn, dtype=np.int32)
+        leaf = np.empty(nn, dtype=np.int32)
+        root = C.c_int32(0)
+        lib().orc_tree_export_nodes(self._h, _f(boxes), _i(left), _i(right), _i(leaf), C.byref(root))
+        return boxes, left, right, leaf, int(root.value)
+
     def score_viewpoint(self, weights, normals, K, width, Rt, window=None, height=None, opts: Optional[ScoreOpts] = None):
         """getRaycastHitVoxelsWithInformationScore for one viewpoint (sorted by leaf index)."""
         opts = opts or default_opts()
@@ -243,6 +270,22 @@ def pose_to_rt(quat_wxyz, trans) -> np.ndarray:
     out = np.empty(12, dtype=np.float32)
     lib().orc_pose_to_rt(_f(_f32(quat_wxyz, (4,))), _f(_f32(trans, (3,))), _f(out))
     return out
+
+
+def camera_rays(K, Rt, x0, x1, y0, y1):
+    """(origins, normalised directions) of the window's pixel rays, row-major, as the query sees them."""
+    K = _f32(K, (4,))
+    Rt = _f32(Rt).reshape(12)
+    n = (x1 - x0) * (y1 - y0)
+    o = np.empty((n, 3), dtype=np.float32)
+    d = np.empty((n, 3), dtype=np.float32)
+    lib().orc_camera_rays(_f(K), _f(Rt), x0, x1, y0, y1, _f(o), _f(d))
+    return o, d
+
+
+def set_sqnorm_sequential(on: bool) -> None:
+    """Pin-test switch (see q3dr_oracle.h); always reset to False afterwards."""
+    lib().orc_set_sqnorm_sequential(1 if on else 0)
 
 
 def max_threads() -> int:

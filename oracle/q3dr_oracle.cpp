@@ -135,10 +135,21 @@ inline bool boxIntersects(const Box& b, const Ray& r, float* intersection) {
   return intersect;
 }
 
-// (a - b).squaredNorm() with Eigen's fixed-size-3 reduction order a0 + (a1 + a2).
+// Association of (a - b).squaredNorm() in the query.  0 (default, THE contract): Eigen's fixed-size-3
+// reduction a0 + (a1 + a2), the reference's CPU path.  1: the sequential loop ((0 + a0) + a1) + a2 of
+// the reference's device code (include/bh/cuda_math.h:135-141) -- used only by the test that pins this
+// oracle bit for bit against the reference's own bvh.cu compiled under oracle/ref_cuda.
+int g_sqnorm_sequential = 0;
+
+// (a - b).squaredNorm()
 inline float distSq(const float* a, const float* b) {
   float e0 = a[0] - b[0], e1 = a[1] - b[1], e2 = a[2] - b[2];
   float s0 = e0 * e0, s1 = e1 * e1, s2 = e2 * e2;
+  if (g_sqnorm_sequential) {
+    float acc = 0.0f + s0;
+    acc = acc + s1;
+    return acc + s2;
+  }
   float s12 = s1 + s2;
   return s0 + s12;
 }
@@ -472,6 +483,64 @@ void orc_intersect_rays(const orc_tree* t, const float* origins, const float* di
   for (size_t i = 0; i < n; ++i) {
     Ray ray;
     makeRay(origins + 3 * i, directions + 3 * i, &ray);
+    Hit h;
+    const bool ok = treeIntersects(t, ray, min_range, max_range, &h, &visits);
+    if (leaf) leaf[i] = ok ? t->nodes[h.node].leaf : -1;
+    if (dsq) dsq[i] = ok ? h.dist_sq : 0.0f;
+    if (xyz) {
+      xyz[3 * i + 0] = ok ? h.p[0] : 0.0f;
+      xyz[3 * i + 1] = ok ? h.p[1] : 0.0f;
+      xyz[3 * i + 2] = ok ? h.p[2] : 0.0f;
+    }
+    if (depth) depth[i] = ok ? h.depth : 0u;
+  }
+}
+
+void orc_set_sqnorm_sequential(int on) { g_sqnorm_sequential = on ? 1 : 0; }
+
+void orc_tree_export_nodes(const orc_tree* t, float* boxes, int32_t* left, int32_t* right, int32_t* leaf,
+                           int32_t* root) {
+  for (size_t i = 0; i < t->nodes.size(); ++i) {
+    const Node& n = t->nodes[i];
+    for (int a = 0; a < 3; ++a) {
+      boxes[6 * i + a] = n.box.mn[a];
+      boxes[6 * i + 3 + a] = n.box.mx[a];
+    }
+    left[i] = n.left;
+    right[i] = n.right;
+    leaf[i] = n.leaf;
+  }
+  if (root) *root = t->root;
+}
+
+void orc_camera_rays(const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                     float* origins, float* directions) {
+  const uint32_t w = x1 - x0;
+  for (uint32_t y = y0; y < y1; ++y) {
+    for (uint32_t x = x0; x < x1; ++x) {
+      Ray r;
+      cameraRay(K, Rt, x, y, &r);
+      const size_t i = (size_t)(y - y0) * w + (x - x0);
+      for (int a = 0; a < 3; ++a) {
+        origins[3 * i + a] = r.o[a];
+        directions[3 * i + a] = r.d[a];
+      }
+    }
+  }
+}
+
+void orc_intersect_rays_raw(const orc_tree* t, const float* origins, const float* directions, size_t n,
+                            float min_range, float max_range, int32_t* leaf, float* dsq, float* xyz,
+                            uint32_t* depth) {
+#pragma omp parallel for schedule(dynamic, 256)
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t visits = 0;
+    Ray ray;
+    for (int a = 0; a < 3; ++a) {
+      ray.o[a] = origins[3 * i + a];
+      ray.d[a] = directions[3 * i + a];
+      ray.inv[a] = 1.0f / ray.d[a];  // cwiseInverse (bvh.h:380; bvh.cu:458)
+    }
     Hit h;
     const bool ok = treeIntersects(t, ray, min_range, max_range, &h, &visits);
     if (leaf) leaf[i] = ok ? t->nodes[h.node].leaf : -1;

@@ -21,14 +21,22 @@
  *                   include/ait/utilities.h:65-68
  *   aggregation     viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:116-148
  *
- * PARITY UNPINNED: the reference holds no golden vector, known-answer test or fixture
- * for this path, and its CPU path cannot be compiled here (Eigen,
- * Boost, octomap, OMPL, Qt5 are absent).  Third-party arithmetic on the path is Eigen
- * (header-only, version unpinned in-tree; cmake.sh points at eigen-3.3.1): fixed-size-3
- * reductions are restated as  a0 + (a1 + a2)  (Eigen 3.3 redux_novec_unroller halves the
- * range), normalized() as componentwise division by sqrt(squaredNorm()) when that is > 0.
- * The reference compiles this code under "#pragma GCC optimize(fast-math)"; its exact bits
- * are therefore compiler dependent.  This oracle pins strict IEEE as THE definition.
+ * PARITY STATUS.  The reference holds no golden vector, known-answer test or fixture for this path
+ *  and its CPU path cannot be compiled here (Eigen, Boost, octomap, OMPL, Qt5 absent).
+ *   PINNED against outputs of the reference itself: the closest-hit query.  The reference's own device code
+ *     (viewpoint_planner/src/bvh/bvh.cu, the same recursion as bvh.h:842-909) is compiled from the reference
+ *     checkout by oracle/ref_cuda/Makefile and run on the GPU box; with orc_set_sqnorm_sequential(1) -- the one
+ *     arithmetic difference between the reference's device and CPU code (include/bh/cuda_math.h:135-141 vs
+ *     Eigen) -- this oracle equals it BIT FOR BIT on leaf, depth, dist_sq and intersection point over five
+ *     scenes plus tie / inside-a-box / on-a-face / short-range cases (tests/test_gpu_refpin.py).  That pins
+ *     traversal order, tie-breaking, the inside rule, the range rule and the slab arithmetic.
+ *   UNPINNED (stated conventions, no reference output available to check them): Eigen's fixed-size-3
+ *     reduction order, restated as  a0 + (a1 + a2)  (Eigen 3.3 redux_novec_unroller halves the range;
+ *     cmake.sh points at eigen-3.3.1) for squaredNorm / dot / 3x3*vec3; normalized() as componentwise
+ *     division by sqrt(squaredNorm()) when that is > 0; and the scoring formulas of viewpoint_score.cpp /
+ *     viewpoint_planner_scoring.cpp, which exist only on the reference's CPU side.
+ * The reference compiles this code under "#pragma GCC optimize(fast-math)"; its exact bits are therefore
+ * compiler dependent.  This oracle pins strict IEEE as THE definition.
  */
 #ifndef Q3DR_ORACLE_H_
 #define Q3DR_ORACLE_H_
@@ -98,6 +106,25 @@ void orc_raycast_window_brute(const orc_tree* t, const float K[4], const float R
 void orc_intersect_rays(const orc_tree* t, const float* origins, const float* directions, size_t n,
                         float min_range, float max_range, int32_t* leaf, float* dsq, float* xyz,
                         uint32_t* depth);
+
+/* The same query for rays used AS GIVEN (no normalisation; inv = 1 / direction), OpenMP over rays.
+ * This is the form of the reference's device entry CudaTree::intersectsRecursive (bvh.cu:546-579). */
+void orc_intersect_rays_raw(const orc_tree* t, const float* origins, const float* directions, size_t n,
+                            float min_range, float max_range, int32_t* leaf, float* dsq, float* xyz,
+                            uint32_t* depth);
+
+/* The camera rays (origin, normalised direction) of a pixel window, row-major, as the query sees them. */
+void orc_camera_rays(const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                     float* origins, float* directions);
+
+/* Pin-test switch: 1 = squaredNorm associates sequentially like the reference's DEVICE code
+ * (include/bh/cuda_math.h:135-141) instead of Eigen's a0 + (a1 + a2).  Default 0 = the contract. */
+void orc_set_sqnorm_sequential(int on);
+
+/* The binary splitMedian tree itself (for handing it to the reference's CudaTree::createCopyFromHostTree):
+ * boxes n_nodes x 6, left/right child node index or -1, leaf = input leaf index or -1 for inner nodes. */
+void orc_tree_export_nodes(const orc_tree* t, float* boxes, int32_t* left, int32_t* right, int32_t* leaf,
+                           int32_t* root);
 
 /* observation score of one voxel seen from camera centre `cam` (scoring.cpp:116-122). */
 float orc_voxel_information(const float box[6], float weight, const float normal[3],
