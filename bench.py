@@ -165,6 +165,30 @@ def cpu_baseline(leaves, cam, vps, budget_s: float, threads=None):
     }
 
 
+def reference_cuda_baseline(leaves, cam, vps, tree, n_vp: int = 16):
+    """The reference's own recursive CUDA kernel (viewpoint_planner/src/bvh/bvh.cu, built with its own
+    -use_fast_math into oracle/_ref by oracle/ref_cuda/Makefile) recompiled for sm_100a, on the same map and the first
+    n_vp viewpoints of the same workload.  Context only: it is neither the parity oracle nor the product."""
+    try:
+        from oracle import refcuda_py as R
+
+        if not R.available("fast"):
+            return {"unavailable": "oracle/_ref/libq3dr_refcuda_fast.so not built (needs the reference checkout at build time)"}
+        rt = R.RefCudaTree(tree, "fast")
+        n_vp = min(n_vp, vps.shape[0])
+        rt.time_raycasts(cam.K, vps[:2], cam.width, cam.height, 60.0)  # warm-up
+        r = rt.time_raycasts(cam.K, vps[:n_vp], cam.width, cam.height, 60.0)
+        return {
+            "kernel_rays_per_sec": r["rays"] / (r["kernel_ms"] * 1e-3), "api_rays_per_sec": r["rays"] / (r["api_ms"] * 1e-3),
+            "unit": UNIT, "viewpoints": int(n_vp), "kernel_ms": r["kernel_ms"], "api_ms": r["api_ms"],
+            "what": "bvh::CudaTree<float>::raycastWithScreenCoordinatesRecursive: kernel = its __global__ alone (CUDA events); "
+                    "api = the public call incl. cudaDeviceSynchronize + D2H of W*H 56-byte records per viewpoint; "
+                    "traversal only (no dedup, no scoring), 32 KiB device stack per thread as the reference sets it",
+        }
+    except Exception as e:  # context only: never fail the bench on it
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself needs Eigen/Boost, absent
     here) with all host threads; each step a bounded sample of the same workload."""
@@ -363,7 +387,8 @@ def run_ours(args):
             n = cb.pop("_n")
             r = cb.pop("_result")
             cb.pop("_dt")
-            cb.pop("_tree")
+            tree = cb.pop("_tree")
+            line["reference_cuda"] = reference_cuda_baseline(leaves, cam, vps, tree)
             hr = hres
             kept = (hr.offsets[1:n + 1] - hr.offsets[:n]).astype(np.int64)
             same_counts = bool(np.array_equal(kept, r["kept_count"].astype(np.int64)))
