@@ -63,7 +63,8 @@ def committed_traffic(workload: str):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(workload)
+            t = json.load(f).get(workload)
+            return t["dram_bytes_per_launch"] if isinstance(t, dict) else t
     except Exception:
         return None
 

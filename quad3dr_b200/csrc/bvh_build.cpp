@@ -424,6 +424,11 @@ void fill_node(const BuildCtx& c, const Child ch[4], int cnt, uint32_t depth, ui
       n4->child[s] = kEmptyChild;
     }
   }
+  uint32_t leaf_mask = 0;
+  for (int s = 0; s < 4; ++s) {
+    if (n4->child[s] & kLeafFlag) leaf_mask |= 1u << s;
+  }
+  n4->child[0] |= leaf_mask << kLeafMaskShift;
   n4->meta[0] = (uint32_t)cnt;
   n4->meta[1] = leaves;
   n4->meta[2] = depth;
@@ -479,7 +484,6 @@ void splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* 
 void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out) {
   out->nodes.clear();
   out->top_nodes = 0;
-  out->root_axis = 0;
   out->depth = 0;
   out->max_stack = 4;
   if (n == 0) return;
@@ -519,9 +523,7 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
     const int cnt = gather_children(c, p.bin, ch);
     const uint32_t axis = (uint32_t)order_children(c, ch, cnt);
     if (p.parent != ~0u) {
-      flat[p.parent].child[p.slot] = me | (axis << kAxisShift);
-    } else {
-      out->root_axis = axis;
+      flat[p.parent].child[p.slot] |= me;  // slot 0 already holds the parent's leaf mask in its top bits
     }
     fill_node(c, ch, cnt, p.depth, bn[p.bin].count, axis, &flat[me]);
     max_depth = std::max(max_depth, p.depth);

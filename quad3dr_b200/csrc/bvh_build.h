@@ -15,22 +15,24 @@ struct alignas(128) Node4 {
   float mn[3][4];     // mn[axis][child]
   float mx[3][4];     // mx[axis][child]
   uint32_t child[4];
-  uint32_t meta[4];   // meta[0] = number of used slots, meta[1] = leaves below, meta[2] = depth, meta[3] = 0
+  uint32_t meta[4];   // meta[0] = number of used slots, meta[1] = leaves below, meta[2] = depth, meta[3] = order axis
 };
 static_assert(sizeof(Node4) == 128, "Node4 must be one 128-byte line");
 
+// child word: bit 31 = leaf flag; bits 0..26 = node index (inner) or leaf index (leaf).  child[0] additionally
+// carries, in bits 27..30, the LEAF MASK of the whole node (bit 27 + c set: slot c holds a leaf or is unused), so the
+// traversal reads the node's shape with one shift.  Unused slots are kEmptyChild (a leaf flag with an all-ones
+// index) and carry a degenerate box that no ray can hit.
 constexpr uint32_t kLeafFlag = 0x80000000u;
-constexpr uint32_t kEmptyChild = 0xFFFFFFFFu;
-// An inner child reference also carries, in bits 29..30, the ORDER AXIS of the node it points to: that node's
-// four children are stored sorted by box centre along this axis, so a packet travelling in +axis direction
-// meets them in slot order 0,1,2,3 and one travelling in -axis direction in order 3,2,1,0.
-constexpr uint32_t kAxisShift = 29;
-constexpr uint32_t kNodeIndexMask = (1u << kAxisShift) - 1u;
+constexpr uint32_t kPayloadBits = 27;
+constexpr uint32_t kPayloadMask = (1u << kPayloadBits) - 1u;
+constexpr uint32_t kLeafMaskShift = kPayloadBits;
+constexpr uint32_t kEmptyChild = kLeafFlag | kPayloadMask;
+constexpr uint32_t kNodeIndexMask = kPayloadMask;
 
 struct FlatTree {
   std::vector<Node4> nodes;  // nodes[0] is the root; the first `top_nodes` are the top levels in BFS order
   uint32_t top_nodes = 0;
-  uint32_t root_axis = 0;    // order axis of nodes[0]
   uint32_t depth = 0;        // depth of the 4-wide tree (root = 0, deepest internal node)
   uint32_t max_stack = 0;    // upper bound of traversal-stack entries a packet can hold
 };

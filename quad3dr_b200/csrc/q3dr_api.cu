@@ -286,7 +286,6 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   std::memset(p, 0, sizeof(*p));
   p->nodes = m->d_nodes.p;
   p->n_top = m->tree.top_nodes;
-  p->root_ref = m->tree.root_axis << q3dr::kAxisShift;
   p->fx = K[0];
   p->fy = K[1];
   p->cx = K[2];
@@ -544,18 +543,23 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
     const q3dr::Node4& nd = t.nodes[i];
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int s = 0; s < 4; ++s) {
-      const uint32_t c = nd.child[s];
+      uint32_t c = nd.child[s];
+      if (s == 0) {
+        uint32_t lm = 0;
+        for (int q = 0; q < 4; ++q) lm |= ((nd.child[q] >> 31) & 1u) << q;
+        if (((c >> q3dr::kLeafMaskShift) & 0xFu) != lm) return fail(Q3DR_ERR_INTERNAL, "leaf mask mismatch");
+        c &= q3dr::kLeafFlag | q3dr::kPayloadMask;
+      }
       if (c == q3dr::kEmptyChild) continue;
       const float* ref;
       if (c & q3dr::kLeafFlag) {
-        const uint32_t li = c & ~q3dr::kLeafFlag;
+        const uint32_t li = c & q3dr::kPayloadMask;
         if (li >= n || seen[li]) return fail(Q3DR_ERR_INTERNAL, "leaf referenced twice or out of range");
         seen[li] = 1;
         ref = boxes + 6 * (size_t)li;
       } else {
         const uint32_t ci = c & q3dr::kNodeIndexMask;
         if (ci <= i || ci >= nn || referenced[ci]) return fail(Q3DR_ERR_INTERNAL, "bad inner child reference");
-        if ((c >> q3dr::kAxisShift) != t.nodes[ci].meta[3]) return fail(Q3DR_ERR_INTERNAL, "order axis mismatch");
         referenced[ci] = 1;
         ref = nb.data() + 6 * (size_t)ci;
       }
@@ -584,7 +588,7 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
   if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   if (!boxes) return fail(Q3DR_ERR_INVALID_ARG, "boxes is NULL");
-  if (n == 0 || n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "leaf count out of range");
+  if (n == 0 || n >= (size_t)q3dr::kPayloadMask) return fail(Q3DR_ERR_INVALID_ARG, "leaf count out of range (< 2^27 - 1)");
   int count = 0;
   Q3DR_TRY(q3dr_device_count(&count));
   if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
@@ -620,7 +624,7 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
     if (m->tree.max_stack > (uint32_t)q3dr::kStackEntries) {
       st = fail(Q3DR_ERR_INTERNAL, "flattened tree too deep for the traversal stack");
     }
-    if (m->tree.nodes.size() > (size_t)q3dr::kNodeIndexMask) st = fail(Q3DR_ERR_INVALID_ARG, "too many nodes");
+    if (m->tree.nodes.size() >= (size_t)q3dr::kNodeIndexMask) st = fail(Q3DR_ERR_INVALID_ARG, "too many nodes");
   } catch (const std::bad_alloc&) {
     st = fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
   }
@@ -770,7 +774,6 @@ int q3dr_intersect_rays(q3dr_map* m, const float* origins, const float* directio
   std::memset(&rp, 0, sizeof(rp));
   rp.nodes = m->d_nodes.p;
   rp.n_top = m->tree.top_nodes;
-  rp.root_ref = m->tree.root_axis << q3dr::kAxisShift;
   rp.max_range = max_range;
   rp.leaf_depth = m->d_depth.p;
   rp.tile_counter = m->d_counter.p;

@@ -41,7 +41,6 @@ enum RaycastMode : int {
 struct RaycastParams {
   const float4* __restrict__ nodes;  // Node4 = 8 x float4
   uint32_t n_top;                    // nodes staged in shared memory
-  uint32_t root_ref;                 // reference of the root node (index 0 | order axis << kAxisShift)
   const float* __restrict__ rt;      // [n_vp][12] row-major [R|t]
   float fx, fy, cx, cy;
   uint32_t x0, y0, w, h;  // window
@@ -215,9 +214,9 @@ __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& be
   float stack_d[kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
-  uint32_t node = 0;  // inner references carry the order axis in their top bits; this path ignores it
+  uint32_t node = 0;
   while (true) {
-    node &= kNodeIndexMask;
+    node &= kNodeIndexMask;  // slot 0 carries the node's leaf mask in bits 27..30
     const float4* np = (node < n_top) ? (smem_top + (size_t)node * 8) : (nodes + (size_t)node * 8);
     const float4 mnx = np[0], mny = np[1], mnz = np[2];
     const float4 mxx = np[3], mxy = np[4], mxz = np[5];
@@ -232,8 +231,8 @@ __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& be
     // leaves first: they tighten `best` before the inner children are judged
 #define Q3DR_LEAF(CH, H, D, T)                                                         \
     if ((CH) & kLeafFlag) {                                                             \
-      if ((CH) != kEmptyChild) {                                                        \
-        const int32_t li = (int32_t)((CH) & ~kLeafFlag);                                \
+      if (((CH) & kPayloadMask) != kPayloadMask) {                                      \
+        const int32_t li = (int32_t)((CH) & kPayloadMask);                              \
         const bool acc = (H) && ((D) < best.dsq || ((D) == best.dsq && li > best.leaf)); \
         if (acc) {                                                                      \
           best.dsq = (D);                                                               \
@@ -304,57 +303,65 @@ __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& be
 //   * inner children are judged on the entry parameter t against best.tU (see prune_bound): skipping needs
 //     dist_sq > best, which t >= tU implies; visiting more than the reference never changes the result;
 //   * leaves compute dist_sq exactly whenever some lane could still accept them.
-// Visit order: a node's children are stored sorted along the node's order axis (bvh_build.cpp), so the
-// packet's octant alone says whether slot order 0..3 or 3..0 is front to back -- no per-node sorting.
-// Far candidates go on the stack with every lane's entry parameter; a popped entry that no lane can still
-// improve under (warp vote against tU) is dropped without touching memory.
+// Control flow is derived from warp collectives only (redux.or of the per-lane candidate bits, the node's leaf
+// mask), so every branch of the loop is a uniform branch: one node visit costs the slab arithmetic plus a short
+// scalar epilogue.  Visit order: nearest candidate first (warp minimum of the entry parameter over the lanes that
+// still need the child; computed only when more than one inner child survives).  Far candidates go on the stack
+// with every lane's own entry parameter; a popped entry that no lane can still improve under (warp vote against
+// tU) is dropped without touching memory.
+__device__ __forceinline__ uint32_t pick4(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return (k == 0u) ? a : ((k == 1u) ? b : ((k == 2u) ? c : d));
+}
+__device__ __forceinline__ float pick4f(uint32_t k, float a, float b, float c, float d) {
+  return (k == 0u) ? a : ((k == 1u) ? b : ((k == 2u) ? c : d));
+}
+
 template <bool kSmemTop>
 __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
-                                                     const float4* smem_top, uint32_t n_top, uint32_t root_ref,
+                                                     const float4* smem_top, uint32_t n_top,
                                                      uint32_t octant /* bit a set: direction negative on axis a */) {
   float stack_t[kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
-  uint32_t ref = root_ref;
+  uint32_t ref = 0;
   // plane indices inside a node: mn x,y,z = 0,1,2 ; mx x,y,z = 3,4,5
   const uint32_t nx = (octant & 1u) ? 3u : 0u, ny = (octant & 2u) ? 4u : 1u, nz = (octant & 4u) ? 5u : 2u;
   const uint32_t fx = 3u - nx, fy = 5u - ny, fz = 7u - nz;
   const float kInf = __int_as_float(0x7F800000);
   while (true) {
-    const uint32_t base = (ref & kNodeIndexMask) * 8u;
-    const bool reverse = (octant >> (ref >> kAxisShift)) & 1u;
+    const uint32_t base = ref * 8u;
     float4 nrx, nry, nrz, frx, fry, frz;
     uint4 ch;
-    if (kSmemTop && base < n_top * 8u) {
+    if (kSmemTop && ref < n_top) {
       nrx = smem_top[base + nx]; nry = smem_top[base + ny]; nrz = smem_top[base + nz];
       frx = smem_top[base + fx]; fry = smem_top[base + fy]; frz = smem_top[base + fz];
       ch = *reinterpret_cast<const uint4*>(smem_top + base + 6u);
     } else {
-      nrx = __ldg(nodes + (base + nx)); nry = __ldg(nodes + (base + ny)); nrz = __ldg(nodes + (base + nz));
-      frx = __ldg(nodes + (base + fx)); fry = __ldg(nodes + (base + fy)); frz = __ldg(nodes + (base + fz));
-      ch = __ldg(reinterpret_cast<const uint4*>(nodes + (base + 6u)));
+      const float4* np = nodes + base;
+      nrx = __ldg(np + nx); nry = __ldg(np + ny); nrz = __ldg(np + nz);
+      frx = __ldg(np + fx); fry = __ldg(np + fy); frz = __ldg(np + fz);
+      ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
     }
 
-    float t0, t1, t2, t3;
-    bool h0, h1, h2, h3, c0, c1, c2, c3;
-#define Q3DR_SLAB(NX, NY, NZ, FX, FY, FZ, T, H, C)                                                        \
+    float t0, t1, t2, t3, x0, x1, x2, x3;
+#define Q3DR_SLAB(NX, NY, NZ, FX, FY, FZ, T, X)                                                            \
     {                                                                                                       \
       const float lx = __fmul_rn(__fsub_rn(NX, ray.ox), ray.ix), hx = __fmul_rn(__fsub_rn(FX, ray.ox), ray.ix); \
       const float ly = __fmul_rn(__fsub_rn(NY, ray.oy), ray.iy), hy = __fmul_rn(__fsub_rn(FY, ray.oy), ray.iy); \
       const float lz = __fmul_rn(__fsub_rn(NZ, ray.oz), ray.iz), hz = __fmul_rn(__fsub_rn(FZ, ray.oz), ray.iz); \
-      const float tmax = fminf(fminf(fminf(hx, hy), hz), FLT_MAX);                                          \
+      (X) = fminf(fminf(fminf(hx, hy), hz), FLT_MAX);                                                       \
       (T) = fmaxf(fmaxf(fmaxf(lx, ly), lz), 0.0f);                                                          \
-      (H) = tmax > (T);                                                                                     \
-      (C) = tmax == 0.0f;                                                                                   \
     }
-    Q3DR_SLAB(nrx.x, nry.x, nrz.x, frx.x, fry.x, frz.x, t0, h0, c0)
-    Q3DR_SLAB(nrx.y, nry.y, nrz.y, frx.y, fry.y, frz.y, t1, h1, c1)
-    Q3DR_SLAB(nrx.z, nry.z, nrz.z, frx.z, fry.z, frz.z, t2, h2, c2)
-    Q3DR_SLAB(nrx.w, nry.w, nrz.w, frx.w, fry.w, frz.w, t3, h3, c3)
+    Q3DR_SLAB(nrx.x, nry.x, nrz.x, frx.x, fry.x, frz.x, t0, x0)
+    Q3DR_SLAB(nrx.y, nry.y, nrz.y, frx.y, fry.y, frz.y, t1, x1)
+    Q3DR_SLAB(nrx.z, nry.z, nrz.z, frx.z, fry.z, frz.z, t2, x2)
+    Q3DR_SLAB(nrx.w, nry.w, nrz.w, frx.w, fry.w, frz.w, t3, x3)
 #undef Q3DR_SLAB
-    if (__any_sync(Q3DR_FULL_MASK, c0 | c1 | c2 | c3)) {
-      // rare: some lane's origin lies on a face plane of a child box -> the reference's inside / outside
-      // distinction matters; redo this node with the reference's full box test
+    bool h0 = x0 > t0, h1 = x1 > t1, h2 = x2 > t2, h3 = x3 > t3;
+    // tmax == 0 for some child of some lane (exit parameters are >= 0 whenever they matter, so the least
+    // magnitude says it): the lane's origin lies on a face plane of that box, where the reference's inside /
+    // outside distinction decides -- redo this node with the reference's full box test.  Rare.
+    if (__any_sync(Q3DR_FULL_MASK, fminf(fminf(fabsf(x0), fabsf(x1)), fminf(fabsf(x2), fabsf(x3))) == 0.0f)) {
       const float4* np = nodes + base;
       const float4 mnx = np[0], mny = np[1], mnz = np[2], mxx = np[3], mxy = np[4], mxz = np[5];
       float dd;
@@ -364,72 +371,69 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
       h3 = box_test(ray, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t3);
     }
 
-    // leaves first: they tighten the bound before the inner children are judged
-#define Q3DR_LEAF(CH, H, T)                                                                \
-    if ((CH) & kLeafFlag) {                                                                 \
-      const bool cand = (H) && ((T) < best.tU);                                             \
-      if (__any_sync(Q3DR_FULL_MASK, cand)) {                                               \
-        const float d = dist_sq_at(ray, (T));                                               \
-        const int32_t li = (int32_t)((CH) & ~kLeafFlag);                                    \
-        const bool acc = cand && (d < best.dsq || (d == best.dsq && li > best.leaf));       \
-        if (__any_sync(Q3DR_FULL_MASK, acc)) {                                              \
-          const float u = prune_bound(ray, (T), d);                                         \
-          if (acc) {                                                                        \
-            best.dsq = d;                                                                   \
-            best.t = (T);                                                                   \
-            best.leaf = li;                                                                 \
-            best.tU = u;                                                                    \
-          }                                                                                 \
-        }                                                                                   \
-      }                                                                                     \
-    }
-    Q3DR_LEAF(ch.x, h0, t0)
-    Q3DR_LEAF(ch.y, h1, t1)
-    Q3DR_LEAF(ch.z, h2, t2)
-    Q3DR_LEAF(ch.w, h3, t3)
-#undef Q3DR_LEAF
+    // per-lane candidate bits -> warp-wide "some lane still needs child c" mask (uniform)
+    uint32_t mine = ((h0 && t0 < best.tU) ? 1u : 0u) | ((h1 && t1 < best.tU) ? 2u : 0u) |
+                    ((h2 && t2 < best.tU) ? 4u : 0u) | ((h3 && t3 < best.tU) ? 8u : 0u);
+    uint32_t any = __reduce_or_sync(Q3DR_FULL_MASK, mine);
+    const uint32_t leaf_mask = (ch.x >> kLeafMaskShift) & 0xFu;
 
-    // inner children: a child is a candidate while some lane may still improve below it (warp vote)
-    const bool ok0 = h0 && (t0 < best.tU), ok1 = h1 && (t1 < best.tU);
-    const bool ok2 = h2 && (t2 < best.tU), ok3 = h3 && (t3 < best.tU);
-    const bool a0 = !(ch.x & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok0);
-    const bool a1 = !(ch.y & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok1);
-    const bool a2 = !(ch.z & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok2);
-    const bool a3 = !(ch.w & kLeafFlag) && __any_sync(Q3DR_FULL_MASK, ok3);
-    const int ncand = (int)a0 + (int)a1 + (int)a2 + (int)a3;
-    if (ncand == 1) {
-      ref = a0 ? ch.x : (a1 ? ch.y : (a2 ? ch.z : ch.w));
-      continue;
+    // leaves first: they tighten the bound before the inner children are judged
+    uint32_t todo = any & leaf_mask;
+    if (todo) {
+      bool tightened = false;
+      do {
+        const uint32_t k = (uint32_t)__ffs((int)todo) - 1u;
+        todo &= todo - 1u;
+        const float T = pick4f(k, t0, t1, t2, t3);
+        const int32_t li = (int32_t)(pick4(k, ch.x, ch.y, ch.z, ch.w) & kPayloadMask);
+        const float d = dist_sq_at(ray, T);
+        const bool acc = ((mine >> k) & 1u) && (d < best.dsq || (d == best.dsq && li > best.leaf));
+        if (__any_sync(Q3DR_FULL_MASK, acc)) {
+          const float u = prune_bound(ray, T, d);
+          if (acc) {
+            best.dsq = d;
+            best.t = T;
+            best.leaf = li;
+            best.tU = u;
+          }
+          tightened = true;
+        }
+      } while (todo);
+      if (tightened && (any & ~leaf_mask)) {
+        mine = ((h0 && t0 < best.tU) ? 1u : 0u) | ((h1 && t1 < best.tU) ? 2u : 0u) |
+               ((h2 && t2 < best.tU) ? 4u : 0u) | ((h3 && t3 < best.tU) ? 8u : 0u);
+        any = __reduce_or_sync(Q3DR_FULL_MASK, mine);
+      }
     }
-    if (ncand > 1) {
-      // nearest candidate (least entry parameter over the lanes that need it) is entered directly; the
-      // others go on the stack in far-to-near slot order along the node's order axis, each with every
-      // lane's own entry parameter
-      const uint32_t k0 = a0 ? __reduce_min_sync(Q3DR_FULL_MASK, ok0 ? __float_as_uint(t0) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
-      const uint32_t k1 = a1 ? __reduce_min_sync(Q3DR_FULL_MASK, ok1 ? __float_as_uint(t1) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
-      const uint32_t k2 = a2 ? __reduce_min_sync(Q3DR_FULL_MASK, ok2 ? __float_as_uint(t2) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
-      const uint32_t k3 = a3 ? __reduce_min_sync(Q3DR_FULL_MASK, ok3 ? __float_as_uint(t3) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
-      const uint32_t kmin = min(min(k0, k1), min(k2, k3));
-      const int nearest = (k0 == kmin) ? 0 : ((k1 == kmin) ? 1 : ((k2 == kmin) ? 2 : 3));
-#define Q3DR_PUSH(IDX, A, OK, T, CH)                \
-      if ((A) && nearest != (IDX)) {                \
-        stack_t[sp] = (OK) ? (T) : kInf;            \
-        stack_n[sp] = (CH);                         \
-        ++sp;                                       \
+
+    // inner children
+    uint32_t inner = any & ~leaf_mask;
+    if (inner) {
+      if (inner & (inner - 1u)) {
+        // more than one: nearest first; the others go on the stack, farthest first, each with every lane's own
+        // entry parameter (+inf for lanes that do not need it)
+        uint32_t key[4];
+        key[0] = (inner & 1u) ? __reduce_min_sync(Q3DR_FULL_MASK, (mine & 1u) ? __float_as_uint(t0) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        key[1] = (inner & 2u) ? __reduce_min_sync(Q3DR_FULL_MASK, (mine & 2u) ? __float_as_uint(t1) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        key[2] = (inner & 4u) ? __reduce_min_sync(Q3DR_FULL_MASK, (mine & 4u) ? __float_as_uint(t2) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        key[3] = (inner & 8u) ? __reduce_min_sync(Q3DR_FULL_MASK, (mine & 8u) ? __float_as_uint(t3) : 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        while (inner & (inner - 1u)) {
+          // farthest remaining candidate (ties: higher slot)
+          uint32_t far = 0u, far_key = 0u;
+#pragma unroll
+          for (uint32_t c = 0; c < 4u; ++c) {
+            if (((inner >> c) & 1u) && key[c] >= far_key) {
+              far = c;
+              far_key = key[c];
+            }
+          }
+          inner &= ~(1u << far);
+          stack_t[sp] = ((mine >> far) & 1u) ? pick4f(far, t0, t1, t2, t3) : kInf;
+          stack_n[sp] = pick4(far, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
+          ++sp;
+        }
       }
-      if (reverse) {
-        Q3DR_PUSH(0, a0, ok0, t0, ch.x)
-        Q3DR_PUSH(1, a1, ok1, t1, ch.y)
-        Q3DR_PUSH(2, a2, ok2, t2, ch.z)
-        Q3DR_PUSH(3, a3, ok3, t3, ch.w)
-      } else {
-        Q3DR_PUSH(3, a3, ok3, t3, ch.w)
-        Q3DR_PUSH(2, a2, ok2, t2, ch.z)
-        Q3DR_PUSH(1, a1, ok1, t1, ch.y)
-        Q3DR_PUSH(0, a0, ok0, t0, ch.x)
-      }
-#undef Q3DR_PUSH
-      ref = (nearest == 0) ? ch.x : ((nearest == 1) ? ch.y : ((nearest == 2) ? ch.z : ch.w));
+      ref = pick4((uint32_t)__ffs((int)inner) - 1u, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
       continue;
     }
     bool found = false;
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const Raycas
       const float kInf = __int_as_float(0x7F800000);
       best.tU = live ? ((p.max_range > 0.0f) ? prune_bound(ray, p.max_range, range_sq) : kInf) : -1.0f;
       const uint32_t octant = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
-      traverse_packet_fast<kSmemTopLevels>(ray, best, p.nodes, smem_top, p.n_top, p.root_ref, octant);
+      traverse_packet_fast<kSmemTopLevels>(ray, best, p.nodes, smem_top, p.n_top, octant);
     } else {
       best.tU = 0.0f;
       traverse_packet_exact(ray, best, p.nodes, smem_top, p.n_top);
