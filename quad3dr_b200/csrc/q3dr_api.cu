@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "raycast_kernels.cuh"
+#include "raycast2_kernels.cuh"
 
 namespace {
 
@@ -112,6 +112,7 @@ struct q3dr_map {
   int sm_count = 0;
   size_t n = 0;
   uint32_t ref_depth = 0;
+  bool bounded = false;  // all box coordinates finite and below 1e18 in magnitude
   // host copies (kept for q3dr_map_reset)
   std::vector<float> h_boxes, h_weight, h_normal;
   std::vector<uint8_t> h_depth;
@@ -149,6 +150,7 @@ struct q3dr_map {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int grid_ctas[3] = {0, 0, 0};
+  int grid2_ctas[2] = {0, 0};
   size_t smem_bytes = 0;
   q3dr_stats stats{};
 
@@ -207,6 +209,15 @@ int configure_kernel(q3dr_map* m) {
   return Q3DR_OK;
 }
 
+template <int MODE>
+int configure_kernel2(q3dr_map* m) {
+  int per_sm = 0;
+  Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3dr::raycast2_kernel<MODE>, q3dr::kThreadsPerCta, 0));
+  if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
+  m->grid2_ctas[MODE] = per_sm * m->sm_count;
+  return Q3DR_OK;
+}
+
 int upload_map(q3dr_map* m) {
   Q3DR_CUDA(cudaSetDevice(m->device));
   const size_t n = m->n;
@@ -228,6 +239,8 @@ int upload_map(q3dr_map* m) {
   Q3DR_TRY(configure_kernel<q3dr::kModeScore>(m));
   Q3DR_TRY(configure_kernel<q3dr::kModePixels>(m));
   Q3DR_TRY(configure_kernel<q3dr::kModeRays>(m));
+  Q3DR_TRY(configure_kernel2<q3dr::kModeScore>(m));
+  Q3DR_TRY(configure_kernel2<q3dr::kModePixels>(m));
   return Q3DR_OK;
 }
 
@@ -260,7 +273,7 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
 
 size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint64_t cap) {
   // enough packets in flight that the persistent grid's tail is small ...
-  const size_t resident_warps = (size_t)m->grid_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
+  const size_t resident_warps = (size_t)m->grid2_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
   size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;
   // ... and enough viewpoints per chunk that the one-CTA-per-viewpoint scoring kernel fills the machine
   want = std::max<size_t>(want, 2 * (size_t)m->sm_count);
@@ -294,12 +307,13 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   p->y0 = y0;
   p->w = x1 - x0;
   p->h = y1 - y0;
-  p->tiles_x = (p->w + q3dr::kTileW - 1) / q3dr::kTileW;
-  const uint32_t tiles_y = (p->h + q3dr::kTileH - 1) / q3dr::kTileH;
+  p->tiles_x = (p->w + q3dr::kTile2W - 1) / q3dr::kTile2W;
+  const uint32_t tiles_y = (p->h + q3dr::kTile2H - 1) / q3dr::kTile2H;
   p->tiles_per_vp = p->tiles_x * tiles_y;
   p->max_range = max_range;
   p->leaf_depth = m->d_depth.p;
   p->tile_counter = m->d_counter.p;
+  p->bounded_map = m->bounded ? 1u : 0u;
 }
 
 int check_map(const q3dr_map* m) {
@@ -373,9 +387,9 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     rp.total_tiles = (uint32_t)(nb * rp.tiles_per_vp);
     Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), stream));
     Q3DR_CUDA(cudaEventRecord(m->ev[0], stream));
-    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeScore],
+    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore],
                                             ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-    q3dr::raycast_kernel<q3dr::kModeScore><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, stream>>>(rp);
+    q3dr::raycast2_kernel<q3dr::kModeScore><<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev[1], stream));
     sp.rt = d_Rt + 12 * v0;
@@ -600,6 +614,10 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
     m->device = device;
     m->n = n;
     m->h_boxes.assign(boxes, boxes + 6 * n);
+    m->bounded = true;
+    for (size_t i = 0; i < 6 * n; ++i) {
+      if (!(std::fabs(boxes[i]) < 1e18f)) m->bounded = false;
+    }
     if (weights) {
       m->h_weight.assign(weights, weights + n);
     } else {
@@ -737,10 +755,10 @@ int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint3
   rp.rt = m->d_rt.p;
   rp.total_tiles = rp.tiles_per_vp;
   rp.pixels = m->d_pixels.p;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModePixels],
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels],
                                           ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
   Q3DR_CUDA(cudaEventRecord(m->ev[0], s));
-  q3dr::raycast_kernel<q3dr::kModePixels><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  q3dr::raycast2_kernel<q3dr::kModePixels><<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaEventRecord(m->ev[1], s));
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, npix * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
@@ -798,6 +816,13 @@ int q3dr_score_viewpoints_device(q3dr_map* m, const float K[4], uint32_t image_w
   if (!K || (!d_Rt && n) || !opts) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
   Q3DR_TRY(check_window(x0, x1, y0, y1));
   if (image_width == 0) return fail(Q3DR_ERR_INVALID_ARG, "image_width is 0");
+  if ((reinterpret_cast<uintptr_t>(d_Rt) & 15u) != 0 && n) {
+    // the kernel fetches a pose as three 16-byte words: realign a misaligned caller buffer
+    Q3DR_CUDA(cudaSetDevice(m->device));
+    Q3DR_TRY(m->d_rt.ensure(12 * n));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, d_Rt, 12 * n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    d_Rt = m->d_rt.p;
+  }
   return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result);
 }
 

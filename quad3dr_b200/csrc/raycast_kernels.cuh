@@ -60,6 +60,7 @@ struct RaycastParams {
   const uint32_t* __restrict__ pix_list;  // kModeRays alternative: window pixel indices of one viewpoint
   uint32_t n_rays;
   uint32_t* tile_counter;
+  uint32_t bounded_map;  // every box coordinate is below 1e18 in magnitude
 };
 
 // std::min / std::max semantics of the reference (geometry.h:336-343), NaN behaviour included.
