@@ -28,7 +28,7 @@ struct Dir2 {
 struct Best2 {
   float dsq;     // best dist_sq (the range bound while nothing is hit)
   float t;       // ray parameter of the best hit
-  float tU;      // a ray parameter with dist_sq_at(tU) > dsq, verified by evaluation (see prune_bound)
+  float tU;      // every ray parameter >= tU has dist_sq > dsq in the reference's arithmetic (see bound_after)
   int32_t leaf;  // best leaf index, -1 = none
 };
 
@@ -40,36 +40,35 @@ __device__ __forceinline__ float dist_sq_at2(float ox, float oy, float oz, const
   return __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
 }
 
-__device__ __noinline__ float prune_bound_slow(float ox, float oy, float oz, float dx, float dy, float dz, float t,
-                                               float dsq) {
-  Dir2 r;
-  r.dx = dx; r.dy = dy; r.dz = dz;
-  r.ix = r.iy = r.iz = 0.0f;
-  float rel = 1.0f / 128.0f, ab = 1.0f / 512.0f;
-#pragma unroll 1
-  for (int k = 0; k < 2; ++k) {
-    const float u = fmaf(t, rel, t) + ab;
-    if (dist_sq_at2(ox, oy, oz, r, u) > dsq) return u;
-    rel *= 16.0f;
-    ab *= 16.0f;
-  }
-  return __int_as_float(0x7F800000);
-}
+// ---------------------------------------------------------------------------------------------------------------
+// Pruning bound.  best.dsq is the reference's dist_sq of the best hit, computed at ray parameter T.  The traversal
+// skips a box on its ENTRY PARAMETER t alone when t >= tU, where tU must guarantee that the reference's computed
+// dist_sq at any parameter >= tU is strictly greater than best.dsq (the reference prunes on dist_sq > best only).
+//
+//   tU = fl(fl(T * (1 + 2^-11)) + A),   A = 2^-13 + 2^-20 * M,   M = max |origin component|
+//
+// Proof sketch (eps = 2^-24, round to nearest, |dir| = 1 +- 4 eps for a direction normalised from a squared norm in
+// the normal range, no overflow: |origin|, t < 2^60).  For parameter t the reference computes
+//   e_i = fl(o_i - fl(o_i + fl(d_i t))) = -d_i t + eta_i,  |eta_i| <= eps (|o_i| + 3 t)(1 + 8 eps) =: H(t)
+//   dist_sq = fl-sum of e_i^2 = |e|^2 (1 + theta), |theta| <= 3.01 eps                 (all terms non-negative)
+// hence  sqrt(dist_sq(t)) in [ L(t), U(t) ],  L(t) = (t (1 - 4 eps) - sqrt(3) H(t)) (1 - 2 eps),
+//                                             U(t) = (t (1 + 4 eps) + sqrt(3) H(t)) (1 + 2 eps),  L increasing in t.
+// L(u) > U(T) holds as soon as u - T > eps (24 T + 3.5 M) (1 + o(1)) = 2^-19.4 T + 2^-22.2 M; the tU above exceeds
+// T by at least 2^-11.01 T + 0.99 A, i.e. by a factor > 4 on either term, and L(tU) > 0 because tU >= A >= 2^-20 M.
+// So dist_sq(t') >= L(t')^2 >= L(tU)^2 > U(T)^2 >= best.dsq for every t' >= tU.  The same bound with T = max_range
+// covers the initial range limit (best.dsq = fl(max_range^2) <= U(max_range)^2).  The kernel checks the
+// preconditions per packet and sends every packet that violates one to traverse_packet_exact.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 1.0f / 2048.0f, t) + A; }
 
-// See prune_bound in raycast_kernels.cuh: a parameter u > t whose dist_sq, evaluated with the reference's formula,
-// is strictly greater than dsq.  First try inline (practically always enough), escalation out of line.
-__device__ __forceinline__ float prune_bound2(float ox, float oy, float oz, const Dir2& r, float t, float dsq) {
-  const float u = fmaf(t, 1.0f / 2048.0f, t) + 1.0f / 8192.0f;
-  if (dist_sq_at2(ox, oy, oz, r, u) > dsq) return u;
-  return prune_bound_slow(ox, oy, oz, r.dx, r.dy, r.dz, t, dsq);
-}
-
-// kClamp: keep the reference's "tmax starts at FLT_MAX" clamp.  It can only bind when all three exit parameters
-// overflow to +inf, which a ray with |inv| <= 2 on some axis cannot produce over a map whose coordinates are
-// below 1e18 in magnitude -- the kernel checks both and instantiates the clamp-free loop for such packets.
-template <bool kMixed, bool kClamp>
-__device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, const Dir2& r0, const Dir2& r1, Best2& b0,
-                                                 Best2& b1, const float4* __restrict__ nodes, uint32_t octant) {
+// kMixed = false: all 64 rays share one direction octant, near / far planes are picked by address.
+// kMixed = true : lo = min(t0, t1), hi = max(t0, t1) per axis like the reference writes it.
+// The reference's clamp of tmax at FLT_MAX is omitted: it can only bind when all three exit parameters overflow,
+// which a normalised direction (|inv| <= 2 on some axis) cannot produce over a map bounded by 1e18 -- a packet
+// precondition as well.  The exit parameter is kept as x' = min(exit, tU): "hit and still needed" is then entry < x'.
+template <bool kMixed>
+__device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, float A, const Dir2& r0, const Dir2& r1,
+                                                 Best2& b0, Best2& b1, const float4* __restrict__ nodes, uint32_t octant) {
   float stack_t0[kStackEntries];
   float stack_t1[kStackEntries];
   uint32_t stack_n[kStackEntries];
@@ -87,8 +86,8 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
     const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
 
     float t00, t01, t02, t03, t10, t11, t12, t13;  // entry parameter, [ray][child]
-    float x00, x01, x02, x03, x10, x11, x12, x13;  // exit parameter
-#define Q3DR_SLAB1(R, TA, XA)                                                                               \
+    float x00, x01, x02, x03, x10, x11, x12, x13;  // min(exit parameter, tU)
+#define Q3DR_SLAB1(R, B, TA, XA)                                                                            \
       {                                                                                                     \
         float lx = __fmul_rn(anx, R.ix), hx = __fmul_rn(afx, R.ix);                                         \
         float ly = __fmul_rn(any_, R.iy), hy = __fmul_rn(afy, R.iy);                                        \
@@ -98,8 +97,7 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
           hx = fmaxf(lx, hx); hy = fmaxf(ly, hy); hz = fmaxf(lz, hz);                                       \
           lx = sx; ly = sy; lz = sz;                                                                        \
         }                                                                                                   \
-        (XA) = fminf(fminf(hx, hy), hz);                                                                    \
-        if (kClamp) (XA) = fminf((XA), FLT_MAX);                                                            \
+        (XA) = fminf(fminf(fminf(hx, hy), hz), B.tU);                                                       \
         (TA) = fmaxf(fmaxf(fmaxf(lx, ly), lz), 0.0f);                                                       \
       }
 #define Q3DR_SLAB2(C, TA, XA, TB, XB)                                                                      \
@@ -107,8 +105,8 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
       const float anx = __fsub_rn(nrx.C, ox), afx = __fsub_rn(frx.C, ox);                                   \
       const float any_ = __fsub_rn(nry.C, oy), afy = __fsub_rn(fry.C, oy);                                  \
       const float anz = __fsub_rn(nrz.C, oz), afz = __fsub_rn(frz.C, oz);                                   \
-      Q3DR_SLAB1(r0, TA, XA)                                                                                \
-      Q3DR_SLAB1(r1, TB, XB)                                                                                \
+      Q3DR_SLAB1(r0, b0, TA, XA)                                                                            \
+      Q3DR_SLAB1(r1, b1, TB, XB)                                                                            \
     }
     Q3DR_SLAB2(x, t00, x00, t10, x10)
     Q3DR_SLAB2(y, t01, x01, t11, x11)
@@ -116,9 +114,9 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
     Q3DR_SLAB2(w, t03, x03, t13, x13)
 #undef Q3DR_SLAB2
 #undef Q3DR_SLAB1
-    // exit parameter == 0 for some child of some ray: that ray's origin lies on a face plane of the box, where the
-    // reference's inside / outside distinction decides -- redo this node with the reference's full box test and
-    // express its verdict in the same (entry, exit) form: hit <=> exit > entry.  Rare.
+    // exit parameter == 0 for some child of some ray (tU > 0, so x' == 0 says exactly that): the ray's origin lies
+    // on a face plane of the box, where the reference's inside / outside distinction decides -- redo this node with
+    // the reference's full box test and express its verdict in the same form.  Rare.
     {
       const float m0 = fminf(fminf(fabsf(x00), fabsf(x01)), fminf(fabsf(x02), fabsf(x03)));
       const float m1 = fminf(fminf(fabsf(x10), fabsf(x11)), fminf(fabsf(x12), fabsf(x13)));
@@ -128,57 +126,62 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
         float dd;
         q.ox = ox; q.oy = oy; q.oz = oz;
         q.dx = r0.dx; q.dy = r0.dy; q.dz = r0.dz; q.ix = r0.ix; q.iy = r0.iy; q.iz = r0.iz;
-        x00 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t00) ? kInf : -1.0f;
-        x01 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t01) ? kInf : -1.0f;
-        x02 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t02) ? kInf : -1.0f;
-        x03 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t03) ? kInf : -1.0f;
+        x00 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t00) ? b0.tU : -1.0f;
+        x01 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t01) ? b0.tU : -1.0f;
+        x02 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t02) ? b0.tU : -1.0f;
+        x03 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t03) ? b0.tU : -1.0f;
         q.dx = r1.dx; q.dy = r1.dy; q.dz = r1.dz; q.ix = r1.ix; q.iy = r1.iy; q.iz = r1.iz;
-        x10 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t10) ? kInf : -1.0f;
-        x11 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t11) ? kInf : -1.0f;
-        x12 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t12) ? kInf : -1.0f;
-        x13 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t13) ? kInf : -1.0f;
+        x10 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t10) ? b1.tU : -1.0f;
+        x11 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t11) ? b1.tU : -1.0f;
+        x12 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t12) ? b1.tU : -1.0f;
+        x13 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t13) ? b1.tU : -1.0f;
       }
     }
 
-    // "some ray still needs child c": hit (exit > entry) and entry below the ray's bound  <=>  entry < min(exit, tU)
-#define Q3DR_NEED(TA, XA, TB, XB) \
-    __any_sync(Q3DR_FULL_MASK, ((TA) < fminf((XA), b0.tU)) || ((TB) < fminf((XB), b1.tU)))
-    uint32_t any = (Q3DR_NEED(t00, x00, t10, x10) ? 1u : 0u) | (Q3DR_NEED(t01, x01, t11, x11) ? 2u : 0u) |
-                   (Q3DR_NEED(t02, x02, t12, x12) ? 4u : 0u) | (Q3DR_NEED(t03, x03, t13, x13) ? 8u : 0u);
+    // "some ray still needs child c"
+    uint32_t any = (__any_sync(Q3DR_FULL_MASK, (t00 < x00) || (t10 < x10)) ? 1u : 0u) |
+                   (__any_sync(Q3DR_FULL_MASK, (t01 < x01) || (t11 < x11)) ? 2u : 0u) |
+                   (__any_sync(Q3DR_FULL_MASK, (t02 < x02) || (t12 < x12)) ? 4u : 0u) |
+                   (__any_sync(Q3DR_FULL_MASK, (t03 < x03) || (t13 < x13)) ? 8u : 0u);
     const uint32_t leaf_mask = (ch.x >> kLeafMaskShift) & 0xFu;
 
-    // leaves first: they tighten the bounds before the inner children are judged
-    uint32_t todo = any & leaf_mask;
+    // leaves first: they tighten the bounds before the inner children are judged.  A ray accepts a leaf on the
+    // reference's own terms: the slab test passes and dist_sq < best, or == best with a higher leaf index
+    // (x' > t is implied for every ray that can pass the dist_sq comparison, see bound_after).
+    const uint32_t todo = any & leaf_mask;
     if (todo) {
       bool tightened = false;
-      do {
-        const uint32_t k = (uint32_t)__ffs((int)todo) - 1u;
-        todo &= todo - 1u;
-        const int32_t li = (int32_t)(pick4(k, ch.x, ch.y, ch.z, ch.w) & kPayloadMask);
-        const float T0 = pick4f(k, t00, t01, t02, t03), X0 = pick4f(k, x00, x01, x02, x03);
-        const float T1 = pick4f(k, t10, t11, t12, t13), X1 = pick4f(k, x10, x11, x12, x13);
-        const float d0 = dist_sq_at2(ox, oy, oz, r0, T0);
-        const float d1 = dist_sq_at2(ox, oy, oz, r1, T1);
-        const bool acc0 = (X0 > T0) && (d0 < b0.dsq || (d0 == b0.dsq && li > b0.leaf));
-        const bool acc1 = (X1 > T1) && (d1 < b1.dsq || (d1 == b1.dsq && li > b1.leaf));
-        if (__any_sync(Q3DR_FULL_MASK, acc0 || acc1)) {
-          const float u0 = prune_bound2(ox, oy, oz, r0, T0, d0);
-          const float u1 = prune_bound2(ox, oy, oz, r1, T1, d1);
-          if (acc0) {
-            b0.dsq = d0; b0.t = T0; b0.leaf = li; b0.tU = u0;
-          }
-          if (acc1) {
-            b1.dsq = d1; b1.t = T1; b1.leaf = li; b1.tU = u1;
-          }
-          tightened = true;
-        }
-      } while (todo);
+#define Q3DR_LEAF2(BIT, CH, TA, XA, TB, XB)                                                        \
+      if (todo & (BIT)) {                                                                           \
+        const int32_t li = (int32_t)((CH) & kPayloadMask);                                          \
+        const float d0 = dist_sq_at2(ox, oy, oz, r0, (TA));                                         \
+        const float d1 = dist_sq_at2(ox, oy, oz, r1, (TB));                                         \
+        const bool acc0 = ((XA) > (TA)) && (d0 < b0.dsq || (d0 == b0.dsq && li > b0.leaf));         \
+        const bool acc1 = ((XB) > (TB)) && (d1 < b1.dsq || (d1 == b1.dsq && li > b1.leaf));         \
+        if (__any_sync(Q3DR_FULL_MASK, acc0 || acc1)) {                                             \
+          if (acc0) {                                                                               \
+            b0.dsq = d0; b0.t = (TA); b0.leaf = li; b0.tU = bound_after((TA), A);                   \
+          }                                                                                         \
+          if (acc1) {                                                                               \
+            b1.dsq = d1; b1.t = (TB); b1.leaf = li; b1.tU = bound_after((TB), A);                   \
+          }                                                                                         \
+          tightened = true;                                                                         \
+        }                                                                                           \
+      }
+      Q3DR_LEAF2(1u, ch.x, t00, x00, t10, x10)
+      Q3DR_LEAF2(2u, ch.y, t01, x01, t11, x11)
+      Q3DR_LEAF2(4u, ch.z, t02, x02, t12, x12)
+      Q3DR_LEAF2(8u, ch.w, t03, x03, t13, x13)
+#undef Q3DR_LEAF2
       if (tightened && (any & ~leaf_mask)) {
-        any = (Q3DR_NEED(t00, x00, t10, x10) ? 1u : 0u) | (Q3DR_NEED(t01, x01, t11, x11) ? 2u : 0u) |
-              (Q3DR_NEED(t02, x02, t12, x12) ? 4u : 0u) | (Q3DR_NEED(t03, x03, t13, x13) ? 8u : 0u);
+        x00 = fminf(x00, b0.tU); x01 = fminf(x01, b0.tU); x02 = fminf(x02, b0.tU); x03 = fminf(x03, b0.tU);
+        x10 = fminf(x10, b1.tU); x11 = fminf(x11, b1.tU); x12 = fminf(x12, b1.tU); x13 = fminf(x13, b1.tU);
+        any = (__any_sync(Q3DR_FULL_MASK, (t00 < x00) || (t10 < x10)) ? 1u : 0u) |
+              (__any_sync(Q3DR_FULL_MASK, (t01 < x01) || (t11 < x11)) ? 2u : 0u) |
+              (__any_sync(Q3DR_FULL_MASK, (t02 < x02) || (t12 < x12)) ? 4u : 0u) |
+              (__any_sync(Q3DR_FULL_MASK, (t03 < x03) || (t13 < x13)) ? 8u : 0u);
       }
     }
-#undef Q3DR_NEED
 
     // inner children
     uint32_t inner = any & ~leaf_mask;
@@ -189,8 +192,8 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
         const uint32_t kNone = 0xFFFFFFFFu;
 #define Q3DR_KEY(C, TA, XA, TB, XB)                                                                       \
         ((inner & (1u << (C)))                                                                            \
-             ? __reduce_min_sync(Q3DR_FULL_MASK, min(((TA) < fminf((XA), b0.tU)) ? __float_as_uint(TA) : kNone, \
-                                                    ((TB) < fminf((XB), b1.tU)) ? __float_as_uint(TB) : kNone)) \
+             ? __reduce_min_sync(Q3DR_FULL_MASK, min(((TA) < (XA)) ? __float_as_uint(TA) : kNone,          \
+                                                    ((TB) < (XB)) ? __float_as_uint(TB) : kNone))          \
              : kNone)
         uint32_t key[4];
         key[0] = Q3DR_KEY(0, t00, x00, t10, x10);
@@ -210,8 +213,8 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
           inner &= ~(1u << far);
           const float T0 = pick4f(far, t00, t01, t02, t03), X0 = pick4f(far, x00, x01, x02, x03);
           const float T1 = pick4f(far, t10, t11, t12, t13), X1 = pick4f(far, x10, x11, x12, x13);
-          stack_t0[sp] = (X0 > T0) ? T0 : kInf;  // tU only shrinks: an entry parameter >= tU now stays >= tU
-          stack_t1[sp] = (X1 > T1) ? T1 : kInf;
+          stack_t0[sp] = (T0 < X0) ? T0 : kInf;  // tU only shrinks: an entry parameter >= tU now stays >= tU
+          stack_t1[sp] = (T1 < X1) ? T1 : kInf;
           stack_n[sp] = pick4(far, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
           ++sp;
         }
@@ -235,7 +238,8 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, c
 }
 
 // Camera ray direction of pixel column x (c0 precomputed) and row y: see camera_ray in raycast_kernels.cuh.
-__device__ __forceinline__ void camera_dir2(const float* __restrict__ R /* 12 floats in registers */, float c0, float fy,
+// Returns whether the squared norm lay in [1e-30, 1e30] (the direction is then normalised to 1 +- 4 eps).
+__device__ __forceinline__ bool camera_dir2(const float* __restrict__ R /* 12 floats in registers */, float c0, float fy,
                                             float cy, uint32_t y, Dir2& r) {
   const float c1 = __fdiv_rn(__fsub_rn((float)y, cy), fy);
   const float d0 = __fadd_rn(__fmul_rn(R[0], c0), __fadd_rn(__fmul_rn(R[1], c1), R[2]));
@@ -255,6 +259,7 @@ __device__ __forceinline__ void camera_dir2(const float* __restrict__ R /* 12 fl
   r.ix = __fdiv_rn(1.0f, r.dx);
   r.iy = __fdiv_rn(1.0f, r.dy);
   r.iz = __fdiv_rn(1.0f, r.dz);
+  return n2 >= 1e-30f && n2 <= 1e30f;
 }
 
 __device__ __forceinline__ void copy_dir_from_lane(Dir2& r, const Dir2& src_ray, int src_lane, bool take) {
@@ -270,7 +275,7 @@ __device__ __forceinline__ void copy_dir_from_lane(Dir2& r, const Dir2& src_ray,
 
 // MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_kernel<kModeRays>).
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerCta, 3) raycast2_kernel(const RaycastParams p) {
+__global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const RaycastParams p) {
   __shared__ uint32_t s_tile[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -307,8 +312,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) raycast2_kernel(const Rayca
     const float ox = R[3], oy = R[7], oz = R[11];
     const float c0 = __fdiv_rn(__fsub_rn((float)(p.x0 + px), p.cx), p.fx);
     Dir2 r0, r1;
-    camera_dir2(R, c0, p.fy, p.cy, p.y0 + py0, r0);
-    camera_dir2(R, c0, p.fy, p.cy, p.y0 + py1, r1);
+    const bool unit0 = camera_dir2(R, c0, p.fy, p.cy, p.y0 + py0, r0);
+    const bool unit1 = camera_dir2(R, c0, p.fy, p.cy, p.y0 + py1, r1);
     {
       // a dead ray rides along with a copy of a live one and never accepts anything (dist_sq >= 0 > -1, t >= 0 > -1)
       const int src = __ffs(live_mask) - 1;
@@ -324,37 +329,33 @@ __global__ void __launch_bounds__(kThreadsPerCta, 3) raycast2_kernel(const Rayca
     b0.dsq = live0 ? range_sq : -1.0f;
     b1.dsq = live1 ? range_sq : -1.0f;
 
+    // preconditions of the fast loops (see bound_after / traverse_packet2); dead rays are copies of live ones
+    const float M = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
     const bool finite = (fabsf(r0.ix) <= FLT_MAX) && (fabsf(r0.iy) <= FLT_MAX) && (fabsf(r0.iz) <= FLT_MAX) &&
                         (fabsf(r1.ix) <= FLT_MAX) && (fabsf(r1.iy) <= FLT_MAX) && (fabsf(r1.iz) <= FLT_MAX);
-    if (__all_sync(Q3DR_FULL_MASK, finite)) {
-      if (p.max_range > 0.0f) {
-        const float u0 = prune_bound2(ox, oy, oz, r0, p.max_range, range_sq);
-        const float u1 = prune_bound2(ox, oy, oz, r1, p.max_range, range_sq);
-        b0.tU = live0 ? u0 : -1.0f;
-        b1.tU = live1 ? u1 : -1.0f;
-      } else {
-        b0.tU = live0 ? kInf : -1.0f;
-        b1.tU = live1 ? kInf : -1.0f;
-      }
-      // per axis: 0 = all rays positive, 1 = all negative, 2 = mixed
+    const bool tame = finite && (unit0 || !live0) && (unit1 || !live1) && p.bounded_map && (M <= 1e18f) &&
+                      !(p.max_range > 1e18f);
+    if (__all_sync(Q3DR_FULL_MASK, tame)) {
+      const float A = fmaf(M, 1.0f / 1048576.0f, 1.0f / 8192.0f);
+      const float u = (p.max_range > 0.0f) ? bound_after(p.max_range, A) : kInf;
+      b0.tU = live0 ? u : -1.0f;
+      b1.tU = live1 ? u : -1.0f;
+      // per axis: all rays positive, all negative, or mixed
       const uint32_t bx = __ballot_sync(Q3DR_FULL_MASK, r0.ix < 0.0f), cx = __ballot_sync(Q3DR_FULL_MASK, r1.ix < 0.0f);
       const uint32_t by = __ballot_sync(Q3DR_FULL_MASK, r0.iy < 0.0f), cy = __ballot_sync(Q3DR_FULL_MASK, r1.iy < 0.0f);
       const uint32_t bz = __ballot_sync(Q3DR_FULL_MASK, r0.iz < 0.0f), cz = __ballot_sync(Q3DR_FULL_MASK, r1.iz < 0.0f);
       const bool ux = ((bx | cx) == 0u) || ((bx & cx) == Q3DR_FULL_MASK);
       const bool uy = ((by | cy) == 0u) || ((by & cy) == Q3DR_FULL_MASK);
       const bool uz = ((bz | cz) == 0u) || ((bz & cz) == Q3DR_FULL_MASK);
-      // a ray with |inv| <= 2 on some axis has a finite exit parameter on that axis over a bounded map: the
-      // reference's FLT_MAX clamp on tmax cannot bind (see traverse_packet2)
-      const bool tame = p.bounded_map && (fminf(fminf(fabsf(r0.ix), fabsf(r0.iy)), fabsf(r0.iz)) <= 2.0f) &&
-                        (fminf(fminf(fabsf(r1.ix), fabsf(r1.iy)), fabsf(r1.iz)) <= 2.0f);
-      if (ux && uy && uz && __all_sync(Q3DR_FULL_MASK, tame)) {
+      if (ux && uy && uz) {
         const uint32_t octant = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
-        traverse_packet2<false, false>(ox, oy, oz, r0, r1, b0, b1, p.nodes, octant);
+        traverse_packet2<false>(ox, oy, oz, A, r0, r1, b0, b1, p.nodes, octant);
       } else {
-        traverse_packet2<true, true>(ox, oy, oz, r0, r1, b0, b1, p.nodes, 0u);
+        traverse_packet2<true>(ox, oy, oz, A, r0, r1, b0, b1, p.nodes, 0u);
       }
     } else {
-      // some ray is exactly parallel to an axis: the literal reference box test, one ray after the other
+      // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge
+      // coordinates, degenerate pose): the literal reference box test, one ray after the other
       Ray q;
       PacketHit h;
       q.ox = ox; q.oy = oy; q.oz = oz;
