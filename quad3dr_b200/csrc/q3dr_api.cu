@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "raycast2_kernels.cuh"
+#include "score_kernels.cuh"
 
 namespace {
 
@@ -119,11 +120,16 @@ struct q3dr_map {
   q3dr::FlatTree tree;
   // device: the map
   DevBuf<float4> d_nodes;
-  DevBuf<float> d_boxes, d_weight, d_normal;
+  DevBuf<float4> d_leaf_rec;  // [n][3]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}
   DevBuf<uint8_t> d_depth;
   DevBuf<uint32_t> d_counter;
   // device: per-chunk scratch
   DevBuf<uint32_t> d_first_pix, d_bitmap, d_kept;
+  DevBuf<uint32_t> d_seg_u32;  // [2][slots][n_segs]: hits, off
+  DevBuf<uint32_t> d_blk_u32;  // [slots + 1] blk_off, then [2][max blocks]: kept, koff
+  DevBuf<double> d_seg_f64;    // [max blocks] blk_total
+  size_t max_blocks = 0;
+  uint32_t n_segs = 0;
   size_t slots = 0;
   uint64_t leaf_stride = 0, word_stride = 0;
   DevBuf<int32_t> t_leaf;
@@ -155,7 +161,7 @@ struct q3dr_map {
   q3dr_stats stats{};
 
   uint64_t device_bytes() const {
-    return d_nodes.bytes() + d_boxes.bytes() + d_weight.bytes() + d_normal.bytes() + d_depth.bytes() +
+    return d_nodes.bytes() + d_leaf_rec.bytes() + d_depth.bytes() + d_seg_u32.bytes() + d_blk_u32.bytes() + d_seg_f64.bytes() +
            d_counter.bytes() + d_first_pix.bytes() + d_bitmap.bytes() + d_kept.bytes() + t_leaf.bytes() +
            t_info.bytes() + t_dsq.bytes() + t_pix.bytes() + d_offsets.bytes() + d_total.bytes() +
            d_hit_count.bytes() + r_leaf.bytes() + r_info.bytes() + r_dsq.bytes() + r_pix.bytes() + d_rt.bytes() +
@@ -167,9 +173,11 @@ namespace {
 
 void release_device(q3dr_map* m) {
   m->d_nodes.release();
-  m->d_boxes.release();
-  m->d_weight.release();
-  m->d_normal.release();
+  m->d_leaf_rec.release();
+  m->d_seg_u32.release();
+  m->d_blk_u32.release();
+  m->d_seg_f64.release();
+  m->max_blocks = 0;
   m->d_depth.release();
   m->d_counter.release();
   m->d_first_pix.release();
@@ -224,20 +232,23 @@ int upload_map(q3dr_map* m) {
   const size_t nn = m->tree.nodes.size();
   Q3DR_TRY(m->d_nodes.ensure(nn * 8));
   Q3DR_CUDA(cudaMemcpy(m->d_nodes.p, m->tree.nodes.data(), nn * sizeof(q3dr::Node4), cudaMemcpyHostToDevice));
-  Q3DR_TRY(m->d_boxes.ensure(n * 6));
-  Q3DR_CUDA(cudaMemcpy(m->d_boxes.p, m->h_boxes.data(), n * 6 * sizeof(float), cudaMemcpyHostToDevice));
-  Q3DR_TRY(m->d_weight.ensure(n));
-  Q3DR_CUDA(cudaMemcpy(m->d_weight.p, m->h_weight.data(), n * sizeof(float), cudaMemcpyHostToDevice));
-  Q3DR_TRY(m->d_normal.ensure(n * 3));
-  Q3DR_CUDA(cudaMemcpy(m->d_normal.p, m->h_normal.data(), n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    std::vector<float4> rec(3 * n);
+    for (size_t k = 0; k < n; ++k) {
+      const float* b = m->h_boxes.data() + 6 * k;
+      rec[3 * k + 0] = make_float4(b[0], b[1], b[2], m->h_weight[k]);
+      rec[3 * k + 1] = make_float4(b[3], b[4], b[5], 0.0f);
+      rec[3 * k + 2] = make_float4(m->h_normal[3 * k], m->h_normal[3 * k + 1], m->h_normal[3 * k + 2], 0.0f);
+    }
+    Q3DR_TRY(m->d_leaf_rec.ensure(3 * n));
+    Q3DR_CUDA(cudaMemcpy(m->d_leaf_rec.p, rec.data(), 3 * n * sizeof(float4), cudaMemcpyHostToDevice));
+  }
   Q3DR_TRY(m->d_depth.ensure(n));
   Q3DR_CUDA(cudaMemcpy(m->d_depth.p, m->h_depth.data(), n, cudaMemcpyHostToDevice));
   Q3DR_TRY(m->d_counter.ensure(4));
   Q3DR_CUDA(cudaMemset(m->d_counter.p, 0, 4 * sizeof(uint32_t)));
   Q3DR_TRY(m->h_scalar.ensure(8));
   m->smem_bytes = (size_t)m->tree.top_nodes * sizeof(q3dr::Node4);
-  Q3DR_TRY(configure_kernel<q3dr::kModeScore>(m));
-  Q3DR_TRY(configure_kernel<q3dr::kModePixels>(m));
   Q3DR_TRY(configure_kernel<q3dr::kModeRays>(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModeScore>(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModePixels>(m));
@@ -246,11 +257,16 @@ int upload_map(q3dr_map* m) {
 
 // scratch for `slots` viewpoints in flight, `cap` result entries per viewpoint
 int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
-  const uint64_t leaf_stride = (m->n + 31) / 32 * 32;
+  const uint64_t leaf_stride = (m->n + q3dr::kSegLeaves - 1) / q3dr::kSegLeaves * q3dr::kSegLeaves;
   const uint64_t word_stride = leaf_stride / 32;
+  const uint32_t n_segs = (uint32_t)(leaf_stride / q3dr::kSegLeaves);
   if (slots > m->slots) {
     m->d_first_pix.release();
     m->d_bitmap.release();
+    m->d_seg_u32.release();
+    Q3DR_TRY(m->d_seg_u32.ensure(2 * slots * n_segs));
+    Q3DR_CUDA(cudaMemsetAsync(m->d_seg_u32.p, 0, m->d_seg_u32.bytes(), m->stream));
+    m->n_segs = n_segs;
     Q3DR_TRY(m->d_first_pix.ensure(slots * leaf_stride));
     Q3DR_TRY(m->d_bitmap.ensure(slots * word_stride));
     Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), m->stream));
@@ -259,6 +275,17 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
     m->slots = slots;
     m->leaf_stride = leaf_stride;
     m->word_stride = word_stride;
+  }
+  {
+    const size_t sl = std::max<size_t>(slots, m->slots);
+    const size_t max_blocks = sl * ((cap + q3dr::kSegThreads - 1) / q3dr::kSegThreads + 1);
+    if (max_blocks > m->max_blocks || m->d_blk_u32.cap < sl + 1 + 2 * max_blocks) {
+      m->d_blk_u32.release();
+      m->d_seg_f64.release();
+      Q3DR_TRY(m->d_blk_u32.ensure(sl + 1 + 2 * max_blocks));
+      Q3DR_TRY(m->d_seg_f64.ensure(max_blocks));
+      m->max_blocks = max_blocks;
+    }
   }
   const size_t need = std::max<size_t>(slots, m->slots) * cap;
   if (need > m->t_leaf.cap || cap != m->tmp_cap) {
@@ -279,7 +306,7 @@ size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint6
   want = std::max<size_t>(want, 2 * (size_t)m->sm_count);
   if (const char* e = std::getenv("Q3DR_CHUNK")) want = (size_t)std::max(1, atoi(e));
   // ... bounded by scratch memory (first-pixel tables + temporary lists)
-  const uint64_t per_slot = ((m->n + 31) / 32 * 32) * 4 + cap * 16;
+  const uint64_t per_slot = ((m->n + q3dr::kSegLeaves - 1) / q3dr::kSegLeaves * q3dr::kSegLeaves) * 4 + cap * 16;
   const uint64_t budget = 8ull << 30;
   const size_t by_mem = (size_t)std::max<uint64_t>(1, budget / std::max<uint64_t>(per_slot, 1));
   size_t b = std::min(want, by_mem);
@@ -345,11 +372,16 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   Q3DR_CUDA(cudaMemsetAsync(m->d_offsets.p, 0, sizeof(uint64_t), stream));
 
   const Derived dv = derive(*opts);
-  q3dr::ScoreParams sp;
+  const uint32_t S = m->n_segs;
+  uint32_t* seg_hits = m->d_seg_u32.p;
+  uint32_t* seg_off = seg_hits + m->slots * S;
+  uint32_t* blk_off = m->d_blk_u32.p;
+  uint32_t* blk_kept = blk_off + m->slots + 1;
+  uint32_t* blk_koff = blk_kept + m->max_blocks;
+  const int flat_grid = m->sm_count * 8;
+  q3dr::ScoreParams2 sp;
   std::memset(&sp, 0, sizeof(sp));
-  sp.leaf_box = m->d_boxes.p;
-  sp.weight = m->d_weight.p;
-  sp.normal = m->d_normal.p;
+  sp.leaf_rec = m->d_leaf_rec.p;
   sp.fx = K[0];
   sp.fy = K[1];
   sp.cx = K[2];
@@ -364,18 +396,30 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   sp.ka = dv.ka;
   sp.ignore_sign = opts->incidence_ignore_dot_product_sign;
   sp.ignore_zero = opts->ignore_voxels_with_zero_information;
-  sp.n_words = (uint32_t)m->word_stride;
+  sp.n_segs = S;
   sp.first_pix = m->d_first_pix.p;
   sp.bitmap = m->d_bitmap.p;
   sp.leaf_stride = m->leaf_stride;
   sp.word_stride = m->word_stride;
   sp.cap = cap;
+  sp.tmp_leaf = m->t_leaf.p;
+  sp.tmp_info = m->t_info.p;
+  sp.tmp_pix = m->t_pix.p;
+  sp.tmp_dsq = m->t_dsq.p;
+  sp.seg_hits = seg_hits;
+  sp.seg_off = seg_off;
+  sp.blk_off = blk_off;
+  sp.blk_kept = blk_kept;
+  sp.blk_koff = blk_koff;
+  sp.blk_total = m->d_seg_f64.p;
   sp.kept_count = m->d_kept.p;
 
   rp.first_pix = m->d_first_pix.p;
   rp.bitmap = m->d_bitmap.p;
   rp.leaf_stride = m->leaf_stride;
   rp.word_stride = m->word_stride;
+  rp.seg_hits = seg_hits;
+  rp.n_segs = S;
 
   q3dr_stats st{};
   st.viewpoints_per_chunk = (uint32_t)B;
@@ -393,15 +437,19 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev[1], stream));
     sp.rt = d_Rt + 12 * v0;
-    sp.tmp_leaf = m->t_leaf.p;
-    sp.tmp_info = m->t_info.p;
-    sp.tmp_pix = m->t_pix.p;
-    sp.tmp_dsq = m->t_dsq.p;
     sp.hit_count = m->d_hit_count.p + v0;
     sp.total = m->d_total.p + v0;
-    q3dr::score_compact_kernel<<<(unsigned)nb, q3dr::kScoreThreads, 0, stream>>>(sp);
+    q3dr::seg_scan_kernel<<<(unsigned)nb, q3dr::kSegThreads, 0, stream>>>(seg_hits, seg_off, S, sp.hit_count);
     Q3DR_CUDA(cudaGetLastError());
-    q3dr::scan_counts_kernel<<<1, 32, 0, stream>>>(m->d_kept.p, (uint32_t)nb, m->d_offsets.p + v0);
+    q3dr::emit_list_kernel<<<dim3(S, (unsigned)nb), q3dr::kSegThreads, 0, stream>>>(sp);
+    Q3DR_CUDA(cudaGetLastError());
+    q3dr::block_offsets_kernel<<<1, q3dr::kSegThreads, 0, stream>>>(sp.hit_count, (uint32_t)nb, blk_off);
+    Q3DR_CUDA(cudaGetLastError());
+    q3dr::score_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+    Q3DR_CUDA(cudaGetLastError());
+    q3dr::finalize_viewpoints_kernel<<<(unsigned)nb, q3dr::kSegThreads, 0, stream>>>(sp);
+    Q3DR_CUDA(cudaGetLastError());
+    q3dr::csr_offsets_kernel<<<1, q3dr::kSegThreads, 0, stream>>>(m->d_kept.p, (uint32_t)nb, m->d_offsets.p + v0);
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaMemcpyAsync(m->h_scalar.p, m->d_offsets.p + v0 + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     Q3DR_CUDA(cudaStreamSynchronize(stream));
@@ -411,9 +459,13 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_TRY(m->r_info.ensure(want, true, stream));
     Q3DR_TRY(m->r_pix.ensure(want, true, stream));
     Q3DR_TRY(m->r_dsq.ensure(want, true, stream));
-    q3dr::PackParams pp;
+    q3dr::PackParams2 pp;
     pp.offsets = m->d_offsets.p + v0;
-    pp.kept = m->d_kept.p;
+    pp.blk_off = blk_off;
+    pp.blk_koff = blk_koff;
+    pp.hit_count = sp.hit_count;
+    pp.n_vp = (uint32_t)nb;
+    pp.ignore_zero = sp.ignore_zero;
     pp.cap = cap;
     pp.tmp_leaf = m->t_leaf.p;
     pp.tmp_info = m->t_info.p;
@@ -423,14 +475,13 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     pp.out_info = m->r_info.p;
     pp.out_pix = m->r_pix.p;
     pp.out_dsq = m->r_dsq.p;
-    const unsigned bx = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(64, (cap + 255) / 256));
-    q3dr::pack_results_kernel<<<dim3(bx, (unsigned)nb), 256, 0, stream>>>(pp);
+    q3dr::pack_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(pp);
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev[2], stream));
     Q3DR_CUDA(cudaEventSynchronize(m->ev[2]));
     st.raycast_ms += elapsed_ms(m->ev[0], m->ev[1]);
     st.score_ms += elapsed_ms(m->ev[1], m->ev[2]);
-    st.kernel_launches += 4;
+    st.kernel_launches += 8;
     st.chunks += 1;
   }
   Q3DR_CUDA(cudaStreamSynchronize(stream));
@@ -676,7 +727,8 @@ int q3dr_map_update_weights(q3dr_map* m, const float* weights) {
   if (!weights) return fail(Q3DR_ERR_INVALID_ARG, "weights is NULL");
   Q3DR_CUDA(cudaSetDevice(m->device));
   m->h_weight.assign(weights, weights + m->n);
-  Q3DR_CUDA(cudaMemcpy(m->d_weight.p, weights, m->n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 12, 3 * sizeof(float4), weights, sizeof(float),
+                         sizeof(float), m->n, cudaMemcpyHostToDevice));
   return Q3DR_OK;
 }
 
@@ -685,7 +737,8 @@ int q3dr_map_update_normals(q3dr_map* m, const float* normals) {
   if (!normals) return fail(Q3DR_ERR_INVALID_ARG, "normals is NULL");
   Q3DR_CUDA(cudaSetDevice(m->device));
   m->h_normal.assign(normals, normals + 3 * m->n);
-  Q3DR_CUDA(cudaMemcpy(m->d_normal.p, normals, 3 * m->n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 32, 3 * sizeof(float4), normals, 3 * sizeof(float),
+                         3 * sizeof(float), m->n, cudaMemcpyHostToDevice));
   return Q3DR_OK;
 }
 

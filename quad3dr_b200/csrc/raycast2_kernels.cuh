@@ -383,7 +383,10 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
         const bool leader = (leaf >= 0) && ((__ffs(grp) - 1) == lane);
         if (leader) {
           const uint32_t old = atomicMin(fpv + (uint32_t)leaf, pix);
-          if (old == kEmptyPixel) atomicOr(bmv + ((uint32_t)leaf >> 5), 1u << (leaf & 31));
+          if (old == kEmptyPixel) {
+            atomicOr(bmv + ((uint32_t)leaf >> 5), 1u << (leaf & 31));
+            atomicAdd(p.seg_hits + (size_t)vp * p.n_segs + ((uint32_t)leaf >> 15), 1u);
+          }
         }
       }
     } else {

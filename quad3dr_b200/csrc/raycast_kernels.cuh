@@ -4,11 +4,9 @@
 // correctly rounded binary32 operation in the reference's order (explicit __f*_rn intrinsics, the
 // translation unit is also compiled with -fmad=false, no fast-math, no FTZ).
 //
-// Kernel 1  raycast_kernel<MODE>      one warp = one 8x4 pixel packet of one viewpoint, persistent
-//                                     grid, packet traversal of the 4-wide node array.
-// Kernel 2  score_compact_kernel      one CTA per viewpoint: bitmap scan -> score -> ordered list.
-// Kernel 3  scan_counts_kernel        CSR offsets of the chunk.
-// Kernel 4  pack_results_kernel       per-viewpoint lists -> dense CSR pool.
+// raycast_kernel<MODE>   one warp = one 32-ray packet (ray lists, pixel lists); persistent grid, packet traversal
+//                        of the 4-wide node array.  Camera windows use raycast2_kernel (raycast2_kernels.cuh),
+//                        scoring lives in score_kernels.cuh.
 #pragma once
 
 #include <cfloat>
@@ -52,6 +50,8 @@ struct RaycastParams {
   uint32_t* bitmap;     // [slot][word_stride]
   uint64_t leaf_stride;
   uint64_t word_stride;
+  uint32_t* seg_hits;   // [slot][n_segs]: set bits per 32768-leaf segment of the bitmap (score_kernels.cuh)
+  uint32_t n_segs;
   // kModePixels / kModeRays
   q3dr_pixel_hit* pixels;
   const uint8_t* __restrict__ leaf_depth;
@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const Raycas
         const uint32_t old = atomicMin(fp, pix);
         if (old == kEmptyPixel) {
           atomicOr(p.bitmap + (size_t)vp * p.word_stride + ((uint32_t)best.leaf >> 5), 1u << (best.leaf & 31));
+          atomicAdd(p.seg_hits + (size_t)vp * p.n_segs + ((uint32_t)best.leaf >> 15), 1u);
         }
       }
     } else {
@@ -571,258 +572,6 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const Raycas
         dst[1] = make_float4(__uint_as_float(out.depth), out.dist_sq, out.screen_x, out.screen_y);
       }
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// scoring
-// ---------------------------------------------------------------------------------------------
-
-struct ScoreParams {
-  const float* __restrict__ leaf_box;  // [n][6]
-  const float* __restrict__ weight;    // [n]
-  const float* __restrict__ normal;    // [n][3]
-  const float* __restrict__ rt;        // [n_vp][12] (chunk)
-  float fx, fy, cx, cy;
-  float image_width_f;
-  uint32_t x0, y0, w;
-  float thr, kf, a_thr, ka;  // derived constants (viewpoint_score.cpp:20-28)
-  int32_t ignore_sign;
-  int32_t ignore_zero;
-  uint32_t n_words;
-  uint32_t* first_pix;
-  uint32_t* bitmap;
-  uint64_t leaf_stride, word_stride;
-  // per-viewpoint temporary lists, capacity `cap` entries per slot
-  uint64_t cap;
-  int32_t* tmp_leaf;
-  float* tmp_info;
-  uint32_t* tmp_pix;
-  float* tmp_dsq;
-  uint32_t* kept_count;  // [slots]
-  uint32_t* hit_count;   // [n_vp_total] (already offset to the chunk)
-  float* total;          // [n_vp_total] (already offset to the chunk)
-};
-
-// computeViewpointObservationScore (viewpoint_planner_scoring.cpp:11-24,67-73,116-122;
-// viewpoint_score.cpp:45-68) for one voxel.
-__device__ __forceinline__ float voxel_information(const ScoreParams& p, uint32_t leaf, float camx, float camy,
-                                                   float camz) {
-  const float* b = p.leaf_box + 6 * (size_t)leaf;
-  const float mnx = __ldg(b + 0), mny = __ldg(b + 1), mnz = __ldg(b + 2);
-  const float mxx = __ldg(b + 3), mxy = __ldg(b + 4), mxz = __ldg(b + 5);
-  const float gx = __fsub_rn(camx, __fdiv_rn(__fadd_rn(mnx, mxx), 2.0f));
-  const float gy = __fsub_rn(camy, __fdiv_rn(__fadd_rn(mny, mxy), 2.0f));
-  const float gz = __fsub_rn(camz, __fdiv_rn(__fadd_rn(mnz, mxz), 2.0f));
-  const float n2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
-  const float dist = __fsqrt_rn(n2);
-  const float size_x = __fsub_rn(mxx, mnx);
-  const float rel = __fdiv_rn(__fdiv_rn(__fmul_rn(p.fx, size_x), dist), p.image_width_f);
-  float res;
-  if (rel >= p.thr) {
-    res = 1.0f;
-  } else {
-    res = expf(__fmul_rn(-p.kf, __fsub_rn(p.thr, rel)));
-  }
-  const float nx = __ldg(p.normal + 3 * (size_t)leaf), ny = __ldg(p.normal + 3 * (size_t)leaf + 1),
-              nz = __ldg(p.normal + 3 * (size_t)leaf + 2);
-  float inc;
-  if (nx == 0.0f && ny == 0.0f && nz == 0.0f) {
-    inc = 1.0f;
-  } else {
-    float vx = gx, vy = gy, vz = gz;
-    if (n2 > 0.0f) {
-      vx = __fdiv_rn(gx, dist);
-      vy = __fdiv_rn(gy, dist);
-      vz = __fdiv_rn(gz, dist);
-    }
-    float dot = __fadd_rn(__fmul_rn(vx, nx), __fadd_rn(__fmul_rn(vy, ny), __fmul_rn(vz, nz)));
-    dot = smax(smin(dot, 1.0f), -1.0f);
-    bool zero = false;
-    if (dot <= 0.0f) {
-      if (p.ignore_sign) {
-        dot = fabsf(dot);
-      } else {
-        zero = true;
-      }
-    }
-    if (zero) {
-      inc = 0.0f;
-    } else {
-      const float angle = acosf(dot);
-      if (angle <= p.a_thr) {
-        inc = 1.0f;
-      } else {
-        inc = expf(__fmul_rn(-p.ka, __fsub_rn(angle, p.a_thr)));
-      }
-    }
-  }
-  return __fmul_rn(__fmul_rn(res, inc), __ldg(p.weight + leaf));
-}
-
-// Block-wide exclusive scan of one uint per thread (fixed order => deterministic); returns the exclusive
-// prefix of `v` and the block total.  s_warp: kScoreThreads / 32 + 1 words of shared memory.
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(Q3DR_FULL_MASK, inc, o);
-    if (lane >= o) inc += y;
-  }
-  __syncthreads();  // s_warp may still be read by the previous call
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = (lane < kScoreThreads / 32) ? s_warp[lane] : 0u;
-    uint32_t winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(Q3DR_FULL_MASK, winc, o);
-      if (lane >= o) winc += y;
-    }
-    if (lane < kScoreThreads / 32) s_warp[lane] = winc - w;
-    if (lane == 31) s_warp[kScoreThreads / 32] = winc;
-  }
-  __syncthreads();
-  total = s_warp[kScoreThreads / 32];
-  return s_warp[warp] + inc - v;
-}
-
-// Fixed-tree block sum of one double per thread (deterministic for a given block size).
-__device__ __forceinline__ double block_sum_ordered(double v, double* s_warp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(Q3DR_FULL_MASK, v, o);
-  __syncthreads();
-  if (lane == 0) s_warp[warp] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kScoreThreads / 32; ++i) t += s_warp[i];
-  }
-  return t;  // valid in thread 0
-}
-
-// One CTA per viewpoint of the chunk.
-//   phase A  bitmap -> ordered list of hit leaves (coalesced word reads, block scan of popcounts);
-//            the bitmap is cleared on the way.
-//   phase B  the list is scored blockDim entries at a time (balanced), entries that survive the
-//            information > 0 filter are compacted in place in ascending leaf order, the first-pixel
-//            table is reset, the total is accumulated in fp64 in a fixed order.
-__global__ void __launch_bounds__(kScoreThreads) score_compact_kernel(const ScoreParams p) {
-  __shared__ uint32_t s_scan[kScoreThreads / 32 + 1];
-  __shared__ double s_dsum[kScoreThreads / 32];
-  const uint32_t slot = blockIdx.x;
-  const uint32_t tid = threadIdx.x;
-  const float* rt = p.rt + 12 * (size_t)slot;
-  const float camx = __ldg(rt + 3), camy = __ldg(rt + 7), camz = __ldg(rt + 11);
-  uint32_t* bitmap = p.bitmap + (size_t)slot * p.word_stride;
-  uint32_t* first_pix = p.first_pix + (size_t)slot * p.leaf_stride;
-  int32_t* list = p.tmp_leaf + (size_t)slot * p.cap;
-  float* o_info = p.tmp_info + (size_t)slot * p.cap;
-  uint32_t* o_pix = p.tmp_pix + (size_t)slot * p.cap;
-  float* o_dsq = p.tmp_dsq + (size_t)slot * p.cap;
-
-  // phase A
-  uint32_t n_hit = 0;
-  for (uint32_t w0 = 0; w0 < p.n_words; w0 += kScoreThreads) {
-    const uint32_t w = w0 + tid;
-    uint32_t bits = (w < p.n_words) ? bitmap[w] : 0u;
-    if (!__syncthreads_or(bits != 0u)) continue;
-    uint32_t chunk_total;
-    uint32_t pos = n_hit + block_exclusive_scan(__popc(bits), s_scan, chunk_total);
-    if (bits) bitmap[w] = 0u;
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      list[pos++] = (int32_t)(w * 32u + b);
-    }
-    n_hit += chunk_total;
-  }
-  __syncthreads();
-
-  // phase B
-  uint32_t n_kept = 0;
-  double total = 0.0;
-  for (uint32_t i0 = 0; i0 < n_hit; i0 += kScoreThreads) {
-    const uint32_t i = i0 + tid;
-    const bool valid = i < n_hit;
-    int32_t leaf = 0;
-    float info = 0.0f, dsq = 0.0f;
-    uint32_t pix = 0;
-    bool keep = false;
-    if (valid) {
-      leaf = list[i];
-      info = voxel_information(p, (uint32_t)leaf, camx, camy, camz);
-      pix = first_pix[leaf];
-      first_pix[leaf] = kEmptyPixel;
-      keep = !p.ignore_zero || info > 0.0f;
-      if (keep) {
-        // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
-        const uint32_t py = pix / p.w, px = pix - py * p.w;
-        Ray ray;
-        camera_ray(rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
-        const float* bx = p.leaf_box + 6 * (size_t)leaf;
-        float t;
-        box_test(ray, __ldg(bx + 0), __ldg(bx + 1), __ldg(bx + 2), __ldg(bx + 3), __ldg(bx + 4), __ldg(bx + 5), dsq, t);
-      }
-    }
-    uint32_t chunk_kept;
-    const uint32_t dst = n_kept + block_exclusive_scan(keep ? 1u : 0u, s_scan, chunk_kept);
-    // every thread of the chunk has read list[i] before the scan's barriers; dst <= i, so in place is safe
-    if (keep) {
-      list[dst] = leaf;
-      o_info[dst] = info;
-      o_pix[dst] = pix;
-      o_dsq[dst] = dsq;
-    }
-    const double part = block_sum_ordered(keep ? (double)info : 0.0, s_dsum);
-    if (tid == 0) total += part;
-    n_kept += chunk_kept;
-  }
-  if (tid == 0) {
-    p.kept_count[slot] = n_kept;
-    p.hit_count[slot] = n_hit;
-    p.total[slot] = (float)total;
-  }
-}
-
-// offsets[v0 + i + 1] = offsets[v0] + inclusive_scan(kept)[i]; one block, n <= a few thousand.
-__global__ void scan_counts_kernel(const uint32_t* __restrict__ kept, uint32_t n, uint64_t* offsets /* at v0 */) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    uint64_t run = offsets[0];
-    for (uint32_t i = 0; i < n; ++i) {
-      run += kept[i];
-      offsets[i + 1] = run;
-    }
-  }
-}
-
-struct PackParams {
-  const uint64_t* __restrict__ offsets;  // at v0
-  const uint32_t* __restrict__ kept;
-  uint64_t cap;
-  const int32_t* __restrict__ tmp_leaf;
-  const float* __restrict__ tmp_info;
-  const uint32_t* __restrict__ tmp_pix;
-  const float* __restrict__ tmp_dsq;
-  int32_t* out_leaf;
-  float* out_info;
-  uint32_t* out_pix;
-  float* out_dsq;
-};
-
-__global__ void pack_results_kernel(const PackParams p) {
-  const uint32_t slot = blockIdx.y;
-  const uint32_t n = p.kept[slot];
-  const uint64_t dst = p.offsets[slot];
-  const size_t src = (size_t)slot * p.cap;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    p.out_leaf[dst + i] = p.tmp_leaf[src + i];
-    p.out_info[dst + i] = p.tmp_info[src + i];
-    p.out_pix[dst + i] = p.tmp_pix[src + i];
-    p.out_dsq[dst + i] = p.tmp_dsq[src + i];
   }
 }
 
