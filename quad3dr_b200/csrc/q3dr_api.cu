@@ -85,6 +85,18 @@ struct PinnedBuf {
     cap = want;
     return Q3DR_OK;
   }
+  // grows keeping the first `used` elements (caller makes sure no copy into the old block is in flight)
+  int grow_keep(size_t n, size_t used) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    Q3DR_CUDA(cudaHostAlloc(&q, want * sizeof(T), cudaHostAllocDefault));
+    if (p && used) std::memcpy(q, p, used * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return Q3DR_OK;
+  }
   void release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
@@ -154,6 +166,9 @@ struct q3dr_map {
   PinnedBuf<int32_t> h_leaf;
   PinnedBuf<float> h_rt;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
+  cudaEvent_t ev_packed = nullptr;
+  bool host_result_valid = false;      // the host pools already hold the entries of the last call
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int grid_ctas[3] = {0, 0, 0};
   int grid2_ctas[2] = {0, 0};
@@ -357,9 +372,11 @@ int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
 
 int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
                       uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
-                      q3dr_result* result) {
+                      q3dr_result* result, bool stream_to_host) {
   Q3DR_CUDA(cudaSetDevice(m->device));
   m->stream = stream;
+  m->host_result_valid = false;
+  uint64_t copied_entries = 0;
   q3dr::RaycastParams rp;
   fill_raycast_params(m, K, x0, x1, y0, y1, opts->raycast_max_range, &rp);
   const uint64_t cap = std::min<uint64_t>((uint64_t)rp.w * rp.h, m->n);
@@ -477,6 +494,24 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     pp.out_dsq = m->r_dsq.p;
     q3dr::pack_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(pp);
     Q3DR_CUDA(cudaGetLastError());
+    if (stream_to_host && total_entries > copied_entries) {
+      // this chunk's slice of the CSR pool is final: ship it while the next chunk is being cast
+      if (total_entries > m->h_leaf.cap) {
+        Q3DR_CUDA(cudaStreamSynchronize(m->copy_stream));
+        Q3DR_TRY(m->h_leaf.grow_keep(total_entries, copied_entries));
+        Q3DR_TRY(m->h_info.grow_keep(total_entries, copied_entries));
+        Q3DR_TRY(m->h_pix.grow_keep(total_entries, copied_entries));
+        Q3DR_TRY(m->h_dsq.grow_keep(total_entries, copied_entries));
+      }
+      const size_t c0 = copied_entries, cn = total_entries - copied_entries;
+      Q3DR_CUDA(cudaEventRecord(m->ev_packed, stream));
+      Q3DR_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_packed, 0));
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_leaf.p + c0, m->r_leaf.p + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, m->copy_stream));
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_info.p + c0, m->r_info.p + c0, cn * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p + c0, m->r_pix.p + c0, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->copy_stream));
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p + c0, m->r_dsq.p + c0, cn * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+      copied_entries = total_entries;
+    }
     Q3DR_CUDA(cudaEventRecord(m->ev[2], stream));
     Q3DR_CUDA(cudaEventSynchronize(m->ev[2]));
     st.raycast_ms += elapsed_ms(m->ev[0], m->ev[1]);
@@ -485,6 +520,10 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     st.chunks += 1;
   }
   Q3DR_CUDA(cudaStreamSynchronize(stream));
+  if (stream_to_host) {
+    Q3DR_CUDA(cudaStreamSynchronize(m->copy_stream));
+    m->host_result_valid = true;
+  }
   if (n_vp > 0) st.total_ms = elapsed_ms(m->ev[3], m->ev[2]);
   st.rays = (uint64_t)n_vp * rp.w * rp.h;
   m->stats = st;
@@ -711,6 +750,8 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
   if (st == Q3DR_OK) {
     cudaError_t e = cudaSetDevice(device);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_packed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) st = fail(Q3DR_ERR_CUDA, std::string("event setup: ") + cudaGetErrorString(e));
   }
   if (st == Q3DR_OK) st = upload_map(m);
@@ -786,6 +827,8 @@ int q3dr_map_destroy(q3dr_map* m) {
   for (int i = 0; i < 4; ++i) {
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   }
+  if (m->ev_packed) cudaEventDestroy(m->ev_packed);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   cudaGetLastError();
   delete m;
   return Q3DR_OK;
@@ -876,7 +919,7 @@ int q3dr_score_viewpoints_device(q3dr_map* m, const float K[4], uint32_t image_w
     Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, d_Rt, 12 * n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     d_Rt = m->d_rt.p;
   }
-  return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result);
+  return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result, false);
 }
 
 int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
@@ -897,7 +940,7 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
     Q3DR_CUDA(cudaMemcpyAsync(m->h_total.p, m->d_total.p, nv * sizeof(float), cudaMemcpyDeviceToHost, s));
     Q3DR_CUDA(cudaMemcpyAsync(m->h_hit_count.p, m->d_hit_count.p, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   }
-  if (ne) {
+  if (ne && !m->host_result_valid) {
     Q3DR_CUDA(cudaMemcpyAsync(m->h_leaf.p, m->r_leaf.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     Q3DR_CUDA(cudaMemcpyAsync(m->h_info.p, m->r_info.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
     Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p, m->r_pix.p, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -926,7 +969,7 @@ int q3dr_score_viewpoints(q3dr_map* m, const float K[4], uint32_t image_width, u
   cudaStream_t s = nullptr;
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
-  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr));
+  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true));
   return q3dr_result_to_host(m, result);
 }
 
