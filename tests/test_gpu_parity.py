@@ -328,3 +328,135 @@ def test_full_size_map_full_resolution_against_oracle():
     refpx = sc.oracle.raycast_window(cam.K, vps[0], 0, 640, 0, 480, 0.0, 60.0)
     gotpx = sc.gpu_map.raycast_window(cam.K, vps[0], 0, 640, 0, 480, 0.0, 60.0)
     _assert_pixels_equal(gotpx, refpx)
+
+
+# ----------------------------------------------------------------------------------------------------
+# paths of the camera-window kernel (raycast2_kernels.cuh): analytic pruning bound at coarse fp32 resolution,
+# mixed-octant packets, packets outside the fast loops' proven domain (exact fallback)
+# ----------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shift", [[1.0e5, -3.0e5, 2.0e5], [2.0e6, 1.0e6, -4.0e6], [3.0e7, 0.0, 1.0e7]])
+def test_analytic_bound_at_coarse_resolution(shift):
+    """Kilometres to tens of thousands of kilometres from the origin: ulp(coordinate) grows to metres, dist_sq values
+    collide massively, and the pruning bound's |origin| term carries the correctness."""
+    leaves = synth.map_tiny(unknown_interior=True)
+    shift = np.asarray(shift, np.float32)
+    boxes = (leaves.boxes + np.concatenate([shift, shift])).astype(np.float32)
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    gmap = E.OccupancyMap(boxes, leaves.weight[order], leaves.normal[order], depth)
+    cam = synth.make_camera(96, 72)
+    vps = synth.make_viewpoints(leaves, 5, config_id=43)
+    vps[:, [3, 7, 11]] += shift
+    for v in range(5):
+        for max_range in (60.0, -1.0, 7.0):
+            ref = oracle.raycast_window(cam.K, vps[v], 0, 96, 0, 72, 0.0, max_range)
+            got = gmap.raycast_window(cam.K, vps[v], 0, 96, 0, 72, 0.0, max_range)
+            _assert_pixels_equal(got, ref)
+    res = gmap.score_viewpoints(cam.K, 96, (0, 96, 0, 72), vps)
+    for v in range(5):
+        ref = oracle.score_viewpoint(leaves.weight[order], leaves.normal[order], cam.K, 96, vps[v], height=72)
+        got = res.viewpoint(v)
+        assert np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(got["pixel"], ref["pixel"])
+        assert np.array_equal(bits(got["dsq"]), bits(ref["dsq"]))
+    gmap.close()
+
+
+def test_tiny_scale_scene():
+    """Millimetre-sized boxes close to the camera: the bound's absolute term (2^-13) is large against the scene."""
+    rng = np.random.default_rng(21)
+    c = rng.uniform(-0.02, 0.02, size=(3000, 3)).astype(np.float32)
+    s = rng.choice([0.0005, 0.001, 0.002], size=(3000, 1)).astype(np.float32)
+    boxes = np.concatenate([c - s, c + s], axis=1).astype(np.float32)
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    gmap = E.OccupancyMap(boxes, None, None, depth)
+    cam = synth.make_camera(64, 48)
+    for k in range(4):
+        eye = rng.uniform(-0.05, 0.05, size=3).astype(np.float32)
+        eye[2] = 0.06
+        f = -eye / np.linalg.norm(eye)
+        r = np.cross(f, [0.0, 1.0, 0.1]); r /= np.linalg.norm(r)
+        u = np.cross(f, r)
+        Rt = np.concatenate([np.stack([r, u, f], axis=1), eye[:, None]], axis=1).astype(np.float32).reshape(12)
+        for max_range in (-1.0, 0.08):
+            ref = oracle.raycast_window(cam.K, Rt, 0, 64, 0, 48, 0.0, max_range)
+            got = gmap.raycast_window(cam.K, Rt, 0, 64, 0, 48, 0.0, max_range)
+            _assert_pixels_equal(got, ref)
+        assert (ref["leaf"] >= 0).sum() > 200
+    gmap.close()
+
+
+def test_mixed_octant_packets_everywhere():
+    """A wide-angle camera looking straight down an axis: the optical axis crosses two sign planes, so every packet
+    around the image centre mixes octants; a tiny image makes almost all packets mixed or ragged."""
+    sc = scene("tiny_unknown")
+    for (w, h) in [(16, 16), (24, 8), (9, 23)]:
+        cam = synth.make_camera(w, h)
+        K = cam.K.copy()
+        K[0] = K[1] = 0.35 * w  # ~110 degrees
+        for R in (np.eye(3), np.array([[0, 0, 1], [-1, 0, 0], [0, -1, 0]]), np.array([[1, 0, 0], [0, 0, 1], [0, -1, 0]])):
+            for t in ([0.37, -6.21, 2.13], [1.11, 2.52, 9.3], [-3.3, 0.4, 1.7]):
+                Rt = np.concatenate([np.asarray(R, np.float32), np.asarray(t, np.float32)[:, None]], axis=1).reshape(12)
+                ref = sc.oracle.raycast_window(K, Rt, 0, w, 0, h, 0.0, 60.0)
+                got = sc.gpu_map.raycast_window(K, Rt, 0, w, 0, h, 0.0, 60.0)
+                _assert_pixels_equal(got, ref)
+                res = sc.gpu_map.score_viewpoints(K, w, (0, w, 0, h), Rt[None])
+                sref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, K, w, Rt, height=h)
+                assert np.array_equal(res.viewpoint(0)["leaf"], sref["leaf"])
+                assert np.array_equal(res.viewpoint(0)["pixel"], sref["pixel"])
+
+
+def test_packets_outside_the_fast_domain_fall_back_to_the_exact_path():
+    """Huge coordinates in the map (not 'bounded'), a huge max_range and a scaled (non-rotation) pose matrix: the
+    fast loops' preconditions fail and every packet takes the literal reference test -- results must not change."""
+    leaves = synth.map_tiny()
+    boxes = leaves.boxes.copy()
+    far = np.array([[1e20, 1e20, 1e20, 1.0001e20, 1.0001e20, 1.0001e20]], np.float32)  # one absurdly far voxel
+    boxes = np.concatenate([boxes, far]).astype(np.float32)
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    oracle = O.OracleTree(boxes)
+    gmap = E.OccupancyMap(boxes, None, None, depth)
+    cam = synth.make_camera(64, 48)
+    vps = synth.make_viewpoints(leaves, 3, config_id=47)
+    for v in range(3):
+        for max_range in (60.0, -1.0, 3e19):
+            ref = oracle.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, max_range)
+            got = gmap.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, max_range)
+            _assert_pixels_equal(got, ref)
+    gmap.close()
+    # bounded map, but a pose whose rotation block is scaled by 1e-18 (squared norm of the direction ~ 1e-36) and a
+    # huge max_range: still the reference's answer
+    sc = scene("tiny")
+    for v in range(3):
+        Rt = vps[v].reshape(3, 4).copy()
+        Rt[:, :3] *= np.float32(1e-18)
+        ref = sc.oracle.raycast_window(cam.K, Rt.reshape(12), 0, 64, 0, 48, 0.0, 60.0)
+        got = sc.gpu_map.raycast_window(cam.K, Rt.reshape(12), 0, 64, 0, 48, 0.0, 60.0)
+        _assert_pixels_equal(got, ref)
+        ref = sc.oracle.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, 5e18)
+        got = sc.gpu_map.raycast_window(cam.K, vps[v], 0, 64, 0, 48, 0.0, 5e18)
+        _assert_pixels_equal(got, ref)
+
+
+def test_scoring_with_many_chunks_and_dense_hits():
+    """More viewpoints than one chunk holds (Q3DR_CHUNK is not set: the library picks), dense hit lists from a camera
+    close to a wall, both filter settings; the flat block numbering must reproduce per-viewpoint order and counts."""
+    sc = scene("small_unknown")
+    w, h = 96, 72
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(sc.leaves, 700, config_id=59)
+    for iz in (1, 0):
+        res = sc.gpu_map.score_viewpoints(cam.K, w, (0, w, 0, h), vps, E.default_opts(ignore_voxels_with_zero_information=iz))
+        assert res.n_viewpoints == 700 and res.offsets[-1] == res.n_entries
+        for v in (0, 1, 255, 256, 257, 511, 699):
+            ref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, cam.K, w, vps[v], height=h,
+                                            opts=O.default_opts(ignore_voxels_with_zero_information=iz))
+            got = res.viewpoint(v)
+            assert np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(got["pixel"], ref["pixel"])
+            assert got["hit_count"] == ref["hit_count"]
+            np.testing.assert_allclose(got["info"], ref["info"], rtol=REL_TOL)
+            assert abs(got["total"] - ref["total"]) <= REL_TOL * max(abs(ref["total"]), 1e-30)
