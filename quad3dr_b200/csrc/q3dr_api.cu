@@ -326,7 +326,7 @@ size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint6
   const size_t by_mem = (size_t)std::max<uint64_t>(1, budget / std::max<uint64_t>(per_slot, 1));
   size_t b = std::min(want, by_mem);
   b = std::min(b, n_vp);
-  b = std::min<size_t>(b, 4096);
+  b = std::min<size_t>(b, q3dr::kMaxChunkViewpoints);
   return std::max<size_t>(b, 1);
 }
 
@@ -395,6 +395,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   uint32_t* blk_off = m->d_blk_u32.p;
   uint32_t* blk_kept = blk_off + m->slots + 1;
   uint32_t* blk_koff = blk_kept + m->max_blocks;
+  const int score_grid = m->sm_count * 3;  // 79 registers x 256 threads: three CTAs per SM
   const int flat_grid = m->sm_count * 8;
   q3dr::ScoreParams2 sp;
   std::memset(&sp, 0, sizeof(sp));
@@ -462,7 +463,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     q3dr::block_offsets_kernel<<<1, q3dr::kSegThreads, 0, stream>>>(sp.hit_count, (uint32_t)nb, blk_off);
     Q3DR_CUDA(cudaGetLastError());
-    q3dr::score_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+    q3dr::score_blocks_kernel<<<score_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
     Q3DR_CUDA(cudaGetLastError());
     q3dr::finalize_viewpoints_kernel<<<(unsigned)nb, q3dr::kSegThreads, 0, stream>>>(sp);
     Q3DR_CUDA(cudaGetLastError());

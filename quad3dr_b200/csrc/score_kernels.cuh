@@ -104,61 +104,6 @@ __global__ void __launch_bounds__(kSegThreads) seg_scan_kernel(const uint32_t* _
   if (totals != nullptr && threadIdx.x == 0) totals[vp] = run;
 }
 
-// computeViewpointObservationScore for one voxel; also returns the box.
-__device__ __forceinline__ float voxel_information2(const ScoreParams2& p, uint32_t leaf, float camx, float camy, float camz,
-                                                    float4& ra, float4& rb) {
-  const float4* rec = p.leaf_rec + 3 * (size_t)leaf;
-  ra = __ldg(rec);
-  rb = __ldg(rec + 1);
-  const float4 rc = __ldg(rec + 2);
-  const float gx = __fsub_rn(camx, __fdiv_rn(__fadd_rn(ra.x, rb.x), 2.0f));
-  const float gy = __fsub_rn(camy, __fdiv_rn(__fadd_rn(ra.y, rb.y), 2.0f));
-  const float gz = __fsub_rn(camz, __fdiv_rn(__fadd_rn(ra.z, rb.z), 2.0f));
-  const float n2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
-  const float dist = __fsqrt_rn(n2);
-  const float size_x = __fsub_rn(rb.x, ra.x);
-  const float rel = __fdiv_rn(__fdiv_rn(__fmul_rn(p.fx, size_x), dist), p.image_width_f);
-  float res;
-  if (rel >= p.thr) {
-    res = 1.0f;
-  } else {
-    res = expf(__fmul_rn(-p.kf, __fsub_rn(p.thr, rel)));
-  }
-  const float nx = rc.x, ny = rc.y, nz = rc.z;
-  float inc;
-  if (nx == 0.0f && ny == 0.0f && nz == 0.0f) {
-    inc = 1.0f;
-  } else {
-    float vx = gx, vy = gy, vz = gz;
-    if (n2 > 0.0f) {
-      vx = __fdiv_rn(gx, dist);
-      vy = __fdiv_rn(gy, dist);
-      vz = __fdiv_rn(gz, dist);
-    }
-    float dot = __fadd_rn(__fmul_rn(vx, nx), __fadd_rn(__fmul_rn(vy, ny), __fmul_rn(vz, nz)));
-    dot = smax(smin(dot, 1.0f), -1.0f);
-    bool zero = false;
-    if (dot <= 0.0f) {
-      if (p.ignore_sign) {
-        dot = fabsf(dot);
-      } else {
-        zero = true;
-      }
-    }
-    if (zero) {
-      inc = 0.0f;
-    } else {
-      const float angle = acosf(dot);
-      if (angle <= p.a_thr) {
-        inc = 1.0f;
-      } else {
-        inc = expf(__fmul_rn(-p.ka, __fsub_rn(angle, p.a_thr)));
-      }
-    }
-  }
-  return __fmul_rn(__fmul_rn(res, inc), ra.w);
-}
-
 // bits -> ordered leaf list of the viewpoint (thread t owns 4 consecutive words of the segment); the bitmap is
 // cleared on the way and the segment counter reset for the next chunk.
 __global__ void __launch_bounds__(kSegThreads) emit_list_kernel(const ScoreParams2 p) {
@@ -207,11 +152,20 @@ __global__ void __launch_bounds__(kSegThreads) block_offsets_kernel(const uint32
   if (threadIdx.x == 0) blk_off[n_vp] = run;
 }
 
-__device__ __forceinline__ uint32_t find_viewpoint(const uint32_t* __restrict__ blk_off, uint32_t n_vp, uint32_t blk) {
-  uint32_t lo = 0, hi = n_vp;  // largest v with blk_off[v] <= blk
+constexpr uint32_t kMaxChunkViewpoints = 4096;  // choose_chunk() never exceeds it: blk_off fits in shared memory
+
+// blk_off (n_vp + 1 entries) staged in shared memory once per CTA; every thread then finds the viewpoint of a block
+// with a dozen shared-memory probes instead of a chain of dependent global loads.
+__device__ __forceinline__ void stage_block_offsets(const uint32_t* __restrict__ blk_off, uint32_t n_vp, uint32_t* s_off) {
+  for (uint32_t i = threadIdx.x; i <= n_vp; i += blockDim.x) s_off[i] = __ldg(blk_off + i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t find_viewpoint(const uint32_t* s_off, uint32_t n_vp, uint32_t blk) {
+  uint32_t lo = 0, hi = n_vp;  // largest v with s_off[v] <= blk
   while (hi - lo > 1u) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(blk_off + mid) <= blk) {
+    if (s_off[mid] <= blk) {
       lo = mid;
     } else {
       hi = mid;
@@ -220,66 +174,151 @@ __device__ __forceinline__ uint32_t find_viewpoint(const uint32_t* __restrict__ 
   return lo;
 }
 
+// information of one voxel from its record (computeViewpointObservationScore)
+__device__ __forceinline__ float voxel_information_rec(const ScoreParams2& p, const float4& ra, const float4& rb,
+                                                       const float4& rc, float camx, float camy, float camz) {
+  const float gx = __fsub_rn(camx, __fdiv_rn(__fadd_rn(ra.x, rb.x), 2.0f));
+  const float gy = __fsub_rn(camy, __fdiv_rn(__fadd_rn(ra.y, rb.y), 2.0f));
+  const float gz = __fsub_rn(camz, __fdiv_rn(__fadd_rn(ra.z, rb.z), 2.0f));
+  const float n2 = __fadd_rn(__fmul_rn(gx, gx), __fadd_rn(__fmul_rn(gy, gy), __fmul_rn(gz, gz)));
+  const float dist = __fsqrt_rn(n2);
+  const float size_x = __fsub_rn(rb.x, ra.x);
+  const float rel = __fdiv_rn(__fdiv_rn(__fmul_rn(p.fx, size_x), dist), p.image_width_f);
+  float res;
+  if (rel >= p.thr) {
+    res = 1.0f;
+  } else {
+    res = expf(__fmul_rn(-p.kf, __fsub_rn(p.thr, rel)));
+  }
+  const float nx = rc.x, ny = rc.y, nz = rc.z;
+  float inc;
+  if (nx == 0.0f && ny == 0.0f && nz == 0.0f) {
+    inc = 1.0f;
+  } else {
+    float vx = gx, vy = gy, vz = gz;
+    if (n2 > 0.0f) {
+      vx = __fdiv_rn(gx, dist);
+      vy = __fdiv_rn(gy, dist);
+      vz = __fdiv_rn(gz, dist);
+    }
+    float dot = __fadd_rn(__fmul_rn(vx, nx), __fadd_rn(__fmul_rn(vy, ny), __fmul_rn(vz, nz)));
+    dot = smax(smin(dot, 1.0f), -1.0f);
+    bool zero = false;
+    if (dot <= 0.0f) {
+      if (p.ignore_sign) {
+        dot = fabsf(dot);
+      } else {
+        zero = true;
+      }
+    }
+    if (zero) {
+      inc = 0.0f;
+    } else {
+      const float angle = acosf(dot);
+      if (angle <= p.a_thr) {
+        inc = 1.0f;
+      } else {
+        inc = expf(__fmul_rn(-p.ka, __fsub_rn(angle, p.a_thr)));
+      }
+    }
+  }
+  return __fmul_rn(__fmul_rn(res, inc), ra.w);
+}
+
 // Scores every entry of every hit list of the chunk in place (position i of the list keeps position i of the
 // tmp arrays); per block: number of entries that survive the information > 0 filter and their fp64 sum.
+// The pass is bound by the latency of two dependent random fetches per voxel (list -> first pixel + record), so a
+// CTA works on kScoreUnroll blocks at once and issues all their fetches before any arithmetic.
+constexpr int kScoreUnroll = 4;
+
 __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScoreParams2 p, uint32_t n_vp) {
-  __shared__ uint32_t s_cnt[kSegThreads / 32];
-  __shared__ double s_dsum[kSegThreads / 32];
-  __shared__ uint32_t s_vp;
+  __shared__ uint32_t s_cnt[kScoreUnroll][kSegThreads / 32];
+  __shared__ double s_dsum[kScoreUnroll][kSegThreads / 32];
+  __shared__ uint32_t s_off[kMaxChunkViewpoints + 1];
   const uint32_t tid = threadIdx.x;
-  const uint32_t total_blocks = __ldg(p.blk_off + n_vp);
-  for (uint32_t blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
-    if (tid == 0) s_vp = find_viewpoint(p.blk_off, n_vp, blk);
-    __syncthreads();
-    const uint32_t vp = s_vp;
-    const uint32_t j = blk - __ldg(p.blk_off + vp);
-    const uint32_t hits = p.hit_count[vp];
-    const uint32_t i = j * kSegThreads + tid;
-    const float* rt = p.rt + 12 * (size_t)vp;
-    bool keep = false;
-    float info = 0.0f;
-    if (i < hits) {
-      const size_t at = (size_t)vp * p.cap + i;
-      const int32_t leaf = p.tmp_leaf[at];
-      uint32_t* fp = p.first_pix + (size_t)vp * p.leaf_stride + (uint32_t)leaf;
-      const uint32_t pix = *fp;
-      *fp = kEmptyPixel;
-      float4 ra, rb;
-      info = voxel_information2(p, (uint32_t)leaf, __ldg(rt + 3), __ldg(rt + 7), __ldg(rt + 11), ra, rb);
-      keep = !p.ignore_zero || info > 0.0f;
-      float dsq = 0.0f;
-      if (keep) {
-        // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
-        const uint32_t py = pix / p.w, px = pix - py * p.w;
-        Ray ray;
-        camera_ray(rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
-        float t;
-        box_test(ray, ra.x, ra.y, ra.z, rb.x, rb.y, rb.z, dsq, t);
-      }
-      p.tmp_info[at] = info;
-      p.tmp_pix[at] = pix;
-      p.tmp_dsq[at] = dsq;
-    }
-    // fixed-tree block reductions
-    const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t wc = __popc(__ballot_sync(Q3DR_FULL_MASK, keep));
-    double part = keep ? (double)info : 0.0;
+  const int lane = tid & 31, warp = tid >> 5;
+  stage_block_offsets(p.blk_off, n_vp, s_off);
+  const uint32_t total_blocks = s_off[n_vp];
+  for (uint32_t blk0 = blockIdx.x * kScoreUnroll; blk0 < total_blocks; blk0 += gridDim.x * kScoreUnroll) {
+    uint32_t vp[kScoreUnroll];
+    size_t at[kScoreUnroll];
+    bool valid[kScoreUnroll];
+    int32_t leaf[kScoreUnroll];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(Q3DR_FULL_MASK, part, o);
-    if (lane == 0) {
-      s_cnt[warp] = wc;
-      s_dsum[warp] = part;
+    for (int u = 0; u < kScoreUnroll; ++u) {
+      const uint32_t blk = blk0 + u;
+      valid[u] = false;
+      vp[u] = 0;
+      at[u] = 0;
+      leaf[u] = 0;
+      if (blk < total_blocks) {
+        vp[u] = find_viewpoint(s_off, n_vp, blk);
+        const uint32_t i = (blk - s_off[vp[u]]) * kSegThreads + tid;
+        valid[u] = i < p.hit_count[vp[u]];
+        at[u] = (size_t)vp[u] * p.cap + i;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScoreUnroll; ++u) {
+      if (valid[u]) leaf[u] = p.tmp_leaf[at[u]];
+    }
+    uint32_t pix[kScoreUnroll];
+    float4 ra[kScoreUnroll], rb[kScoreUnroll], rc[kScoreUnroll];
+#pragma unroll
+    for (int u = 0; u < kScoreUnroll; ++u) {
+      pix[u] = 0;
+      ra[u] = rb[u] = rc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid[u]) {
+        uint32_t* fp = p.first_pix + (size_t)vp[u] * p.leaf_stride + (uint32_t)leaf[u];
+        pix[u] = *fp;
+        *fp = kEmptyPixel;
+        const float4* rec = p.leaf_rec + 3 * (size_t)leaf[u];
+        ra[u] = __ldg(rec);
+        rb[u] = __ldg(rec + 1);
+        rc[u] = __ldg(rec + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScoreUnroll; ++u) {
+      bool keep = false;
+      float info = 0.0f;
+      if (valid[u]) {
+        const float* rt = p.rt + 12 * (size_t)vp[u];
+        info = voxel_information_rec(p, ra[u], rb[u], rc[u], __ldg(rt + 3), __ldg(rt + 7), __ldg(rt + 11));
+        keep = !p.ignore_zero || info > 0.0f;
+        float dsq = 0.0f;
+        if (keep) {
+          // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
+          const uint32_t py = pix[u] / p.w, px = pix[u] - py * p.w;
+          Ray ray;
+          camera_ray(rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+          float t;
+          box_test(ray, ra[u].x, ra[u].y, ra[u].z, rb[u].x, rb[u].y, rb[u].z, dsq, t);
+        }
+        p.tmp_info[at[u]] = info;
+        p.tmp_pix[at[u]] = pix[u];
+        p.tmp_dsq[at[u]] = dsq;
+      }
+      // fixed-tree reductions: warp level here, block level below
+      const uint32_t wc = __popc(__ballot_sync(Q3DR_FULL_MASK, keep));
+      double part = keep ? (double)info : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(Q3DR_FULL_MASK, part, o);
+      if (lane == 0) {
+        s_cnt[u][warp] = wc;
+        s_dsum[u][warp] = part;
+      }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < kScoreUnroll && blk0 + tid < total_blocks) {
       uint32_t c = 0;
       double t = 0.0;
       for (int w = 0; w < kSegThreads / 32; ++w) {
-        c += s_cnt[w];
-        t += s_dsum[w];
+        c += s_cnt[tid][w];
+        t += s_dsum[tid][w];
       }
-      p.blk_kept[blk] = c;
-      p.blk_total[blk] = t;
+      p.blk_kept[blk0 + tid] = c;
+      p.blk_total[blk0 + tid] = t;
     }
     __syncthreads();
   }
@@ -333,14 +372,13 @@ struct PackParams2 {
 // kept entries -> dense CSR pool, ascending leaf order preserved (block-local scan of the keep flags)
 __global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const PackParams2 p) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
-  __shared__ uint32_t s_vp;
+  __shared__ uint32_t s_off[kMaxChunkViewpoints + 1];
   const uint32_t tid = threadIdx.x;
-  const uint32_t total_blocks = __ldg(p.blk_off + p.n_vp);
+  stage_block_offsets(p.blk_off, p.n_vp, s_off);
+  const uint32_t total_blocks = s_off[p.n_vp];
   for (uint32_t blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
-    if (tid == 0) s_vp = find_viewpoint(p.blk_off, p.n_vp, blk);
-    __syncthreads();
-    const uint32_t vp = s_vp;
-    const uint32_t j = blk - __ldg(p.blk_off + vp);
+    const uint32_t vp = find_viewpoint(s_off, p.n_vp, blk);
+    const uint32_t j = blk - s_off[vp];
     const uint32_t i = j * kSegThreads + tid;
     const size_t at = (size_t)vp * p.cap + i;
     float info = 0.0f;
