@@ -132,7 +132,7 @@ struct q3dr_map {
   q3dr::FlatTree tree;
   // device: the map
   DevBuf<float4> d_nodes;
-  DevBuf<float4> d_leaf_rec;  // [n][3]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}
+  DevBuf<float4> d_leaf_rec;  // [n][4]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}, pad (64-byte records)
   DevBuf<uint8_t> d_depth;
   DevBuf<uint32_t> d_counter;
   // device: per-chunk scratch
@@ -248,15 +248,16 @@ int upload_map(q3dr_map* m) {
   Q3DR_TRY(m->d_nodes.ensure(nn * 8));
   Q3DR_CUDA(cudaMemcpy(m->d_nodes.p, m->tree.nodes.data(), nn * sizeof(q3dr::Node4), cudaMemcpyHostToDevice));
   {
-    std::vector<float4> rec(3 * n);
+    constexpr size_t R = q3dr::kLeafRecStride;
+    std::vector<float4> rec(R * n, make_float4(0.f, 0.f, 0.f, 0.f));
     for (size_t k = 0; k < n; ++k) {
       const float* b = m->h_boxes.data() + 6 * k;
-      rec[3 * k + 0] = make_float4(b[0], b[1], b[2], m->h_weight[k]);
-      rec[3 * k + 1] = make_float4(b[3], b[4], b[5], 0.0f);
-      rec[3 * k + 2] = make_float4(m->h_normal[3 * k], m->h_normal[3 * k + 1], m->h_normal[3 * k + 2], 0.0f);
+      rec[R * k + 0] = make_float4(b[0], b[1], b[2], m->h_weight[k]);
+      rec[R * k + 1] = make_float4(b[3], b[4], b[5], 0.0f);
+      rec[R * k + 2] = make_float4(m->h_normal[3 * k], m->h_normal[3 * k + 1], m->h_normal[3 * k + 2], 0.0f);
     }
-    Q3DR_TRY(m->d_leaf_rec.ensure(3 * n));
-    Q3DR_CUDA(cudaMemcpy(m->d_leaf_rec.p, rec.data(), 3 * n * sizeof(float4), cudaMemcpyHostToDevice));
+    Q3DR_TRY(m->d_leaf_rec.ensure(R * n));
+    Q3DR_CUDA(cudaMemcpy(m->d_leaf_rec.p, rec.data(), R * n * sizeof(float4), cudaMemcpyHostToDevice));
   }
   Q3DR_TRY(m->d_depth.ensure(n));
   Q3DR_CUDA(cudaMemcpy(m->d_depth.p, m->h_depth.data(), n, cudaMemcpyHostToDevice));
@@ -769,7 +770,7 @@ int q3dr_map_update_weights(q3dr_map* m, const float* weights) {
   if (!weights) return fail(Q3DR_ERR_INVALID_ARG, "weights is NULL");
   Q3DR_CUDA(cudaSetDevice(m->device));
   m->h_weight.assign(weights, weights + m->n);
-  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 12, 3 * sizeof(float4), weights, sizeof(float),
+  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 12, q3dr::kLeafRecStride * sizeof(float4), weights, sizeof(float),
                          sizeof(float), m->n, cudaMemcpyHostToDevice));
   return Q3DR_OK;
 }
@@ -779,7 +780,7 @@ int q3dr_map_update_normals(q3dr_map* m, const float* normals) {
   if (!normals) return fail(Q3DR_ERR_INVALID_ARG, "normals is NULL");
   Q3DR_CUDA(cudaSetDevice(m->device));
   m->h_normal.assign(normals, normals + 3 * m->n);
-  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 32, 3 * sizeof(float4), normals, 3 * sizeof(float),
+  Q3DR_CUDA(cudaMemcpy2D(reinterpret_cast<char*>(m->d_leaf_rec.p) + 32, q3dr::kLeafRecStride * sizeof(float4), normals, 3 * sizeof(float),
                          3 * sizeof(float), m->n, cudaMemcpyHostToDevice));
   return Q3DR_OK;
 }

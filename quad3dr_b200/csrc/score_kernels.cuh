@@ -28,12 +28,13 @@
 namespace q3dr {
 
 constexpr int kSegThreads = 256;
+constexpr int kLeafRecStride = 4;  // float4s per leaf record: 64 bytes, so a record never straddles a 128-byte line
 constexpr uint32_t kSegWords = 4u * kSegThreads;   // 1024 bitmap words
 constexpr uint32_t kSegLeaves = 32u * kSegWords;   // 32768 leaves per segment
 constexpr uint32_t kSegShift = 15;                 // leaf >> kSegShift = segment
 
 struct ScoreParams2 {
-  const float4* __restrict__ leaf_rec;  // [n][3]: {min xyz, weight}, {max xyz, -}, {normal xyz, -}
+  const float4* __restrict__ leaf_rec;  // [n][4] (one 64-byte line half): {min xyz, weight}, {max xyz, -}, {normal xyz, -}, pad
   const float* __restrict__ rt;         // [B][12]
   float fx, fy, cx, cy;
   float image_width_f;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScorePa
         uint32_t* fp = p.first_pix + (size_t)vp[u] * p.leaf_stride + (uint32_t)leaf[u];
         pix[u] = *fp;
         *fp = kEmptyPixel;
-        const float4* rec = p.leaf_rec + 3 * (size_t)leaf[u];
+        const float4* rec = p.leaf_rec + kLeafRecStride * (size_t)leaf[u];
         ra[u] = __ldg(rec);
         rb[u] = __ldg(rec + 1);
         rc[u] = __ldg(rec + 2);
