@@ -229,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(workload, leaves, cam, nvp_per_rank, world):
@@ -240,7 +240,8 @@ def workload_config(workload, leaves, cam, nvp_per_rank, world):
         "n_leaves": int(leaves.n), "viewpoints": int(nvp_per_rank * world), "viewpoints_per_gpu": int(nvp_per_rank),
         "width": cam.width, "height": cam.height,
         "parallelism": f"viewpoint-sharded x{world}, map replicated",
-        "l2": "flushed between timed steps (256 MiB device write); map node array is smaller than L2",
+        "l2": "flushed between timed steps (256 MiB device write); node array "
+              + ("fits in the 126 MB L2" if leaves.n < 2_000_000 else "is larger than the 126 MB L2"),
         "timing": "CUDA events on the launch stream around each step (flush excluded), summed over steps, max over ranks",
     }
 
@@ -374,7 +375,7 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {
-                "bound": "hbm", "kernel": "raycast_kernel<kModeScore>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "bound": "hbm", "kernel": "raycast2_kernel<kModeScore>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": committed_traffic(args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rays_per_launch, "launch_ms": launch_ms,
                 "launches_timed": raycast_launches,
@@ -397,10 +398,29 @@ def run_ours(args):
             cb["parity_on_sample"] = {"viewpoints": int(n), "hit_list_sizes_equal": same_counts,
                                       "max_rel_score_err": float(rel.max()) if n else 0.0}
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on stdout.
+    Everything except that line is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -414,10 +434,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (args.impl == "ours" and args.gpus > 1 and world == 1):
+        _quiet_stdout()  # (the torchrun re-launch below passes its children's stdout through untouched)
     if args.impl == "reference":
         run_reference(args)
         return
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
