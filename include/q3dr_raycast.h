@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define Q3DR_ABI_VERSION 1
+#define Q3DR_ABI_VERSION 2
 
 enum q3dr_status {
   Q3DR_OK = 0,
@@ -196,6 +196,37 @@ int q3dr_score_viewpoints_device(q3dr_map* map, const float K[4], uint32_t image
 /* Copies the device-resident result of the last q3dr_score_viewpoints_device call to host memory
  * owned by the map. */
 int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);
+
+/* ---- consumers of the voxel sets: the planner's path search ----
+ *
+ * They work on the CSR result of the LAST q3dr_score_viewpoints[_device] call on the map, in device memory;
+ * `viewpoint` arguments index that result.  A q3dr_observed is one ViewpointPath::observed_voxel_map
+ * (viewpoint_planner.h: unordered_map<voxel, accumulated information>) held as a dense per-leaf array on the device.
+ * Per-voxel arithmetic is the reference's; sums over a set are fp64 sums rounded once (the reference sums in hash
+ * order, fp32). */
+typedef struct q3dr_observed q3dr_observed;
+
+int q3dr_observed_create(q3dr_map* map, q3dr_observed** out); /* empty map */
+int q3dr_observed_clear(q3dr_observed* obs);
+int q3dr_observed_destroy(q3dr_observed* obs);
+/* out: n_leaves floats, NaN = voxel not in the map */
+int q3dr_observed_download(const q3dr_observed* obs, float* out);
+
+/* ViewpointPlanner::computeNewInformation (viewpoint_planner_scoring.cpp:124-147) for n viewpoints of the result
+ * (viewpoints == NULL: viewpoints 0..n-1):  sum over the voxel set of
+ *   observed ? min(f * info, weight - observed) : f * info,      f = viewpoint_information_factor (1/3). */
+int q3dr_new_information(q3dr_map* map, const q3dr_observed* obs, float viewpoint_information_factor,
+                         const uint32_t* viewpoints, size_t n, float* out);
+
+/* addObservedVoxelsToViewpointPath (viewpoint_planner_path.cpp:203-233): folds the voxel set of `viewpoint` into
+ * the map (insert f * info, or add it clamped at the voxel weight) and returns the novel information. */
+int q3dr_observed_add_viewpoint(q3dr_map* map, q3dr_observed* obs, float viewpoint_information_factor,
+                                uint32_t viewpoint, float* new_information);
+
+/* compute_overlap_information_lambda (viewpoint_planner_path.cpp:838-848) of each viewpoint others[i] (set1)
+ * against viewpoint `ref` (set2).  Like the reference's lookup (VoxelWithInformation::operator==,
+ * occupied_tree.h:73-79) a voxel counts only if it carries bit-identical information in both sets. */
+int q3dr_overlap_information(q3dr_map* map, uint32_t ref, const uint32_t* others, size_t n, float* out);
 
 #ifdef __cplusplus
 }

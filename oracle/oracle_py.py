@@ -87,6 +87,13 @@ def lib():
     L.orc_score_batch.argtypes = [
         C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
     ]
+    dp = C.POINTER(C.c_double)
+    L.orc_new_information.restype = C.c_float
+    L.orc_new_information.argtypes = [i32p, fp, C.c_size_t, fp, fp, C.c_float, dp]
+    L.orc_observed_add.restype = C.c_float
+    L.orc_observed_add.argtypes = [i32p, fp, C.c_size_t, fp, fp, C.c_float, dp]
+    L.orc_overlap_information.restype = C.c_float
+    L.orc_overlap_information.argtypes = [i32p, fp, C.c_size_t, i32p, fp, C.c_size_t, dp]
     L.orc_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -286,6 +293,35 @@ def camera_rays(K, Rt, x0, x1, y0, y1):
 def set_sqnorm_sequential(on: bool) -> None:
     """Pin-test switch (see q3dr_oracle.h); always reset to False afterwards."""
     lib().orc_set_sqnorm_sequential(1 if on else 0)
+
+
+def new_information(leaf, info, observed, weight, factor):
+    """(fp32 running sum, fp64 sum) of computeNewInformation for one voxel set."""
+    leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+    info = _f32(info)
+    s = C.c_double(0)
+    v = lib().orc_new_information(_i(leaf), _f(info), len(leaf), _f(_f32(observed)), _f(_f32(weight)), float(factor), C.byref(s))
+    return float(v), float(s.value)
+
+
+def observed_add(leaf, info, observed, weight, factor):
+    """addObservedVoxelsToViewpointPath; `observed` (float32, contiguous) is updated in place."""
+    leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+    info = _f32(info)
+    assert observed.dtype == np.float32 and observed.flags.c_contiguous
+    s = C.c_double(0)
+    v = lib().orc_observed_add(_i(leaf), _f(info), len(leaf), _f(observed), _f(_f32(weight)), float(factor), C.byref(s))
+    return float(v), float(s.value)
+
+
+def overlap_information(leaf1, info1, leaf2, info2):
+    leaf1 = np.ascontiguousarray(leaf1, dtype=np.int32)
+    leaf2 = np.ascontiguousarray(leaf2, dtype=np.int32)
+    info1 = _f32(info1)
+    info2 = _f32(info2)
+    s = C.c_double(0)
+    v = lib().orc_overlap_information(_i(leaf1), _f(info1), len(leaf1), _i(leaf2), _f(info2), len(leaf2), C.byref(s))
+    return float(v), float(s.value)
 
 
 def max_threads() -> int:

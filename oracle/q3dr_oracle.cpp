@@ -618,6 +618,75 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
   return (uint64_t)n_vp * width * height;
 }
 
+// ---- consumers of the voxel sets (path search) ----
+
+// ViewpointPlanner::computeNewInformation (viewpoint_planner_scoring.cpp:124-147).  observed: dense over the
+// leaves, NaN = not in observed_voxel_map.  The reference accumulates in hash order; here ascending entry order.
+float orc_new_information(const int32_t* leaf, const float* info, size_t n, const float* observed, const float* weight,
+                          float factor, double* sum_f64) {
+  float acc = 0.0f;
+  double acc64 = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    const float observation_information = factor * info[i];
+    float novel_information = observation_information;
+    const float seen = observed[leaf[i]];
+    if (!std::isnan(seen)) {
+      const float voxel_weight = weight[leaf[i]];
+      novel_information = smin(observation_information, voxel_weight - seen);
+    }
+    acc = acc + novel_information;
+    acc64 += (double)novel_information;
+  }
+  if (sum_f64) *sum_f64 = acc64;
+  return acc;
+}
+
+// addObservedVoxelsToViewpointPath (viewpoint_planner_path.cpp:203-233); observed is updated in place.
+float orc_observed_add(const int32_t* leaf, const float* info, size_t n, float* observed, const float* weight,
+                       float factor, double* sum_f64) {
+  float new_information = 0.0f;
+  double acc64 = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    const float observation_information = factor * info[i];
+    float novel_observation_information;
+    float& slot = observed[leaf[i]];
+    if (std::isnan(slot)) {
+      slot = observation_information;
+      novel_observation_information = observation_information;
+    } else {
+      const float voxel_weight = weight[leaf[i]];
+      novel_observation_information = smin(observation_information, voxel_weight - slot);
+      if (slot <= voxel_weight) {
+        slot += observation_information;
+        if (slot > voxel_weight) slot = voxel_weight;
+      }
+    }
+    new_information += novel_observation_information;
+    acc64 += (double)novel_observation_information;
+  }
+  if (sum_f64) *sum_f64 = acc64;
+  return new_information;
+}
+
+// compute_overlap_information_lambda (viewpoint_planner_path.cpp:838-848): for every element of set 1, look it up in
+// set 2 with VoxelWithInformation's equality (voxel AND information, occupied_tree.h:73-79); both lists ascending.
+float orc_overlap_information(const int32_t* leaf1, const float* info1, size_t n1, const int32_t* leaf2,
+                              const float* info2, size_t n2, double* sum_f64) {
+  float overlap_information = 0.0f;
+  double acc64 = 0.0;
+  size_t j = 0;
+  for (size_t i = 0; i < n1; ++i) {
+    while (j < n2 && leaf2[j] < leaf1[i]) ++j;
+    if (j < n2 && leaf2[j] == leaf1[i] && info2[j] == info1[i]) {
+      const float v = smin(info2[j], info1[i]);
+      overlap_information += v;
+      acc64 += (double)v;
+    }
+  }
+  if (sum_f64) *sum_f64 = acc64;
+  return overlap_information;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

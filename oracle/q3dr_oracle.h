@@ -157,6 +157,17 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
                          const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,
                          uint32_t* kept_count, uint32_t* hit_count, float* total);
 
+/* ---- consumers of the voxel sets ----
+ * leaf / info: one viewpoint's voxel set, ascending leaf index.  observed: dense over the leaves, NaN = voxel not
+ * in ViewpointPath::observed_voxel_map.  Return value: the fp32 running sum in entry order (the reference sums in
+ * hash order); *sum_f64 (nullable): the same sum accumulated in fp64. */
+float orc_new_information(const int32_t* leaf, const float* info, size_t n, const float* observed, const float* weight,
+                          float factor, double* sum_f64);
+float orc_observed_add(const int32_t* leaf, const float* info, size_t n, float* observed, const float* weight,
+                       float factor, double* sum_f64);
+float orc_overlap_information(const int32_t* leaf1, const float* info1, size_t n1, const int32_t* leaf2,
+                              const float* info2, size_t n2, double* sum_f64);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -15,6 +15,7 @@
 
 #include "raycast2_kernels.cuh"
 #include "score_kernels.cuh"
+#include "setops_kernels.cuh"
 
 namespace {
 
@@ -165,6 +166,12 @@ struct q3dr_map {
   PinnedBuf<uint32_t> h_hit_count, h_pix;
   PinnedBuf<int32_t> h_leaf;
   PinnedBuf<float> h_rt;
+  // set consumers (setops_kernels.cuh)
+  DevBuf<float> d_dense;     // [n] scratch: one viewpoint's informations scattered over the leaves (NaN elsewhere)
+  DevBuf<float> d_set_out;   // per-viewpoint sums
+  DevBuf<uint32_t> d_set_idx;
+  DevBuf<double> d_set_part;
+  bool dense_ready = false;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
   cudaEvent_t ev_packed = nullptr;
@@ -189,6 +196,11 @@ namespace {
 void release_device(q3dr_map* m) {
   m->d_nodes.release();
   m->d_leaf_rec.release();
+  m->d_dense.release();
+  m->d_set_out.release();
+  m->d_set_idx.release();
+  m->d_set_part.release();
+  m->dense_ready = false;
   m->d_seg_u32.release();
   m->d_blk_u32.release();
   m->d_seg_f64.release();
@@ -1012,6 +1024,163 @@ int q3dr_raycast_unique(q3dr_map* m, const float K[4], const float Rt[12], uint3
   for (size_t i = 0; i < ne; ++i) {
     if (out[i].leaf != r.leaf[i]) return fail(Q3DR_ERR_INTERNAL, "kept pixel does not re-hit its voxel");
   }
+  return Q3DR_OK;
+}
+
+// ---- consumers of the voxel sets ----
+
+}  // extern "C"
+
+struct q3dr_observed {
+  q3dr_map* map = nullptr;
+  DevBuf<float> d;  // [n_leaves], NaN = absent
+};
+
+namespace {
+
+int fill_set_params(const q3dr_map* m, float factor, q3dr::SetParams* sp) {
+  if (m->last_n_vp == 0 && m->d_offsets.p == nullptr) return fail(Q3DR_ERR_INVALID_ARG, "no scoring result on this map yet");
+  sp->offsets = m->d_offsets.p;
+  sp->leaf = m->r_leaf.p;
+  sp->info = m->r_info.p;
+  sp->leaf_rec = m->d_leaf_rec.p;
+  sp->rec_stride = (uint32_t)q3dr::kLeafRecStride;
+  sp->factor = factor;
+  return Q3DR_OK;
+}
+
+int fill_nan(float* p, size_t n, cudaStream_t s) {
+  q3dr::fill_f32_kernel<<<256, 256, 0, s>>>(p, n, std::nanf(""));
+  Q3DR_CUDA(cudaGetLastError());
+  return Q3DR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int q3dr_observed_create(q3dr_map* m, q3dr_observed** out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  Q3DR_TRY(check_map(m));
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  q3dr_observed* o = new (std::nothrow) q3dr_observed;
+  if (!o) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  o->map = m;
+  int st = o->d.ensure(m->n);
+  if (st == Q3DR_OK) st = fill_nan(o->d.p, m->n, m->stream);
+  if (st == Q3DR_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) st = fail(Q3DR_ERR_CUDA, "sync failed");
+  if (st != Q3DR_OK) {
+    o->d.release();
+    delete o;
+    return st;
+  }
+  *out = o;
+  return Q3DR_OK;
+}
+
+int q3dr_observed_clear(q3dr_observed* o) {
+  if (!o) return fail(Q3DR_ERR_INVALID_ARG, "obs is NULL");
+  Q3DR_CUDA(cudaSetDevice(o->map->device));
+  Q3DR_TRY(fill_nan(o->d.p, o->map->n, o->map->stream));
+  Q3DR_CUDA(cudaStreamSynchronize(o->map->stream));
+  return Q3DR_OK;
+}
+
+int q3dr_observed_destroy(q3dr_observed* o) {
+  if (!o) return Q3DR_OK;
+  cudaSetDevice(o->map->device);
+  o->d.release();
+  delete o;
+  return Q3DR_OK;
+}
+
+int q3dr_observed_download(const q3dr_observed* o, float* out) {
+  if (!o || !out) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_CUDA(cudaSetDevice(o->map->device));
+  Q3DR_CUDA(cudaMemcpy(out, o->d.p, o->map->n * sizeof(float), cudaMemcpyDeviceToHost));
+  return Q3DR_OK;
+}
+
+int q3dr_new_information(q3dr_map* m, const q3dr_observed* o, float factor, const uint32_t* viewpoints, size_t n,
+                         float* out) {
+  Q3DR_TRY(check_map(m));
+  if (!o || (!out && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (o->map != m) return fail(Q3DR_ERR_INVALID_ARG, "observed map belongs to another occupancy map");
+  if (n == 0) return Q3DR_OK;
+  if (n > m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "more viewpoints than the last result holds");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, factor, &sp));
+  Q3DR_TRY(m->d_set_out.ensure(n));
+  const uint32_t* d_idx = nullptr;
+  if (viewpoints) {
+    for (size_t i = 0; i < n; ++i) {
+      if (viewpoints[i] >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+    }
+    Q3DR_TRY(m->d_set_idx.ensure(n));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_set_idx.p, viewpoints, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    d_idx = m->d_set_idx.p;
+  }
+  q3dr::new_information_kernel<<<(unsigned)n, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, d_idx, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_set_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+int q3dr_observed_add_viewpoint(q3dr_map* m, q3dr_observed* o, float factor, uint32_t viewpoint, float* new_information) {
+  Q3DR_TRY(check_map(m));
+  if (!o) return fail(Q3DR_ERR_INVALID_ARG, "obs is NULL");
+  if (o->map != m) return fail(Q3DR_ERR_INVALID_ARG, "observed map belongs to another occupancy map");
+  if (viewpoint >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, factor, &sp));
+  const unsigned grid = 64;
+  Q3DR_TRY(m->d_set_part.ensure(grid));
+  Q3DR_TRY(m->d_set_out.ensure(1));
+  q3dr::observed_add_kernel<<<grid, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, viewpoint, m->d_set_part.p);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::sum_parts_kernel<<<1, 32, 0, s>>>(m->d_set_part.p, grid, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  float v = 0.f;
+  Q3DR_CUDA(cudaMemcpyAsync(&v, m->d_set_out.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (new_information) *new_information = v;
+  return Q3DR_OK;
+}
+
+int q3dr_overlap_information(q3dr_map* m, uint32_t ref, const uint32_t* others, size_t n, float* out) {
+  Q3DR_TRY(check_map(m));
+  if ((!others || !out) && n) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (ref >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  for (size_t i = 0; i < n; ++i) {
+    if (others[i] >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  }
+  if (n == 0) return Q3DR_OK;
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, 1.0f, &sp));
+  if (!m->dense_ready || m->d_dense.cap < m->n) {
+    Q3DR_TRY(m->d_dense.ensure(m->n));
+    Q3DR_TRY(fill_nan(m->d_dense.p, m->n, s));
+    m->dense_ready = true;
+  }
+  Q3DR_TRY(m->d_set_idx.ensure(n));
+  Q3DR_TRY(m->d_set_out.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_set_idx.p, others, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  q3dr::scatter_set_kernel<<<64, 256, 0, s>>>(sp, ref, m->d_dense.p, 0);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::overlap_information_kernel<<<(unsigned)n, q3dr::kSetThreads, 0, s>>>(sp, m->d_dense.p, m->d_set_idx.p, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::scatter_set_kernel<<<64, 256, 0, s>>>(sp, ref, m->d_dense.p, 1);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_set_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
   return Q3DR_OK;
 }
 

@@ -142,6 +142,13 @@ def load_library() -> C.CDLL:
         [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [vp, C.c_size_t, C.POINTER(ScoreOpts), vp, C.POINTER(_Result)]
     )
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
+    L.q3dr_observed_create.argtypes = [vp, C.POINTER(vp)]
+    L.q3dr_observed_clear.argtypes = [vp]
+    L.q3dr_observed_destroy.argtypes = [vp]
+    L.q3dr_observed_download.argtypes = [vp, fp]
+    L.q3dr_new_information.argtypes = [vp, vp, C.c_float, u32p, C.c_size_t, fp]
+    L.q3dr_observed_add_viewpoint.argtypes = [vp, vp, C.c_float, C.c_uint32, fp]
+    L.q3dr_overlap_information.argtypes = [vp, C.c_uint32, u32p, C.c_size_t, fp]
     for name in dir(L):
         pass
     _lib = L
@@ -380,3 +387,61 @@ class OccupancyMap:
         r = _Result()
         _check(load_library().q3dr_result_to_host(self._h, C.byref(r)))
         return ScoreResult(r, copy=copy)
+
+
+class ObservedVoxels:
+    """One ViewpointPath::observed_voxel_map on the device (q3dr_observed): accumulated information per voxel.
+
+    All methods refer to the viewpoints of the LAST scoring call on `gmap` (its result stays resident in HBM)."""
+
+    def __init__(self, gmap: "OccupancyMap"):
+        self.map = gmap
+        h = C.c_void_p()
+        _check(load_library().q3dr_observed_create(gmap._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().q3dr_observed_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        _check(load_library().q3dr_observed_clear(self._h))
+
+    def download(self) -> np.ndarray:
+        out = np.empty(int(self.map.info().n_leaves), dtype=np.float32)
+        _check(load_library().q3dr_observed_download(self._h, _fp(out)))
+        return out
+
+    def new_information(self, factor: float, viewpoints=None, n: Optional[int] = None) -> np.ndarray:
+        """computeNewInformation for the given viewpoints (None: the first n of the result)."""
+        if viewpoints is None:
+            assert n is not None
+            idx = None
+        else:
+            idx = np.ascontiguousarray(viewpoints, dtype=np.uint32)
+            n = len(idx)
+        out = np.empty(n, dtype=np.float32)
+        _check(load_library().q3dr_new_information(
+            self.map._h, self._h, float(factor), None if idx is None else idx.ctypes.data_as(C.POINTER(C.c_uint32)), n, _fp(out)))
+        return out
+
+    def add_viewpoint(self, factor: float, viewpoint: int) -> float:
+        """addObservedVoxelsToViewpointPath; returns the novel information."""
+        v = C.c_float(0)
+        _check(load_library().q3dr_observed_add_viewpoint(self.map._h, self._h, float(factor), int(viewpoint), C.byref(v)))
+        return float(v.value)
+
+
+def overlap_information(gmap: "OccupancyMap", ref: int, others) -> np.ndarray:
+    """compute_overlap_information_lambda of each viewpoint in `others` (set 1) against `ref` (set 2)."""
+    idx = np.ascontiguousarray(others, dtype=np.uint32)
+    out = np.empty(len(idx), dtype=np.float32)
+    _check(load_library().q3dr_overlap_information(gmap._h, int(ref), idx.ctypes.data_as(C.POINTER(C.c_uint32)), len(idx), _fp(out)))
+    return out
