@@ -228,6 +228,26 @@ int q3dr_observed_add_viewpoint(q3dr_map* map, q3dr_observed* obs, float viewpoi
  * occupied_tree.h:73-79) a voxel counts only if it carries bit-identical information in both sets. */
 int q3dr_overlap_information(q3dr_map* map, uint32_t ref, const uint32_t* others, size_t n, float* out);
 
+/* ---- box-vs-map overlap queries ---- */
+
+/* bvh::Tree::intersects(bbox) (bvh.h:544-554,911-939) for n boxes (n x 6: min xyz, max xyz): per box the leaves
+ * whose box overlaps it (touching counts, geometry.h:277-285), ascending leaf index = the reference's visiting
+ * order.  CSR arrays are host memory owned by the map, valid until the next overlap call on it. */
+typedef struct q3dr_overlap_result {
+  uint64_t n_boxes;
+  uint64_t n_entries;
+  const uint64_t* offsets; /* n_boxes + 1 */
+  const int32_t* leaf;
+} q3dr_overlap_result;
+
+int q3dr_overlap_boxes(q3dr_map* map, const float* boxes, size_t n, q3dr_overlap_result* result);
+
+/* ViewpointPlannerData::isValidObjectPosition (viewpoint_planner_data.cpp:209-235) for n positions (n x 3), without
+ * the no-fly-zone polygons (test those on the host first).  object_bbox: the drone's box relative to its position;
+ * bvh_bbox: ViewpointPlannerData::bvh_bbox_.  valid[i] = 1 / 0. */
+int q3dr_valid_object_positions(q3dr_map* map, const float* positions, size_t n, const float object_bbox[6],
+                                const float bvh_bbox[6], float obstacle_free_height, uint8_t* valid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,10 @@ def lib():
     L.orc_score_batch.argtypes = [
         C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
     ]
+    L.orc_overlap_box.restype = C.c_size_t
+    L.orc_overlap_box.argtypes = [C.c_void_p, fp, C.c_size_t, i32p]
+    L.orc_valid_object_position.restype = C.c_int
+    L.orc_valid_object_position.argtypes = [C.c_void_p, fp, fp, fp, C.c_float]
     dp = C.POINTER(C.c_double)
     L.orc_new_information.restype = C.c_float
     L.orc_new_information.argtypes = [i32p, fp, C.c_size_t, fp, fp, C.c_float, dp]
@@ -217,6 +221,19 @@ class OracleTree:
         root = C.c_int32(0)
         lib().orc_tree_export_nodes(self._h, _f(boxes), _i(left), _i(right), _i(leaf), C.byref(root))
         return boxes, left, right, leaf, int(root.value)
+
+    def overlap_box(self, box) -> np.ndarray:
+        """Tree::intersects(bbox): overlapping leaves in the reference's visiting order."""
+        b = _f32(box, (6,))
+        n = lib().orc_overlap_box(self._h, _f(b), 0, None)
+        out = np.empty(n, dtype=np.int32)
+        if n:
+            lib().orc_overlap_box(self._h, _f(b), n, _i(out))
+        return out
+
+    def valid_object_position(self, position, object_bbox, bvh_bbox, obstacle_free_height) -> bool:
+        return bool(lib().orc_valid_object_position(self._h, _f(_f32(position, (3,))), _f(_f32(object_bbox, (6,))),
+                                                    _f(_f32(bvh_bbox, (6,))), float(obstacle_free_height)))
 
     def score_viewpoint(self, weights, normals, K, width, Rt, window=None, height=None, opts: Optional[ScoreOpts] = None):
         """getRaycastHitVoxelsWithInformationScore for one viewpoint (sorted by leaf index)."""

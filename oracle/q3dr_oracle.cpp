@@ -618,6 +618,76 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
   return (uint64_t)n_vp * width * height;
 }
 
+// ---- box-vs-map overlap queries ----
+
+namespace {
+// geometry.h:277-285 BoundingBox3D::intersects(other)
+inline bool boxIntersectsBox(const Box& a, const Box& other) {
+  for (int i = 0; i < 3; ++i) {
+    if (a.mx[i] < other.mn[i]) return false;
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (other.mx[i] < a.mn[i]) return false;
+  }
+  return true;
+}
+
+// bvh.h:911-939 intersectsRecursive(bbox, node, depth, results)
+void bboxRecursive(const orc_tree* t, const Box& bbox, int32_t cur, std::vector<int32_t>* results) {
+  const Node& n = t->nodes[cur];
+  if (!boxIntersectsBox(n.box, bbox)) return;
+  if (n.left < 0 && n.right < 0) {
+    results->push_back(n.leaf);
+    return;
+  }
+  if (n.left >= 0) bboxRecursive(t, bbox, n.left, results);
+  if (n.right >= 0) bboxRecursive(t, bbox, n.right, results);
+}
+}  // namespace
+
+// bvh.h:544-554 Tree::intersects(bbox): input leaf indices in the reference's visiting order.  Returns the count;
+// writes at most cap of them.
+size_t orc_overlap_box(const orc_tree* t, const float box[6], size_t cap, int32_t* out_leaf) {
+  Box b;
+  for (int i = 0; i < 3; ++i) {
+    b.mn[i] = box[i];
+    b.mx[i] = box[3 + i];
+  }
+  std::vector<int32_t> res;
+  bboxRecursive(t, b, t->root, &res);
+  for (size_t i = 0; i < res.size() && i < cap; ++i) out_leaf[i] = res[i];
+  return res.size();
+}
+
+// viewpoint_planner_data.cpp:209-235 isValidObjectPosition without the no-fly zones
+int orc_valid_object_position(const orc_tree* t, const float position[3], const float object_bbox[6],
+                              const float bvh_bbox[6], float obstacle_free_height) {
+  const float* p = position;
+  if (p[2] >= obstacle_free_height) {
+    // geometry.h:240-243 isInside
+    return p[0] >= bvh_bbox[0] && p[1] >= bvh_bbox[1] && p[2] >= bvh_bbox[2] && p[0] <= bvh_bbox[3] &&
+           p[1] <= bvh_bbox[4] && p[2] <= bvh_bbox[5];
+  }
+  const Box& root = t->nodes[t->root].box;
+  const bool inside_root = p[0] >= root.mn[0] && p[1] >= root.mn[1] && p[2] >= root.mn[2] && p[0] <= root.mx[0] &&
+                           p[1] <= root.mx[1] && p[2] <= root.mx[2];
+  if (!inside_root) return 0;
+  Box c;  // object_bbox + position (geometry.h:179-181)
+  for (int i = 0; i < 3; ++i) {
+    c.mn[i] = object_bbox[i] + p[i];
+    c.mx[i] = object_bbox[3 + i] + p[i];
+  }
+  if (c.mx[2] >= obstacle_free_height) {
+    // Vector3 cropped_maximum = object_bbox.getMaximum(); cropped_maximum(2) = obstacle_free_height  (sic: un-centred)
+    c.mx[0] = object_bbox[3];
+    c.mx[1] = object_bbox[4];
+    c.mx[2] = obstacle_free_height;
+  }
+  std::vector<int32_t> res;
+  bboxRecursive(t, c, t->root, &res);
+  return res.empty() ? 1 : 0;
+}
+
 // ---- consumers of the voxel sets (path search) ----
 
 // ViewpointPlanner::computeNewInformation (viewpoint_planner_scoring.cpp:124-147).  observed: dense over the

@@ -157,6 +157,13 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
                          const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,
                          uint32_t* kept_count, uint32_t* hit_count, float* total);
 
+/* ---- box-vs-map overlap queries ---- */
+/* Tree::intersects(bbox) (bvh.h:544-554,911-939): input indices of the overlapping leaves in visiting order. */
+size_t orc_overlap_box(const orc_tree* t, const float box[6], size_t cap, int32_t* out_leaf);
+/* ViewpointPlannerData::isValidObjectPosition (viewpoint_planner_data.cpp:209-235), no-fly zones excluded. */
+int orc_valid_object_position(const orc_tree* t, const float position[3], const float object_bbox[6],
+                              const float bvh_bbox[6], float obstacle_free_height);
+
 /* ---- consumers of the voxel sets ----
  * leaf / info: one viewpoint's voxel set, ascending leaf index.  observed: dense over the leaves, NaN = voxel not
  * in ViewpointPath::observed_voxel_map.  Return value: the fp32 running sum in entry order (the reference sums in

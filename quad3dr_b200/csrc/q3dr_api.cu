@@ -16,6 +16,9 @@
 #include "raycast2_kernels.cuh"
 #include "score_kernels.cuh"
 #include "setops_kernels.cuh"
+#include "overlap_kernels.cuh"
+
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 namespace {
 
@@ -127,6 +130,7 @@ struct q3dr_map {
   size_t n = 0;
   uint32_t ref_depth = 0;
   bool bounded = false;  // all box coordinates finite and below 1e18 in magnitude
+  float root_box[6] = {0, 0, 0, 0, 0, 0};  // union of the leaf boxes = the reference root node's bounding box
   // host copies (kept for q3dr_map_reset)
   std::vector<float> h_boxes, h_weight, h_normal;
   std::vector<uint8_t> h_depth;
@@ -172,6 +176,14 @@ struct q3dr_map {
   DevBuf<uint32_t> d_set_idx;
   DevBuf<double> d_set_part;
   bool dense_ready = false;
+  // overlap queries (overlap_kernels.cuh)
+  DevBuf<float> d_q_boxes;
+  DevBuf<uint32_t> d_q_counts;
+  DevBuf<uint64_t> d_q_offsets;
+  DevBuf<int32_t> d_q_leaf, d_q_sorted;
+  DevBuf<uint8_t> d_q_tmp, d_q_valid;
+  std::vector<uint64_t> h_q_offsets;
+  std::vector<int32_t> h_q_leaf;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
   cudaEvent_t ev_packed = nullptr;
@@ -196,6 +208,13 @@ namespace {
 void release_device(q3dr_map* m) {
   m->d_nodes.release();
   m->d_leaf_rec.release();
+  m->d_q_boxes.release();
+  m->d_q_counts.release();
+  m->d_q_offsets.release();
+  m->d_q_leaf.release();
+  m->d_q_sorted.release();
+  m->d_q_tmp.release();
+  m->d_q_valid.release();
   m->d_dense.release();
   m->d_set_out.release();
   m->d_set_idx.release();
@@ -722,6 +741,16 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
     for (size_t i = 0; i < 6 * n; ++i) {
       if (!(std::fabs(boxes[i]) < 1e18f)) m->bounded = false;
     }
+    for (int a = 0; a < 3; ++a) {
+      m->root_box[a] = FLT_MAX;
+      m->root_box[3 + a] = -FLT_MAX;
+    }
+    for (size_t k = 0; k < n; ++k) {
+      for (int a = 0; a < 3; ++a) {
+        m->root_box[a] = std::min(m->root_box[a], boxes[6 * k + a]);
+        m->root_box[3 + a] = std::max(m->root_box[3 + a], boxes[6 * k + 3 + a]);
+      }
+    }
     if (weights) {
       m->h_weight.assign(weights, weights + n);
     } else {
@@ -1180,6 +1209,87 @@ int q3dr_overlap_information(q3dr_map* m, uint32_t ref, const uint32_t* others, 
   q3dr::scatter_set_kernel<<<64, 256, 0, s>>>(sp, ref, m->d_dense.p, 1);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_set_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+// ---- box-vs-map overlap queries ----
+
+int q3dr_overlap_boxes(q3dr_map* m, const float* boxes, size_t n, q3dr_overlap_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!result || (!boxes && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many boxes for one call");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  m->h_q_offsets.assign(n + 1, 0);
+  m->h_q_leaf.clear();
+  if (n) {
+    Q3DR_TRY(m->d_q_boxes.ensure(6 * n));
+    Q3DR_TRY(m->d_q_counts.ensure(n));
+    Q3DR_TRY(m->d_q_offsets.ensure(n + 1));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_q_boxes.p, boxes, 6 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    const unsigned grid = (unsigned)((n + q3dr::kOverlapThreads - 1) / q3dr::kOverlapThreads);
+    q3dr::overlap_boxes_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n,
+                                                                     m->d_q_counts.p, nullptr, nullptr);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaMemsetAsync(m->d_q_offsets.p, 0, sizeof(uint64_t), s));
+    for (size_t v0 = 0; v0 < n; v0 += q3dr::kMaxChunkViewpoints) {  // csr_offsets_kernel continues from offsets[v0]
+      const size_t nb = std::min<size_t>(q3dr::kMaxChunkViewpoints, n - v0);
+      q3dr::csr_offsets_kernel<<<1, q3dr::kSegThreads, 0, s>>>(m->d_q_counts.p + v0, (uint32_t)nb, m->d_q_offsets.p + v0);
+      Q3DR_CUDA(cudaGetLastError());
+    }
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_q_offsets.data(), m->d_q_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaStreamSynchronize(s));
+    const uint64_t ne = m->h_q_offsets[n];
+    if (ne >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "overlap result too large for one call");
+    if (ne) {
+      Q3DR_TRY(m->d_q_leaf.ensure(ne));
+      Q3DR_TRY(m->d_q_sorted.ensure(ne));
+      q3dr::overlap_boxes_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n,
+                                                                       m->d_q_counts.p, m->d_q_offsets.p, m->d_q_leaf.p);
+      Q3DR_CUDA(cudaGetLastError());
+      // ascending leaf index inside each box's list = the reference's left-to-right visiting order
+      size_t tmp_bytes = 0;
+      Q3DR_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, m->d_q_leaf.p, m->d_q_sorted.p, (int)ne, (int)n,
+                                                        m->d_q_offsets.p, m->d_q_offsets.p + 1, 0, 32, s));
+      Q3DR_TRY(m->d_q_tmp.ensure(tmp_bytes));
+      Q3DR_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(m->d_q_tmp.p, tmp_bytes, m->d_q_leaf.p, m->d_q_sorted.p, (int)ne, (int)n,
+                                                        m->d_q_offsets.p, m->d_q_offsets.p + 1, 0, 32, s));
+      m->h_q_leaf.resize(ne);
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_q_leaf.data(), m->d_q_sorted.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      Q3DR_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  result->n_boxes = n;
+  result->n_entries = m->h_q_offsets[n];
+  result->offsets = m->h_q_offsets.data();
+  result->leaf = m->h_q_leaf.data();
+  return Q3DR_OK;
+}
+
+int q3dr_valid_object_positions(q3dr_map* m, const float* positions, size_t n, const float object_bbox[6],
+                                const float bvh_bbox[6], float obstacle_free_height, uint8_t* valid) {
+  Q3DR_TRY(check_map(m));
+  if (!object_bbox || !bvh_bbox || ((!positions || !valid) && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n == 0) return Q3DR_OK;
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many positions for one call");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::ValidParams vp;
+  for (int i = 0; i < 6; ++i) {
+    vp.obj[i] = object_bbox[i];
+    vp.bvh_bbox[i] = bvh_bbox[i];
+    vp.root_box[i] = m->root_box[i];
+  }
+  vp.obstacle_free_height = obstacle_free_height;
+  Q3DR_TRY(m->d_q_boxes.ensure(3 * n));
+  Q3DR_TRY(m->d_q_valid.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_q_boxes.p, positions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  const unsigned grid = (unsigned)((n + q3dr::kOverlapThreads - 1) / q3dr::kOverlapThreads);
+  q3dr::valid_positions_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n, vp,
+                                                                     m->d_q_valid.p);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(valid, m->d_q_valid.p, n, cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));
   return Q3DR_OK;
 }

@@ -58,6 +58,10 @@ class _Result(C.Structure):
     ]
 
 
+class _OverlapResult(C.Structure):
+    _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
+
+
 class MapInfo(C.Structure):
     _fields_ = [
         ("n_leaves", C.c_uint64),
@@ -142,6 +146,8 @@ def load_library() -> C.CDLL:
         [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [vp, C.c_size_t, C.POINTER(ScoreOpts), vp, C.POINTER(_Result)]
     )
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
+    L.q3dr_overlap_boxes.argtypes = [vp, fp, C.c_size_t, C.POINTER(_OverlapResult)]
+    L.q3dr_valid_object_positions.argtypes = [vp, fp, C.c_size_t, fp, fp, C.c_float, C.POINTER(C.c_uint8)]
     L.q3dr_observed_create.argtypes = [vp, C.POINTER(vp)]
     L.q3dr_observed_clear.argtypes = [vp]
     L.q3dr_observed_destroy.argtypes = [vp]
@@ -382,6 +388,27 @@ class OccupancyMap:
             )
         )
         return DeviceResult(r)
+
+    def overlap_boxes(self, boxes) -> Tuple[np.ndarray, np.ndarray]:
+        """bvh::Tree::intersects(bbox) for many boxes: CSR (offsets uint64 (n+1), leaf int32) of the overlapping
+        leaves, ascending leaf index per box."""
+        b = _f32(boxes).reshape(-1, 6)
+        r = _OverlapResult()
+        _check(load_library().q3dr_overlap_boxes(self._h, _fp(b), b.shape[0], C.byref(r)))
+        n, ne = int(r.n_boxes), int(r.n_entries)
+        off = np.ctypeslib.as_array(C.cast(r.offsets, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+        leaf = (np.ctypeslib.as_array(C.cast(r.leaf, C.POINTER(C.c_int32)), shape=(ne,)).copy()
+                if ne else np.empty(0, np.int32))
+        return off, leaf
+
+    def valid_object_positions(self, positions, object_bbox, bvh_bbox, obstacle_free_height: float) -> np.ndarray:
+        """ViewpointPlannerData::isValidObjectPosition for many positions (no-fly zones excluded)."""
+        p = _f32(positions).reshape(-1, 3)
+        out = np.empty(p.shape[0], dtype=np.uint8)
+        _check(load_library().q3dr_valid_object_positions(
+            self._h, _fp(p), p.shape[0], _fp(_f32(object_bbox, (6,))), _fp(_f32(bvh_bbox, (6,))),
+            float(obstacle_free_height), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out.astype(bool)
 
     def result_to_host(self, copy: bool = True) -> ScoreResult:
         r = _Result()
