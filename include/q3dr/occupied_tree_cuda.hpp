@@ -16,6 +16,10 @@
 //                                            <- ViewpointPlanner::getRaycastHitVoxelsWithInformationScore
 //                                               viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:89-148
 //   q3dr::VoxelWithInformation / VoxelWithInformationSet  <- planner/occupied_tree.h:62-92
+//   ...::intersects(bbox) / isValidObjectPositionBatch    <- bvh.h:544-554 ; viewpoint_planner_data.cpp:209-235
+//   q3dr::ObservedVoxelMapCuda<NodeT>        <- ViewpointPath::observed_voxel_map + computeNewInformation /
+//                                               addObservedVoxelsToViewpointPath / the stereo overlap sum
+//                                               viewpoint_planner_scoring.cpp:124-147, viewpoint_planner_path.cpp:203-233,838-848
 //
 // Matrices are taken as templates that only need operator()(row, col): Eigen::Matrix4f / Matrix<float,3,4> in the
 // reference tree, any small POD matrix elsewhere.  No Eigen, Boost or CUDA headers are needed to include this file.
@@ -143,6 +147,7 @@ class OccupiedTreeCuda {
       depth[k] = leaves[k].depth;
       nodes_[k] = leaves[k].node;
     }
+    depth_ = depth;
     check(q3dr_map_create(boxes.data(), weights.data(), normals.data(), depth.data(), n, cuda_gpu_id, &map_));
   }
 
@@ -161,6 +166,7 @@ class OccupiedTreeCuda {
     if (map_ != nullptr) q3dr_map_destroy(map_);
     map_ = nullptr;
     nodes_.clear();
+    depth_.clear();
   }
 
   /// ViewpointPlannerData::updateWeights*: NodeObject::weight changed on the host, refresh the device copy.
@@ -219,6 +225,43 @@ class OccupiedTreeCuda {
     return out;
   }
 
+  /// bvh::Tree::intersects(bbox) (bvh.h:544-554): the leaf nodes whose box overlaps [bbox_min, bbox_max], in the
+  /// reference's visiting order (left to right).
+  struct BBoxIntersectionResult {  // bvh.h:184-195
+    NodeT* node;
+    std::size_t depth;
+  };
+  std::vector<BBoxIntersectionResult> intersects(const float bbox_min[3], const float bbox_max[3]) {
+    float b[6] = {bbox_min[0], bbox_min[1], bbox_min[2], bbox_max[0], bbox_max[1], bbox_max[2]};
+    return intersectsBatch(b, 1)[0];
+  }
+  /// Many boxes at once (boxes: n x 6, min xyz then max xyz).
+  std::vector<std::vector<BBoxIntersectionResult> > intersectsBatch(const float* boxes, std::size_t n) {
+    requireMap();
+    q3dr_overlap_result r;
+    check(q3dr_overlap_boxes(map_, boxes, n, &r));
+    std::vector<std::vector<BBoxIntersectionResult> > out(n);
+    for (std::size_t i = 0; i < n; ++i) {
+      for (std::uint64_t e = r.offsets[i]; e < r.offsets[i + 1]; ++e) {
+        BBoxIntersectionResult br;
+        br.node = nodes_[static_cast<std::size_t>(r.leaf[e])];
+        br.depth = depth_.empty() ? 0 : depth_[static_cast<std::size_t>(r.leaf[e])];
+        out[i].push_back(br);
+      }
+    }
+    return out;
+  }
+
+  /// ViewpointPlannerData::isValidObjectPosition (viewpoint_planner_data.cpp:209-235) for a batch of positions
+  /// (n x 3); no-fly zones are the caller's business.  object_bbox / bvh_bbox: min xyz, max xyz.
+  std::vector<bool> isValidObjectPositionBatch(const float* positions, std::size_t n, const float object_bbox[6],
+                                               const float bvh_bbox[6], float obstacle_free_height) {
+    requireMap();
+    std::vector<std::uint8_t> v(n);
+    check(q3dr_valid_object_positions(map_, positions, n, object_bbox, bvh_bbox, obstacle_free_height, v.data()));
+    return std::vector<bool>(v.begin(), v.end());
+  }
+
   IntersectionResult convert(const q3dr_pixel_hit& h) const {
     IntersectionResult r;
     r.intersection[0] = h.intersection[0];
@@ -275,6 +318,7 @@ class OccupiedTreeCuda {
  private:
   q3dr_map* map_ = nullptr;
   std::vector<NodeT*> nodes_;  // leaf index -> host node
+  std::vector<std::uint32_t> depth_;  // leaf index -> depth in the host tree
 };
 
 /// viewpoint_planner::ViewpointRaycast with enable_cuda = true, plus the planner's scoring facade.
@@ -390,6 +434,50 @@ class ViewpointRaycastCuda {
   float min_range_;
   float max_range_;
   q3dr_score_opts opts_;
+};
+
+/// One ViewpointPath::observed_voxel_map on the device plus the information sums the path search evaluates against
+/// it (viewpoint_planner_scoring.cpp:124-147, viewpoint_planner_path.cpp:203-233,838-848).  Viewpoint indices refer to
+/// the last (batched) scoring call on the tree.
+template <typename NodeT>
+class ObservedVoxelMapCuda {
+ public:
+  typedef OccupiedTreeCuda<NodeT> TreeType;
+  explicit ObservedVoxelMapCuda(TreeType* tree, float viewpoint_information_factor = 1.0f / 3.0f)
+      : tree_(tree), factor_(viewpoint_information_factor), obs_(nullptr) {
+    check(q3dr_observed_create(tree_->handle(), &obs_));
+  }
+  ObservedVoxelMapCuda(const ObservedVoxelMapCuda&) = delete;
+  ObservedVoxelMapCuda& operator=(const ObservedVoxelMapCuda&) = delete;
+  ~ObservedVoxelMapCuda() { q3dr_observed_destroy(obs_); }
+
+  void clear() { check(q3dr_observed_clear(obs_)); }
+  /// computeNewInformation for the given viewpoints of the last result
+  std::vector<float> computeNewInformation(const std::vector<std::uint32_t>& viewpoints) const {
+    std::vector<float> out(viewpoints.size());
+    check(q3dr_new_information(tree_->handle(), obs_, factor_, viewpoints.data(), viewpoints.size(), out.data()));
+    return out;
+  }
+  /// addObservedVoxelsToViewpointPath; returns the novel information
+  float addObservedVoxels(std::uint32_t viewpoint) {
+    float v = 0;
+    check(q3dr_observed_add_viewpoint(tree_->handle(), obs_, factor_, viewpoint, &v));
+    return v;
+  }
+  /// compute_overlap_information_lambda(set1 = others[i], set2 = ref)
+  std::vector<float> computeOverlapInformation(std::uint32_t ref, const std::vector<std::uint32_t>& others) const {
+    std::vector<float> out(others.size());
+    check(q3dr_overlap_information(tree_->handle(), ref, others.data(), others.size(), out.data()));
+    return out;
+  }
+
+ private:
+  void check(int status) const {
+    if (status != Q3DR_OK) throw typename TreeType::CudaError(status, q3dr_last_error());
+  }
+  TreeType* tree_;
+  float factor_;
+  q3dr_observed* obs_;
 };
 
 }  // namespace q3dr

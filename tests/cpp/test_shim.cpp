@@ -306,6 +306,76 @@ int main(int argc, char** argv) {
     }
   }
 
+  // bbox queries (bvh.h:544-554) and isValidObjectPosition batches (viewpoint_planner_data.cpp:209-235)
+  {
+    const float qmin[3] = {-0.6f, 1.6f, 0.1f}, qmax[3] = {0.6f, 2.6f, 0.9f};
+    auto bb = tree.intersects(qmin, qmax);
+    const float q6[6] = {qmin[0], qmin[1], qmin[2], qmax[0], qmax[1], qmax[2]};
+    std::vector<int32_t> ref(n);
+    const size_t cnt = orc_overlap_box(oracle, q6, n, ref.data());
+    CHECK(cnt > 4 && bb.size() == cnt);
+    for (size_t i = 0; i < cnt; ++i) {
+      CHECK(bb[i].node == leaves[ref[i]].node);
+      CHECK(bb[i].depth == odepth[ref[i]]);
+    }
+    const float obj[6] = {-0.3f, -0.3f, -0.15f, 0.3f, 0.3f, 0.15f};
+    float root[6];
+    orc_tree_root_box(oracle, root);
+    std::vector<float> pos;
+    for (int i = 0; i < 400; ++i) {
+      pos.push_back(-5.5f + 0.027f * i);
+      pos.push_back(-4.0f + 0.019f * i);
+      pos.push_back(-0.2f + 0.011f * i);
+    }
+    auto valid = tree.isValidObjectPositionBatch(pos.data(), pos.size() / 3, obj, root, 3.5f);
+    size_t n_valid = 0;
+    for (size_t i = 0; i < valid.size(); ++i) {
+      CHECK((int)valid[i] == orc_valid_object_position(oracle, &pos[3 * i], obj, root, 3.5f));
+      n_valid += valid[i];
+    }
+    CHECK(n_valid > 20 && n_valid < valid.size() - 20);
+  }
+
+  // the path search's information sums on the device-resident batch result
+  {
+    std::vector<const mock::Viewpoint*> batch;
+    for (const mock::Viewpoint& vp : vps) batch.push_back(&vp);
+    auto scored = raycaster.getRaycastHitVoxelsWithInformationScoreBatch(batch, 0, cam.w, 0, cam.h, true);
+    std::unordered_map<const mock::Node*, int32_t> leaf_of;
+    for (std::size_t k = 0; k < n; ++k) leaf_of[leaves[k].node] = (int32_t)k;
+    q3dr::ObservedVoxelMapCuda<mock::Node> observed(&tree);
+    std::vector<float> obs_ref(n, std::nanf(""));
+    std::vector<uint32_t> all;
+    for (uint32_t v = 0; v < batch.size(); ++v) all.push_back(v);
+    for (uint32_t round = 0; round < 3; ++round) {
+      auto ni = observed.computeNewInformation(all);
+      uint32_t best = 0;
+      for (uint32_t v = 0; v < batch.size(); ++v) {
+        // the same voxel set as (leaf, info) arrays in ascending leaf order
+        std::vector<std::pair<int32_t, float> > set;
+        for (const auto& vi : scored[v].first) set.push_back(std::make_pair((int32_t)leaf_of[vi.voxel], vi.information));
+        std::sort(set.begin(), set.end());
+        std::vector<int32_t> sl;
+        std::vector<float> si;
+        for (const auto& e : set) { sl.push_back(e.first); si.push_back(e.second); }
+        double s64 = 0;
+        orc_new_information(sl.data(), si.data(), sl.size(), obs_ref.data(), weights.data(), 1.0f / 3.0f, &s64);
+        CHECK(std::fabs(ni[v] - s64) <= 1e-5 * std::fabs(s64) + 1e-30);
+        if (ni[v] > ni[best]) best = v;
+      }
+      std::vector<std::pair<int32_t, float> > set;
+      for (const auto& vi : scored[best].first) set.push_back(std::make_pair((int32_t)leaf_of[vi.voxel], vi.information));
+      std::sort(set.begin(), set.end());
+      std::vector<int32_t> sl;
+      std::vector<float> si;
+      for (const auto& e : set) { sl.push_back(e.first); si.push_back(e.second); }
+      double s64 = 0;
+      orc_observed_add(sl.data(), si.data(), sl.size(), obs_ref.data(), weights.data(), 1.0f / 3.0f, &s64);
+      const float added = observed.addObservedVoxels(best);
+      CHECK(std::fabs(added - s64) <= 1e-5 * std::fabs(s64) + 1e-30);
+    }
+  }
+
   // error convention: callers catch OccupiedTreeType::Error
   bool threw = false;
   try {

@@ -102,16 +102,16 @@ def test_reference_device_code_edge_semantics(sequential_oracle):
 
 
 def test_reference_upload_drops_its_last_batch():
-    """Documents the reference defect the harness works around (bvh.cu:40-75): without the tail patch the last
-    nodes in breadth-first order never reach the device."""
-    sc = scene("tiny")
-    o, d = _rays_of(sc, 64, 48, 6, config_id=51)
-    patched = R.RefCudaTree(sc.oracle, "ieee", patch_tail=True).intersect(o, d, 0.0, 60.0)
-    raw = R.RefCudaTree(sc.oracle, "ieee", patch_tail=False).intersect(o, d, 0.0, 60.0)
-    nn = sc.oracle.num_nodes
-    assert nn % max(nn // 20, 1) != 0  # 2N-1 is odd: there is always a partial last batch
-    same = raw["leaf"] == patched["leaf"]
-    assert same.mean() > 0.95  # only rays whose answer lies in the dropped 1..19 leaves can differ
+    """Documents the reference defect the harness works around (bvh.cu:40-75): nodes are uploaded in batches of
+    num_of_nodes / 20 and the last partial batch is never flushed.  A splitMedian tree has 2N - 1 nodes (odd), so
+    there is always a remainder of 1..19 nodes -- the deepest leaves in breadth-first order -- that stay uninitialised
+    on the device.  The unpatched tree is NOT run here: walking uninitialised child pointers is undefined."""
+    for name in ("tiny", "small", "1m"):
+        nn = scene(name).oracle.num_nodes
+        assert nn % 2 == 1
+        batch = nn // 20
+        dropped = nn - (nn // batch) * batch
+        assert 1 <= dropped <= 19
 
 
 @pytest.mark.parametrize("name,w,h,nvp", [("small", 160, 120, 4), ("1m", 320, 240, 2)])
