@@ -395,8 +395,14 @@ def run_ours(args):
             kept = (hr.offsets[1:n + 1] - hr.offsets[:n]).astype(np.int64)
             same_counts = bool(np.array_equal(kept, r["kept_count"].astype(np.int64)))
             rel = np.abs(hr.total[:n] - r["total"]) / np.maximum(np.abs(r["total"]), 1e-30)
+            from oracle import oracle_py as O
+
+            chk = O.set_checksums(hr.offsets[:n + 1], hr.leaf[:int(hr.offsets[n])], hr.first_pixel[:int(hr.offsets[n])])
             cb["parity_on_sample"] = {"viewpoints": int(n), "hit_list_sizes_equal": same_counts,
-                                      "max_rel_score_err": float(rel.max()) if n else 0.0}
+                                      "voxel_sets_and_first_pixels_equal": bool(np.array_equal(chk, r["set_checksum"])),
+                                      "max_rel_score_err": float(rel.max()) if n else 0.0,
+                                      "how": "per viewpoint: kept count, 64-bit checksum over (leaf, first pixel) of the "
+                                             "voxel set, total within 1e-5 relative of the oracle"}
             line["cpu_baseline"] = cb
         emit(line)
     if dist is not None:

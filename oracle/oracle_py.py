@@ -98,6 +98,11 @@ def lib():
     L.orc_observed_add.argtypes = [i32p, fp, C.c_size_t, fp, fp, C.c_float, dp]
     L.orc_overlap_information.restype = C.c_float
     L.orc_overlap_information.argtypes = [i32p, fp, C.c_size_t, i32p, fp, C.c_size_t, dp]
+    L.orc_score_batch_checksum.restype = C.c_uint64
+    L.orc_score_batch_checksum.argtypes = [
+        C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
+        C.POINTER(C.c_uint64),
+    ]
     L.orc_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -274,10 +279,12 @@ class OracleTree:
         kept = np.empty(n, dtype=np.uint32)
         hit = np.empty(n, dtype=np.uint32)
         tot = np.empty(n, dtype=np.float32)
-        rays = lib().orc_score_batch(
-            self._h, _f(w), _f(nr), _f(K), width, height, _f(Rt), n, C.byref(opts), threads, _u(kept), _u(hit), _f(tot)
+        chk = np.empty(n, dtype=np.uint64)
+        rays = lib().orc_score_batch_checksum(
+            self._h, _f(w), _f(nr), _f(K), width, height, _f(Rt), n, C.byref(opts), threads, _u(kept), _u(hit), _f(tot),
+            chk.ctypes.data_as(C.POINTER(C.c_uint64)),
         )
-        return dict(kept_count=kept, hit_count=hit, total=tot, rays=int(rays))
+        return dict(kept_count=kept, hit_count=hit, total=tot, rays=int(rays), set_checksum=chk)
 
 
 def voxel_information(box, weight, normal, cam, fx, width, opts: Optional[ScoreOpts] = None) -> float:
@@ -339,6 +346,21 @@ def overlap_information(leaf1, info1, leaf2, info2):
     s = C.c_double(0)
     v = lib().orc_overlap_information(_i(leaf1), _f(info1), len(leaf1), _i(leaf2), _f(info2), len(leaf2), C.byref(s))
     return float(v), float(s.value)
+
+
+def set_checksums(offsets, leaf, pixel) -> np.ndarray:
+    """The checksum of orc_score_batch_checksum for CSR voxel sets (numpy, vectorised)."""
+    leaf = np.asarray(leaf).astype(np.uint64)
+    pixel = np.asarray(pixel).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        z = (leaf << np.uint64(32)) | pixel
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        c = np.concatenate([[np.uint64(0)], np.cumsum(z, dtype=np.uint64)])
+        off = np.asarray(offsets).astype(np.int64)
+        return c[off[1:]] - c[off[:-1]]
 
 
 def max_threads() -> int:

@@ -599,23 +599,51 @@ size_t orc_score_viewpoint(const orc_tree* t, const float* weights, const float*
   return overflow ? (size_t)-1 : n_out;
 }
 
-uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* normals, const float K[4],
-                         uint32_t width, uint32_t height, const float* Rt, size_t n_vp,
-                         const orc_score_opts* opts, int threads, uint32_t* kept_count, uint32_t* hit_count,
-                         float* total) {
+// order-independent 64-bit checksum of a voxel set: sum over the entries of splitmix64(leaf << 32 | pixel)
+static inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+uint64_t orc_score_batch_checksum(const orc_tree* t, const float* weights, const float* normals, const float K[4],
+                                  uint32_t width, uint32_t height, const float* Rt, size_t n_vp,
+                                  const orc_score_opts* opts, int threads, uint32_t* kept_count, uint32_t* hit_count,
+                                  float* total, uint64_t* set_checksum) {
   if (threads < 1) threads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
   for (long v = 0; v < (long)n_vp; ++v) {
     uint32_t hc = 0;
     float tot = 0, tot32 = 0;
-    // all output arrays NULL => counting mode (no capacity check)
-    size_t kc = orc_score_viewpoint(t, weights, normals, K, width, Rt + 12 * v, 0, width, 0, height, opts, 0,
-                                    nullptr, nullptr, nullptr, nullptr, &hc, &tot, &tot32);
+    size_t kc;
+    if (set_checksum) {
+      const size_t cap = (size_t)width * height;
+      std::vector<int32_t> leaf(cap);
+      std::vector<uint32_t> pix(cap);
+      kc = orc_score_viewpoint(t, weights, normals, K, width, Rt + 12 * v, 0, width, 0, height, opts, cap, leaf.data(),
+                               nullptr, pix.data(), nullptr, &hc, &tot, &tot32);
+      uint64_t h = 0;
+      for (size_t i = 0; i < kc; ++i) h += mix64(((uint64_t)(uint32_t)leaf[i] << 32) | pix[i]);
+      set_checksum[v] = h;
+    } else {
+      // all output arrays NULL => counting mode (no capacity check)
+      kc = orc_score_viewpoint(t, weights, normals, K, width, Rt + 12 * v, 0, width, 0, height, opts, 0, nullptr,
+                               nullptr, nullptr, nullptr, &hc, &tot, &tot32);
+    }
     if (hit_count) hit_count[v] = hc;
     if (total) total[v] = tot;
     if (kept_count) kept_count[v] = (uint32_t)kc;
   }
   return (uint64_t)n_vp * width * height;
+}
+
+uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* normals, const float K[4],
+                         uint32_t width, uint32_t height, const float* Rt, size_t n_vp,
+                         const orc_score_opts* opts, int threads, uint32_t* kept_count, uint32_t* hit_count,
+                         float* total) {
+  return orc_score_batch_checksum(t, weights, normals, K, width, height, Rt, n_vp, opts, threads, kept_count, hit_count,
+                                  total, nullptr);
 }
 
 // ---- box-vs-map overlap queries ----

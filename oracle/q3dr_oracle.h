@@ -175,6 +175,13 @@ float orc_observed_add(const int32_t* leaf, const float* info, size_t n, float* 
 float orc_overlap_information(const int32_t* leaf1, const float* info1, size_t n1, const int32_t* leaf2,
                               const float* info2, size_t n2, double* sum_f64);
 
+/* orc_score_batch plus, per viewpoint, an order-independent checksum of its voxel set:
+ * sum over the kept entries of splitmix64((uint64)leaf << 32 | first_pixel)  (mod 2^64). */
+uint64_t orc_score_batch_checksum(const orc_tree* t, const float* weights, const float* normals,
+                                  const float K[4], uint32_t width, uint32_t height,
+                                  const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,
+                                  uint32_t* kept_count, uint32_t* hit_count, float* total, uint64_t* set_checksum);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus
