@@ -136,6 +136,10 @@ void q3dr_score_opts_default(q3dr_score_opts* opts);
  * depth (nullable): depth[k] = depth of that leaf in the reference tree. */
 int q3dr_splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* depth);
 
+/* out[k] = position of the k-th leaf (left to right) in the reference's all-node iterator (bvh.h:226-235) = the
+ * voxel index its viewpoint-graph serialisation stores (viewpoint_planner_serialization.h:88-105). */
+int q3dr_voxel_indices(size_t n, uint32_t* out);
+
 /* Quaternion (w, x, y, z) + translation -> row-major 3x4 [R|t], image-to-world. */
 int q3dr_pose_to_rt(const float quat_wxyz[4], const float trans[3], float rt_out[12]);
 

@@ -459,6 +459,26 @@ uint32_t splitmedian_leaf_depth(size_t n, size_t k) {
   return d;
 }
 
+void splitmedian_voxel_indices(size_t n, uint32_t* out) {
+  struct Range {
+    size_t b, e;
+  };
+  std::vector<Range> stack;
+  stack.push_back(Range{0, n});
+  uint32_t voxel_index = 0;
+  while (!stack.empty()) {
+    const Range r = stack.back();
+    stack.pop_back();
+    if (r.e - r.b == 1) out[r.b] = voxel_index;
+    ++voxel_index;
+    if (r.e - r.b > 1) {
+      const size_t m = r.b + (r.e - r.b) / 2;
+      stack.push_back(Range{r.b, m});  // left pushed first: the right subtree is visited first
+      stack.push_back(Range{m, r.e});
+    }
+  }
+}
+
 void splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* depth) {
   std::vector<float> cen[3];
   for (int a = 0; a < 3; ++a) cen[a].resize(n);

@@ -45,6 +45,11 @@ void build_flat_tree(const float* boxes, size_t n, int top_levels, FlatTree* out
 // depth (nullable): depth[k] = depth of that leaf in the reference tree.
 void splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32_t* depth);
 
+// Position of every leaf in the reference's all-node iterator (bvh.h:226-235: stack DFS pushing left then right,
+// i.e. root, right subtree, left subtree) -- the voxel index its serialisation stores
+// (viewpoint_planner_serialization.h:88-105).  Depends on n only: splitMedian halves ranges exactly.
+void splitmedian_voxel_indices(size_t n, uint32_t* out);
+
 // Depth of the k-th leaf (left to right) of a splitMedian tree over n leaves: ranges halve exactly.
 uint32_t splitmedian_leaf_depth(size_t n, size_t k);
 

@@ -632,6 +632,17 @@ int q3dr_splitmedian_order(const float* boxes, size_t n, uint32_t* order, uint32
   return Q3DR_OK;
 }
 
+int q3dr_voxel_indices(size_t n, uint32_t* out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  if (n == 0 || n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "leaf count out of range");
+  try {
+    q3dr::splitmedian_voxel_indices(n, out);
+  } catch (const std::bad_alloc&) {
+    return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  }
+  return Q3DR_OK;
+}
+
 // Eigen's QuaternionBase::toRotationMatrix in binary32, as Pose::getTransformationImageToWorld uses it.
 int q3dr_pose_to_rt(const float q[4], const float trans[3], float rt[12]) {
   if (!q || !trans || !rt) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");

@@ -126,6 +126,7 @@ def load_library() -> C.CDLL:
     L.q3dr_score_opts_default.restype = None
     L.q3dr_splitmedian_order.argtypes = [fp, C.c_size_t, u32p, u32p]
     L.q3dr_pose_to_rt.argtypes = [fp, fp, fp]
+    L.q3dr_voxel_indices.argtypes = [C.c_size_t, u32p]
     L.q3dr_debug_flat_tree.argtypes = [fp, C.c_size_t, C.c_int, C.POINTER(C.c_uint64), u32p, u32p, u32p]
     L.q3dr_map_create.argtypes = [fp, fp, fp, u32p, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.q3dr_map_update_weights.argtypes = [vp, fp]
@@ -205,6 +206,13 @@ def splitmedian_order(boxes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         )
     )
     return order, depth
+
+
+def voxel_indices(n: int) -> np.ndarray:
+    """Voxel index (position in the reference's all-node iterator) of every leaf, left to right."""
+    out = np.empty(n, dtype=np.uint32)
+    _check(load_library().q3dr_voxel_indices(n, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
 
 
 def pose_to_rt(quat_wxyz, trans) -> np.ndarray:

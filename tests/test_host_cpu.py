@@ -150,3 +150,15 @@ def test_synthetic_generators_are_deterministic():
     m = synth.map_tiny(unknown_interior=True)
     sides = m.boxes[:, 3] - m.boxes[:, 0]
     assert sides.max() > 0.25 and np.all((m.normal[sides > 0.25] == 0))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 1000, 13207])
+def test_voxel_indices_equal_the_reference_iterator_order(n):
+    rng = np.random.default_rng(n)
+    c = rng.uniform(-5, 5, size=(n, 3)).astype(np.float32)
+    boxes = np.concatenate([c - 0.1, c + 0.1], axis=1).astype(np.float32)
+    order, _ = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    t = O.OracleTree(boxes)
+    assert np.array_equal(t.dfs_order(), np.arange(n))
+    assert np.array_equal(E.voxel_indices(n), t.voxel_index())
