@@ -252,6 +252,29 @@ int q3dr_overlap_boxes(q3dr_map* map, const float* boxes, size_t n, q3dr_overlap
 int q3dr_valid_object_positions(q3dr_map* map, const float* positions, size_t n, const float object_bbox[6],
                                 const float bvh_bbox[6], float obstacle_free_height, uint8_t* valid);
 
+/* ---- occupancy octree -> BVH leaves, grid weights ---- */
+
+/* ViewpointPlannerData::generateBVHTree's per-leaf rule (viewpoint_planner_data.cpp:820-863) for n octree leaves in
+ * begin_tree() order: center (n x 3, it.getCoordinate()), size (it.getSize()), occupancy, observation_count.
+ * A leaf is dropped if it is free (occupancy <= occupancy_threshold, 0.51) and known (observation_count >=
+ * observation_threshold, 1), or if its box -- center -/+ size/2, constrained to bvh_bbox, cropped at
+ * obstacle_free_height -- is empty.  out_boxes (capacity n x 6) / out_source (capacity n, index of the octree leaf)
+ * receive the surviving leaves in input order; *n_out their number.  Runs on `device`; host buffers in and out. */
+int q3dr_octree_leaves_to_boxes(const float* center, const float* size, const float* occupancy,
+                                const uint32_t* observation_count, size_t n, const float bvh_bbox[6],
+                                float obstacle_free_height, float occupancy_threshold, uint32_t observation_threshold,
+                                int device, float* out_boxes, uint32_t* out_source, size_t* n_out);
+
+/* ViewpointPlannerData::updateWeights (viewpoint_planner_data.cpp:438-482,573-577) on the device: every grid cell
+ * (centre grid_origin + grid_increment * (ix, iy, iz), edge grid_increment) writes
+ * grid_weight[ix][iy][iz] * exp(-voxel_information_lambda * observation_count) into the leaves its box overlaps,
+ * cells in ix, iy, iz order (the last overlapping cell wins); other leaves keep their weight.
+ * observation_count: n_leaves, leaf order.  weights_out (nullable): the resulting n_leaves weights. */
+int q3dr_map_update_weights_from_grid(q3dr_map* map, const float grid_origin[3], float grid_increment,
+                                      const int32_t grid_dim[3], const float* grid_weight,
+                                      float voxel_information_lambda, const uint32_t* observation_count,
+                                      float* weights_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,9 @@ def lib():
     L.orc_score_batch.argtypes = [
         C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
     ]
+    L.orc_octree_leaf_to_box.restype = C.c_int
+    L.orc_octree_leaf_to_box.argtypes = [fp, C.c_float, C.c_float, C.c_uint32, fp, C.c_float, C.c_float, C.c_uint32, fp]
+    L.orc_update_weights_from_grid.argtypes = [fp, C.c_size_t, fp, C.c_float, i32p, fp, C.c_float, u32p, fp]
     L.orc_overlap_box.restype = C.c_size_t
     L.orc_overlap_box.argtypes = [C.c_void_p, fp, C.c_size_t, i32p]
     L.orc_valid_object_position.restype = C.c_int
@@ -317,6 +320,34 @@ def camera_rays(K, Rt, x0, x1, y0, y1):
 def set_sqnorm_sequential(on: bool) -> None:
     """Pin-test switch (see q3dr_oracle.h); always reset to False afterwards."""
     lib().orc_set_sqnorm_sequential(1 if on else 0)
+
+
+def octree_leaves_to_boxes(center, size, occupancy, count, bvh_bbox, obstacle_free_height, occ_thr=0.51, obs_thr=1):
+    """generateBVHTree's leaf rule, leaf by leaf: (boxes (k, 6), source index (k,))."""
+    center = _f32(center).reshape(-1, 3)
+    size = _f32(size)
+    occupancy = _f32(occupancy)
+    count = np.ascontiguousarray(count, dtype=np.uint32)
+    bb = _f32(bvh_bbox, (6,))
+    boxes, src = [], []
+    out = np.empty(6, dtype=np.float32)
+    for i in range(center.shape[0]):
+        c = np.ascontiguousarray(center[i])
+        if lib().orc_octree_leaf_to_box(_f(c), float(size[i]), float(occupancy[i]), int(count[i]), _f(bb),
+                                        float(obstacle_free_height), float(occ_thr), int(obs_thr), _f(out)):
+            boxes.append(out.copy())
+            src.append(i)
+    return (np.array(boxes, dtype=np.float32).reshape(-1, 6), np.array(src, dtype=np.uint32))
+
+
+def update_weights_from_grid(boxes, weight, grid_origin, grid_increment, grid_dim, grid_weight, lam, count):
+    """updateWeights' BVH writes (brute force over cells x leaves); returns the new weights."""
+    boxes = _f32(boxes).reshape(-1, 6)
+    w = _f32(weight).copy()
+    dim = np.ascontiguousarray(grid_dim, dtype=np.int32)
+    lib().orc_update_weights_from_grid(_f(boxes), boxes.shape[0], _f(_f32(grid_origin, (3,))), float(grid_increment), _i(dim),
+                                       _f(_f32(grid_weight)), float(lam), _u(np.ascontiguousarray(count, dtype=np.uint32)), _f(w))
+    return w
 
 
 def new_information(leaf, info, observed, weight, factor):

@@ -646,6 +646,83 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
                                   total, nullptr);
 }
 
+// ---- occupancy octree -> BVH leaves, grid weights ----
+
+// viewpoint_planner_data.cpp:820-863 for one octree leaf.  Returns 1 and the box if it becomes a BVH leaf.
+int orc_octree_leaf_to_box(const float center[3], float size, float occupancy, uint32_t observation_count,
+                           const float bvh_bbox[6], float obstacle_free_height, float occupancy_threshold,
+                           uint32_t observation_threshold, float box_out[6]) {
+  // occupancy_map.h:75-106
+  const bool is_occupied = occupancy > occupancy_threshold;
+  const bool is_free = !is_occupied;
+  const bool is_known = observation_count >= observation_threshold;
+  if (is_free && is_known) return 0;
+  // geometry.h:159-160 BoundingBox3D(center, size)
+  float mn[3], mx[3];
+  for (int i = 0; i < 3; ++i) {
+    mn[i] = center[i] - size / 2;
+    mx[i] = center[i] + size / 2;
+  }
+  // geometry.h:373-376 constrainTo
+  for (int i = 0; i < 3; ++i) {
+    mn[i] = std::max(mn[i], bvh_bbox[i]);
+    mx[i] = std::min(mx[i], bvh_bbox[3 + i]);
+  }
+  // geometry.h:175-177 isEmpty: (min >= max).any()
+  auto is_empty = [&]() { return mn[0] >= mx[0] || mn[1] >= mx[1] || mn[2] >= mx[2]; };
+  if (is_empty()) return 0;
+  if (mx[2] >= obstacle_free_height) {
+    mn[2] = std::min(obstacle_free_height, mn[2]);
+    mx[2] = obstacle_free_height;
+  }
+  if (is_empty()) return 0;
+  for (int i = 0; i < 3; ++i) {
+    box_out[i] = mn[i];
+    box_out[3 + i] = mx[i];
+  }
+  return 1;
+}
+
+// viewpoint_planner_data.cpp:438-482,573-577 updateWeights, BVH part: literally every cell in ix, iy, iz order,
+// every overlapping leaf (brute force over the leaves; test sizes only).
+void orc_update_weights_from_grid(const float* boxes, size_t n, const float grid_origin[3], float grid_increment,
+                                  const int32_t grid_dim[3], const float* grid_weight, float lambda,
+                                  const uint32_t* observation_count, float* weight /* in/out */) {
+  for (int ix = 0; ix < grid_dim[0]; ++ix) {
+    for (int iy = 0; iy < grid_dim[1]; ++iy) {
+      for (int iz = 0; iz < grid_dim[2]; ++iz) {
+        // getGridPosition: grid_origin_ + grid_increment_ * indices.cast<float>()
+        const float xyz[3] = {grid_origin[0] + grid_increment * (float)ix, grid_origin[1] + grid_increment * (float)iy,
+                              grid_origin[2] + grid_increment * (float)iz};
+        Box cell;
+        for (int a = 0; a < 3; ++a) {
+          cell.mn[a] = xyz[a] - grid_increment / 2;
+          cell.mx[a] = xyz[a] + grid_increment / 2;
+        }
+        const float w = grid_weight[((size_t)ix * grid_dim[1] + iy) * grid_dim[2] + iz];
+        for (size_t k = 0; k < n; ++k) {
+          Box leaf;
+          for (int a = 0; a < 3; ++a) {
+            leaf.mn[a] = boxes[6 * k + a];
+            leaf.mx[a] = boxes[6 * k + 3 + a];
+          }
+          bool hit = true;  // geometry.h:277-285, node box vs cell
+          for (int a = 0; a < 3; ++a) {
+            if (leaf.mx[a] < cell.mn[a]) hit = false;
+          }
+          for (int a = 0; a < 3; ++a) {
+            if (cell.mx[a] < leaf.mn[a]) hit = false;
+          }
+          if (hit) {
+            const float observation_count_factor = std::exp(-lambda * observation_count[k]);
+            weight[k] = w * observation_count_factor;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---- box-vs-map overlap queries ----
 
 namespace {

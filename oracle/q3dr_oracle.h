@@ -157,6 +157,16 @@ uint64_t orc_score_batch(const orc_tree* t, const float* weights, const float* n
                          const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,
                          uint32_t* kept_count, uint32_t* hit_count, float* total);
 
+/* ---- occupancy octree -> BVH leaves, grid weights ---- */
+/* generateBVHTree's rule for one octree leaf (viewpoint_planner_data.cpp:820-863). */
+int orc_octree_leaf_to_box(const float center[3], float size, float occupancy, uint32_t observation_count,
+                           const float bvh_bbox[6], float obstacle_free_height, float occupancy_threshold,
+                           uint32_t observation_threshold, float box_out[6]);
+/* updateWeights' writes into the BVH leaves (viewpoint_planner_data.cpp:438-482,573-577), brute force. */
+void orc_update_weights_from_grid(const float* boxes, size_t n, const float grid_origin[3], float grid_increment,
+                                  const int32_t grid_dim[3], const float* grid_weight, float lambda,
+                                  const uint32_t* observation_count, float* weight);
+
 /* ---- box-vs-map overlap queries ---- */
 /* Tree::intersects(bbox) (bvh.h:544-554,911-939): input indices of the overlapping leaves in visiting order. */
 size_t orc_overlap_box(const orc_tree* t, const float box[6], size_t cap, int32_t* out_leaf);

@@ -17,7 +17,9 @@
 #include "score_kernels.cuh"
 #include "setops_kernels.cuh"
 #include "overlap_kernels.cuh"
+#include "octree_kernels.cuh"
 
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 namespace {
@@ -1302,6 +1304,119 @@ int q3dr_valid_object_positions(q3dr_map* m, const float* positions, size_t n, c
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaMemcpyAsync(valid, m->d_q_valid.p, n, cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+// ---- occupancy octree -> BVH leaves, grid weights ----
+
+int q3dr_octree_leaves_to_boxes(const float* center, const float* size, const float* occupancy,
+                                const uint32_t* observation_count, size_t n, const float bvh_bbox[6],
+                                float obstacle_free_height, float occupancy_threshold, uint32_t observation_threshold,
+                                int device, float* out_boxes, uint32_t* out_source, size_t* n_out) {
+  if (!n_out) return fail(Q3DR_ERR_INVALID_ARG, "n_out is NULL");
+  *n_out = 0;
+  if (n == 0) return Q3DR_OK;
+  if (!center || !size || !occupancy || !observation_count || !bvh_bbox || !out_boxes || !out_source)
+    return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many octree leaves for one call");
+  int count = 0;
+  Q3DR_TRY(q3dr_device_count(&count));
+  if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  if (device < 0 || device >= count) return fail(Q3DR_ERR_INVALID_ARG, "device index out of range");
+  Q3DR_CUDA(cudaSetDevice(device));
+  DevBuf<float> d_center, d_size, d_occ, d_box, d_out_box;
+  DevBuf<uint32_t> d_cnt, d_pos, d_out_src, d_keep;
+  DevBuf<uint8_t> d_tmp;
+  struct Guard {
+    DevBuf<float>*a, *b, *c, *d, *e;
+    DevBuf<uint32_t>*f, *g, *h, *i;
+    DevBuf<uint8_t>* j;
+    ~Guard() {
+      a->release(); b->release(); c->release(); d->release(); e->release();
+      f->release(); g->release(); h->release(); i->release(); j->release();
+    }
+  } guard{&d_center, &d_size, &d_occ, &d_box, &d_out_box, &d_cnt, &d_pos, &d_out_src, &d_keep, &d_tmp};
+  Q3DR_TRY(d_center.ensure(3 * n));
+  Q3DR_TRY(d_size.ensure(n));
+  Q3DR_TRY(d_occ.ensure(n));
+  Q3DR_TRY(d_cnt.ensure(n));
+  Q3DR_TRY(d_keep.ensure(n));
+  Q3DR_TRY(d_box.ensure(6 * n));
+  Q3DR_TRY(d_pos.ensure(n + 1));
+  Q3DR_CUDA(cudaMemcpy(d_center.p, center, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_size.p, size, n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_occ.p, occupancy, n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_cnt.p, observation_count, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  q3dr::LeafRuleParams lp;
+  lp.center = d_center.p;
+  lp.size = d_size.p;
+  lp.occupancy = d_occ.p;
+  lp.observation_count = d_cnt.p;
+  lp.n = (uint32_t)n;
+  for (int i = 0; i < 6; ++i) lp.bvh_bbox[i] = bvh_bbox[i];
+  lp.obstacle_free_height = obstacle_free_height;
+  lp.occupancy_threshold = occupancy_threshold;
+  lp.observation_threshold = observation_threshold;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  q3dr::leaf_rule_kernel<<<grid, 256>>>(lp, d_keep.p, d_box.p);
+  Q3DR_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  Q3DR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_keep.p, d_pos.p, (int)n));
+  Q3DR_TRY(d_tmp.ensure(tmp_bytes));
+  Q3DR_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_keep.p, d_pos.p, (int)n));
+  uint32_t last_pos = 0, last_keep = 0;
+  Q3DR_CUDA(cudaMemcpy(&last_pos, d_pos.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  Q3DR_CUDA(cudaMemcpy(&last_keep, d_keep.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const size_t kept = (size_t)last_pos + last_keep;
+  if (kept) {
+    Q3DR_TRY(d_out_box.ensure(6 * kept));
+    Q3DR_TRY(d_out_src.ensure(kept));
+    q3dr::leaf_compact_kernel<<<grid, 256>>>(d_keep.p, d_pos.p, d_box.p, (uint32_t)n, d_out_box.p, d_out_src.p);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaMemcpy(out_boxes, d_out_box.p, 6 * kept * sizeof(float), cudaMemcpyDeviceToHost));
+    Q3DR_CUDA(cudaMemcpy(out_source, d_out_src.p, kept * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  *n_out = kept;
+  return Q3DR_OK;
+}
+
+int q3dr_map_update_weights_from_grid(q3dr_map* m, const float grid_origin[3], float grid_increment,
+                                      const int32_t grid_dim[3], const float* grid_weight,
+                                      float voxel_information_lambda, const uint32_t* observation_count,
+                                      float* weights_out) {
+  Q3DR_TRY(check_map(m));
+  if (!grid_origin || !grid_dim || !grid_weight || !observation_count) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (!(grid_increment > 0.0f) || grid_dim[0] <= 0 || grid_dim[1] <= 0 || grid_dim[2] <= 0)
+    return fail(Q3DR_ERR_INVALID_ARG, "bad grid");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t cells = (size_t)grid_dim[0] * grid_dim[1] * grid_dim[2];
+  DevBuf<float> d_gw, d_w;
+  DevBuf<uint32_t> d_cnt;
+  struct Guard {
+    DevBuf<float>*a, *b;
+    DevBuf<uint32_t>* c;
+    ~Guard() { a->release(); b->release(); c->release(); }
+  } guard{&d_gw, &d_w, &d_cnt};
+  Q3DR_TRY(d_gw.ensure(cells));
+  Q3DR_TRY(d_w.ensure(m->n));
+  Q3DR_TRY(d_cnt.ensure(m->n));
+  Q3DR_CUDA(cudaMemcpyAsync(d_gw.p, grid_weight, cells * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemcpyAsync(d_cnt.p, observation_count, m->n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  q3dr::GridParams g;
+  for (int i = 0; i < 3; ++i) {
+    g.origin[i] = grid_origin[i];
+    g.dim[i] = grid_dim[i];
+  }
+  g.increment = grid_increment;
+  g.lambda = voxel_information_lambda;
+  q3dr::grid_weights_kernel<<<(unsigned)((m->n + 255) / 256), 256, 0, s>>>(m->d_leaf_rec.p, (uint32_t)q3dr::kLeafRecStride,
+                                                                          (uint32_t)m->n, g, d_gw.p, d_cnt.p, d_w.p);
+  Q3DR_CUDA(cudaGetLastError());
+  // the host copy of the weights follows (q3dr_map_reset re-uploads from it)
+  Q3DR_CUDA(cudaMemcpyAsync(m->h_weight.data(), d_w.p, m->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (weights_out) std::memcpy(weights_out, m->h_weight.data(), m->n * sizeof(float));
   return Q3DR_OK;
 }
 

@@ -149,6 +149,9 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_overlap_boxes.argtypes = [vp, fp, C.c_size_t, C.POINTER(_OverlapResult)]
     L.q3dr_valid_object_positions.argtypes = [vp, fp, C.c_size_t, fp, fp, C.c_float, C.POINTER(C.c_uint8)]
+    L.q3dr_octree_leaves_to_boxes.argtypes = [fp, fp, fp, u32p, C.c_size_t, fp, C.c_float, C.c_float, C.c_uint32, C.c_int,
+                                              fp, u32p, C.POINTER(C.c_size_t)]
+    L.q3dr_map_update_weights_from_grid.argtypes = [vp, fp, C.c_float, C.POINTER(C.c_int32), fp, C.c_float, u32p, fp]
     L.q3dr_observed_create.argtypes = [vp, C.POINTER(vp)]
     L.q3dr_observed_clear.argtypes = [vp]
     L.q3dr_observed_destroy.argtypes = [vp]
@@ -206,6 +209,24 @@ def splitmedian_order(boxes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
         )
     )
     return order, depth
+
+
+def octree_leaves_to_boxes(center, size, occupancy, observation_count, bvh_bbox, obstacle_free_height: float,
+                           occupancy_threshold: float = 0.51, observation_threshold: int = 1, device: int = 0):
+    """generateBVHTree's leaf rule on the device: (boxes (k, 6), index of the source octree leaf (k,))."""
+    center = _f32(center).reshape(-1, 3)
+    n = center.shape[0]
+    size = _f32(size, (n,))
+    occupancy = _f32(occupancy, (n,))
+    cnt = np.ascontiguousarray(observation_count, dtype=np.uint32)
+    boxes = np.empty((n, 6), dtype=np.float32)
+    src = np.empty(n, dtype=np.uint32)
+    k = C.c_size_t(0)
+    _check(load_library().q3dr_octree_leaves_to_boxes(
+        _fp(center), _fp(size), _fp(occupancy), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), n, _fp(_f32(bvh_bbox, (6,))),
+        float(obstacle_free_height), float(occupancy_threshold), int(observation_threshold), int(device),
+        _fp(boxes), src.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(k)))
+    return boxes[:k.value].copy(), src[:k.value].copy()
 
 
 def voxel_indices(n: int) -> np.ndarray:
@@ -396,6 +417,21 @@ class OccupancyMap:
             )
         )
         return DeviceResult(r)
+
+    def update_weights_from_grid(self, grid_origin, grid_increment: float, grid_dim, grid_weight, lam: float,
+                                 observation_count) -> np.ndarray:
+        """ViewpointPlannerData::updateWeights' writes into the BVH leaves; returns the resulting weights."""
+        n = int(self.info().n_leaves)
+        dim = np.ascontiguousarray(grid_dim, dtype=np.int32)
+        gw = _f32(grid_weight).reshape(-1)
+        assert gw.size == int(dim[0]) * int(dim[1]) * int(dim[2])
+        cnt = np.ascontiguousarray(observation_count, dtype=np.uint32)
+        assert cnt.shape == (n,)
+        out = np.empty(n, dtype=np.float32)
+        _check(load_library().q3dr_map_update_weights_from_grid(
+            self._h, _fp(_f32(grid_origin, (3,))), float(grid_increment), dim.ctypes.data_as(C.POINTER(C.c_int32)), _fp(gw),
+            float(lam), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(out)))
+        return out
 
     def overlap_boxes(self, boxes) -> Tuple[np.ndarray, np.ndarray]:
         """bvh::Tree::intersects(bbox) for many boxes: CSR (offsets uint64 (n+1), leaf int32) of the overlapping
