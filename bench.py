@@ -58,15 +58,20 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def committed_traffic(workload: str):
-    """dram bytes per raycast launch from the committed ncu --set full capture, if any."""
+def committed_ncu(workload: str) -> dict:
+    """Figures of the committed ncu --set full capture of the raycast kernel (profiles/traffic.json), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
             t = json.load(f).get(workload)
-            return t["dram_bytes_per_launch"] if isinstance(t, dict) else t
+            return t if isinstance(t, dict) else {}
     except Exception:
-        return None
+        return {}
+
+
+def committed_traffic(workload: str):
+    """dram bytes per raycast launch from the committed capture, scaled to nothing: per launch of that capture."""
+    return committed_ncu(workload).get("dram_bytes_per_launch")
 
 
 class ClockSampler:
@@ -380,6 +385,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rays_per_launch, "launch_ms": launch_ms,
                 "launches_timed": raycast_launches,
                 "kernel_share_of_step": raycast_ms_max / max(dev_ms, 1e-9),
+                "note": "algorithmic bytes assume every ray walks a binary tree out of HBM (SURVEY.md 8d); the kernel walks a "
+                        "4-wide tree once per 64-ray packet out of L1/L2, so frac > 1 and the real limiter is instruction "
+                        "issue: see ncu (committed capture, profiles/)",
+                "ncu": {k: v for k, v in committed_ncu(args.workload).items() if k not in ("source",)},
             },
             "result_entries": int(n_entries),
         }
