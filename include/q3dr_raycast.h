@@ -275,6 +275,30 @@ int q3dr_map_update_weights_from_grid(q3dr_map* map, const float grid_origin[3],
                                       float voxel_information_lambda, const uint32_t* observation_count,
                                       float* weights_out);
 
+/* ---- one process, several GPUs: the map replicated in every GPU's HBM, the viewpoints of a
+ * call sharded in contiguous slices, one host thread per GPU, results left per GPU (no merge copy).  For one process
+ * per GPU (torchrun / MPI) use q3dr_map_* on each rank instead and gather with NCCL (quad3dr_b200/dist.py). ---- */
+typedef struct q3dr_multi q3dr_multi;
+
+typedef struct q3dr_multi_result {
+  uint32_t n_parts;                 /* = number of GPUs */
+  uint64_t n_viewpoints;
+  const uint64_t* first_viewpoint;  /* n_parts + 1: part g holds viewpoints [first[g], first[g+1]) of the call */
+  const q3dr_result* parts;         /* n_parts results with LOCAL viewpoint numbering, host memory owned by the maps */
+} q3dr_multi_result;
+
+/* devices: n_devices CUDA device indices, or NULL for devices 0 .. n_devices-1 (n_devices <= 0: all visible).
+ * The tree is flattened once and uploaded to every device. */
+int q3dr_multi_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                      const int* devices, int n_devices, q3dr_multi** out);
+int q3dr_multi_destroy(q3dr_multi* multi);
+int q3dr_multi_device_count(const q3dr_multi* multi);
+q3dr_map* q3dr_multi_map(q3dr_multi* multi, int i); /* the replica on the i-th device (for the single-GPU entry points) */
+int q3dr_multi_update_weights(q3dr_multi* multi, const float* weights);
+int q3dr_multi_score_viewpoints(q3dr_multi* multi, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                uint32_t y0, uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts,
+                                q3dr_multi_result* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,8 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "raycast2_kernels.cuh"
@@ -136,7 +138,7 @@ struct q3dr_map {
   // host copies (kept for q3dr_map_reset)
   std::vector<float> h_boxes, h_weight, h_normal;
   std::vector<uint8_t> h_depth;
-  q3dr::FlatTree tree;
+  std::shared_ptr<const q3dr::FlatTree> tree;  // shared between the per-GPU replicas of a q3dr_multi
   // device: the map
   DevBuf<float4> d_nodes;
   DevBuf<float4> d_leaf_rec;  // [n][4]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}, pad (64-byte records)
@@ -277,9 +279,9 @@ int configure_kernel2(q3dr_map* m) {
 int upload_map(q3dr_map* m) {
   Q3DR_CUDA(cudaSetDevice(m->device));
   const size_t n = m->n;
-  const size_t nn = m->tree.nodes.size();
+  const size_t nn = m->tree->nodes.size();
   Q3DR_TRY(m->d_nodes.ensure(nn * 8));
-  Q3DR_CUDA(cudaMemcpy(m->d_nodes.p, m->tree.nodes.data(), nn * sizeof(q3dr::Node4), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(m->d_nodes.p, m->tree->nodes.data(), nn * sizeof(q3dr::Node4), cudaMemcpyHostToDevice));
   {
     constexpr size_t R = q3dr::kLeafRecStride;
     std::vector<float4> rec(R * n, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -297,7 +299,7 @@ int upload_map(q3dr_map* m) {
   Q3DR_TRY(m->d_counter.ensure(4));
   Q3DR_CUDA(cudaMemset(m->d_counter.p, 0, 4 * sizeof(uint32_t)));
   Q3DR_TRY(m->h_scalar.ensure(8));
-  m->smem_bytes = (size_t)m->tree.top_nodes * sizeof(q3dr::Node4);
+  m->smem_bytes = (size_t)m->tree->top_nodes * sizeof(q3dr::Node4);
   Q3DR_TRY(configure_kernel<q3dr::kModeRays>(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModeScore>(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModePixels>(m));
@@ -374,7 +376,7 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
                          float max_range, q3dr::RaycastParams* p) {
   std::memset(p, 0, sizeof(*p));
   p->nodes = m->d_nodes.p;
-  p->n_top = m->tree.top_nodes;
+  p->n_top = m->tree->top_nodes;
   p->fx = K[0];
   p->fy = K[1];
   p->cx = K[2];
@@ -733,8 +735,11 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
   return Q3DR_OK;
 }
 
-int q3dr_map_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
-                    int device, q3dr_map** out) {
+}  // extern "C"
+
+namespace {
+int map_create_impl(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                    int device, std::shared_ptr<const q3dr::FlatTree> shared_tree, q3dr_map** out) {
   if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
   if (!boxes) return fail(Q3DR_ERR_INVALID_ARG, "boxes is NULL");
@@ -782,13 +787,19 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
       ref_depth = std::max(ref_depth, d);
     }
     m->ref_depth = ref_depth;
-    int top_levels = 4;
-    if (const char* e = std::getenv("Q3DR_TOP_LEVELS")) top_levels = std::max(1, std::min(6, atoi(e)));
-    q3dr::build_flat_tree(m->h_boxes.data(), n, top_levels, &m->tree);
-    if (m->tree.max_stack > (uint32_t)q3dr::kStackEntries) {
+    if (shared_tree) {
+      m->tree = shared_tree;
+    } else {
+      int top_levels = 4;
+      if (const char* e = std::getenv("Q3DR_TOP_LEVELS")) top_levels = std::max(1, std::min(6, atoi(e)));
+      std::shared_ptr<q3dr::FlatTree> t = std::make_shared<q3dr::FlatTree>();
+      q3dr::build_flat_tree(m->h_boxes.data(), n, top_levels, t.get());
+      m->tree = t;
+    }
+    if (m->tree->max_stack > (uint32_t)q3dr::kStackEntries) {
       st = fail(Q3DR_ERR_INTERNAL, "flattened tree too deep for the traversal stack");
     }
-    if (m->tree.nodes.size() >= (size_t)q3dr::kNodeIndexMask) st = fail(Q3DR_ERR_INVALID_ARG, "too many nodes");
+    if (m->tree->nodes.size() >= (size_t)q3dr::kNodeIndexMask) st = fail(Q3DR_ERR_INVALID_ARG, "too many nodes");
   } catch (const std::bad_alloc&) {
     st = fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
   }
@@ -818,6 +829,14 @@ int q3dr_map_create(const float* boxes, const float* weights, const float* norma
   *out = m;
   return Q3DR_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int q3dr_map_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                    int device, q3dr_map** out) {
+  return map_create_impl(boxes, weights, normals, depth, n, device, nullptr, out);
+}
 
 int q3dr_map_update_weights(q3dr_map* m, const float* weights) {
   Q3DR_TRY(check_map(m));
@@ -842,10 +861,10 @@ int q3dr_map_update_normals(q3dr_map* m, const float* normals) {
 int q3dr_map_get_info(const q3dr_map* m, q3dr_map_info* info) {
   if (!m || !info) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
   info->n_leaves = m->n;
-  info->n_nodes = m->tree.nodes.size();
-  info->tree_depth = m->tree.depth;
+  info->n_nodes = m->tree->nodes.size();
+  info->tree_depth = m->tree->depth;
   info->ref_depth = m->ref_depth;
-  info->node_bytes = m->tree.nodes.size() * sizeof(q3dr::Node4);
+  info->node_bytes = m->tree->nodes.size() * sizeof(q3dr::Node4);
   info->device_bytes = m->device_bytes();
   info->device = m->device;
   info->sm_count = m->sm_count;
@@ -943,7 +962,7 @@ int q3dr_intersect_rays(q3dr_map* m, const float* origins, const float* directio
   q3dr::RaycastParams rp;
   std::memset(&rp, 0, sizeof(rp));
   rp.nodes = m->d_nodes.p;
-  rp.n_top = m->tree.top_nodes;
+  rp.n_top = m->tree->top_nodes;
   rp.max_range = max_range;
   rp.leaf_depth = m->d_depth.p;
   rp.tile_counter = m->d_counter.p;
@@ -1417,6 +1436,102 @@ int q3dr_map_update_weights_from_grid(q3dr_map* m, const float grid_origin[3], f
   Q3DR_CUDA(cudaMemcpyAsync(m->h_weight.data(), d_w.p, m->n * sizeof(float), cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));
   if (weights_out) std::memcpy(weights_out, m->h_weight.data(), m->n * sizeof(float));
+  return Q3DR_OK;
+}
+
+// ---- one process, several GPUs: the map replicated, viewpoints sharded ----
+
+}  // extern "C"
+
+struct q3dr_multi {
+  std::vector<q3dr_map*> maps;
+  std::vector<int> devices;
+  std::vector<q3dr_result> parts;
+  std::vector<uint64_t> first;
+};
+
+extern "C" {
+
+int q3dr_multi_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                      const int* devices, int n_devices, q3dr_multi** out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  Q3DR_TRY(q3dr_device_count(&count));
+  if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  if (n_devices <= 0) n_devices = count;
+  if (n_devices > count && devices == nullptr) return fail(Q3DR_ERR_INVALID_ARG, "more devices requested than visible");
+  q3dr_multi* mm = new (std::nothrow) q3dr_multi;
+  if (!mm) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  int st = Q3DR_OK;
+  std::shared_ptr<const q3dr::FlatTree> tree;  // flattened once, uploaded to every device
+  for (int i = 0; i < n_devices && st == Q3DR_OK; ++i) {
+    const int dev = devices ? devices[i] : i;
+    q3dr_map* m = nullptr;
+    st = map_create_impl(boxes, weights, normals, depth, n, dev, tree, &m);
+    if (st == Q3DR_OK) {
+      tree = m->tree;
+      mm->maps.push_back(m);
+      mm->devices.push_back(dev);
+    }
+  }
+  if (st != Q3DR_OK) {
+    const std::string msg = g_last_error;
+    for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
+    delete mm;
+    return fail(st, msg);
+  }
+  mm->parts.resize(mm->maps.size());
+  mm->first.assign(mm->maps.size() + 1, 0);
+  *out = mm;
+  return Q3DR_OK;
+}
+
+int q3dr_multi_destroy(q3dr_multi* mm) {
+  if (!mm) return Q3DR_OK;
+  for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
+  delete mm;
+  return Q3DR_OK;
+}
+
+int q3dr_multi_device_count(const q3dr_multi* mm) { return mm ? (int)mm->maps.size() : 0; }
+
+q3dr_map* q3dr_multi_map(q3dr_multi* mm, int i) {
+  if (!mm || i < 0 || i >= (int)mm->maps.size()) return nullptr;
+  return mm->maps[(size_t)i];
+}
+
+int q3dr_multi_update_weights(q3dr_multi* mm, const float* weights) {
+  if (!mm) return fail(Q3DR_ERR_INVALID_ARG, "multi is NULL");
+  for (q3dr_map* m : mm->maps) Q3DR_TRY(q3dr_map_update_weights(m, weights));
+  return Q3DR_OK;
+}
+
+int q3dr_multi_score_viewpoints(q3dr_multi* mm, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                uint32_t y0, uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts,
+                                q3dr_multi_result* result) {
+  if (!mm || !result || !K || !opts || (!Rt && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  const size_t G = mm->maps.size();
+  // contiguous slices, sizes differing by at most one
+  for (size_t g = 0; g <= G; ++g) mm->first[g] = (uint64_t)((n / G) * g + std::min<size_t>(g, n % G));
+  std::vector<int> status(G, Q3DR_OK);
+  std::vector<std::string> message(G);
+  std::vector<std::thread> workers;
+  for (size_t g = 0; g < G; ++g) {
+    workers.emplace_back([&, g]() {
+      const size_t lo = (size_t)mm->first[g], hi = (size_t)mm->first[g + 1];
+      status[g] = q3dr_score_viewpoints(mm->maps[g], K, image_width, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts, &mm->parts[g]);
+      if (status[g] != Q3DR_OK) message[g] = q3dr_last_error();  // thread-local: carry it out of the worker
+    });
+  }
+  for (std::thread& t : workers) t.join();
+  for (size_t g = 0; g < G; ++g) {
+    if (status[g] != Q3DR_OK) return fail(status[g], "device " + std::to_string(mm->devices[g]) + ": " + message[g]);
+  }
+  result->n_parts = (uint32_t)G;
+  result->n_viewpoints = n;
+  result->first_viewpoint = mm->first.data();
+  result->parts = mm->parts.data();
   return Q3DR_OK;
 }
 

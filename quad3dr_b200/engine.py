@@ -62,6 +62,10 @@ class _OverlapResult(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
 
 
+class _MultiResult(C.Structure):
+    _fields_ = [("n_parts", C.c_uint32), ("n_viewpoints", C.c_uint64), ("first_viewpoint", C.c_void_p), ("parts", C.c_void_p)]
+
+
 class MapInfo(C.Structure):
     _fields_ = [
         ("n_leaves", C.c_uint64),
@@ -152,6 +156,15 @@ def load_library() -> C.CDLL:
     L.q3dr_octree_leaves_to_boxes.argtypes = [fp, fp, fp, u32p, C.c_size_t, fp, C.c_float, C.c_float, C.c_uint32, C.c_int,
                                               fp, u32p, C.POINTER(C.c_size_t)]
     L.q3dr_map_update_weights_from_grid.argtypes = [vp, fp, C.c_float, C.POINTER(C.c_int32), fp, C.c_float, u32p, fp]
+    L.q3dr_multi_create.argtypes = [fp, fp, fp, u32p, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.q3dr_multi_destroy.argtypes = [vp]
+    L.q3dr_multi_device_count.argtypes = [vp]
+    L.q3dr_multi_map.argtypes = [vp, C.c_int]
+    L.q3dr_multi_map.restype = vp
+    L.q3dr_multi_update_weights.argtypes = [vp, fp]
+    L.q3dr_multi_score_viewpoints.argtypes = (
+        [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_MultiResult)]
+    )
     L.q3dr_observed_create.argtypes = [vp, C.POINTER(vp)]
     L.q3dr_observed_clear.argtypes = [vp]
     L.q3dr_observed_destroy.argtypes = [vp]
@@ -516,3 +529,49 @@ def overlap_information(gmap: "OccupancyMap", ref: int, others) -> np.ndarray:
     out = np.empty(len(idx), dtype=np.float32)
     _check(load_library().q3dr_overlap_information(gmap._h, int(ref), idx.ctypes.data_as(C.POINTER(C.c_uint32)), len(idx), _fp(out)))
     return out
+
+
+class MultiGpuMap:
+    """q3dr_multi: the map replicated on several GPUs of this process, viewpoints sharded, one host thread per GPU."""
+
+    def __init__(self, boxes, weights=None, normals=None, depth=None, devices=None):
+        boxes = _f32(boxes)
+        n = boxes.shape[0]
+        w = None if weights is None else _f32(weights, (n,))
+        nr = None if normals is None else _f32(normals, (n, 3))
+        d = None if depth is None else np.ascontiguousarray(depth, dtype=np.uint32)
+        devs = None if devices is None else (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(load_library().q3dr_multi_create(
+            _fp(boxes), None if w is None else _fp(w), None if nr is None else _fp(nr),
+            None if d is None else d.ctypes.data_as(C.POINTER(C.c_uint32)), n, devs, 0 if devices is None else len(devices),
+            C.byref(h)))
+        self._h = h
+        self.n_devices = int(load_library().q3dr_multi_device_count(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().q3dr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_weights(self, weights):
+        _check(load_library().q3dr_multi_update_weights(self._h, _fp(_f32(weights))))
+
+    def score_viewpoints(self, K, image_width: int, window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None):
+        """Returns [(first_viewpoint, ScoreResult)] per GPU; viewpoint v of part g is viewpoint first + v of the call."""
+        K = _f32(K, (4,))
+        Rt = np.ascontiguousarray(_f32(Rt).reshape(-1, 12))
+        opts = opts or default_opts()
+        x0, x1, y0, y1 = window
+        r = _MultiResult()
+        _check(load_library().q3dr_multi_score_viewpoints(
+            self._h, _fp(K), image_width, x0, x1, y0, y1, _fp(Rt), Rt.shape[0], C.byref(opts), C.byref(r)))
+        first = np.ctypeslib.as_array(C.cast(r.first_viewpoint, C.POINTER(C.c_uint64)), shape=(r.n_parts + 1,)).copy()
+        parts = C.cast(r.parts, C.POINTER(_Result))
+        return [(int(first[g]), ScoreResult(parts[g], copy=True)) for g in range(r.n_parts)]
