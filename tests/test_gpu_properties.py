@@ -140,3 +140,83 @@ def test_device_resident_entry_point_matches_host_entry_point():
     assert np.array_equal(back.leaf, host.leaf)
     st = sc.gpu_map.stats()
     assert st.rays == 24 * 640 * 480 and st.kernel_launches >= 4 and st.raycast_ms > 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# C3 (10.2 M leaves) and C4 (unknown-space cubes, 1280x960): the oracle's splitMedian build alone takes minutes at
+# these sizes, so parity is checked through properties plus a brute-force spot check that needs no tree at all
+# ----------------------------------------------------------------------------------------------------
+
+def _brute_force_pixels(boxes, K, Rt, w, pix, max_range):
+    """Closest hit of a few pixels by testing EVERY leaf with the reference's arithmetic (numpy fp32, vectorised over
+    the leaves): the definition of the result, independent of any tree."""
+    f32 = np.float32
+    out = []
+    R = Rt.reshape(3, 4).astype(f32)
+    o = R[:, 3]
+    for p in pix:
+        x, y = f32(p % w), f32(p // w)
+        c0, c1 = (x - K[2]) / K[0], (y - K[3]) / K[1]
+        d = np.array([R[i, 0] * c0 + (R[i, 1] * c1 + R[i, 2]) for i in range(3)], dtype=f32)
+        n2 = d[0] * d[0] + (d[1] * d[1] + d[2] * d[2])
+        d = (d / np.sqrt(n2)).astype(f32)
+        inv = (f32(1) / d).astype(f32)
+        t0 = (boxes[:, :3] - o) * inv
+        t1 = (boxes[:, 3:] - o) * inv
+        tmin = np.maximum(np.minimum(t0, t1).max(axis=1), f32(0))
+        tmax = np.minimum(np.maximum(t0, t1).min(axis=1), np.finfo(f32).max)
+        inside = np.all((o >= boxes[:, :3]) & (o <= boxes[:, 3:]), axis=1)
+        hit = (tmax > tmin) | inside
+        pt = o[None, :] + d[None, :] * tmin[:, None]
+        e = o[None, :] - pt
+        dsq = e[:, 0] * e[:, 0] + (e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2])
+        dsq = np.where(inside, f32(0), dsq)
+        ok = hit & (dsq <= f32(max_range) * f32(max_range))
+        if not ok.any():
+            out.append((-1, f32(0)))
+            continue
+        best = dsq[ok].min()
+        idx = np.where(ok & (dsq == best))[0].max()  # equal dist_sq: the later leaf wins
+        out.append((int(idx), best))
+    return out
+
+
+@pytest.mark.parametrize("name,w,h", [("10m", 640, 480), ("1m_unknown", 1280, 960)])
+def test_full_size_maps_properties_and_brute_force_spot_check(name, w, h):
+    if name == "10m":
+        leaves = synth.map_10m()
+    else:
+        leaves = synth.map_1m(unknown_interior=True)
+    order, depth = E.splitmedian_order(leaves.boxes)
+    leaves = leaves.permuted(order)
+    gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth)
+    cam = synth.make_camera(w, h)
+    n = 12
+    vps = synth.make_viewpoints(leaves, n, config_id=3 if name == "10m" else 4)
+    win = (0, w, 0, h)
+    res = gmap.score_viewpoints(cam.K, w, win, vps)
+    assert res.n_viewpoints == n and res.offsets[-1] == res.n_entries and res.n_entries > 1000
+    rng = np.random.default_rng(5)
+    for v in range(n):
+        e = res.viewpoint(v)
+        assert np.all(np.diff(e["leaf"]) > 0) and np.all(e["info"] > 0) and np.all(e["pixel"] < w * h)
+    # the de-duplicated lists are exactly what the per-pixel path implies: unique leaves, first pixel, its dist_sq
+    for v in (0, 7):
+        px = gmap.raycast_window(cam.K, vps[v], 0, w, 0, h, 0.0, 60.0)
+        uniq, first = np.unique(px["leaf"], return_index=True)
+        first, uniq = first[uniq >= 0], uniq[uniq >= 0]
+        full = gmap.score_viewpoints(cam.K, w, win, vps[v:v + 1], E.default_opts(ignore_voxels_with_zero_information=0))
+        e = full.viewpoint(0)
+        assert np.array_equal(e["leaf"], uniq) and np.array_equal(e["pixel"], first)
+        assert np.array_equal(bits(e["dsq"]), bits(px["dist_sq"][first]))
+        # brute force over ALL leaves for a handful of pixels (hits, misses, image corners)
+        pix = np.concatenate([rng.integers(0, w * h, size=10), [0, w - 1, w * (h - 1), w * h - 1]])
+        for p, (leaf, dsq) in zip(pix, _brute_force_pixels(leaves.boxes, cam.K, vps[v], w, pix, 60.0)):
+            assert px["leaf"][p] == leaf, (v, p)
+            if leaf >= 0:
+                assert bits(px["dist_sq"][p:p + 1])[0] == bits(np.array([dsq], np.float32))[0]
+    # batching independence and idempotence
+    parts = [gmap.score_viewpoints(cam.K, w, win, vps[a:b]) for a, b in ((0, 5), (5, n))]
+    assert np.array_equal(np.concatenate([p.leaf for p in parts]), res.leaf)
+    assert np.array_equal(np.concatenate([bits(p.total) for p in parts]), bits(res.total))
+    gmap.close()
