@@ -460,3 +460,15 @@ def test_scoring_with_many_chunks_and_dense_hits():
             assert got["hit_count"] == ref["hit_count"]
             np.testing.assert_allclose(got["info"], ref["info"], rtol=REL_TOL)
             assert abs(got["total"] - ref["total"]) <= REL_TOL * max(abs(ref["total"]), 1e-30)
+
+
+def test_fuzz_parity_short():
+    """A short run of tools/fuzz_parity.py (random degenerate scenes, cameras on faces / inside boxes / axis-aligned,
+    random windows and ranges, random ray lists): every pixel and every voxel set equal to the oracle's."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "12", "7"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr

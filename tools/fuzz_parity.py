@@ -1,0 +1,118 @@
+"""Randomised parity fuzzing of the engine against the CPU oracle: random scenes (overlapping / nested / degenerate /
+grid-aligned boxes), random cameras (inside boxes, on faces, axis-aligned, wide and narrow), random windows and
+ranges.  python tools/fuzz_parity.py [seconds] [seed]  ->  exits non-zero at the first mismatch."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle import oracle_py as O
+from quad3dr_b200 import engine as E
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rng = np.random.default_rng(seed)
+bits = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def random_scene():
+    kind = rng.integers(0, 5)
+    n = int(rng.integers(1, 3000))
+    if kind == 0:      # voxel grid, multiples of 0.25 (ties, faces, corners everywhere)
+        c = rng.integers(-20, 20, size=(n, 3)).astype(np.float32) * 0.25
+        s = (0.25 * 2.0 ** rng.integers(0, 3, size=(n, 1))).astype(np.float32)
+        b = np.concatenate([c, c + s], axis=1)
+    elif kind == 1:    # random overlapping boxes
+        c = rng.uniform(-10, 10, size=(n, 3)); s = rng.uniform(0.01, 3, size=(n, 3))
+        b = np.concatenate([c - s, c + s], axis=1)
+    elif kind == 2:    # flat / degenerate boxes (zero thickness on an axis), duplicates
+        c = rng.uniform(-8, 8, size=(n, 3)); s = rng.uniform(0.0, 2, size=(n, 3))
+        s[rng.random(n) < 0.3, rng.integers(0, 3)] = 0.0
+        b = np.concatenate([c - s, c + s], axis=1)
+        b = np.concatenate([b, b[: n // 4]])
+    elif kind == 3:    # nested shells
+        r = np.sort(rng.uniform(0.1, 12, size=n))[:, None]
+        c = rng.normal(scale=0.2, size=(n, 3))
+        b = np.concatenate([c - r, c + r], axis=1)
+    else:              # far from the origin, mixed scales
+        off = rng.uniform(-1, 1, size=3) * 10.0 ** rng.integers(2, 6)
+        c = rng.uniform(-30, 30, size=(n, 3)) + off; s = 10.0 ** rng.uniform(-2, 1, size=(n, 1))
+        b = np.concatenate([c - s, c + s], axis=1)
+    return np.ascontiguousarray(b, dtype=np.float32)
+
+
+def random_pose(boxes):
+    lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
+    mode = rng.integers(0, 4)
+    if mode == 0:      # outside, looking at the scene
+        eye = (lo + hi) / 2 + rng.normal(size=3) * (hi - lo + 1)
+    elif mode == 1:    # inside a random box
+        k = rng.integers(0, len(boxes)); eye = rng.uniform(boxes[k, :3], boxes[k, 3:])
+    elif mode == 2:    # exactly on a face / corner of a random box
+        k = rng.integers(0, len(boxes)); eye = np.where(rng.random(3) < 0.5, boxes[k, :3], boxes[k, 3:]).astype(np.float64)
+        if rng.random() < 0.5: eye[rng.integers(0, 3)] = rng.uniform(lo.min(), hi.max())
+    else:
+        eye = rng.uniform(lo - 1, hi + 1)
+    if rng.random() < 0.25:   # axis-aligned rotation: exact zeros in directions
+        P = np.eye(3)[rng.permutation(3)] * rng.choice([-1, 1], size=3)[:, None]
+        R = P
+    else:
+        A = rng.normal(size=(3, 3)); Q, _ = np.linalg.qr(A); R = Q * np.sign(np.linalg.det(Q))
+    return np.concatenate([R, eye[:, None]], axis=1).astype(np.float32).reshape(12)
+
+
+t_end = time.time() + budget
+scenes = rays = 0
+while time.time() < t_end:
+    boxes = random_scene()
+    order, depth = E.splitmedian_order(boxes)
+    boxes = np.ascontiguousarray(boxes[order])
+    w = rng.uniform(0, 1, size=len(boxes)).astype(np.float32)
+    nr = rng.normal(size=(len(boxes), 3)).astype(np.float32); nr[rng.random(len(boxes)) < 0.3] = 0
+    nr /= np.maximum(np.linalg.norm(nr, axis=1, keepdims=True), 1e-9).astype(np.float32); nr = nr.astype(np.float32)
+    oracle = O.OracleTree(boxes)
+    assert np.array_equal(oracle.dfs_order(), np.arange(len(boxes)))
+    gmap = E.OccupancyMap(boxes, w, nr, depth)
+    for _ in range(6):
+        W, H = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        f = W * 10.0 ** rng.uniform(-0.7, 0.7)
+        K = np.array([f, f * rng.uniform(0.8, 1.2), W / 2 + rng.uniform(-2, 2), H / 2 + rng.uniform(-2, 2)], np.float32)
+        Rt = random_pose(boxes)
+        x0 = int(rng.integers(0, W)); x1 = int(rng.integers(x0 + 1, W + 1)); y0 = int(rng.integers(0, H)); y1 = int(rng.integers(y0 + 1, H + 1))
+        max_range = float(rng.choice([-1.0, 60.0, 5.0, 0.5, 1e6]))
+        ref = oracle.raycast_window(K, Rt, x0, x1, y0, y1, 0.0, max_range)
+        got = gmap.raycast_window(K, Rt, x0, x1, y0, y1, 0.0, max_range)
+        ok = (np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(bits(got["dist_sq"]), bits(ref["dsq"]))
+              and np.array_equal(got["intersection"], ref["xyz"]))
+        opts = dict(raycast_max_range=max_range, ignore_voxels_with_zero_information=int(rng.integers(0, 2)))
+        res = gmap.score_viewpoints(K, W, (x0, x1, y0, y1), Rt[None], E.default_opts(**opts)).viewpoint(0)
+        sref = oracle.score_viewpoint(w, nr, K, W, Rt, window=(x0, x1, y0, y1), opts=O.default_opts(**opts))
+        ok = ok and np.array_equal(res["leaf"], sref["leaf"]) and np.array_equal(res["pixel"], sref["pixel"]) \
+            and np.array_equal(bits(res["dsq"]), bits(sref["dsq"])) and res["hit_count"] == sref["hit_count"] \
+            and np.allclose(res["info"], sref["info"], rtol=1e-5, atol=0) and abs(res["total"] - sref["total"]) <= 1e-5 * max(abs(sref["total"]), 1e-30)
+        if not ok:
+            np.savez("gpurun_out/fuzz_fail.npz", boxes=boxes, w=w, nr=nr, K=K, Rt=Rt, win=[x0, x1, y0, y1], max_range=max_range)
+            bad = np.where(got["leaf"] != ref["leaf"])[0]
+            print("MISMATCH scene", scenes, "n", len(boxes), "win", (x0, x1, y0, y1), "range", max_range, "bad pixels", bad[:8],
+                  got["leaf"][bad[:8]], ref["leaf"][bad[:8]])
+            sys.exit(1)
+        rays += (x1 - x0) * (y1 - y0)
+    # ray-list entry point (intersectsCuda): random rays, some axis-parallel, some starting on box planes
+    m = 1500
+    lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
+    ro = rng.uniform(lo - 1, hi + 1, size=(m, 3)).astype(np.float32)
+    k = rng.integers(0, len(boxes), size=m)
+    onp = rng.random(m) < 0.2
+    ro[onp, 0] = boxes[k[onp], 0]
+    rd = rng.normal(size=(m, 3)).astype(np.float32)
+    rd[rng.random(m) < 0.1, rng.integers(0, 3)] = 0.0
+    rd[np.all(rd == 0, axis=1)] = [1, 0, 0]
+    mr = float(rng.choice([-1.0, 10.0]))
+    ref = oracle.intersect_rays(ro, rd, 0.0, mr)
+    got = gmap.intersect_rays(ro, rd, 0.0, mr)
+    if not (np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(bits(got["dist_sq"]), bits(ref["dsq"]))):
+        np.savez("gpurun_out/fuzz_fail_rays.npz", boxes=boxes, ro=ro, rd=rd, max_range=mr)
+        print("MISMATCH (rays) scene", scenes)
+        sys.exit(1)
+    rays += m
+    gmap.close()
+    scenes += 1
+print(f"fuzz ok: {scenes} scenes, {rays} rays, seed {seed}")
