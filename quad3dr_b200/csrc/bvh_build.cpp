@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -153,8 +154,16 @@ struct BuildCtx {
   const float* cen(int a) const { return a == 0 ? cx.data() : (a == 1 ? cy.data() : cz.data()); }
 };
 
-constexpr int kBins = 16;
+constexpr int kMaxBins = 64;
 constexpr size_t kSmallRange = 64;
+
+// build-quality knobs (experiments only; defaults are what ships)
+inline int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? atoi(e) : dflt;
+}
+const int kBins = std::max(4, std::min(kMaxBins, env_int("Q3DR_BINS", 16)));
+const int kCollapse = env_int("Q3DR_COLLAPSE", 0);  // 0: largest area first, 1: most leaves first, 2: area x leaves
 
 // Exact SAH sweep for a small range with the cut restricted to multiples of 4 leaves.
 size_t split_small(BuildCtx& c, size_t b, size_t e) {
@@ -227,8 +236,8 @@ int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
       const float ext = cmx[a] - cmn[a];
       if (!(ext > 0)) continue;
       const float scale = (float)kBins / ext;
-      Box3 bin_box[kBins];
-      uint32_t bin_cnt[kBins];
+      Box3 bin_box[kMaxBins];
+      uint32_t bin_cnt[kMaxBins];
       for (int k = 0; k < kBins; ++k) {
         bin_box[k].reset();
         bin_cnt[k] = 0;
@@ -241,8 +250,8 @@ int64_t build_binary(BuildCtx& c, size_t b, size_t e, int64_t base) {
         bin_box[k].grow(c.boxes + 6 * (size_t)li);
         ++bin_cnt[k];
       }
-      double right_area[kBins];
-      uint32_t right_cnt[kBins];
+      double right_area[kMaxBins];
+      uint32_t right_cnt[kMaxBins];
       Box3 acc;
       acc.reset();
       uint32_t cnt = 0;
@@ -332,7 +341,9 @@ int gather_children(const BuildCtx& c, int64_t node, Child out[4]) {
     double best = -1.0;
     for (int i = 0; i < cnt; ++i) {
       if (out[i].bin < 0 || bn[out[i].bin].left < 0) continue;
-      const double a = bn[out[i].bin].box.half_area();
+      double a = bn[out[i].bin].box.half_area();
+      if (kCollapse == 1) a = (double)bn[out[i].bin].count;
+      if (kCollapse == 2) a *= (double)bn[out[i].bin].count;
       if (a > best) {
         best = a;
         pick = i;
