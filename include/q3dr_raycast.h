@@ -150,7 +150,10 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
 
 /* ---- occupancy map: flatten + upload ---- */
 
-/* boxes   n x 6 floats, leaf k has tie-break priority k (see header comment).
+/* boxes   n x 6 floats, leaf k has tie-break priority k (see header comment).  Boxes should have positive extent on
+ *         every axis, as the reference guarantees (generateBVHTree drops isEmpty() boxes): for a zero-thickness box a
+ *         ray exactly parallel to an axis AND lying in the box's plane sends 0 * inf = NaN through the reference's
+ *         order-dependent min / max, and the reference's own answer then depends on the shape of its tree.
  * weights n floats or NULL (=> 1).   normals n x 3 floats or NULL (=> zero vectors).
  * depth   n uint32 (depth of each leaf in the reference tree, only echoed in q3dr_pixel_hit.depth)
  *         or NULL (=> the splitMedian depth implied by n and k). */
