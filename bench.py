@@ -229,7 +229,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, leaves, cam, vps.shape[0], 1),
+        "config": workload_config(args.workload, leaves, cam, vps.shape[0], max(int(args.gpus), 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": int(threads), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
