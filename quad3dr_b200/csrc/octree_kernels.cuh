@@ -24,7 +24,7 @@ struct LeafRuleParams {
 };
 
 // keep[i] = 1 and box[i] = the BVH leaf box if octree leaf i becomes a BVH leaf
-__global__ void leaf_rule_kernel(const LeafRuleParams p, uint32_t* keep, float* box /* [n][6] */) {
+static __global__ void leaf_rule_kernel(const LeafRuleParams p, uint32_t* keep, float* box /* [n][6] */) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   bool k = true;
@@ -58,7 +58,7 @@ __global__ void leaf_rule_kernel(const LeafRuleParams p, uint32_t* keep, float* 
 }
 
 // ordered compaction given the exclusive scan of keep[]
-__global__ void leaf_compact_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, const float* __restrict__ box,
+static __global__ void leaf_compact_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos, const float* __restrict__ box,
                                     uint32_t n, float* out_box, uint32_t* out_src) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
@@ -100,7 +100,7 @@ __device__ __forceinline__ int last_cell(float origin, float inc, float half, in
 // updateWeights: every grid cell writes weight(cell) * exp(-lambda * observation_count) into the leaves its box
 // overlaps, cells visited in ix, iy, iz order, so a leaf ends up with the value of the LAST overlapping cell;
 // leaves no cell overlaps keep their weight.  weight slot = leaf_rec[stride * leaf].w.
-__global__ void grid_weights_kernel(float4* leaf_rec, uint32_t rec_stride, uint32_t n, const GridParams g,
+static __global__ void grid_weights_kernel(float4* leaf_rec, uint32_t rec_stride, uint32_t n, const GridParams g,
                                     const float* __restrict__ grid_weight, const uint32_t* __restrict__ observation_count,
                                     float* weight_out /* [n], mirror for the host copy */) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

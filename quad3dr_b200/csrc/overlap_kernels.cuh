@@ -56,7 +56,7 @@ __device__ __forceinline__ bool for_each_overlapping_leaf(const float4* __restri
 
 // counts[i] = number of leaves overlapping boxes[i]; with out_leaf != nullptr also writes them (unordered) at
 // out_leaf[offsets[i] ...].
-__global__ void __launch_bounds__(kOverlapThreads) overlap_boxes_kernel(const float4* __restrict__ nodes,
+static __global__ void __launch_bounds__(kOverlapThreads) overlap_boxes_kernel(const float4* __restrict__ nodes,
                                                                         const float* __restrict__ boxes, uint32_t n,
                                                                         uint32_t* counts, const uint64_t* __restrict__ offsets,
                                                                         int32_t* out_leaf) {
@@ -83,7 +83,7 @@ struct ValidParams {
 };
 
 // ViewpointPlannerData::isValidObjectPosition without the no-fly-zone polygons (those stay on the host).
-__global__ void __launch_bounds__(kOverlapThreads) valid_positions_kernel(const float4* __restrict__ nodes,
+static __global__ void __launch_bounds__(kOverlapThreads) valid_positions_kernel(const float4* __restrict__ nodes,
                                                                           const float* __restrict__ pos, uint32_t n,
                                                                           const ValidParams p, uint8_t* valid) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,214 @@
+// q3dr_internal.cuh -- shared by the translation units of libq3dr_raycast.so (not installed): error plumbing, device /
+// pinned buffers, the q3dr_map object.
+#pragma once
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/q3dr_raycast.h"
+#include "bvh_build.h"
+
+namespace q3dr_detail {
+
+std::string& last_error();  // thread-local message of the last failing call (defined in q3dr_api.cu)
+
+inline int fail(int status, const std::string& msg) {
+  last_error() = msg;
+  return status;
+}
+
+}  // namespace q3dr_detail
+
+using q3dr_detail::fail;
+
+
+#define Q3DR_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      int st__ = (err__ == cudaErrorMemoryAllocation) ? Q3DR_ERR_OUT_OF_MEMORY : Q3DR_ERR_CUDA;  \
+      if (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver) st__ = Q3DR_ERR_NO_DEVICE; \
+      return fail(st__, std::string(#call) + ": " + cudaGetErrorString(err__));                  \
+    }                                                                                            \
+  } while (0)
+
+#define Q3DR_TRY(expr)             \
+  do {                             \
+    int st__ = (expr);             \
+    if (st__ != Q3DR_OK) return st__; \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  int ensure(size_t n, bool keep = false, cudaStream_t s = 0) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    Q3DR_CUDA(cudaMalloc(&q, want * sizeof(T)));
+    if (keep && p && cap) {
+      cudaError_t e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return fail(Q3DR_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(e));
+      }
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return Q3DR_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  size_t bytes() const { return cap * sizeof(T); }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    Q3DR_CUDA(cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+    return Q3DR_OK;
+  }
+  // grows keeping the first `used` elements (caller makes sure no copy into the old block is in flight)
+  int grow_keep(size_t n, size_t used) {
+    if (n <= cap) return Q3DR_OK;
+    size_t want = std::max(n, cap + cap / 2);
+    T* q = nullptr;
+    Q3DR_CUDA(cudaHostAlloc(&q, want * sizeof(T), cudaHostAllocDefault));
+    if (p && used) std::memcpy(q, p, used * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = q;
+    cap = want;
+    return Q3DR_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Derived {
+  float thr, kf, a_thr, ka;
+};
+
+// viewpoint_score.cpp:20-28 / viewpoint_planner.cpp:107-109 of the reference (fp32, same order)
+inline Derived derive(const q3dr_score_opts& o) {
+  Derived d;
+  d.thr = o.voxel_sensor_size_ratio_threshold;
+  d.kf = 1.0f / o.voxel_sensor_size_ratio_inv_falloff_factor;
+  d.a_thr = o.incidence_angle_threshold_degrees * float(M_PI) / float(180);
+  d.ka = 1.0f / (o.incidence_angle_inv_falloff_factor_degrees * float(M_PI) / float(180));
+  return d;
+}
+
+
+struct q3dr_map {
+  int device = 0;
+  int sm_count = 0;
+  size_t n = 0;
+  uint32_t ref_depth = 0;
+  bool bounded = false;  // all box coordinates finite and below 1e18 in magnitude
+  float root_box[6] = {0, 0, 0, 0, 0, 0};  // union of the leaf boxes = the reference root node's bounding box
+  // host copies (kept for q3dr_map_reset)
+  std::vector<float> h_boxes, h_weight, h_normal;
+  std::vector<uint8_t> h_depth;
+  std::shared_ptr<const q3dr::FlatTree> tree;  // shared between the per-GPU replicas of a q3dr_multi
+  // device: the map
+  DevBuf<float4> d_nodes;
+  DevBuf<float4> d_leaf_rec;  // [n][4]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}, pad (64-byte records)
+  DevBuf<uint8_t> d_depth;
+  DevBuf<uint32_t> d_counter;
+  // device: per-chunk scratch
+  DevBuf<uint32_t> d_first_pix, d_bitmap, d_kept;
+  DevBuf<uint32_t> d_seg_u32;  // [2][slots][n_segs]: hits, off
+  DevBuf<uint32_t> d_blk_u32;  // [slots + 1] blk_off, then [2][max blocks]: kept, koff
+  DevBuf<double> d_seg_f64;    // [max blocks] blk_total
+  size_t max_blocks = 0;
+  uint32_t n_segs = 0;
+  size_t slots = 0;
+  uint64_t leaf_stride = 0, word_stride = 0;
+  DevBuf<int32_t> t_leaf;
+  DevBuf<float> t_info, t_dsq;
+  DevBuf<uint32_t> t_pix;
+  uint64_t tmp_cap = 0;
+  // device: results of the last scoring call
+  DevBuf<uint64_t> d_offsets;
+  DevBuf<float> d_total;
+  DevBuf<uint32_t> d_hit_count;
+  DevBuf<int32_t> r_leaf;
+  DevBuf<float> r_info, r_dsq;
+  DevBuf<uint32_t> r_pix;
+  uint64_t last_n_vp = 0, last_n_entries = 0;
+  // staging
+  DevBuf<float> d_rt, d_ray_o, d_ray_d;
+  DevBuf<q3dr_pixel_hit> d_pixels;
+  PinnedBuf<uint64_t> h_scalar;
+  PinnedBuf<uint64_t> h_offsets;
+  PinnedBuf<float> h_total, h_info, h_dsq;
+  PinnedBuf<uint32_t> h_hit_count, h_pix;
+  PinnedBuf<int32_t> h_leaf;
+  PinnedBuf<float> h_rt;
+  // set consumers (setops_kernels.cuh)
+  DevBuf<float> d_dense;     // [n] scratch: one viewpoint's informations scattered over the leaves (NaN elsewhere)
+  DevBuf<float> d_set_out;   // per-viewpoint sums
+  DevBuf<uint32_t> d_set_idx;
+  DevBuf<double> d_set_part;
+  bool dense_ready = false;
+  bool scratch_dirty = false;  // a scoring call failed between its raycast and its clean-up: tables need a reset
+  // overlap queries (overlap_kernels.cuh)
+  DevBuf<float> d_q_boxes;
+  DevBuf<uint32_t> d_q_counts;
+  DevBuf<uint64_t> d_q_offsets;
+  DevBuf<int32_t> d_q_leaf, d_q_sorted;
+  DevBuf<uint8_t> d_q_tmp, d_q_valid;
+  std::vector<uint64_t> h_q_offsets;
+  std::vector<int32_t> h_q_leaf;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
+  cudaEvent_t ev_packed = nullptr;
+  bool host_result_valid = false;      // the host pools already hold the entries of the last call
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int grid_ctas[3] = {0, 0, 0};
+  int grid2_ctas[2] = {0, 0};
+  size_t smem_bytes = 0;
+  q3dr_stats stats{};
+
+  uint64_t device_bytes() const {
+    return d_nodes.bytes() + d_leaf_rec.bytes() + d_depth.bytes() + d_seg_u32.bytes() + d_blk_u32.bytes() + d_seg_f64.bytes() +
+           d_counter.bytes() + d_first_pix.bytes() + d_bitmap.bytes() + d_kept.bytes() + t_leaf.bytes() +
+           t_info.bytes() + t_dsq.bytes() + t_pix.bytes() + d_offsets.bytes() + d_total.bytes() +
+           d_hit_count.bytes() + r_leaf.bytes() + r_info.bytes() + r_dsq.bytes() + r_pix.bytes() + d_rt.bytes() +
+           d_ray_o.bytes() + d_ray_d.bytes() + d_pixels.bytes();
+  }
+};
+
+namespace q3dr_detail {
+int check_map(const q3dr_map* m);
+int map_create_impl(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                    int device, std::shared_ptr<const q3dr::FlatTree> shared_tree, q3dr_map** out);
+}  // namespace q3dr_detail

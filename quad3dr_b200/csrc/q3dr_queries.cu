@@ -1,0 +1,465 @@
+// q3dr_queries.cu -- the C ABI entry points around the hot path: consumers of the voxel sets,
+// box-vs-map overlap queries, octree leaves -> BVH leaves and grid weights, and q3dr_multi (one process, several GPUs).
+#include "q3dr_internal.cuh"
+
+#include "setops_kernels.cuh"
+#include "overlap_kernels.cuh"
+#include "octree_kernels.cuh"
+#include "score_kernels.cuh"  // kLeafRecStride, kMaxChunkViewpoints, csr_offsets_kernel
+
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
+
+using q3dr_detail::check_map;
+using q3dr_detail::map_create_impl;
+
+extern "C" {
+
+// ---- consumers of the voxel sets ----
+
+}  // extern "C"
+
+struct q3dr_observed {
+  q3dr_map* map = nullptr;
+  DevBuf<float> d;  // [n_leaves], NaN = absent
+};
+
+namespace {
+
+int fill_set_params(const q3dr_map* m, float factor, q3dr::SetParams* sp) {
+  if (m->last_n_vp == 0 && m->d_offsets.p == nullptr) return fail(Q3DR_ERR_INVALID_ARG, "no scoring result on this map yet");
+  sp->offsets = m->d_offsets.p;
+  sp->leaf = m->r_leaf.p;
+  sp->info = m->r_info.p;
+  sp->leaf_rec = m->d_leaf_rec.p;
+  sp->rec_stride = (uint32_t)q3dr::kLeafRecStride;
+  sp->factor = factor;
+  return Q3DR_OK;
+}
+
+int fill_nan(float* p, size_t n, cudaStream_t s) {
+  q3dr::fill_f32_kernel<<<256, 256, 0, s>>>(p, n, std::nanf(""));
+  Q3DR_CUDA(cudaGetLastError());
+  return Q3DR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int q3dr_observed_create(q3dr_map* m, q3dr_observed** out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  Q3DR_TRY(check_map(m));
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  q3dr_observed* o = new (std::nothrow) q3dr_observed;
+  if (!o) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  o->map = m;
+  int st = o->d.ensure(m->n);
+  if (st == Q3DR_OK) st = fill_nan(o->d.p, m->n, m->stream);
+  if (st == Q3DR_OK && cudaStreamSynchronize(m->stream) != cudaSuccess) st = fail(Q3DR_ERR_CUDA, "sync failed");
+  if (st != Q3DR_OK) {
+    o->d.release();
+    delete o;
+    return st;
+  }
+  *out = o;
+  return Q3DR_OK;
+}
+
+int q3dr_observed_clear(q3dr_observed* o) {
+  if (!o) return fail(Q3DR_ERR_INVALID_ARG, "obs is NULL");
+  Q3DR_CUDA(cudaSetDevice(o->map->device));
+  Q3DR_TRY(fill_nan(o->d.p, o->map->n, o->map->stream));
+  Q3DR_CUDA(cudaStreamSynchronize(o->map->stream));
+  return Q3DR_OK;
+}
+
+int q3dr_observed_destroy(q3dr_observed* o) {
+  if (!o) return Q3DR_OK;
+  cudaSetDevice(o->map->device);
+  o->d.release();
+  delete o;
+  return Q3DR_OK;
+}
+
+int q3dr_observed_download(const q3dr_observed* o, float* out) {
+  if (!o || !out) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_CUDA(cudaSetDevice(o->map->device));
+  Q3DR_CUDA(cudaMemcpy(out, o->d.p, o->map->n * sizeof(float), cudaMemcpyDeviceToHost));
+  return Q3DR_OK;
+}
+
+int q3dr_new_information(q3dr_map* m, const q3dr_observed* o, float factor, const uint32_t* viewpoints, size_t n,
+                         float* out) {
+  Q3DR_TRY(check_map(m));
+  if (!o || (!out && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (o->map != m) return fail(Q3DR_ERR_INVALID_ARG, "observed map belongs to another occupancy map");
+  if (n == 0) return Q3DR_OK;
+  if (n > m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "more viewpoints than the last result holds");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, factor, &sp));
+  Q3DR_TRY(m->d_set_out.ensure(n));
+  const uint32_t* d_idx = nullptr;
+  if (viewpoints) {
+    for (size_t i = 0; i < n; ++i) {
+      if (viewpoints[i] >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+    }
+    Q3DR_TRY(m->d_set_idx.ensure(n));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_set_idx.p, viewpoints, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    d_idx = m->d_set_idx.p;
+  }
+  q3dr::new_information_kernel<<<(unsigned)n, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, d_idx, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_set_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+int q3dr_observed_add_viewpoint(q3dr_map* m, q3dr_observed* o, float factor, uint32_t viewpoint, float* new_information) {
+  Q3DR_TRY(check_map(m));
+  if (!o) return fail(Q3DR_ERR_INVALID_ARG, "obs is NULL");
+  if (o->map != m) return fail(Q3DR_ERR_INVALID_ARG, "observed map belongs to another occupancy map");
+  if (viewpoint >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, factor, &sp));
+  const unsigned grid = 64;
+  Q3DR_TRY(m->d_set_part.ensure(grid));
+  Q3DR_TRY(m->d_set_out.ensure(1));
+  q3dr::observed_add_kernel<<<grid, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, viewpoint, m->d_set_part.p);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::sum_parts_kernel<<<1, 32, 0, s>>>(m->d_set_part.p, grid, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  float v = 0.f;
+  Q3DR_CUDA(cudaMemcpyAsync(&v, m->d_set_out.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (new_information) *new_information = v;
+  return Q3DR_OK;
+}
+
+int q3dr_overlap_information(q3dr_map* m, uint32_t ref, const uint32_t* others, size_t n, float* out) {
+  Q3DR_TRY(check_map(m));
+  if ((!others || !out) && n) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (ref >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  for (size_t i = 0; i < n; ++i) {
+    if (others[i] >= m->last_n_vp) return fail(Q3DR_ERR_INVALID_ARG, "viewpoint index out of range");
+  }
+  if (n == 0) return Q3DR_OK;
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  Q3DR_TRY(fill_set_params(m, 1.0f, &sp));
+  if (!m->dense_ready || m->d_dense.cap < m->n) {
+    Q3DR_TRY(m->d_dense.ensure(m->n));
+    Q3DR_TRY(fill_nan(m->d_dense.p, m->n, s));
+    m->dense_ready = true;
+  }
+  Q3DR_TRY(m->d_set_idx.ensure(n));
+  Q3DR_TRY(m->d_set_out.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_set_idx.p, others, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  q3dr::scatter_set_kernel<<<64, 256, 0, s>>>(sp, ref, m->d_dense.p, 0);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::overlap_information_kernel<<<(unsigned)n, q3dr::kSetThreads, 0, s>>>(sp, m->d_dense.p, m->d_set_idx.p, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::scatter_set_kernel<<<64, 256, 0, s>>>(sp, ref, m->d_dense.p, 1);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(out, m->d_set_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+// ---- box-vs-map overlap queries ----
+
+int q3dr_overlap_boxes(q3dr_map* m, const float* boxes, size_t n, q3dr_overlap_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!result || (!boxes && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many boxes for one call");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  m->h_q_offsets.assign(n + 1, 0);
+  m->h_q_leaf.clear();
+  if (n) {
+    Q3DR_TRY(m->d_q_boxes.ensure(6 * n));
+    Q3DR_TRY(m->d_q_counts.ensure(n));
+    Q3DR_TRY(m->d_q_offsets.ensure(n + 1));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_q_boxes.p, boxes, 6 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    const unsigned grid = (unsigned)((n + q3dr::kOverlapThreads - 1) / q3dr::kOverlapThreads);
+    q3dr::overlap_boxes_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n,
+                                                                     m->d_q_counts.p, nullptr, nullptr);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaMemsetAsync(m->d_q_offsets.p, 0, sizeof(uint64_t), s));
+    for (size_t v0 = 0; v0 < n; v0 += q3dr::kMaxChunkViewpoints) {  // csr_offsets_kernel continues from offsets[v0]
+      const size_t nb = std::min<size_t>(q3dr::kMaxChunkViewpoints, n - v0);
+      q3dr::csr_offsets_kernel<<<1, q3dr::kSegThreads, 0, s>>>(m->d_q_counts.p + v0, (uint32_t)nb, m->d_q_offsets.p + v0);
+      Q3DR_CUDA(cudaGetLastError());
+    }
+    Q3DR_CUDA(cudaMemcpyAsync(m->h_q_offsets.data(), m->d_q_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    Q3DR_CUDA(cudaStreamSynchronize(s));
+    const uint64_t ne = m->h_q_offsets[n];
+    if (ne >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "overlap result too large for one call");
+    if (ne) {
+      Q3DR_TRY(m->d_q_leaf.ensure(ne));
+      Q3DR_TRY(m->d_q_sorted.ensure(ne));
+      q3dr::overlap_boxes_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n,
+                                                                       m->d_q_counts.p, m->d_q_offsets.p, m->d_q_leaf.p);
+      Q3DR_CUDA(cudaGetLastError());
+      // ascending leaf index inside each box's list = the reference's left-to-right visiting order
+      size_t tmp_bytes = 0;
+      Q3DR_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, m->d_q_leaf.p, m->d_q_sorted.p, (int)ne, (int)n,
+                                                        m->d_q_offsets.p, m->d_q_offsets.p + 1, 0, 32, s));
+      Q3DR_TRY(m->d_q_tmp.ensure(tmp_bytes));
+      Q3DR_CUDA(cub::DeviceSegmentedRadixSort::SortKeys(m->d_q_tmp.p, tmp_bytes, m->d_q_leaf.p, m->d_q_sorted.p, (int)ne, (int)n,
+                                                        m->d_q_offsets.p, m->d_q_offsets.p + 1, 0, 32, s));
+      m->h_q_leaf.resize(ne);
+      Q3DR_CUDA(cudaMemcpyAsync(m->h_q_leaf.data(), m->d_q_sorted.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      Q3DR_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  result->n_boxes = n;
+  result->n_entries = m->h_q_offsets[n];
+  result->offsets = m->h_q_offsets.data();
+  result->leaf = m->h_q_leaf.data();
+  return Q3DR_OK;
+}
+
+int q3dr_valid_object_positions(q3dr_map* m, const float* positions, size_t n, const float object_bbox[6],
+                                const float bvh_bbox[6], float obstacle_free_height, uint8_t* valid) {
+  Q3DR_TRY(check_map(m));
+  if (!object_bbox || !bvh_bbox || ((!positions || !valid) && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n == 0) return Q3DR_OK;
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many positions for one call");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::ValidParams vp;
+  for (int i = 0; i < 6; ++i) {
+    vp.obj[i] = object_bbox[i];
+    vp.bvh_bbox[i] = bvh_bbox[i];
+    vp.root_box[i] = m->root_box[i];
+  }
+  vp.obstacle_free_height = obstacle_free_height;
+  Q3DR_TRY(m->d_q_boxes.ensure(3 * n));
+  Q3DR_TRY(m->d_q_valid.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(m->d_q_boxes.p, positions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  const unsigned grid = (unsigned)((n + q3dr::kOverlapThreads - 1) / q3dr::kOverlapThreads);
+  q3dr::valid_positions_kernel<<<grid, q3dr::kOverlapThreads, 0, s>>>(m->d_nodes.p, m->d_q_boxes.p, (uint32_t)n, vp,
+                                                                     m->d_q_valid.p);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(valid, m->d_q_valid.p, n, cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  return Q3DR_OK;
+}
+
+// ---- occupancy octree -> BVH leaves, grid weights ----
+
+int q3dr_octree_leaves_to_boxes(const float* center, const float* size, const float* occupancy,
+                                const uint32_t* observation_count, size_t n, const float bvh_bbox[6],
+                                float obstacle_free_height, float occupancy_threshold, uint32_t observation_threshold,
+                                int device, float* out_boxes, uint32_t* out_source, size_t* n_out) {
+  if (!n_out) return fail(Q3DR_ERR_INVALID_ARG, "n_out is NULL");
+  *n_out = 0;
+  if (n == 0) return Q3DR_OK;
+  if (!center || !size || !occupancy || !observation_count || !bvh_bbox || !out_boxes || !out_source)
+    return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "too many octree leaves for one call");
+  int count = 0;
+  Q3DR_TRY(q3dr_device_count(&count));
+  if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  if (device < 0 || device >= count) return fail(Q3DR_ERR_INVALID_ARG, "device index out of range");
+  Q3DR_CUDA(cudaSetDevice(device));
+  DevBuf<float> d_center, d_size, d_occ, d_box, d_out_box;
+  DevBuf<uint32_t> d_cnt, d_pos, d_out_src, d_keep;
+  DevBuf<uint8_t> d_tmp;
+  struct Guard {
+    DevBuf<float>*a, *b, *c, *d, *e;
+    DevBuf<uint32_t>*f, *g, *h, *i;
+    DevBuf<uint8_t>* j;
+    ~Guard() {
+      a->release(); b->release(); c->release(); d->release(); e->release();
+      f->release(); g->release(); h->release(); i->release(); j->release();
+    }
+  } guard{&d_center, &d_size, &d_occ, &d_box, &d_out_box, &d_cnt, &d_pos, &d_out_src, &d_keep, &d_tmp};
+  Q3DR_TRY(d_center.ensure(3 * n));
+  Q3DR_TRY(d_size.ensure(n));
+  Q3DR_TRY(d_occ.ensure(n));
+  Q3DR_TRY(d_cnt.ensure(n));
+  Q3DR_TRY(d_keep.ensure(n));
+  Q3DR_TRY(d_box.ensure(6 * n));
+  Q3DR_TRY(d_pos.ensure(n + 1));
+  Q3DR_CUDA(cudaMemcpy(d_center.p, center, 3 * n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_size.p, size, n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_occ.p, occupancy, n * sizeof(float), cudaMemcpyHostToDevice));
+  Q3DR_CUDA(cudaMemcpy(d_cnt.p, observation_count, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  q3dr::LeafRuleParams lp;
+  lp.center = d_center.p;
+  lp.size = d_size.p;
+  lp.occupancy = d_occ.p;
+  lp.observation_count = d_cnt.p;
+  lp.n = (uint32_t)n;
+  for (int i = 0; i < 6; ++i) lp.bvh_bbox[i] = bvh_bbox[i];
+  lp.obstacle_free_height = obstacle_free_height;
+  lp.occupancy_threshold = occupancy_threshold;
+  lp.observation_threshold = observation_threshold;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  q3dr::leaf_rule_kernel<<<grid, 256>>>(lp, d_keep.p, d_box.p);
+  Q3DR_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  Q3DR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_keep.p, d_pos.p, (int)n));
+  Q3DR_TRY(d_tmp.ensure(tmp_bytes));
+  Q3DR_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp.p, tmp_bytes, d_keep.p, d_pos.p, (int)n));
+  uint32_t last_pos = 0, last_keep = 0;
+  Q3DR_CUDA(cudaMemcpy(&last_pos, d_pos.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  Q3DR_CUDA(cudaMemcpy(&last_keep, d_keep.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  const size_t kept = (size_t)last_pos + last_keep;
+  if (kept) {
+    Q3DR_TRY(d_out_box.ensure(6 * kept));
+    Q3DR_TRY(d_out_src.ensure(kept));
+    q3dr::leaf_compact_kernel<<<grid, 256>>>(d_keep.p, d_pos.p, d_box.p, (uint32_t)n, d_out_box.p, d_out_src.p);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaMemcpy(out_boxes, d_out_box.p, 6 * kept * sizeof(float), cudaMemcpyDeviceToHost));
+    Q3DR_CUDA(cudaMemcpy(out_source, d_out_src.p, kept * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  *n_out = kept;
+  return Q3DR_OK;
+}
+
+int q3dr_map_update_weights_from_grid(q3dr_map* m, const float grid_origin[3], float grid_increment,
+                                      const int32_t grid_dim[3], const float* grid_weight,
+                                      float voxel_information_lambda, const uint32_t* observation_count,
+                                      float* weights_out) {
+  Q3DR_TRY(check_map(m));
+  if (!grid_origin || !grid_dim || !grid_weight || !observation_count) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (!(grid_increment > 0.0f) || grid_dim[0] <= 0 || grid_dim[1] <= 0 || grid_dim[2] <= 0)
+    return fail(Q3DR_ERR_INVALID_ARG, "bad grid");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  const size_t cells = (size_t)grid_dim[0] * grid_dim[1] * grid_dim[2];
+  DevBuf<float> d_gw, d_w;
+  DevBuf<uint32_t> d_cnt;
+  struct Guard {
+    DevBuf<float>*a, *b;
+    DevBuf<uint32_t>* c;
+    ~Guard() { a->release(); b->release(); c->release(); }
+  } guard{&d_gw, &d_w, &d_cnt};
+  Q3DR_TRY(d_gw.ensure(cells));
+  Q3DR_TRY(d_w.ensure(m->n));
+  Q3DR_TRY(d_cnt.ensure(m->n));
+  Q3DR_CUDA(cudaMemcpyAsync(d_gw.p, grid_weight, cells * sizeof(float), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemcpyAsync(d_cnt.p, observation_count, m->n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  q3dr::GridParams g;
+  for (int i = 0; i < 3; ++i) {
+    g.origin[i] = grid_origin[i];
+    g.dim[i] = grid_dim[i];
+  }
+  g.increment = grid_increment;
+  g.lambda = voxel_information_lambda;
+  q3dr::grid_weights_kernel<<<(unsigned)((m->n + 255) / 256), 256, 0, s>>>(m->d_leaf_rec.p, (uint32_t)q3dr::kLeafRecStride,
+                                                                          (uint32_t)m->n, g, d_gw.p, d_cnt.p, d_w.p);
+  Q3DR_CUDA(cudaGetLastError());
+  // the host copy of the weights follows (q3dr_map_reset re-uploads from it)
+  Q3DR_CUDA(cudaMemcpyAsync(m->h_weight.data(), d_w.p, m->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (weights_out) std::memcpy(weights_out, m->h_weight.data(), m->n * sizeof(float));
+  return Q3DR_OK;
+}
+
+// ---- one process, several GPUs: the map replicated, viewpoints sharded ----
+
+}  // extern "C"
+
+struct q3dr_multi {
+  std::vector<q3dr_map*> maps;
+  std::vector<int> devices;
+  std::vector<q3dr_result> parts;
+  std::vector<uint64_t> first;
+};
+
+extern "C" {
+
+int q3dr_multi_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
+                      const int* devices, int n_devices, q3dr_multi** out) {
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  Q3DR_TRY(q3dr_device_count(&count));
+  if (count <= 0) return fail(Q3DR_ERR_NO_DEVICE, "no CUDA device visible; this engine has no CPU path");
+  if (n_devices <= 0) n_devices = count;
+  if (n_devices > count && devices == nullptr) return fail(Q3DR_ERR_INVALID_ARG, "more devices requested than visible");
+  q3dr_multi* mm = new (std::nothrow) q3dr_multi;
+  if (!mm) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");
+  int st = Q3DR_OK;
+  std::shared_ptr<const q3dr::FlatTree> tree;  // flattened once, uploaded to every device
+  for (int i = 0; i < n_devices && st == Q3DR_OK; ++i) {
+    const int dev = devices ? devices[i] : i;
+    q3dr_map* m = nullptr;
+    st = map_create_impl(boxes, weights, normals, depth, n, dev, tree, &m);
+    if (st == Q3DR_OK) {
+      tree = m->tree;
+      mm->maps.push_back(m);
+      mm->devices.push_back(dev);
+    }
+  }
+  if (st != Q3DR_OK) {
+    const std::string msg = q3dr_detail::last_error();
+    for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
+    delete mm;
+    return fail(st, msg);
+  }
+  mm->parts.resize(mm->maps.size());
+  mm->first.assign(mm->maps.size() + 1, 0);
+  *out = mm;
+  return Q3DR_OK;
+}
+
+int q3dr_multi_destroy(q3dr_multi* mm) {
+  if (!mm) return Q3DR_OK;
+  for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
+  delete mm;
+  return Q3DR_OK;
+}
+
+int q3dr_multi_device_count(const q3dr_multi* mm) { return mm ? (int)mm->maps.size() : 0; }
+
+q3dr_map* q3dr_multi_map(q3dr_multi* mm, int i) {
+  if (!mm || i < 0 || i >= (int)mm->maps.size()) return nullptr;
+  return mm->maps[(size_t)i];
+}
+
+int q3dr_multi_update_weights(q3dr_multi* mm, const float* weights) {
+  if (!mm) return fail(Q3DR_ERR_INVALID_ARG, "multi is NULL");
+  for (q3dr_map* m : mm->maps) Q3DR_TRY(q3dr_map_update_weights(m, weights));
+  return Q3DR_OK;
+}
+
+int q3dr_multi_score_viewpoints(q3dr_multi* mm, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                uint32_t y0, uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts,
+                                q3dr_multi_result* result) {
+  if (!mm || !result || !K || !opts || (!Rt && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  const size_t G = mm->maps.size();
+  // contiguous slices, sizes differing by at most one
+  for (size_t g = 0; g <= G; ++g) mm->first[g] = (uint64_t)((n / G) * g + std::min<size_t>(g, n % G));
+  std::vector<int> status(G, Q3DR_OK);
+  std::vector<std::string> message(G);
+  std::vector<std::thread> workers;
+  for (size_t g = 0; g < G; ++g) {
+    workers.emplace_back([&, g]() {
+      const size_t lo = (size_t)mm->first[g], hi = (size_t)mm->first[g + 1];
+      status[g] = q3dr_score_viewpoints(mm->maps[g], K, image_width, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts, &mm->parts[g]);
+      if (status[g] != Q3DR_OK) message[g] = q3dr_last_error();  // thread-local: carry it out of the worker
+    });
+  }
+  for (std::thread& t : workers) t.join();
+  for (size_t g = 0; g < G; ++g) {
+    if (status[g] != Q3DR_OK) return fail(status[g], "device " + std::to_string(mm->devices[g]) + ": " + message[g]);
+  }
+  result->n_parts = (uint32_t)G;
+  result->n_viewpoints = n;
+  result->first_viewpoint = mm->first.data();
+  result->parts = mm->parts.data();
+  return Q3DR_OK;
+}
+
+}  // extern "C"

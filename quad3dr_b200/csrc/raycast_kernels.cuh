@@ -210,7 +210,7 @@ __device__ __forceinline__ void cswap(uint32_t& ka, uint32_t& na, float& da, uin
 // reference's own test (miss, or dist_sq > best), and rounding is monotone, so the box of an ancestor
 // never fails when a descendant leaf would pass.  Equal dist_sq: higher leaf
 // index wins (= later in the reference's depth-first order).
-__device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
+static __device__ __noinline__ void traverse_packet_exact(const Ray& ray, PacketHit& best, const float4* __restrict__ nodes,
                                                    const float4* smem_top, uint32_t n_top) {
   float stack_d[kStackEntries];
   uint32_t stack_n[kStackEntries];
@@ -453,7 +453,7 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const RaycastParams p) {
+static __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const RaycastParams p) {
   extern __shared__ float4 smem_top[];
   __shared__ uint32_t s_tile[kWarpsPerCta];
   for (uint32_t i = threadIdx.x; i < p.n_top * 8; i += blockDim.x) smem_top[i] = p.nodes[i];
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const Raycas
   }
 }
 
-__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+static __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t seg_block_scan(uint32_t v, uint32_t* s_warp,
   return before + inc - v;
 }
 
-__global__ void __launch_bounds__(kSegThreads) seg_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* offsets,
+static __global__ void __launch_bounds__(kSegThreads) seg_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* offsets,
                                                                uint32_t n_segs, uint32_t* totals /* [B] or null */) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   const uint32_t vp = blockIdx.x;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_scan_kernel(const uint32_t* _
 
 // bits -> ordered leaf list of the viewpoint (thread t owns 4 consecutive words of the segment); the bitmap is
 // cleared on the way and the segment counter reset for the next chunk.
-__global__ void __launch_bounds__(kSegThreads) emit_list_kernel(const ScoreParams2 p) {
+static __global__ void __launch_bounds__(kSegThreads) emit_list_kernel(const ScoreParams2 p) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   const uint32_t seg = blockIdx.x, vp = blockIdx.y, tid = threadIdx.x;
   const size_t sidx = (size_t)vp * p.n_segs + seg;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kSegThreads) emit_list_kernel(const ScoreParam
 // Work decomposition of the scoring / packing passes: viewpoint v owns ceil(hit_count[v] / 256) BLOCKS of 256 list
 // entries; blocks of all viewpoints of the chunk are numbered consecutively (blk_off = exclusive scan) and handed
 // out round-robin to a persistent grid, so a viewpoint with many visible voxels is spread over many CTAs.
-__global__ void __launch_bounds__(kSegThreads) block_offsets_kernel(const uint32_t* __restrict__ hit_count, uint32_t n_vp,
+static __global__ void __launch_bounds__(kSegThreads) block_offsets_kernel(const uint32_t* __restrict__ hit_count, uint32_t n_vp,
                                                                     uint32_t* blk_off /* [n_vp + 1] */) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   uint32_t run = 0;
@@ -232,7 +232,7 @@ __device__ __forceinline__ float voxel_information_rec(const ScoreParams2& p, co
 // CTA works on kScoreUnroll blocks at once and issues all their fetches before any arithmetic.
 constexpr int kScoreUnroll = 4;
 
-__global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScoreParams2 p, uint32_t n_vp) {
+static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScoreParams2 p, uint32_t n_vp) {
   __shared__ uint32_t s_cnt[kScoreUnroll][kSegThreads / 32];
   __shared__ double s_dsum[kScoreUnroll][kSegThreads / 32];
   __shared__ uint32_t s_off[kMaxChunkViewpoints + 1];
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScorePa
 }
 
 // per viewpoint: exclusive scan of its blocks' kept counts, fp64 total over its blocks in ascending order
-__global__ void __launch_bounds__(kSegThreads) finalize_viewpoints_kernel(const ScoreParams2 p) {
+static __global__ void __launch_bounds__(kSegThreads) finalize_viewpoints_kernel(const ScoreParams2 p) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   __shared__ double s_dsum[kSegThreads];
   const uint32_t vp = blockIdx.x;
@@ -371,7 +371,7 @@ struct PackParams2 {
 };
 
 // kept entries -> dense CSR pool, ascending leaf order preserved (block-local scan of the keep flags)
-__global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const PackParams2 p) {
+static __global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const PackParams2 p) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   __shared__ uint32_t s_off[kMaxChunkViewpoints + 1];
   const uint32_t tid = threadIdx.x;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const PackPara
 }
 
 // offsets[i + 1] = offsets[0] + inclusive_scan(kept)[i]; one block, n <= 4096 viewpoints per chunk.
-__global__ void __launch_bounds__(kSegThreads) csr_offsets_kernel(const uint32_t* __restrict__ kept, uint32_t n,
+static __global__ void __launch_bounds__(kSegThreads) csr_offsets_kernel(const uint32_t* __restrict__ kept, uint32_t n,
                                                                   uint64_t* offsets /* at the chunk's first viewpoint */) {
   __shared__ uint32_t s_warp[kSegThreads / 32 + 1];
   uint64_t run = offsets[0];

@@ -47,7 +47,7 @@ __device__ __forceinline__ float novel_information(float obs_info, float observe
 }
 
 // one CTA per requested viewpoint
-__global__ void __launch_bounds__(kSetThreads) new_information_kernel(const SetParams p, const float* __restrict__ observed,
+static __global__ void __launch_bounds__(kSetThreads) new_information_kernel(const SetParams p, const float* __restrict__ observed,
                                                                       const uint32_t* __restrict__ vp_index /* nullable */,
                                                                       float* out) {
   __shared__ double s_part[kSetThreads / 32];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kSetThreads) new_information_kernel(const SetP
 
 // folds viewpoint vp's voxel set into the observed map; each voxel occurs once in the set, so the update is free of
 // conflicts.  Grid-stride over the entries, per-CTA partial sums in part[blockIdx.x].
-__global__ void __launch_bounds__(kSetThreads) observed_add_kernel(const SetParams p, float* observed, uint32_t vp,
+static __global__ void __launch_bounds__(kSetThreads) observed_add_kernel(const SetParams p, float* observed, uint32_t vp,
                                                                    double* part) {
   __shared__ double s_part[kSetThreads / 32];
   const uint64_t b = p.offsets[vp], e = p.offsets[vp + 1];
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kSetThreads) observed_add_kernel(const SetPara
   if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
-__global__ void sum_parts_kernel(const double* __restrict__ part, uint32_t n, float* out) {
+static __global__ void sum_parts_kernel(const double* __restrict__ part, uint32_t n, float* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (uint32_t i = 0; i < n; ++i) t += part[i];
@@ -103,7 +103,7 @@ __global__ void sum_parts_kernel(const double* __restrict__ part, uint32_t n, fl
 }
 
 // dense[leaf] = info for every entry of viewpoint vp (value = NaN: remove them again)
-__global__ void scatter_set_kernel(const SetParams p, uint32_t vp, float* dense, int clear) {
+static __global__ void scatter_set_kernel(const SetParams p, uint32_t vp, float* dense, int clear) {
   const uint64_t b = p.offsets[vp], e = p.offsets[vp + 1];
   const float nan = __int_as_float(0x7FC00000);
   for (uint64_t i = b + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -114,7 +114,7 @@ __global__ void scatter_set_kernel(const SetParams p, uint32_t vp, float* dense,
 // compute_overlap_information_lambda(set1 = viewpoint b, set2 = the scattered viewpoint a): the reference looks b's
 // entry up in a with VoxelWithInformation::operator== (occupied_tree.h:73-79), which compares voxel AND information,
 // so only voxels carrying bit-identical information in both sets count; each adds min(info_a, info_b).
-__global__ void __launch_bounds__(kSetThreads) overlap_information_kernel(const SetParams p, const float* __restrict__ dense_a,
+static __global__ void __launch_bounds__(kSetThreads) overlap_information_kernel(const SetParams p, const float* __restrict__ dense_a,
                                                                           const uint32_t* __restrict__ vp_index, float* out) {
   __shared__ double s_part[kSetThreads / 32];
   const uint32_t vp = vp_index[blockIdx.x];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kSetThreads) overlap_information_kernel(const 
   if (threadIdx.x == 0) out[blockIdx.x] = (float)t;
 }
 
-__global__ void fill_f32_kernel(float* p, size_t n, float v) {
+static __global__ void fill_f32_kernel(float* p, size_t n, float v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
