@@ -62,17 +62,16 @@ void release_device(q3dr_map* m) {
   m->last_n_vp = m->last_n_entries = 0;
 }
 
-template <int MODE>
-int configure_kernel(q3dr_map* m) {
+int configure_rays_kernel(q3dr_map* m) {
   if (m->smem_bytes > 48 * 1024) {
-    Q3DR_CUDA(cudaFuncSetAttribute(q3dr::raycast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    Q3DR_CUDA(cudaFuncSetAttribute(q3dr::raycast_rays_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)m->smem_bytes));
   }
   int per_sm = 0;
-  Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3dr::raycast_kernel<MODE>, q3dr::kThreadsPerCta,
+  Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3dr::raycast_rays_kernel, q3dr::kThreadsPerCta,
                                                           m->smem_bytes));
   if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast kernel does not fit on an SM");
-  m->grid_ctas[MODE] = per_sm * m->sm_count;
+  m->grid_rays_ctas = per_sm * m->sm_count;
   return Q3DR_OK;
 }
 
@@ -109,7 +108,7 @@ int upload_map(q3dr_map* m) {
   Q3DR_CUDA(cudaMemset(m->d_counter.p, 0, 4 * sizeof(uint32_t)));
   Q3DR_TRY(m->h_scalar.ensure(8));
   m->smem_bytes = (size_t)m->tree->top_nodes * sizeof(q3dr::Node4);
-  Q3DR_TRY(configure_kernel<q3dr::kModeRays>(m));
+  Q3DR_TRY(configure_rays_kernel(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModeScore>(m));
   Q3DR_TRY(configure_kernel2<q3dr::kModePixels>(m));
   return Q3DR_OK;
@@ -795,9 +794,9 @@ int q3dr_intersect_rays(q3dr_map* m, const float* origins, const float* directio
   rp.n_rays = (uint32_t)n;
   rp.total_tiles = (uint32_t)((n + 31) / 32);
   rp.pixels = m->d_pixels.p;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeRays],
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_rays_ctas,
                                           ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-  q3dr::raycast_kernel<q3dr::kModeRays><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  q3dr::raycast_rays_kernel<<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, n * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));
@@ -900,9 +899,9 @@ int q3dr_raycast_unique(q3dr_map* m, const float K[4], const float Rt[12], uint3
   rp.n_rays = (uint32_t)ne;
   rp.total_tiles = (uint32_t)((ne + 31) / 32);
   rp.pixels = m->d_pixels.p;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_ctas[q3dr::kModeRays],
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid_rays_ctas,
                                           ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-  q3dr::raycast_kernel<q3dr::kModeRays><<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
+  q3dr::raycast_rays_kernel<<<grid, q3dr::kThreadsPerCta, m->smem_bytes, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, ne * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));

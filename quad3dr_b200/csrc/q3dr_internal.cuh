@@ -193,7 +193,7 @@ struct q3dr_map {
   cudaEvent_t ev_packed = nullptr;
   bool host_result_valid = false;      // the host pools already hold the entries of the last call
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int grid_ctas[3] = {0, 0, 0};
+  int grid_rays_ctas = 0;
   int grid2_ctas[2] = {0, 0};
   size_t smem_bytes = 0;
   q3dr_stats stats{};

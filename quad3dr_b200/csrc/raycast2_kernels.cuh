@@ -273,7 +273,7 @@ __device__ __forceinline__ void copy_dir_from_lane(Dir2& r, const Dir2& src_ray,
   }
 }
 
-// MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_kernel<kModeRays>).
+// MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_rays_kernel).
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const RaycastParams p) {
   __shared__ uint32_t s_tile[kWarpsPerCta];

@@ -4,9 +4,10 @@
 // correctly rounded binary32 operation in the reference's order (explicit __f*_rn intrinsics, the
 // translation unit is also compiled with -fmad=false, no fast-math, no FTZ).
 //
-// raycast_kernel<MODE>   one warp = one 32-ray packet (ray lists, pixel lists); persistent grid, packet traversal
+// raycast_rays_kernel   one warp = one 32-ray packet (ray lists, pixel lists); persistent grid, packet traversal
 //                        of the 4-wide node array.  Camera windows use raycast2_kernel (raycast2_kernels.cuh),
-//                        scoring lives in score_kernels.cuh.
+//                        scoring lives in score_kernels.cuh.  This header also holds what both share: the
+//                        reference's box test and camera ray in exact binary32, the exact fallback traversal.
 #pragma once
 
 #include <cfloat>
@@ -22,18 +23,15 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kStackEntries = 64;
 constexpr uint32_t kEmptyPixel = 0xFFFFFFFFu;
-constexpr int kTileW = 8;
-constexpr int kTileH = 4;
 constexpr int kScoreThreads = 512;
 #ifndef Q3DR_SMEM_TOP
 #define Q3DR_SMEM_TOP 1
 #endif
 constexpr bool kSmemTopLevels = (Q3DR_SMEM_TOP != 0);
 
-enum RaycastMode : int {
+enum RaycastMode : int {   // raycast2_kernel<MODE>
   kModeScore = 0,   // dedup into the per-viewpoint first-pixel table + bitmap
-  kModePixels = 1,  // per-pixel q3dr_pixel_hit records (raycastCuda compat)
-  kModeRays = 2     // arbitrary ray list (intersectsCuda compat)
+  kModePixels = 1   // per-pixel q3dr_pixel_hit records (raycastCuda compat)
 };
 
 struct RaycastParams {
@@ -52,12 +50,12 @@ struct RaycastParams {
   uint64_t word_stride;
   uint32_t* seg_hits;   // [slot][n_segs]: set bits per 32768-leaf segment of the bitmap (score_kernels.cuh)
   uint32_t n_segs;
-  // kModePixels / kModeRays
+  // kModePixels / raycast_rays_kernel
   q3dr_pixel_hit* pixels;
   const uint8_t* __restrict__ leaf_depth;
-  const float* __restrict__ ray_o;  // kModeRays: [n][3]
+  const float* __restrict__ ray_o;  // raycast_rays_kernel: [n][3]
   const float* __restrict__ ray_d;
-  const uint32_t* __restrict__ pix_list;  // kModeRays alternative: window pixel indices of one viewpoint
+  const uint32_t* __restrict__ pix_list;  // or: window pixel indices of one viewpoint
   uint32_t n_rays;
   uint32_t* tile_counter;
   uint32_t bounded_map;  // every box coordinate is below 1e18 in magnitude
@@ -452,8 +450,10 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
   }
 }
 
-template <int MODE>
-static __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const RaycastParams p) {
+// Ray lists (q3dr_intersect_rays: origins + directions) and pixel lists of one viewpoint (the second pass of
+// q3dr_raycast_unique): 32 rays per warp, one per lane, q3dr_pixel_hit records out.  Camera windows are cast by
+// raycast2_kernel (raycast2_kernels.cuh).
+static __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_rays_kernel(const RaycastParams p) {
   extern __shared__ float4 smem_top[];
   __shared__ uint32_t s_tile[kWarpsPerCta];
   for (uint32_t i = threadIdx.x; i < p.n_top * 8; i += blockDim.x) smem_top[i] = p.nodes[i];
@@ -475,32 +475,17 @@ static __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const
     best.leaf = -1;
     best.t = 0.0f;
     best.tU = 0.0f;
-    bool live;
-    uint32_t vp = 0, pix = 0, px = 0, py = 0;
-    if (MODE == kModeRays) {
-      const uint32_t i = tile * 32u + lane;
-      live = i < p.n_rays;
-      pix = i;
-      if (live && p.pix_list != nullptr) {
-        const uint32_t wp = __ldg(p.pix_list + i);
-        py = wp / p.w;
-        px = wp - py * p.w;
-        camera_ray(p.rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
-      } else if (live) {
-        make_ray(__ldg(p.ray_o + 3 * (size_t)i), __ldg(p.ray_o + 3 * (size_t)i + 1), __ldg(p.ray_o + 3 * (size_t)i + 2),
-                 __ldg(p.ray_d + 3 * (size_t)i), __ldg(p.ray_d + 3 * (size_t)i + 1), __ldg(p.ray_d + 3 * (size_t)i + 2),
-                 ray);
-      }
-    } else {
-      vp = tile / p.tiles_per_vp;
-      const uint32_t rem = tile - vp * p.tiles_per_vp;
-      const uint32_t ty = rem / p.tiles_x;
-      const uint32_t tx = rem - ty * p.tiles_x;
-      px = tx * kTileW + (lane & (kTileW - 1));
-      py = ty * kTileH + (lane >> 3);
-      live = (px < p.w) && (py < p.h);
-      pix = py * p.w + px;
-      camera_ray(p.rt + 12 * (size_t)vp, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+    uint32_t px = 0, py = 0;
+    const uint32_t i = tile * 32u + lane;
+    const bool live = i < p.n_rays;
+    if (live && p.pix_list != nullptr) {
+      const uint32_t wp = __ldg(p.pix_list + i);
+      py = wp / p.w;
+      px = wp - py * p.w;
+      camera_ray(p.rt, p.fx, p.fy, p.cx, p.cy, p.x0 + px, p.y0 + py, ray);
+    } else if (live) {
+      make_ray(__ldg(p.ray_o + 3 * (size_t)i), __ldg(p.ray_o + 3 * (size_t)i + 1), __ldg(p.ray_o + 3 * (size_t)i + 2),
+               __ldg(p.ray_d + 3 * (size_t)i), __ldg(p.ray_d + 3 * (size_t)i + 1), __ldg(p.ray_d + 3 * (size_t)i + 2), ray);
     }
     const uint32_t live_mask = __ballot_sync(Q3DR_FULL_MASK, live);
     if (live_mask == 0u) continue;
@@ -539,38 +524,18 @@ static __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast_kernel(const
       traverse_packet_exact(ray, best, p.nodes, smem_top, p.n_top);
     }
 
-    if (MODE == kModeScore) {
-      // warp-aggregated dedup: lanes are in row-major pixel order inside the tile, so the lowest lane of
-      // each equal-leaf group owns the group's first pixel; only group leaders touch the tables.
-      const uint32_t grp = __match_any_sync(Q3DR_FULL_MASK, best.leaf);
-      const bool leader = (best.leaf >= 0) && ((__ffs(grp) - 1) == lane);
-      if (leader) {
-        uint32_t* fp = p.first_pix + (size_t)vp * p.leaf_stride + (uint32_t)best.leaf;
-        const uint32_t old = atomicMin(fp, pix);
-        if (old == kEmptyPixel) {
-          atomicOr(p.bitmap + (size_t)vp * p.word_stride + ((uint32_t)best.leaf >> 5), 1u << (best.leaf & 31));
-          atomicAdd(p.seg_hits + (size_t)vp * p.n_segs + ((uint32_t)best.leaf >> 15), 1u);
-        }
-      }
-    } else {
-      if (live) {
-        q3dr_pixel_hit out;
-        const bool hit = best.leaf >= 0;
-        // intersection = origin + direction * t  (geometry.h:345-348); t = 0 when the origin is inside
-        out.intersection[0] = hit ? __fadd_rn(ray.ox, __fmul_rn(ray.dx, best.t)) : 0.0f;
-        out.intersection[1] = hit ? __fadd_rn(ray.oy, __fmul_rn(ray.dy, best.t)) : 0.0f;
-        out.intersection[2] = hit ? __fadd_rn(ray.oz, __fmul_rn(ray.dz, best.t)) : 0.0f;
-        out.leaf = best.leaf;
-        out.depth = hit ? (uint32_t)__ldg(p.leaf_depth + best.leaf) : 0u;
-        out.dist_sq = hit ? best.dsq : 0.0f;
-        const bool has_xy = (MODE == kModePixels) || (p.pix_list != nullptr);
-        out.screen_x = has_xy ? (float)(p.x0 + px) : 0.0f;
-        out.screen_y = has_xy ? (float)(p.y0 + py) : 0.0f;
-        const size_t oi = (MODE == kModePixels) ? ((size_t)vp * p.w * p.h + pix) : (size_t)pix;
-        float4* dst = reinterpret_cast<float4*>(p.pixels + oi);
-        dst[0] = make_float4(out.intersection[0], out.intersection[1], out.intersection[2], __int_as_float(out.leaf));
-        dst[1] = make_float4(__uint_as_float(out.depth), out.dist_sq, out.screen_x, out.screen_y);
-      }
+    if (live) {
+      const bool hit = best.leaf >= 0;
+      // intersection = origin + direction * t  (geometry.h:345-348); t = 0 when the origin is inside
+      const float hx = hit ? __fadd_rn(ray.ox, __fmul_rn(ray.dx, best.t)) : 0.0f;
+      const float hy = hit ? __fadd_rn(ray.oy, __fmul_rn(ray.dy, best.t)) : 0.0f;
+      const float hz = hit ? __fadd_rn(ray.oz, __fmul_rn(ray.dz, best.t)) : 0.0f;
+      const uint32_t depth = hit ? (uint32_t)__ldg(p.leaf_depth + best.leaf) : 0u;
+      const bool has_xy = p.pix_list != nullptr;
+      float4* dst = reinterpret_cast<float4*>(p.pixels + (size_t)i);
+      dst[0] = make_float4(hx, hy, hz, __int_as_float(best.leaf));
+      dst[1] = make_float4(__uint_as_float(depth), hit ? best.dsq : 0.0f, has_xy ? (float)(p.x0 + px) : 0.0f,
+                           has_xy ? (float)(p.y0 + py) : 0.0f);
     }
   }
 }
