@@ -30,6 +30,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <unordered_set>
 #include <utility>
 #include <vector>
@@ -167,6 +168,7 @@ class OccupiedTreeCuda {
     map_ = nullptr;
     nodes_.clear();
     depth_.clear();
+    leaf_of_.clear();
   }
 
   /// ViewpointPlannerData::updateWeights*: NodeObject::weight changed on the host, refresh the device copy.
@@ -175,6 +177,15 @@ class OccupiedTreeCuda {
   }
 
   std::size_t getNumOfLeafNodes() const { return nodes_.size(); }
+  /// leaf index of a host node (the inverse of leafNode); -1 if the node is not a leaf of this tree
+  std::int32_t leafIndex(const NodeT* node) const {
+    if (leaf_of_.empty()) {
+      leaf_of_.reserve(nodes_.size());
+      for (std::size_t k = 0; k < nodes_.size(); ++k) leaf_of_[nodes_[k]] = static_cast<std::int32_t>(k);
+    }
+    typename std::unordered_map<const NodeT*, std::int32_t>::const_iterator it = leaf_of_.find(node);
+    return it == leaf_of_.end() ? -1 : it->second;
+  }
   NodeT* leafNode(std::int32_t leaf) const { return leaf < 0 ? nullptr : nodes_[static_cast<std::size_t>(leaf)]; }
   q3dr_map* handle() const { return map_; }
 
@@ -319,6 +330,7 @@ class OccupiedTreeCuda {
   q3dr_map* map_ = nullptr;
   std::vector<NodeT*> nodes_;  // leaf index -> host node
   std::vector<std::uint32_t> depth_;  // leaf index -> depth in the host tree
+  mutable std::unordered_map<const NodeT*, std::int32_t> leaf_of_;  // host node -> leaf index (built on first use)
 };
 
 /// viewpoint_planner::ViewpointRaycast with enable_cuda = true, plus the planner's scoring facade.
@@ -464,6 +476,10 @@ class ObservedVoxelMapCuda {
     check(q3dr_observed_add_viewpoint(tree_->handle(), obs_, factor_, viewpoint, &v));
     return v;
   }
+  /// computeNewInformation / addObservedVoxelsToViewpointPath for a stored ViewpointEntry::voxel_set
+  float computeNewInformation(const VoxelWithInformationSet<NodeT>& voxel_set) const { return voxelSet(voxel_set, 0); }
+  float addObservedVoxels(const VoxelWithInformationSet<NodeT>& voxel_set) { return voxelSet(voxel_set, 1); }
+
   /// compute_overlap_information_lambda(set1 = others[i], set2 = ref)
   std::vector<float> computeOverlapInformation(std::uint32_t ref, const std::vector<std::uint32_t>& others) const {
     std::vector<float> out(others.size());
@@ -472,6 +488,19 @@ class ObservedVoxelMapCuda {
   }
 
  private:
+  float voxelSet(const VoxelWithInformationSet<NodeT>& voxel_set, int add) const {
+    std::vector<std::int32_t> leaf;
+    std::vector<float> info;
+    leaf.reserve(voxel_set.size());
+    info.reserve(voxel_set.size());
+    for (typename VoxelWithInformationSet<NodeT>::const_iterator it = voxel_set.begin(); it != voxel_set.end(); ++it) {
+      leaf.push_back(tree_->leafIndex(it->voxel));
+      info.push_back(it->information);
+    }
+    float v = 0;
+    check(q3dr_observed_voxel_set(tree_->handle(), obs_, factor_, leaf.data(), info.data(), leaf.size(), add, &v));
+    return v;
+  }
   void check(int status) const {
     if (status != Q3DR_OK) throw typename TreeType::CudaError(status, q3dr_last_error());
   }

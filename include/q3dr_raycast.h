@@ -230,6 +230,12 @@ int q3dr_new_information(q3dr_map* map, const q3dr_observed* obs, float viewpoin
 int q3dr_observed_add_viewpoint(q3dr_map* map, q3dr_observed* obs, float viewpoint_information_factor,
                                 uint32_t viewpoint, float* new_information);
 
+/* The same two operations for a voxel set handed over explicitly (host arrays, each voxel at most once, any order):
+ * a stored ViewpointEntry::voxel_set that is not part of the resident result.  add != 0: fold it into the map
+ * (addObservedVoxelsToViewpointPath); add == 0: only evaluate it (computeNewInformation). */
+int q3dr_observed_voxel_set(q3dr_map* map, q3dr_observed* obs, float viewpoint_information_factor, const int32_t* leaf,
+                            const float* information, size_t n, int add, float* new_information);
+
 /* compute_overlap_information_lambda (viewpoint_planner_path.cpp:838-848) of each viewpoint others[i] (set1)
  * against viewpoint `ref` (set2).  Like the reference's lookup (VoxelWithInformation::operator==,
  * occupied_tree.h:73-79) a voxel counts only if it carries bit-identical information in both sets. */

@@ -141,6 +141,53 @@ int q3dr_observed_add_viewpoint(q3dr_map* m, q3dr_observed* o, float factor, uin
   return Q3DR_OK;
 }
 
+int q3dr_observed_voxel_set(q3dr_map* m, q3dr_observed* o, float factor, const int32_t* leaf, const float* information,
+                            size_t n, int add, float* new_information) {
+  Q3DR_TRY(check_map(m));
+  if (!o || ((!leaf || !information) && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (o->map != m) return fail(Q3DR_ERR_INVALID_ARG, "observed map belongs to another occupancy map");
+  if (n >= 0x7FFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "voxel set too large");
+  for (size_t i = 0; i < n; ++i) {
+    if (leaf[i] < 0 || (size_t)leaf[i] >= m->n) return fail(Q3DR_ERR_INVALID_ARG, "leaf index out of range");
+  }
+  if (new_information) *new_information = 0.0f;
+  if (n == 0) return Q3DR_OK;
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->stream;
+  q3dr::SetParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.leaf_rec = m->d_leaf_rec.p;
+  sp.rec_stride = (uint32_t)q3dr::kLeafRecStride;
+  sp.factor = factor;
+  DevBuf<int32_t> d_leaf;
+  DevBuf<float> d_info;
+  struct Guard {
+    DevBuf<int32_t>* a;
+    DevBuf<float>* b;
+    ~Guard() { a->release(); b->release(); }
+  } guard{&d_leaf, &d_info};
+  Q3DR_TRY(d_leaf.ensure(n));
+  Q3DR_TRY(d_info.ensure(n));
+  Q3DR_CUDA(cudaMemcpyAsync(d_leaf.p, leaf, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  Q3DR_CUDA(cudaMemcpyAsync(d_info.p, information, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  const unsigned grid = 64;
+  Q3DR_TRY(m->d_set_part.ensure(grid));
+  Q3DR_TRY(m->d_set_out.ensure(1));
+  if (add) {
+    q3dr::observed_add_list_kernel<<<grid, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, d_leaf.p, d_info.p, (uint32_t)n, m->d_set_part.p);
+  } else {
+    q3dr::new_information_list_kernel<<<grid, q3dr::kSetThreads, 0, s>>>(sp, o->d.p, d_leaf.p, d_info.p, (uint32_t)n, m->d_set_part.p);
+  }
+  Q3DR_CUDA(cudaGetLastError());
+  q3dr::sum_parts_kernel<<<1, 32, 0, s>>>(m->d_set_part.p, grid, m->d_set_out.p);
+  Q3DR_CUDA(cudaGetLastError());
+  float v = 0.f;
+  Q3DR_CUDA(cudaMemcpyAsync(&v, m->d_set_out.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (new_information) *new_information = v;
+  return Q3DR_OK;
+}
+
 int q3dr_overlap_information(q3dr_map* m, uint32_t ref, const uint32_t* others, size_t n, float* out) {
   Q3DR_TRY(check_map(m));
   if ((!others || !out) && n) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");

@@ -94,6 +94,53 @@ static __global__ void __launch_bounds__(kSetThreads) observed_add_kernel(const 
   if (threadIdx.x == 0) part[blockIdx.x] = t;
 }
 
+// The same two sums for a voxel set handed over explicitly (device arrays leaf / info of n entries) instead of a
+// viewpoint of the resident result.
+static __global__ void __launch_bounds__(kSetThreads) new_information_list_kernel(const SetParams p, const float* __restrict__ observed,
+                                                                                  const int32_t* __restrict__ leaf,
+                                                                                  const float* __restrict__ info, uint32_t n,
+                                                                                  double* part) {
+  __shared__ double s_part[kSetThreads / 32];
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * kSetThreads + threadIdx.x; i < n; i += gridDim.x * kSetThreads) {
+    const int32_t l = leaf[i];
+    const float obs_info = __fmul_rn(p.factor, info[i]);
+    const float w = __ldg(&p.leaf_rec[(size_t)p.rec_stride * l].w);
+    acc += (double)novel_information(obs_info, observed[l], w);
+  }
+  const double t = block_sum_f64(acc, s_part);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+static __global__ void __launch_bounds__(kSetThreads) observed_add_list_kernel(const SetParams p, float* observed,
+                                                                               const int32_t* __restrict__ leaf,
+                                                                               const float* __restrict__ info, uint32_t n,
+                                                                               double* part) {
+  __shared__ double s_part[kSetThreads / 32];
+  double acc = 0.0;
+  for (uint32_t i = blockIdx.x * kSetThreads + threadIdx.x; i < n; i += gridDim.x * kSetThreads) {
+    const int32_t l = leaf[i];
+    const float obs_info = __fmul_rn(p.factor, info[i]);
+    const float cur = observed[l];
+    float novel;
+    if (cur != cur) {
+      observed[l] = obs_info;
+      novel = obs_info;
+    } else {
+      const float w = __ldg(&p.leaf_rec[(size_t)p.rec_stride * l].w);
+      novel = smin(obs_info, __fsub_rn(w, cur));
+      if (cur <= w) {
+        float nv = __fadd_rn(cur, obs_info);
+        if (nv > w) nv = w;
+        observed[l] = nv;
+      }
+    }
+    acc += (double)novel;
+  }
+  const double t = block_sum_f64(acc, s_part);
+  if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
 static __global__ void sum_parts_kernel(const double* __restrict__ part, uint32_t n, float* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;

@@ -172,6 +172,7 @@ def load_library() -> C.CDLL:
     L.q3dr_new_information.argtypes = [vp, vp, C.c_float, u32p, C.c_size_t, fp]
     L.q3dr_observed_add_viewpoint.argtypes = [vp, vp, C.c_float, C.c_uint32, fp]
     L.q3dr_overlap_information.argtypes = [vp, C.c_uint32, u32p, C.c_size_t, fp]
+    L.q3dr_observed_voxel_set.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int32), fp, C.c_size_t, C.c_int, fp]
     for name in dir(L):
         pass
     _lib = L
@@ -515,6 +516,15 @@ class ObservedVoxels:
         _check(load_library().q3dr_new_information(
             self.map._h, self._h, float(factor), None if idx is None else idx.ctypes.data_as(C.POINTER(C.c_uint32)), n, _fp(out)))
         return out
+
+    def voxel_set(self, factor: float, leaf, information, add: bool) -> float:
+        """computeNewInformation (add=False) / addObservedVoxelsToViewpointPath (add=True) for an explicit voxel set."""
+        leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+        info = _f32(information, (len(leaf),))
+        v = C.c_float(0)
+        _check(load_library().q3dr_observed_voxel_set(self.map._h, self._h, float(factor), leaf.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                      _fp(info), len(leaf), int(bool(add)), C.byref(v)))
+        return float(v.value)
 
     def add_viewpoint(self, factor: float, viewpoint: int) -> float:
         """addObservedVoxelsToViewpointPath; returns the novel information."""

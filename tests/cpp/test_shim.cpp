@@ -374,6 +374,19 @@ int main(int argc, char** argv) {
       const float added = observed.addObservedVoxels(best);
       CHECK(std::fabs(added - s64) <= 1e-5 * std::fabs(s64) + 1e-30);
     }
+    // the same through the reference's own set type (a stored ViewpointEntry::voxel_set)
+    {
+      q3dr::ObservedVoxelMapCuda<mock::Node> by_set(&tree);
+      q3dr::ObservedVoxelMapCuda<mock::Node> by_index(&tree);
+      for (uint32_t v = 0; v < batch.size(); ++v) {
+        const float g1 = by_set.computeNewInformation(scored[v].first);
+        const float g2 = by_index.computeNewInformation(std::vector<uint32_t>(1, v))[0];
+        CHECK(std::fabs(g1 - g2) <= 1e-6f * std::fabs(g2));
+        const float a1 = by_set.addObservedVoxels(scored[v].first);
+        const float a2 = by_index.addObservedVoxels(v);
+        CHECK(std::fabs(a1 - a2) <= 1e-6f * std::fabs(a2));
+      }
+    }
   }
 
   // error convention: callers catch OccupiedTreeType::Error

@@ -119,6 +119,25 @@ def test_greedy_selection_on_device_equals_cpu_selection(scored):
 
 
 @pytest.mark.gpu
+def test_explicit_voxel_sets_match_resident_ones(scored):
+    """A stored voxel set handed over from the host gives the same sums and the same map as the resident viewpoint."""
+    sc, res = scored
+    a, b = E.ObservedVoxels(sc.gpu_map), E.ObservedVoxels(sc.gpu_map)
+    rng = np.random.default_rng(4)
+    for v in (2, 9, 2, 30):
+        e = res.viewpoint(v)
+        perm = rng.permutation(len(e["leaf"]))  # any order
+        assert a.voxel_set(F, e["leaf"][perm], e["info"][perm], add=False) == pytest.approx(b.new_information(F, viewpoints=[v])[0], rel=1e-6)
+        assert a.voxel_set(F, e["leaf"][perm], e["info"][perm], add=True) == pytest.approx(b.add_viewpoint(F, v), rel=1e-6)
+        assert np.array_equal(bits(a.download()), bits(b.download()))
+    assert a.voxel_set(F, [], [], add=True) == 0.0
+    with pytest.raises(E.Q3drError):
+        a.voxel_set(F, [sc.leaves.n], [1.0], add=False)
+    a.close()
+    b.close()
+
+
+@pytest.mark.gpu
 def test_setops_argument_checks(scored):
     sc, res = scored
     obs = E.ObservedVoxels(sc.gpu_map)
