@@ -30,6 +30,14 @@
  *        bvh::Tree::build -> splitMedian (defines the tie-break order)     bvh.h:361-373,764-788
  *   q3dr_pose_to_rt
  *        Pose::getTransformationImageToWorld                               include/bh/pose.h:122-127
+ *   q3dr_mesh_create / q3dr_mesh_render_normals / q3dr_decode_normal
+ *        ViewpointOffscreenRenderer::uploadPoissonMesh, drawPoissonMeshNormals, computePoissonMeshNormalVector
+ *        viewpoint_planner/src/planner/viewpoint_offscreen_renderer.cpp:138-200,276-293,361-397,499-527 ;
+ *        viewpoint_planner/src/shaders/triangles_normals.{v,f}.glsl
+ *   q3dr_score_viewpoints_mesh_normals / q3dr_score_viewpoints_normal_images
+ *        getRaycastHitVoxelsWithInformationScore with options_.enable_opengl = true: computeNormalVector takes the
+ *        normal from the mesh-normal image at the voxel's kept pixel
+ *        viewpoint_planner/src/planner/viewpoint_planner_scoring.cpp:26-38
  *
  * Numeric contract: strict IEEE-754 binary32 in the reference's operation
  * order, no FMA contraction.  hit(ray) = leaf of least dist_sq among leaves the ray's slab test
@@ -48,7 +56,7 @@
 extern "C" {
 #endif
 
-#define Q3DR_ABI_VERSION 2
+#define Q3DR_ABI_VERSION 3
 
 enum q3dr_status {
   Q3DR_OK = 0,
@@ -283,6 +291,70 @@ int q3dr_map_update_weights_from_grid(q3dr_map* map, const float grid_origin[3],
                                       const int32_t grid_dim[3], const float* grid_weight,
                                       float voxel_information_lambda, const uint32_t* observation_count,
                                       float* weights_out);
+
+/* ---- image-space normals: the reference's enable_opengl = true branch ----
+ *
+ * The reference renders the Poisson mesh's vertex normals off screen with OpenGL and scores every voxel with the
+ * normal found at the voxel's kept pixel.  Here the image is DEFINED by a ray cast through the pixel centres of the
+ * reference's projection matrix against the triangles (closest camera-space depth inside [near, far], equal depth
+ * -> lower triangle index, barycentric blend of the vertex normals, the shader's 0.5 n + 0.5 into 8 bits, no hit =
+ * clear colour); quad3dr_b200/csrc/mesh_kernels.cuh states the arithmetic.  It equals an OpenGL render except at
+ * pixels whose centre is within rounding distance of a triangle edge or a depth tie.  A caller who keeps the
+ * reference's renderer hands its images to q3dr_score_viewpoints_normal_images instead. */
+typedef struct q3dr_mesh q3dr_mesh;
+
+typedef struct q3dr_render_opts {
+  float near_plane;    /* 0.5  (viewpoint_offscreen_renderer.cpp:21) */
+  float far_plane;     /* 1e5  (:22) */
+  uint32_t clear_argb; /* 0xFFFFFFFF = clear_color_ (1,1,1,1) (:19); it decodes to the normal (1,1,1)/sqrt(3) */
+} q3dr_render_opts;
+
+typedef struct q3dr_mesh_info {
+  uint64_t n_triangles;
+  uint64_t n_nodes;
+  uint32_t tree_depth;
+  int32_t device;
+  uint64_t device_bytes;
+  float last_render_ms; /* device time of the last q3dr_mesh_render_normals kernel */
+} q3dr_mesh_info;
+
+void q3dr_render_opts_default(q3dr_render_opts* opts);
+
+/* tri_vertices: nf x 9 floats (three corners per triangle), tri_normals: nf x 9 floats (the unit normals
+ * uploadPoissonMesh attaches to the corners) or NULL => every corner gets normalize(cross(v2 - v1, v3 - v2))
+ * (viewpoint_offscreen_renderer.cpp:162-166). */
+int q3dr_mesh_create(const float* tri_vertices, const float* tri_normals, size_t nf, int device, q3dr_mesh** out);
+int q3dr_mesh_destroy(q3dr_mesh* mesh);
+int q3dr_mesh_get_info(const q3dr_mesh* mesh, q3dr_mesh_info* info);
+
+/* drawPoissonMeshNormals for n poses (Rt: n x 12, host): out_argb receives n x height x width QImage::Format_ARGB32
+ * pixels (0xAARRGGBB, row 0 on top) in HOST memory.  K = {fx, fy, cx, cy}. */
+int q3dr_mesh_render_normals(q3dr_mesh* mesh, const float K[4], uint32_t width, uint32_t height, const float* Rt,
+                             size_t n, const q3dr_render_opts* ropts, uint32_t* out_argb);
+
+/* The pixel decode of computePoissonMeshNormalVector (viewpoint_offscreen_renderer.cpp:519-526); host only. */
+int q3dr_decode_normal(uint32_t argb, float normal_out[3]);
+
+/* q3dr_score_viewpoints with image-space normals from `mesh` (same device as the map): only the kept pixel of every
+ * hit voxel is cast against the mesh, inside the scoring pass; the result equals scoring with the images
+ * q3dr_mesh_render_normals returns.  image_width x image_height is the camera (= render target) size. */
+int q3dr_score_viewpoints_mesh_normals(q3dr_map* map, const q3dr_mesh* mesh, const q3dr_render_opts* ropts,
+                                       const float K[4], uint32_t image_width, uint32_t image_height, uint32_t x0,
+                                       uint32_t x1, uint32_t y0, uint32_t y1, const float* Rt, size_t n,
+                                       const q3dr_score_opts* opts, q3dr_result* result);
+/* poses and results in device memory, like q3dr_score_viewpoints_device */
+int q3dr_score_viewpoints_mesh_normals_device(q3dr_map* map, const q3dr_mesh* mesh, const q3dr_render_opts* ropts,
+                                              const float K[4], uint32_t image_width, uint32_t image_height,
+                                              uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, const float* d_Rt,
+                                              size_t n, const q3dr_score_opts* opts, void* stream,
+                                              q3dr_result* result);
+
+/* q3dr_score_viewpoints with the caller's normal images (HOST memory, n x image_height x image_width ARGB32, e.g. the
+ * QImage bits of drawPoissonMeshNormals): every voxel is scored with the decoded pixel at its kept pixel. */
+int q3dr_score_viewpoints_normal_images(q3dr_map* map, const uint32_t* normal_images, const float K[4],
+                                        uint32_t image_width, uint32_t image_height, uint32_t x0, uint32_t x1,
+                                        uint32_t y0, uint32_t y1, const float* Rt, size_t n,
+                                        const q3dr_score_opts* opts, q3dr_result* result);
 
 /* ---- one process, several GPUs: the map replicated in every GPU's HBM, the viewpoints of a
  * call sharded in contiguous slices, one host thread per GPU, results left per GPU (no merge copy).  For one process

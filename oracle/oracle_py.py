@@ -106,6 +106,18 @@ def lib():
         C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
         C.POINTER(C.c_uint64),
     ]
+    L.orc_decode_normal.argtypes = [C.c_uint32, fp]
+    L.orc_mesh_face_normals.argtypes = [fp, C.c_size_t, fp]
+    L.orc_mesh_render_normals.argtypes = [fp, fp, C.c_size_t, fp, C.c_uint32, C.c_uint32, fp, C.c_float, C.c_float,
+                                          C.c_uint32, u32p]
+    L.orc_mesh_cast_pixels.argtypes = [fp, fp, C.c_size_t, fp, C.c_uint32, C.c_uint32, fp, C.c_float, C.c_float,
+                                       C.c_uint32, u32p, u32p, C.c_size_t, u32p]
+    L.orc_score_viewpoint_image_normals.restype = C.c_size_t
+    L.orc_score_viewpoint_image_normals.argtypes = (
+        [C.c_void_p, fp, u32p, C.c_uint32, fp, C.c_uint32, fp]
+        + [C.c_uint32] * 4
+        + [C.POINTER(ScoreOpts), C.c_size_t, i32p, fp, u32p, fp, u32p, fp]
+    )
     L.orc_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -272,6 +284,33 @@ class OracleTree:
             hit_count=int(hc.value), total=float(tot.value), total_f32=float(tot32.value),
         )
 
+    def score_viewpoint_image_normals(self, weights, normal_image, K, width, Rt, window=None,
+                                      opts: Optional[ScoreOpts] = None):
+        """The enable_opengl = true branch: normals decoded from `normal_image` (H x W ARGB32) at the kept pixels."""
+        opts = opts or default_opts()
+        w = _f32(weights, (self.n,))
+        img = np.ascontiguousarray(normal_image, dtype=np.uint32)
+        assert img.ndim == 2 and img.shape[1] == width
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(12)
+        if window is None:
+            window = (0, width, 0, img.shape[0])
+        x0, x1, y0, y1 = window
+        cap = (x1 - x0) * (y1 - y0)
+        leaf = np.empty(cap, dtype=np.int32)
+        info = np.empty(cap, dtype=np.float32)
+        pix = np.empty(cap, dtype=np.uint32)
+        dsq = np.empty(cap, dtype=np.float32)
+        hc = C.c_uint32(0)
+        tot = C.c_float(0)
+        k = lib().orc_score_viewpoint_image_normals(
+            self._h, _f(w), _u(img), img.shape[0], _f(K), width, _f(Rt), x0, x1, y0, y1, C.byref(opts), cap,
+            _i(leaf), _f(info), _u(pix), _f(dsq), C.byref(hc), C.byref(tot),
+        )
+        assert k != C.c_size_t(-1).value
+        return dict(leaf=leaf[:k].copy(), info=info[:k].copy(), pixel=pix[:k].copy(), dsq=dsq[:k].copy(),
+                    hit_count=int(hc.value), total=float(tot.value))
+
     def score_batch(self, weights, normals, K, width, height, Rt, opts: Optional[ScoreOpts] = None, threads: int = 1):
         opts = opts or default_opts()
         w = _f32(weights, (self.n,))
@@ -392,6 +431,44 @@ def set_checksums(offsets, leaf, pixel) -> np.ndarray:
         c = np.concatenate([[np.uint64(0)], np.cumsum(z, dtype=np.uint64)])
         off = np.asarray(offsets).astype(np.int64)
         return c[off[1:]] - c[off[:-1]]
+
+
+def decode_normal(argb: int) -> np.ndarray:
+    """computePoissonMeshNormalVector's pixel decode (viewpoint_offscreen_renderer.cpp:519-526)."""
+    out = np.empty(3, dtype=np.float32)
+    lib().orc_decode_normal(int(argb) & 0xFFFFFFFF, _f(out))
+    return out
+
+
+def mesh_face_normals(tri_vertices) -> np.ndarray:
+    v = _f32(tri_vertices).reshape(-1, 9)
+    out = np.empty_like(v)
+    lib().orc_mesh_face_normals(_f(v), v.shape[0], _f(out))
+    return out
+
+
+def mesh_render_normals(tri_vertices, tri_normals, K, width, height, Rt, near=0.5, far=1e5,
+                        clear_argb=0xFFFFFFFF) -> np.ndarray:
+    """Brute-force restatement of drawPoissonMeshNormals for one pose: (height, width) uint32 ARGB."""
+    v = _f32(tri_vertices).reshape(-1, 9)
+    n = _f32(tri_normals).reshape(-1, 9)
+    assert n.shape == v.shape
+    out = np.empty((height, width), dtype=np.uint32)
+    lib().orc_mesh_render_normals(_f(v), _f(n), v.shape[0], _f(_f32(K, (4,))), width, height, _f(_f32(Rt).reshape(12)),
+                                  near, far, clear_argb, _u(out))
+    return out
+
+
+def mesh_cast_pixels(tri_vertices, tri_normals, K, width, height, Rt, xs, ys, near=0.5, far=1e5,
+                     clear_argb=0xFFFFFFFF) -> np.ndarray:
+    v = _f32(tri_vertices).reshape(-1, 9)
+    n = _f32(tri_normals).reshape(-1, 9)
+    xs = np.ascontiguousarray(xs, dtype=np.uint32)
+    ys = np.ascontiguousarray(ys, dtype=np.uint32)
+    out = np.empty(xs.shape[0], dtype=np.uint32)
+    lib().orc_mesh_cast_pixels(_f(v), _f(n), v.shape[0], _f(_f32(K, (4,))), width, height, _f(_f32(Rt).reshape(12)),
+                               near, far, clear_argb, _u(xs), _u(ys), xs.shape[0], _u(out))
+    return out
 
 
 def max_threads() -> int:

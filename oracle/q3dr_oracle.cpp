@@ -599,6 +599,201 @@ size_t orc_score_viewpoint(const orc_tree* t, const float* weights, const float*
   return overflow ? (size_t)-1 : n_out;
 }
 
+// ---- image-space normals ----
+//
+// The reference renders the mesh normals with OpenGL (viewpoint_offscreen_renderer.cpp:361-397, projection :276-293,
+// shaders/triangles_normals.{v,f}.glsl) and decodes one pixel (:519-526).  A rasteriser cannot be run or pinned here;
+// the image is restated as a brute-force ray cast over ALL triangles through the pixel centres of that projection
+// (PARITY UNPINNED against OpenGL; the decode and the scoring with the decoded normal follow the reference line by
+// line).  Arithmetic: binary32, no FMA, three-term sums a0 + (a1 + a2).
+namespace {
+
+struct MRay {
+  float o[3], d[3];
+};
+
+// pixel centre (x + 0.5, y + 0.5) through proj(0,0) = fx / cx, proj(1,1) = fy / cy (:285-286); camera z = 1, so the
+// ray parameter is the camera-space depth the clip planes and the depth test act on
+inline void meshRay(const float K[4], const float Rt[12], uint32_t W, uint32_t H, uint32_t x, uint32_t y, MRay* r) {
+  const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+  float ndc_x = ((float)x + 0.5f) * 2.0f / (float)W - 1.0f;
+  float ndc_y = ((float)y + 0.5f) * 2.0f / (float)H - 1.0f;
+  float c0 = ndc_x / (fx / cx);
+  float c1 = ndc_y / (fy / cy);
+  for (int i = 0; i < 3; ++i) {
+    float p0 = Rt[4 * i + 0] * c0;
+    float p1 = Rt[4 * i + 1] * c1;
+    float p2 = Rt[4 * i + 2];
+    float p12 = p1 + p2;
+    r->d[i] = p0 + p12;
+    r->o[i] = Rt[4 * i + 3];
+  }
+}
+
+inline float dot3(const float* a, const float* b) {
+  float p0 = a[0] * b[0], p1 = a[1] * b[1], p2 = a[2] * b[2];
+  float p12 = p1 + p2;
+  return p0 + p12;
+}
+
+inline void cross3(const float* a, const float* b, float* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Moeller-Trumbore against the triangle with corners v (9 floats)
+inline bool meshTriangle(const MRay& r, const float* v, float near_t, float far_t, float* u, float* vv, float* t) {
+  float e1[3], e2[3], p[3], s[3], q[3];
+  for (int i = 0; i < 3; ++i) {
+    e1[i] = v[3 + i] - v[i];
+    e2[i] = v[6 + i] - v[i];
+  }
+  cross3(r.d, e2, p);
+  const float det = dot3(e1, p);
+  if (!(det != 0.0f)) return false;
+  const float inv = 1.0f / det;
+  for (int i = 0; i < 3; ++i) s[i] = r.o[i] - v[i];
+  *u = dot3(s, p) * inv;
+  if (!(*u >= 0.0f && *u <= 1.0f)) return false;
+  cross3(s, e1, q);
+  *vv = dot3(r.d, q) * inv;
+  if (!(*vv >= 0.0f && *u + *vv <= 1.0f)) return false;
+  *t = dot3(e2, q) * inv;
+  return *t >= near_t && *t <= far_t;
+}
+
+inline uint32_t unorm8(float n) {
+  float c = 0.5f * n + 0.5f;  // triangles_normals.f.glsl
+  if (c != c) c = 0.0f;
+  if (c < 0.0f) c = 0.0f;
+  if (c > 1.0f) c = 1.0f;
+  return (uint32_t)std::nearbyint(c * 255.0f);  // 8-bit UNORM colour attachment, round to nearest
+}
+
+uint32_t meshPixel(const float* tv, const float* tn, size_t nf, const MRay& r, float near_t, float far_t,
+                   uint32_t clear_argb) {
+  bool found = false;
+  float bt = 0, bu = 0, bv = 0;
+  size_t bi = 0;
+  for (size_t i = 0; i < nf; ++i) {
+    float u, v, t;
+    if (meshTriangle(r, tv + 9 * i, near_t, far_t, &u, &v, &t)) {
+      if (!found || t < bt) {  // GL_LESS: an equal depth keeps the triangle drawn first
+        found = true;
+        bt = t;
+        bu = u;
+        bv = v;
+        bi = i;
+      }
+    }
+  }
+  if (!found) return clear_argb;
+  const float* n = tn + 9 * bi;
+  const float w0 = (1.0f - bu) - bv;
+  uint32_t c[3];
+  for (int k = 0; k < 3; ++k) {
+    float a = w0 * n[k] + bu * n[3 + k];
+    c[k] = unorm8(a + bv * n[6 + k]);
+  }
+  return 0xFF000000u | (c[0] << 16) | (c[1] << 8) | c[2];
+}
+
+// viewpoint_offscreen_renderer.cpp:519-526
+inline void decodeNormal(uint32_t argb, float* n) {
+  const int red = (argb >> 16) & 255, green = (argb >> 8) & 255, blue = argb & 255;  // QColor(QRgb)
+  float v[3] = {(float)red / 255.f, (float)green / 255.f, (float)blue / 255.f};
+  for (int i = 0; i < 3; ++i) n[i] = 2 * (v[i] - 0.5f);
+  float s0 = n[0] * n[0], s1 = n[1] * n[1], s2 = n[2] * n[2];
+  float sq = s0 + (s1 + s2);
+  if (sq < 0.5f) {
+    n[0] = n[1] = n[2] = 0;
+    sq = 0;
+  }
+  if (sq > 0) {  // Eigen 3.3 normalize(): divides only when squaredNorm() > 0
+    float len = std::sqrt(sq);
+    for (int i = 0; i < 3; ++i) n[i] = n[i] / len;
+  }
+}
+
+}  // namespace
+
+void orc_decode_normal(uint32_t argb, float normal_out[3]) { decodeNormal(argb, normal_out); }
+
+void orc_mesh_face_normals(const float* tri_vertices, size_t nf, float* tri_normals) {
+  for (size_t i = 0; i < nf; ++i) {  // viewpoint_offscreen_renderer.cpp:162-166
+    const float* p = tri_vertices + 9 * i;
+    float a[3], b[3], c[3];
+    for (int k = 0; k < 3; ++k) {
+      a[k] = p[3 + k] - p[k];
+      b[k] = p[6 + k] - p[3 + k];
+    }
+    cross3(a, b, c);
+    const float len = std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+    for (int corner = 0; corner < 3; ++corner) {
+      for (int k = 0; k < 3; ++k) tri_normals[9 * i + 3 * corner + k] = c[k] / len;
+    }
+  }
+}
+
+void orc_mesh_cast_pixels(const float* tri_vertices, const float* tri_normals, size_t nf, const float K[4],
+                          uint32_t width, uint32_t height, const float Rt[12], float near_plane, float far_plane,
+                          uint32_t clear_argb, const uint32_t* xs, const uint32_t* ys, size_t n, uint32_t* out_argb) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (long i = 0; i < (long)n; ++i) {
+    MRay r;
+    meshRay(K, Rt, width, height, xs[i], ys[i], &r);
+    out_argb[i] = meshPixel(tri_vertices, tri_normals, nf, r, near_plane, far_plane, clear_argb);
+  }
+}
+
+void orc_mesh_render_normals(const float* tri_vertices, const float* tri_normals, size_t nf, const float K[4],
+                             uint32_t width, uint32_t height, const float Rt[12], float near_plane, float far_plane,
+                             uint32_t clear_argb, uint32_t* out_argb) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (long i = 0; i < (long)width * height; ++i) {
+    MRay r;
+    meshRay(K, Rt, width, height, (uint32_t)(i % width), (uint32_t)(i / width), &r);
+    out_argb[i] = meshPixel(tri_vertices, tri_normals, nf, r, near_plane, far_plane, clear_argb);
+  }
+}
+
+// getRaycastHitVoxelsWithInformationScore with enable_opengl = true (viewpoint_planner_scoring.cpp:26-38):
+// every voxel is scored with the decoded pixel of `normal_image` (image_height x image_width ARGB32) at its kept
+// pixel (window origin added back: screen_coordinates are full-image pixel coordinates, viewpoint_raycast.cpp:203).
+size_t orc_score_viewpoint_image_normals(const orc_tree* t, const float* weights, const uint32_t* normal_image,
+                                         uint32_t image_height, const float K[4], uint32_t image_width,
+                                         const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                                         const orc_score_opts* opts, size_t cap, int32_t* out_leaf, float* out_info,
+                                         uint32_t* out_pixel, float* out_dsq, uint32_t* hit_count, float* total) {
+  (void)image_height;
+  std::vector<Kept> kept;
+  castAndDedup(t, K, Rt, x0, x1, y0, y1, opts->raycast_min_range, opts->raycast_max_range, &kept);
+  const Derived dv = derive(opts);
+  const float cam[3] = {Rt[3], Rt[7], Rt[11]};
+  const uint32_t w = x1 - x0;
+  size_t n_out = 0;
+  double sum64 = 0.0;
+  for (const Kept& k : kept) {
+    const size_t x = x0 + k.pixel % w, y = y0 + k.pixel / w;  // static_cast<size_t>(image_coordinates)
+    float nrm[3];
+    decodeNormal(normal_image[y * image_width + x], nrm);
+    const float info = voxelInformation(t->leaf_boxes[k.leaf], weights[k.leaf], nrm, cam, K[0], image_width, opts, dv);
+    if (!opts->ignore_voxels_with_zero_information || info > 0) {
+      if (n_out >= cap) return (size_t)-1;
+      if (out_leaf) out_leaf[n_out] = k.leaf;
+      if (out_info) out_info[n_out] = info;
+      if (out_pixel) out_pixel[n_out] = k.pixel;
+      if (out_dsq) out_dsq[n_out] = k.dsq;
+      ++n_out;
+      sum64 += (double)info;
+    }
+  }
+  if (hit_count) *hit_count = (uint32_t)kept.size();
+  if (total) *total = (float)sum64;
+  return n_out;
+}
+
 // order-independent 64-bit checksum of a voxel set: sum over the entries of splitmix64(leaf << 32 | pixel)
 static inline uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;

@@ -185,6 +185,30 @@ float orc_observed_add(const int32_t* leaf, const float* info, size_t n, float* 
 float orc_overlap_information(const int32_t* leaf1, const float* info1, size_t n1, const int32_t* leaf2,
                               const float* info2, size_t n2, double* sum_f64);
 
+/* ---- image-space normals: the enable_opengl = true branch ----
+ * PARITY UNPINNED against the reference's OpenGL rasteriser (it cannot run here): the normal image is restated as a
+ * brute-force ray cast over all triangles through the pixel centres of the reference's projection
+ * (viewpoint_offscreen_renderer.cpp:276-293), closest camera-space depth in [near, far], equal depth -> lower
+ * triangle index, barycentric blend of the corner normals, 0.5 n + 0.5 rounded into 8 bits
+ * (shaders/triangles_normals.f.glsl), no hit -> clear colour.  The pixel decode (:519-526) and the scoring with the
+ * decoded normal (viewpoint_planner_scoring.cpp:26-38) follow the reference.
+ * tri_vertices / tri_normals: nf x 9 floats (three corners per triangle). */
+void orc_decode_normal(uint32_t argb, float normal_out[3]);
+/* normalize(cross(v2 - v1, v3 - v2)) on all three corners (viewpoint_offscreen_renderer.cpp:162-166) */
+void orc_mesh_face_normals(const float* tri_vertices, size_t nf, float* tri_normals);
+void orc_mesh_render_normals(const float* tri_vertices, const float* tri_normals, size_t nf, const float K[4],
+                             uint32_t width, uint32_t height, const float Rt[12], float near_plane, float far_plane,
+                             uint32_t clear_argb, uint32_t* out_argb /* height x width, 0xAARRGGBB */);
+void orc_mesh_cast_pixels(const float* tri_vertices, const float* tri_normals, size_t nf, const float K[4],
+                          uint32_t width, uint32_t height, const float Rt[12], float near_plane, float far_plane,
+                          uint32_t clear_argb, const uint32_t* xs, const uint32_t* ys, size_t n, uint32_t* out_argb);
+/* orc_score_viewpoint with the normal of every voxel taken from normal_image at the voxel's kept pixel */
+size_t orc_score_viewpoint_image_normals(const orc_tree* t, const float* weights, const uint32_t* normal_image,
+                                         uint32_t image_height, const float K[4], uint32_t image_width,
+                                         const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                                         const orc_score_opts* opts, size_t cap, int32_t* out_leaf, float* out_info,
+                                         uint32_t* out_pixel, float* out_dsq, uint32_t* hit_count, float* total);
+
 /* orc_score_batch plus, per viewpoint, an order-independent checksum of its voxel set:
  * sum over the kept entries of splitmix64((uint64)leaf << 32 | first_pixel)  (mod 2^64). */
 uint64_t orc_score_batch_checksum(const orc_tree* t, const float* weights, const float* normals,

@@ -221,8 +221,18 @@ int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
 
 int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
                       uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
-                      q3dr_result* result, bool stream_to_host) {
+                      q3dr_result* result, bool stream_to_host, const NormalSource* ns = nullptr) {
   Q3DR_CUDA(cudaSetDevice(m->device));
+  const int nmode = ns ? ns->mode : (int)q3dr::kNormalVoxel;
+  if (nmode != q3dr::kNormalVoxel) {
+    if (ns->img_h == 0 || x1 > image_width || y1 > ns->img_h) {
+      return fail(Q3DR_ERR_INVALID_ARG, "pixel window exceeds the normal image");
+    }
+    if (nmode == q3dr::kNormalCode && (!ns->mesh || !ns->mesh->d_tris.p || ns->mesh->device != m->device)) {
+      return fail(Q3DR_ERR_INVALID_ARG, "mesh is NULL or lives on another device than the map");
+    }
+    if (nmode == q3dr::kNormalImage && !ns->images) return fail(Q3DR_ERR_INVALID_ARG, "normal_images is NULL");
+  }
   m->stream = stream;
   m->host_result_valid = false;
   uint64_t copied_entries = 0;
@@ -232,6 +242,10 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   const size_t B = choose_chunk(m, rp.tiles_per_vp, n_vp, cap);
   if ((uint64_t)B * rp.tiles_per_vp >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "chunk too large");
   Q3DR_TRY(ensure_scratch(m, B, cap));
+  if (nmode == q3dr::kNormalCode) Q3DR_TRY(m->t_code.ensure(std::max<size_t>(B, m->slots) * cap));
+  if (nmode == q3dr::kNormalImage && !ns->images_on_device) {
+    Q3DR_TRY(m->d_nimg.ensure(B * (size_t)image_width * ns->img_h));
+  }
   if (m->scratch_dirty) {
     // the kernels leave the dedup tables clean themselves; after a failed call they may not have
     Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), stream));
@@ -287,6 +301,22 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   sp.blk_koff = blk_koff;
   sp.blk_total = m->d_seg_f64.p;
   sp.kept_count = m->d_kept.p;
+  sp.tmp_code = m->t_code.p;
+  sp.img_w = image_width;
+  sp.img_h = ns ? ns->img_h : 0;
+  q3dr::MeshDev mesh_dev{};
+  q3dr::RenderOptsDev ropts_dev{};
+  if (nmode == q3dr::kNormalCode) {
+    mesh_dev.nodes = ns->mesh->d_nodes.p;
+    mesh_dev.tris = ns->mesh->d_tris.p;
+    mesh_dev.normals = ns->mesh->d_normals.p;
+    mesh_dev.n_tris = (uint32_t)ns->mesh->n_tris;
+    mesh_dev.root_ref = ns->mesh->root_ref;
+    mesh_dev.pad = ns->mesh->pad;
+    ropts_dev.near_plane = ns->ropts.near_plane;
+    ropts_dev.far_plane = ns->ropts.far_plane;
+    ropts_dev.clear_argb = ns->ropts.clear_argb;
+  }
 
   rp.first_pix = m->d_first_pix.p;
   rp.bitmap = m->d_bitmap.p;
@@ -320,7 +350,24 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     q3dr::block_offsets_kernel<<<1, q3dr::kSegThreads, 0, stream>>>(sp.hit_count, (uint32_t)nb, blk_off);
     Q3DR_CUDA(cudaGetLastError());
-    q3dr::score_blocks_kernel<<<score_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+    if (nmode == q3dr::kNormalVoxel) {
+      q3dr::score_blocks_kernel<q3dr::kNormalVoxel><<<score_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+    } else if (nmode == q3dr::kNormalCode) {
+      q3dr::mesh_kept_normals_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb, mesh_dev, ropts_dev);
+      Q3DR_CUDA(cudaGetLastError());
+      q3dr::score_blocks_kernel<q3dr::kNormalCode><<<score_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+      st.kernel_launches += 1;
+    } else {
+      const size_t img_px = (size_t)image_width * ns->img_h;
+      if (ns->images_on_device) {
+        sp.normal_images = ns->images + v0 * img_px;
+      } else {
+        Q3DR_CUDA(cudaMemcpyAsync(m->d_nimg.p, ns->images + v0 * img_px, nb * img_px * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, stream));
+        sp.normal_images = m->d_nimg.p;
+      }
+      q3dr::score_blocks_kernel<q3dr::kNormalImage><<<score_grid, q3dr::kSegThreads, 0, stream>>>(sp, (uint32_t)nb);
+    }
     Q3DR_CUDA(cudaGetLastError());
     q3dr::finalize_viewpoints_kernel<<<(unsigned)nb, q3dr::kSegThreads, 0, stream>>>(sp);
     Q3DR_CUDA(cudaGetLastError());
@@ -868,6 +915,74 @@ int q3dr_score_viewpoints(q3dr_map* m, const float K[4], uint32_t image_width, u
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
   Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true));
+  return q3dr_result_to_host(m, result);
+}
+
+// ---- image-space normals (row N2) ----
+
+int q3dr_score_viewpoints_mesh_normals_device(q3dr_map* m, const q3dr_mesh* mesh, const q3dr_render_opts* ropts,
+                                              const float K[4], uint32_t image_width, uint32_t image_height,
+                                              uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, const float* d_Rt,
+                                              size_t n, const q3dr_score_opts* opts, void* stream,
+                                              q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!K || (!d_Rt && n) || !opts || !mesh || !ropts) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  if (image_width == 0 || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "empty image");
+  if ((reinterpret_cast<uintptr_t>(d_Rt) & 15u) != 0 && n) {
+    Q3DR_CUDA(cudaSetDevice(m->device));
+    Q3DR_TRY(m->d_rt.ensure(12 * n));
+    Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, d_Rt, 12 * n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    d_Rt = m->d_rt.p;
+  }
+  NormalSource ns;
+  ns.mode = q3dr::kNormalCode;
+  ns.mesh = mesh;
+  ns.ropts = *ropts;
+  ns.img_h = image_height;
+  return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result, false, &ns);
+}
+
+int q3dr_score_viewpoints_mesh_normals(q3dr_map* m, const q3dr_mesh* mesh, const q3dr_render_opts* ropts,
+                                       const float K[4], uint32_t image_width, uint32_t image_height, uint32_t x0,
+                                       uint32_t x1, uint32_t y0, uint32_t y1, const float* Rt, size_t n,
+                                       const q3dr_score_opts* opts, q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!K || (!Rt && n) || !opts || !result || !mesh || !ropts) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  if (image_width == 0 || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "empty image");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = nullptr;
+  Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
+  if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  NormalSource ns;
+  ns.mode = q3dr::kNormalCode;
+  ns.mesh = mesh;
+  ns.ropts = *ropts;
+  ns.img_h = image_height;
+  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true, &ns));
+  return q3dr_result_to_host(m, result);
+}
+
+int q3dr_score_viewpoints_normal_images(q3dr_map* m, const uint32_t* normal_images, const float K[4],
+                                        uint32_t image_width, uint32_t image_height, uint32_t x0, uint32_t x1,
+                                        uint32_t y0, uint32_t y1, const float* Rt, size_t n,
+                                        const q3dr_score_opts* opts, q3dr_result* result) {
+  Q3DR_TRY(check_map(m));
+  if (!K || (!Rt && n) || !opts || !result || (!normal_images && n)) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  Q3DR_TRY(check_window(x0, x1, y0, y1));
+  if (image_width == 0 || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "empty image");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = nullptr;
+  Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
+  if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
+  NormalSource ns;
+  ns.mode = q3dr::kNormalImage;
+  ns.images = normal_images;
+  ns.images_on_device = false;
+  ns.img_h = image_height;
+  if (n == 0) ns.mode = q3dr::kNormalVoxel;  // nothing to look up
+  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true, &ns));
   return q3dr_result_to_host(m, result);
 }
 

@@ -155,6 +155,8 @@ struct q3dr_map {
   DevBuf<int32_t> t_leaf;
   DevBuf<float> t_info, t_dsq;
   DevBuf<uint32_t> t_pix;
+  DevBuf<uint32_t> t_code;   // image-space normal codes next to the lists (allocated on first use)
+  DevBuf<uint32_t> d_nimg;   // one chunk of the caller's normal images
   uint64_t tmp_cap = 0;
   // device: results of the last scoring call
   DevBuf<uint64_t> d_offsets;
@@ -201,10 +203,38 @@ struct q3dr_map {
   uint64_t device_bytes() const {
     return d_nodes.bytes() + d_leaf_rec.bytes() + d_depth.bytes() + d_seg_u32.bytes() + d_blk_u32.bytes() + d_seg_f64.bytes() +
            d_counter.bytes() + d_first_pix.bytes() + d_bitmap.bytes() + d_kept.bytes() + t_leaf.bytes() +
-           t_info.bytes() + t_dsq.bytes() + t_pix.bytes() + d_offsets.bytes() + d_total.bytes() +
+           t_info.bytes() + t_dsq.bytes() + t_pix.bytes() + t_code.bytes() + d_nimg.bytes() + d_offsets.bytes() + d_total.bytes() +
            d_hit_count.bytes() + r_leaf.bytes() + r_info.bytes() + r_dsq.bytes() + r_pix.bytes() + d_rt.bytes() +
            d_ray_o.bytes() + d_ray_d.bytes() + d_pixels.bytes();
   }
+};
+
+// Triangle mesh of the image-space normals (row N2): binary BVH + triangles + vertex normals in HBM.
+struct q3dr_mesh {
+  int device = 0;
+  size_t n_tris = 0;
+  size_t n_nodes = 0;
+  uint32_t depth = 0;
+  int32_t root_ref = 0;
+  float pad = 0.f;
+  DevBuf<float4> d_nodes;    // [n_nodes][4]
+  DevBuf<float4> d_tris;     // [n_tris][3] BVH order
+  DevBuf<float4> d_normals;  // [n_tris][3] original order
+  DevBuf<float> d_rt;
+  DevBuf<uint32_t> d_image;
+  float last_render_ms = 0.f;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  uint64_t device_bytes() const { return d_nodes.bytes() + d_tris.bytes() + d_normals.bytes() + d_rt.bytes() + d_image.bytes(); }
+};
+
+// normal source of a scoring call (score_device_impl)
+struct NormalSource {
+  int mode = 0;                          // q3dr::NormalMode
+  const q3dr_mesh* mesh = nullptr;       // kNormalCode
+  q3dr_render_opts ropts{};              // kNormalCode
+  const uint32_t* images = nullptr;      // kNormalImage: n x img_h x img_w ARGB32
+  bool images_on_device = false;
+  uint32_t img_h = 0;
 };
 
 namespace q3dr_detail {

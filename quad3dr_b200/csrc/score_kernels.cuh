@@ -23,9 +23,18 @@
 // Everything is deterministic: fixed assignment of entries to threads, fixed reduction trees.
 #pragma once
 
+#include "mesh_kernels.cuh"
 #include "raycast_kernels.cuh"
 
 namespace q3dr {
+
+// where the normal that scores a voxel comes from (ViewpointPlanner::computeNormalVector,
+// viewpoint_planner_scoring.cpp:26-38)
+enum NormalMode : int {
+  kNormalVoxel = 0,  // enable_opengl = false: NodeObject::normal of the voxel
+  kNormalImage = 1,  // enable_opengl = true: the caller's normal images (QImage ARGB32), looked up at the kept pixel
+  kNormalCode = 2    // enable_opengl = true: the code mesh_kept_normals_kernel left next to the hit list
+};
 
 constexpr int kSegThreads = 256;
 constexpr int kLeafRecStride = 4;  // float4s per leaf record: 64 bytes, so a record never straddles a 128-byte line
@@ -60,6 +69,10 @@ struct ScoreParams2 {
   uint32_t* kept_count;  // [B]
   uint32_t* hit_count;   // [n_vp_total] (already offset to the chunk)
   float* total;          // [n_vp_total] (already offset to the chunk)
+  // image-space normals (row N2)
+  const uint32_t* normal_images;  // kNormalImage: [B][img_h][img_w] ARGB32 of the chunk's viewpoints
+  uint32_t* tmp_code;             // kNormalCode: [B][cap] next to tmp_leaf
+  uint32_t img_w, img_h;
 };
 
 // Block-wide exclusive scan for kSegThreads threads; returns the exclusive prefix, `total` = block sum.
@@ -177,7 +190,8 @@ __device__ __forceinline__ uint32_t find_viewpoint(const uint32_t* s_off, uint32
 
 // information of one voxel from its record (computeViewpointObservationScore)
 __device__ __forceinline__ float voxel_information_rec(const ScoreParams2& p, const float4& ra, const float4& rb,
-                                                       const float4& rc, float camx, float camy, float camz) {
+                                                       float nx, float ny, float nz, float camx, float camy,
+                                                       float camz) {
   const float gx = __fsub_rn(camx, __fdiv_rn(__fadd_rn(ra.x, rb.x), 2.0f));
   const float gy = __fsub_rn(camy, __fdiv_rn(__fadd_rn(ra.y, rb.y), 2.0f));
   const float gz = __fsub_rn(camz, __fdiv_rn(__fadd_rn(ra.z, rb.z), 2.0f));
@@ -191,7 +205,6 @@ __device__ __forceinline__ float voxel_information_rec(const ScoreParams2& p, co
   } else {
     res = expf(__fmul_rn(-p.kf, __fsub_rn(p.thr, rel)));
   }
-  const float nx = rc.x, ny = rc.y, nz = rc.z;
   float inc;
   if (nx == 0.0f && ny == 0.0f && nz == 0.0f) {
     inc = 1.0f;
@@ -232,6 +245,7 @@ __device__ __forceinline__ float voxel_information_rec(const ScoreParams2& p, co
 // CTA works on kScoreUnroll blocks at once and issues all their fetches before any arithmetic.
 constexpr int kScoreUnroll = 4;
 
+template <int NMODE>
 static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const ScoreParams2 p, uint32_t n_vp) {
   __shared__ uint32_t s_cnt[kScoreUnroll][kSegThreads / 32];
   __shared__ double s_dsum[kScoreUnroll][kSegThreads / 32];
@@ -276,7 +290,18 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
         const float4* rec = p.leaf_rec + kLeafRecStride * (size_t)leaf[u];
         ra[u] = __ldg(rec);
         rb[u] = __ldg(rec + 1);
-        rc[u] = __ldg(rec + 2);
+        if (NMODE == kNormalVoxel) {
+          rc[u] = __ldg(rec + 2);
+        } else {
+          uint32_t code;
+          if (NMODE == kNormalImage) {
+            const uint32_t py = pix[u] / p.w, px = pix[u] - py * p.w;
+            code = __ldg(p.normal_images + ((size_t)vp[u] * p.img_h + (p.y0 + py)) * p.img_w + (p.x0 + px));
+          } else {
+            code = p.tmp_code[at[u]];
+          }
+          decode_normal_code(code, rc[u].x, rc[u].y, rc[u].z);
+        }
       }
     }
 #pragma unroll
@@ -285,7 +310,8 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
       float info = 0.0f;
       if (valid[u]) {
         const float* rt = p.rt + 12 * (size_t)vp[u];
-        info = voxel_information_rec(p, ra[u], rb[u], rc[u], __ldg(rt + 3), __ldg(rt + 7), __ldg(rt + 11));
+        info = voxel_information_rec(p, ra[u], rb[u], rc[u].x, rc[u].y, rc[u].z, __ldg(rt + 3), __ldg(rt + 7),
+                                     __ldg(rt + 11));
         keep = !p.ignore_zero || info > 0.0f;
         float dsq = 0.0f;
         if (keep) {
@@ -322,6 +348,32 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
       p.blk_total[blk0 + tid] = t;
     }
     __syncthreads();
+  }
+}
+
+// enable_opengl = true with a mesh: the normal code of every list entry's kept pixel (mesh_kernels.cuh), one thread
+// per entry over the same flat block numbering; runs before score_blocks_kernel (which resets first_pix).
+static __global__ void __launch_bounds__(kSegThreads) mesh_kept_normals_kernel(const ScoreParams2 p, uint32_t n_vp,
+                                                                              const MeshDev mesh,
+                                                                              const RenderOptsDev ropts) {
+  __shared__ uint32_t s_off[kMaxChunkViewpoints + 1];
+  stage_block_offsets(p.blk_off, n_vp, s_off);
+  const uint32_t total_blocks = s_off[n_vp];
+  for (uint32_t blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
+    const uint32_t vp = find_viewpoint(s_off, n_vp, blk);
+    const uint32_t i = (blk - s_off[vp]) * kSegThreads + threadIdx.x;
+    if (i >= p.hit_count[vp]) continue;
+    const size_t at = (size_t)vp * p.cap + i;
+    const int32_t leaf = p.tmp_leaf[at];
+    const uint32_t pix = p.first_pix[(size_t)vp * p.leaf_stride + (uint32_t)leaf];
+    const uint32_t py = pix / p.w, px = pix - py * p.w;
+    const float* rt = p.rt + 12 * (size_t)vp;
+    float m[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = __ldg(rt + k);
+    MeshRay r;
+    mesh_camera_ray(m, p.fx, p.fy, p.cx, p.cy, p.img_w, p.img_h, p.x0 + px, p.y0 + py, r);
+    p.tmp_code[at] = mesh_cast(mesh, ropts, r);
   }
 }
 

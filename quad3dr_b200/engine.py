@@ -66,6 +66,23 @@ class _MultiResult(C.Structure):
     _fields_ = [("n_parts", C.c_uint32), ("n_viewpoints", C.c_uint64), ("first_viewpoint", C.c_void_p), ("parts", C.c_void_p)]
 
 
+class RenderOpts(C.Structure):
+    """q3dr_render_opts: clip planes and clear colour of the reference's off-screen renderer."""
+
+    _fields_ = [("near_plane", C.c_float), ("far_plane", C.c_float), ("clear_argb", C.c_uint32)]
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [
+        ("n_triangles", C.c_uint64),
+        ("n_nodes", C.c_uint64),
+        ("tree_depth", C.c_uint32),
+        ("device", C.c_int32),
+        ("device_bytes", C.c_uint64),
+        ("last_render_ms", C.c_float),
+    ]
+
+
 class MapInfo(C.Structure):
     _fields_ = [
         ("n_leaves", C.c_uint64),
@@ -173,6 +190,22 @@ def load_library() -> C.CDLL:
     L.q3dr_observed_add_viewpoint.argtypes = [vp, vp, C.c_float, C.c_uint32, fp]
     L.q3dr_overlap_information.argtypes = [vp, C.c_uint32, u32p, C.c_size_t, fp]
     L.q3dr_observed_voxel_set.argtypes = [vp, vp, C.c_float, C.POINTER(C.c_int32), fp, C.c_size_t, C.c_int, fp]
+    L.q3dr_render_opts_default.argtypes = [C.POINTER(RenderOpts)]
+    L.q3dr_render_opts_default.restype = None
+    L.q3dr_mesh_create.argtypes = [fp, fp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.q3dr_mesh_destroy.argtypes = [vp]
+    L.q3dr_mesh_get_info.argtypes = [vp, C.POINTER(MeshInfo)]
+    L.q3dr_mesh_render_normals.argtypes = [vp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(RenderOpts), u32p]
+    L.q3dr_decode_normal.argtypes = [C.c_uint32, fp]
+    L.q3dr_score_viewpoints_mesh_normals.argtypes = (
+        [vp, vp, C.POINTER(RenderOpts), fp] + [C.c_uint32] * 6 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_Result)]
+    )
+    L.q3dr_score_viewpoints_mesh_normals_device.argtypes = (
+        [vp, vp, C.POINTER(RenderOpts), fp] + [C.c_uint32] * 6 + [vp, C.c_size_t, C.POINTER(ScoreOpts), vp, C.POINTER(_Result)]
+    )
+    L.q3dr_score_viewpoints_normal_images.argtypes = (
+        [vp, u32p, fp] + [C.c_uint32] * 6 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_Result)]
+    )
     for name in dir(L):
         pass
     _lib = L
@@ -432,6 +465,60 @@ class OccupancyMap:
         )
         return DeviceResult(r)
 
+    def score_viewpoints_mesh_normals(self, mesh: "NormalMesh", K, image_width: int, image_height: int,
+                                      window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None,
+                                      ropts: Optional["RenderOpts"] = None, copy: bool = True) -> ScoreResult:
+        """enable_opengl = true: normals from the mesh at every voxel's kept pixel (host buffers in and out)."""
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        opts = opts or default_opts()
+        ropts = ropts or default_render_opts()
+        x0, x1, y0, y1 = window
+        r = _Result()
+        _check(
+            load_library().q3dr_score_viewpoints_mesh_normals(
+                self._h, mesh._h, C.byref(ropts), _fp(K), image_width, image_height, x0, x1, y0, y1, _fp(Rt),
+                Rt.shape[0], C.byref(opts), C.byref(r),
+            )
+        )
+        return ScoreResult(r, copy=copy)
+
+    def score_viewpoints_mesh_normals_device(self, mesh: "NormalMesh", K, image_width: int, image_height: int,
+                                             window: Sequence[int], d_rt_ptr: int, n: int,
+                                             opts: Optional[ScoreOpts] = None, ropts: Optional["RenderOpts"] = None,
+                                             stream: int = 0) -> DeviceResult:
+        K = _f32(K, (4,))
+        opts = opts or default_opts()
+        ropts = ropts or default_render_opts()
+        x0, x1, y0, y1 = window
+        r = _Result()
+        _check(
+            load_library().q3dr_score_viewpoints_mesh_normals_device(
+                self._h, mesh._h, C.byref(ropts), _fp(K), image_width, image_height, x0, x1, y0, y1,
+                C.c_void_p(d_rt_ptr), n, C.byref(opts), C.c_void_p(stream), C.byref(r),
+            )
+        )
+        return DeviceResult(r)
+
+    def score_viewpoints_normal_images(self, images, K, image_width: int, window: Sequence[int], Rt,
+                                       opts: Optional[ScoreOpts] = None, copy: bool = True) -> ScoreResult:
+        """enable_opengl = true with the caller's normal images: (n, H, W) uint32 ARGB32."""
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        img = np.ascontiguousarray(images, dtype=np.uint32)
+        if img.ndim != 3 or img.shape[0] != Rt.shape[0] or img.shape[2] != image_width:
+            raise ValueError("images must be (n, image_height, image_width)")
+        opts = opts or default_opts()
+        x0, x1, y0, y1 = window
+        r = _Result()
+        _check(
+            load_library().q3dr_score_viewpoints_normal_images(
+                self._h, img.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(K), image_width, img.shape[1], x0, x1, y0, y1,
+                _fp(Rt), Rt.shape[0], C.byref(opts), C.byref(r),
+            )
+        )
+        return ScoreResult(r, copy=copy)
+
     def update_weights_from_grid(self, grid_origin, grid_increment: float, grid_dim, grid_weight, lam: float,
                                  observation_count) -> np.ndarray:
         """ViewpointPlannerData::updateWeights' writes into the BVH leaves; returns the resulting weights."""
@@ -472,6 +559,65 @@ class OccupancyMap:
         r = _Result()
         _check(load_library().q3dr_result_to_host(self._h, C.byref(r)))
         return ScoreResult(r, copy=copy)
+
+
+def default_render_opts(**kw) -> RenderOpts:
+    o = RenderOpts()
+    load_library().q3dr_render_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def decode_normal(argb: int) -> np.ndarray:
+    out = np.empty(3, dtype=np.float32)
+    _check(load_library().q3dr_decode_normal(int(argb) & 0xFFFFFFFF, _fp(out)))
+    return out
+
+
+class NormalMesh:
+    """Device-resident triangle mesh of the image-space normals (q3dr_mesh): the Poisson mesh the reference
+    uploads to its off-screen renderer.  tri_vertices / tri_normals: (nf, 3, 3) corners."""
+
+    def __init__(self, tri_vertices, tri_normals=None, device: int = 0):
+        v = _f32(tri_vertices).reshape(-1, 9)
+        nr = _f32(tri_normals).reshape(-1, 9) if tri_normals is not None else None
+        if nr is not None and nr.shape != v.shape:
+            raise ValueError("tri_normals must match tri_vertices")
+        h = C.c_void_p(None)
+        _check(load_library().q3dr_mesh_create(_fp(v), _fp(nr) if nr is not None else None, v.shape[0], device, C.byref(h)))
+        self._h = h
+        self.n = v.shape[0]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().q3dr_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> MeshInfo:
+        i = MeshInfo()
+        _check(load_library().q3dr_mesh_get_info(self._h, C.byref(i)))
+        return i
+
+    def render_normals(self, K, width: int, height: int, Rt, ropts: Optional[RenderOpts] = None) -> np.ndarray:
+        """drawPoissonMeshNormals for n poses: (n, height, width) uint32 ARGB32."""
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        ropts = ropts or default_render_opts()
+        out = np.empty((Rt.shape[0], height, width), dtype=np.uint32)
+        _check(
+            load_library().q3dr_mesh_render_normals(
+                self._h, _fp(K), width, height, _fp(Rt), Rt.shape[0], C.byref(ropts),
+                out.ctypes.data_as(C.POINTER(C.c_uint32)),
+            )
+        )
+        return out
 
 
 class ObservedVoxels:

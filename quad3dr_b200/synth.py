@@ -339,3 +339,56 @@ CONFIGS = {
     "C3": (map_10m, 10000, 640, 480),
     "C4": (lambda: map_1m(unknown_interior=True), 4000, 1280, 960),
 }
+
+
+# ---------------------------------------------------------------------------------------------
+# Surface mesh (the "Poisson mesh" of the image-space normals)
+# ---------------------------------------------------------------------------------------------
+
+def _face_grid(origin, eu, ev, normal, nu: int, nv: int, seed: int, stream: int, bump: float, tilt: float):
+    """(nu x nv) quads spanning origin + a*eu + b*ev: vertices bumped along the normal, smooth unit vertex normals
+    tilted by up to `tilt`; two triangles per quad.  Returns corners (2*nu*nv, 3, 3) and normals of the same shape."""
+    origin, eu, ev, normal = (np.asarray(a, dtype=np.float64) for a in (origin, eu, ev, normal))
+    a = np.arange(nu + 1, dtype=np.float64) / nu
+    b = np.arange(nv + 1, dtype=np.float64) / nv
+    A, B = np.meshgrid(a, b, indexing="ij")
+    u = uniform01(seed, 3 * (nu + 1) * (nv + 1), stream=stream).reshape(nu + 1, nv + 1, 3)
+    P = origin + A[..., None] * eu + B[..., None] * ev + ((u[..., 0] - 0.5) * 2 * bump)[..., None] * normal
+    tu, tv = eu / np.linalg.norm(eu), ev / np.linalg.norm(ev)
+    N = normal + ((u[..., 1] - 0.5) * 2 * tilt)[..., None] * tu + ((u[..., 2] - 0.5) * 2 * tilt)[..., None] * tv
+    N /= np.linalg.norm(N, axis=-1, keepdims=True)
+    P = P.astype(np.float32)
+    N = N.astype(np.float32)
+    N /= np.sqrt((N.astype(np.float32) ** 2).sum(-1, keepdims=True, dtype=np.float32))
+    p00, p10, p01, p11 = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+    n00, n10, n01, n11 = N[:-1, :-1], N[1:, :-1], N[:-1, 1:], N[1:, 1:]
+    tv_ = np.stack([np.stack([p00, p10, p11], axis=-2), np.stack([p00, p11, p01], axis=-2)], axis=-3)
+    tn_ = np.stack([np.stack([n00, n10, n11], axis=-2), np.stack([n00, n11, n01], axis=-2)], axis=-3)
+    return tv_.reshape(-1, 3, 3), tn_.reshape(-1, 3, 3)
+
+
+def make_surface_mesh(leaves: OccupancyLeaves, cell: float = 1.0, seed: int = MAP_SEED + 7, bump: float = 0.04,
+                      tilt: float = 0.25) -> Tuple[np.ndarray, np.ndarray]:
+    """Triangle mesh over the outer surfaces of the map (ground top, building walls and roofs) with `cell`-sized
+    quads: what a Poisson reconstruction of the scene would look like to the reference's normal renderer.
+    Returns (tri_vertices, tri_normals), each (nf, 3, 3) float32, corner normals unit length."""
+    r = leaves.resolution
+    g = leaves.ground_half * r
+    faces = []
+
+    def add(origin, eu, ev, normal):
+        nu = max(1, int(round(np.linalg.norm(eu) / cell)))
+        nv = max(1, int(round(np.linalg.norm(ev) / cell)))
+        faces.append(_face_grid(origin, eu, ev, normal, nu, nv, seed, len(faces), bump, tilt))
+
+    add((-g, -g, 0.0), (2 * g, 0, 0), (0, 2 * g, 0), (0, 0, 1))
+    for b in leaves.buildings:
+        x0, y0, x1, y1, z1 = b.x0 * r, b.y0 * r, (b.x0 + b.nx) * r, (b.y0 + b.ny) * r, b.nz * r
+        add((x0, y0, 0), (0, y1 - y0, 0), (0, 0, z1), (-1, 0, 0))
+        add((x1, y0, 0), (0, y1 - y0, 0), (0, 0, z1), (1, 0, 0))
+        add((x0, y0, 0), (x1 - x0, 0, 0), (0, 0, z1), (0, -1, 0))
+        add((x0, y1, 0), (x1 - x0, 0, 0), (0, 0, z1), (0, 1, 0))
+        add((x0, y0, z1), (x1 - x0, 0, 0), (0, y1 - y0, 0), (0, 0, 1))
+    tv = np.ascontiguousarray(np.concatenate([f[0] for f in faces]), dtype=np.float32)
+    tn = np.ascontiguousarray(np.concatenate([f[1] for f in faces]), dtype=np.float32)
+    return tv, tn

@@ -1,0 +1,40 @@
+// mesh_host_harness.cu -- TEST INFRASTRUCTURE (not shipped, not linked into libq3dr_raycast.so).
+//
+// Compiles the product's mesh BVH builder (quad3dr_b200/csrc/mesh_build.h) and its traversal (mesh_cast in
+// mesh_kernels.cuh, a __host__ __device__ function) for the HOST, so that the tree-independence of the traversal --
+// padded boxes, slack on the pruning bound, tie rule -- can be checked against the oracle's brute force over all
+// triangles on a machine without a GPU (tests/test_mesh_normals.py).  The GPU tests check the same on the device.
+#include <cstdint>
+#include <vector>
+
+#include "../../quad3dr_b200/csrc/mesh_build.h"
+#include "../../quad3dr_b200/csrc/mesh_kernels.cuh"
+
+extern "C" int mesh_host_cast_pixels(const float* tri_vertices, const float* tri_normals, size_t nf, const float K[4],
+                                     uint32_t width, uint32_t height, const float* Rt, float near_plane,
+                                     float far_plane, uint32_t clear_argb, const uint32_t* xs, const uint32_t* ys,
+                                     size_t n, uint32_t* out_argb, uint32_t* tree_depth, uint64_t* n_nodes) {
+  q3dr::MeshHost hm;
+  q3dr::build_mesh_host(tri_vertices, tri_normals, nf, &hm);
+  if (hm.depth + 2 > (uint32_t)q3dr::kMeshStack) return 1;
+  q3dr::MeshDev md;
+  md.nodes = hm.nodes.data();
+  md.tris = hm.tris.data();
+  md.normals = hm.normals.data();
+  md.n_tris = (uint32_t)nf;
+  md.root_ref = hm.root_ref;
+  md.pad = hm.pad;
+  q3dr::RenderOptsDev ro;
+  ro.near_plane = near_plane;
+  ro.far_plane = far_plane;
+  ro.clear_argb = clear_argb;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (long i = 0; i < (long)n; ++i) {
+    q3dr::MeshRay r;
+    q3dr::mesh_camera_ray(Rt, K[0], K[1], K[2], K[3], width, height, xs[i], ys[i], r);
+    out_argb[i] = q3dr::mesh_cast(md, ro, r);
+  }
+  if (tree_depth) *tree_depth = hm.depth;
+  if (n_nodes) *n_nodes = hm.nodes.size() / 4;
+  return 0;
+}

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/q3dr_raycast.h but not exported"
-    assert lib.q3dr_abi_version() == 2
+    assert lib.q3dr_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
