@@ -274,6 +274,13 @@ def run_ours(args):
     leaves, depth, cam, vps = build_inputs(args.workload, rank, world)
     nvp, w, h = vps.shape[0], cam.width, cam.height
     gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=local_rank)
+    mesh = None
+    if args.normals == "mesh":
+        # the reference's enable_opengl = true branch: normals from a surface mesh at the kept pixel
+        from quad3dr_b200 import synth
+
+        tv, tn = synth.make_surface_mesh(leaves, cell=args.mesh_cell)
+        mesh = E.NormalMesh(tv, tn, device=local_rank)
     opts = E.default_opts()
     window = (0, w, 0, h)
     stream = torch.cuda.current_stream()
@@ -298,11 +305,17 @@ def run_ours(args):
         return qdist.gather_results(off, tot, leaf, info, nvp)
 
     def step_device():
-        res = gmap.score_viewpoints_device(cam.K, w, window, d_rt.data_ptr(), nvp, opts, stream=stream.cuda_stream)
+        if mesh is not None:
+            res = gmap.score_viewpoints_mesh_normals_device(mesh, cam.K, w, h, window, d_rt.data_ptr(), nvp, opts,
+                                                            stream=stream.cuda_stream)
+        else:
+            res = gmap.score_viewpoints_device(cam.K, w, window, d_rt.data_ptr(), nvp, opts, stream=stream.cuda_stream)
         gather(res)
         return res
 
     def step_host():
+        if mesh is not None:
+            return gmap.score_viewpoints_mesh_normals(mesh, cam.K, w, h, window, h_rt.numpy(), opts, copy=False)
         res = gmap.score_viewpoints(cam.K, w, window, h_rt.numpy(), opts, copy=False)
         return res
 
@@ -402,6 +415,13 @@ def run_ours(args):
             },
             "result_entries": int(n_entries),
         }
+        if mesh is not None:
+            mi = mesh.info()
+            line["config"]["normals"] = (f"image-space (enable_opengl branch): surface mesh of {int(mi.n_triangles)} triangles, "
+                                         f"one mesh ray per kept pixel inside the scoring pass")
+            line["config"]["workload"] += ", normals from the mesh at the kept pixel"
+        else:
+            line["config"]["normals"] = "per voxel (enable_opengl = false)"
         if args.cpu_baseline:
             cb = cpu_baseline(leaves, cam, vps, args.cpu_budget)
             # parity spot check of the bench inputs themselves: counts + totals of the sampled viewpoints
@@ -457,6 +477,10 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of wall time for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--normals", default="voxel", choices=["voxel", "mesh"],
+                    help="mesh: image-space normals from a synthetic surface mesh (row N2); the cpu_baseline leg is "
+                         "skipped (the oracle's mesh render is a brute force over all triangles)")
+    ap.add_argument("--mesh-cell", type=float, default=0.25, help="quad size of the synthetic surface mesh in metres")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -470,8 +494,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    if world > 1:
-        args.cpu_baseline = False  # rank 0 at N = 1 only
+    if world > 1 or args.normals == "mesh":
+        args.cpu_baseline = False  # rank 0 at N = 1 only; voxel normals only
     run_ours(args)
 
 

@@ -333,6 +333,100 @@ class OccupiedTreeCuda {
   mutable std::unordered_map<const NodeT*, std::int32_t> leaf_of_;  // host node -> leaf index (built on first use)
 };
 
+/// The normals part of viewpoint_planner::ViewpointOffscreenRenderer (enable_opengl = true): the Poisson mesh uploaded
+/// once (uploadPoissonMesh, viewpoint_offscreen_renderer.cpp:138-200), drawPoissonMeshNormals (:361-397) and
+/// computePoissonMeshNormalVector (:499-527) with its one-pose image cache.  Images are defined by the engine's ray cast
+/// (q3dr_raycast.h, "image-space normals"), not by an OpenGL context.
+class PoissonMeshNormalsCuda {
+ public:
+  /// tri_vertices / tri_normals: 9 floats per triangle (what uploadPoissonMesh puts into OGLTriangleWithNormalData);
+  /// empty tri_normals => the reference's per-face normals
+  PoissonMeshNormalsCuda(const std::vector<float>& tri_vertices, const std::vector<float>& tri_normals,
+                         int cuda_gpu_id = 0)
+      : mesh_(nullptr), cached_valid_(false), cached_w_(0), cached_h_(0) {
+    q3dr_render_opts_default(&ropts_);
+    if (!tri_normals.empty() && tri_normals.size() != tri_vertices.size()) {
+      throw std::runtime_error("tri_normals must be empty or match tri_vertices");
+    }
+    const int st = q3dr_mesh_create(tri_vertices.data(), tri_normals.empty() ? nullptr : tri_normals.data(),
+                                    tri_vertices.size() / 9, cuda_gpu_id, &mesh_);
+    if (st != Q3DR_OK) throw std::runtime_error(std::string("q3dr_mesh_create: ") + q3dr_last_error());
+  }
+  PoissonMeshNormalsCuda(const PoissonMeshNormalsCuda&) = delete;
+  PoissonMeshNormalsCuda& operator=(const PoissonMeshNormalsCuda&) = delete;
+  ~PoissonMeshNormalsCuda() { q3dr_mesh_destroy(mesh_); }
+
+  /// viewpoint_offscreen_renderer.cpp:76-79
+  void setNearFarPlane(float near_plane, float far_plane) {
+    ropts_.near_plane = near_plane;
+    ropts_.far_plane = far_plane;
+    cached_valid_ = false;
+  }
+  /// viewpoint_offscreen_renderer.cpp:43-45 (r, g, b, a in [0, 1])
+  void setClearColor(float r, float g, float b, float a) {
+    ropts_.clear_argb = (unorm8(a) << 24) | (unorm8(r) << 16) | (unorm8(g) << 8) | unorm8(b);
+    cached_valid_ = false;
+  }
+  const q3dr_mesh* handle() const { return mesh_; }
+  const q3dr_render_opts& renderOptions() const { return ropts_; }
+
+  /// drawPoissonMeshNormals: width * height QImage::Format_ARGB32 pixels, row 0 on top
+  template <typename ViewpointT>
+  std::vector<std::uint32_t> drawPoissonMeshNormals(const ViewpointT& viewpoint) const {
+    float K[4], Rt[12];
+    packCamera(viewpoint, K, Rt);
+    const std::uint32_t w = static_cast<std::uint32_t>(viewpoint.camera().width());
+    const std::uint32_t h = static_cast<std::uint32_t>(viewpoint.camera().height());
+    std::vector<std::uint32_t> image(static_cast<std::size_t>(w) * h);
+    const int st = q3dr_mesh_render_normals(mesh_, K, w, h, Rt, 1, &ropts_, image.data());
+    if (st != Q3DR_OK) throw std::runtime_error(std::string("q3dr_mesh_render_normals: ") + q3dr_last_error());
+    return image;
+  }
+
+  /// computePoissonMeshNormalVector(viewpoint, x, y): re-renders only when the pose changed (:505-513)
+  template <typename ViewpointT>
+  void computePoissonMeshNormalVector(const ViewpointT& viewpoint, std::size_t x, std::size_t y, float normal_out[3]) const {
+    float K[4], Rt[12];
+    packCamera(viewpoint, K, Rt);
+    const std::uint32_t w = static_cast<std::uint32_t>(viewpoint.camera().width());
+    const std::uint32_t h = static_cast<std::uint32_t>(viewpoint.camera().height());
+    bool same = cached_valid_ && w == cached_w_ && h == cached_h_;
+    for (int i = 0; same && i < 12; ++i) same = Rt[i] == cached_rt_[i];
+    if (!same) {
+      cached_image_ = drawPoissonMeshNormals(viewpoint);
+      for (int i = 0; i < 12; ++i) cached_rt_[i] = Rt[i];
+      cached_w_ = w;
+      cached_h_ = h;
+      cached_valid_ = true;
+    }
+    q3dr_decode_normal(cached_image_[y * w + x], normal_out);
+  }
+
+ private:
+  static std::uint32_t unorm8(float c) {
+    c = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
+    return static_cast<std::uint32_t>(c * 255.0f + 0.5f);
+  }
+  template <typename ViewpointT>
+  static void packCamera(const ViewpointT& viewpoint, float K[4], float Rt[12]) {
+    const auto& intrinsics = viewpoint.camera().intrinsics();
+    const auto extrinsics = viewpoint.pose().getTransformationImageToWorld();
+    K[0] = intrinsics(0, 0);
+    K[1] = intrinsics(1, 1);
+    K[2] = intrinsics(0, 2);
+    K[3] = intrinsics(1, 2);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 4; ++c) Rt[4 * r + c] = extrinsics(r, c);
+    }
+  }
+  q3dr_mesh* mesh_;
+  q3dr_render_opts ropts_;
+  mutable bool cached_valid_;
+  mutable std::uint32_t cached_w_, cached_h_;
+  mutable float cached_rt_[12];
+  mutable std::vector<std::uint32_t> cached_image_;
+};
+
 /// viewpoint_planner::ViewpointRaycast with enable_cuda = true, plus the planner's scoring facade.
 /// ViewpointT needs camera().intrinsics() (4x4), camera().width(), camera().height() and
 /// pose().getTransformationImageToWorld() (3x4).
@@ -346,13 +440,17 @@ class ViewpointRaycastCuda {
 
   /// viewpoint_raycast.h:28-31 (min_range is accepted and, like in the reference, never used by the query)
   ViewpointRaycastCuda(TreeType* bvh_tree, float min_range = 0, float max_range = 60)
-      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range) {
+      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range), mesh_normals_(nullptr) {
     q3dr_score_opts_default(&opts_);
     opts_.raycast_min_range = min_range;
     opts_.raycast_max_range = max_range;
   }
 
   q3dr_score_opts& scoreOptions() { return opts_; }
+
+  /// options_.enable_opengl = true (ViewpointPlanner::computeNormalVector, viewpoint_planner_scoring.cpp:26-38): score
+  /// every voxel with the mesh normal at its kept pixel instead of NodeObject::normal.  nullptr switches back.
+  void setPoissonMeshNormals(const PoissonMeshNormalsCuda* mesh_normals) { mesh_normals_ = mesh_normals; }
 
   /// viewpoint_raycast.cpp:94-113,254-283,321-335
   template <typename ViewpointT>
@@ -425,11 +523,20 @@ class ViewpointRaycastCuda {
     q3dr_score_opts o = opts_;
     o.ignore_voxels_with_zero_information = ignore_voxels_with_zero_information ? 1 : 0;
     q3dr_result r;
-    bvh_tree_->check(q3dr_score_viewpoints(bvh_tree_->handle(), K,
-                                           static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
-                                           static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
-                                           static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
-                                           Rt.data(), viewpoints.size(), &o, &r));
+    if (mesh_normals_ != nullptr) {
+      bvh_tree_->check(q3dr_score_viewpoints_mesh_normals(
+          bvh_tree_->handle(), mesh_normals_->handle(), &mesh_normals_->renderOptions(), K,
+          static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
+          static_cast<std::uint32_t>(viewpoints[0]->camera().height()), static_cast<std::uint32_t>(x_start),
+          static_cast<std::uint32_t>(x_end), static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
+          Rt.data(), viewpoints.size(), &o, &r));
+    } else {
+      bvh_tree_->check(q3dr_score_viewpoints(bvh_tree_->handle(), K,
+                                             static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
+                                             static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
+                                             static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
+                                             Rt.data(), viewpoints.size(), &o, &r));
+    }
     for (std::size_t v = 0; v < viewpoints.size(); ++v) {
       VoxelSet& set = out[v].first;
       set.reserve(static_cast<std::size_t>(r.offsets[v + 1] - r.offsets[v]));
@@ -446,6 +553,7 @@ class ViewpointRaycastCuda {
   float min_range_;
   float max_range_;
   q3dr_score_opts opts_;
+  const PoissonMeshNormalsCuda* mesh_normals_;
 };
 
 /// One ViewpointPath::observed_voxel_map on the device plus the information sums the path search evaluates against

@@ -35,6 +35,9 @@
  *     cmake.sh points at eigen-3.3.1) for squaredNorm / dot / 3x3*vec3; normalized() as componentwise
  *     division by sqrt(squaredNorm()) when that is > 0; and the scoring formulas of viewpoint_score.cpp /
  *     viewpoint_planner_scoring.cpp, which exist only on the reference's CPU side.
+ *   UNPINNED, image-space normals (row N2): the reference's normal image comes from an OpenGL rasteriser, which cannot
+ *     run here; it is restated as a brute-force ray cast (see the N2 block below).  The pixel decode and the scoring
+ *     with the decoded normal follow viewpoint_offscreen_renderer.cpp:519-526 / viewpoint_planner_scoring.cpp:26-38.
  * The reference compiles this code under "#pragma GCC optimize(fast-math)"; its exact bits are therefore
  * compiler dependent.  This oracle pins strict IEEE as THE definition.
  */

@@ -171,61 +171,114 @@ __host__ __device__ __forceinline__ float mesh_box_entry(const MeshRay& r, float
   return (tmin <= tmax) ? tmin : FLT_MAX * 2.0f;
 }
 
-// closest triangle of the definition in the header; returns the ARGB code
-__host__ __device__ __forceinline__ uint32_t mesh_cast(const MeshDev& m, const RenderOptsDev& o, const MeshRay& r) {
-  const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
-  float best_t = FLT_MAX * 2.0f, best_u = 0.0f, best_v = 0.0f;
-  uint32_t best_tri = 0xFFFFFFFFu;
-  const float t_lo = o.near_plane - (o.near_plane * kMeshSlackRel + m.pad);
-  float t_hi = o.far_plane + (o.far_plane * kMeshSlackRel + m.pad);
-  int32_t stack[kMeshStack];
-  int sp = 0;
-  int32_t ref = m.root_ref;
-  while (true) {
-    if (ref >= 0) {
-      const float4* nd = m.nodes + 4 * (size_t)ref;
-      const float4 a = Q3DR_MESH_LDG(nd), b = Q3DR_MESH_LDG(nd + 1), c = Q3DR_MESH_LDG(nd + 2), d = Q3DR_MESH_LDG(nd + 3);
-      const float tl = mesh_box_entry(r, ix, iy, iz, a.x, a.y, a.z, a.w, b.x, b.y, t_lo, t_hi);
-      const float tr = mesh_box_entry(r, ix, iy, iz, b.z, b.w, c.x, c.y, c.z, c.w, t_lo, t_hi);
-      const int32_t lref = mesh_bits_i32(d.x), rref = mesh_bits_i32(d.y);
-      const bool hl = tl <= FLT_MAX, hr = tr <= FLT_MAX;
-      if (hl && hr) {
-        const bool left_first = tl <= tr;
-        stack[sp++] = left_first ? rref : lref;
-        ref = left_first ? lref : rref;
-        continue;
-      }
-      if (hl || hr) {
-        ref = hl ? lref : rref;
-        continue;
-      }
-    } else {
-      const uint32_t code = (uint32_t)(~ref);
-      const uint32_t first = code >> 2, cnt = (code & 3u) + 1u;
-      for (uint32_t k = 0; k < cnt; ++k) {
-        const float4* tp = m.tris + 3 * (size_t)(first + k);
-        const float4 v0 = Q3DR_MESH_LDG(tp), e1 = Q3DR_MESH_LDG(tp + 1), e2 = Q3DR_MESH_LDG(tp + 2);
-        float u, v, t;
-        if (mesh_tri_test(r, v0.x, v0.y, v0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z, o.near_plane, o.far_plane, u, v, t)) {
-          const uint32_t idx = (uint32_t)mesh_bits_i32(v0.w);
-          if (t < best_t || (t == best_t && idx < best_tri)) {
-            best_t = t;
-            best_u = u;
-            best_v = v;
-            best_tri = idx;
-            t_hi = fminf(t_hi, best_t + (best_t * kMeshSlackRel + m.pad));
-          }
-        }
+// ---- traversal, as steps over an explicit state so that a kernel can interleave rays (mesh_kept_normals_kernel
+// hands a finished lane its next ray while the other lanes of the warp go on) ----
+constexpr int32_t kMeshDone = 0x7FFFFFFF;
+
+struct MeshTrav {
+  MeshRay r;
+  float ix, iy, iz;
+  float best_t, best_u, best_v;
+  uint32_t best_tri;
+  float t_lo, t_hi;
+  int32_t ref;  // >= 0 (and != kMeshDone): inner node to visit; < 0: leaf to test; kMeshDone: finished
+  int sp;
+};
+
+__host__ __device__ __forceinline__ void mesh_trav_init(MeshTrav& s, const MeshDev& m, const RenderOptsDev& o,
+                                                        const MeshRay& r) {
+  s.r = r;
+  s.ix = 1.0f / r.dx;
+  s.iy = 1.0f / r.dy;
+  s.iz = 1.0f / r.dz;
+  s.best_t = FLT_MAX * 2.0f;
+  s.best_u = s.best_v = 0.0f;
+  s.best_tri = 0xFFFFFFFFu;
+  s.t_lo = o.near_plane - (o.near_plane * kMeshSlackRel + m.pad);
+  s.t_hi = o.far_plane + (o.far_plane * kMeshSlackRel + m.pad);
+  s.ref = m.root_ref;
+  s.sp = 0;
+}
+
+// next subtree from the stack; a stacked subtree carries its entry parameter and is dropped without a fetch when a
+// closer hit has been found since it was pushed
+__host__ __device__ __forceinline__ void mesh_trav_pop(MeshTrav& s, const int32_t* stack, const float* stack_t) {
+  s.ref = kMeshDone;
+  while (s.sp > 0) {
+    --s.sp;
+    if (stack_t[s.sp] <= s.t_hi) {
+      s.ref = stack[s.sp];
+      break;
+    }
+  }
+}
+
+// visits inner node s.ref: nearer child next, the other one stacked
+__host__ __device__ __forceinline__ void mesh_trav_inner(MeshTrav& s, const MeshDev& m, int32_t* stack, float* stack_t) {
+  const float4* nd = m.nodes + 4 * (size_t)s.ref;
+  const float4 a = Q3DR_MESH_LDG(nd), b = Q3DR_MESH_LDG(nd + 1), c = Q3DR_MESH_LDG(nd + 2), d = Q3DR_MESH_LDG(nd + 3);
+  const float tl = mesh_box_entry(s.r, s.ix, s.iy, s.iz, a.x, a.y, a.z, a.w, b.x, b.y, s.t_lo, s.t_hi);
+  const float tr = mesh_box_entry(s.r, s.ix, s.iy, s.iz, b.z, b.w, c.x, c.y, c.z, c.w, s.t_lo, s.t_hi);
+  const int32_t lref = mesh_bits_i32(d.x), rref = mesh_bits_i32(d.y);
+  const bool hl = tl <= FLT_MAX, hr = tr <= FLT_MAX;
+  if (hl && hr) {
+    const bool left_first = tl <= tr;
+    stack[s.sp] = left_first ? rref : lref;
+    stack_t[s.sp] = left_first ? tr : tl;
+    ++s.sp;
+    s.ref = left_first ? lref : rref;
+  } else if (hl || hr) {
+    s.ref = hl ? lref : rref;
+  } else {
+    mesh_trav_pop(s, stack, stack_t);
+  }
+}
+
+// tests the triangles of leaf s.ref, then pops
+__host__ __device__ __forceinline__ void mesh_trav_leaf(MeshTrav& s, const MeshDev& m, const RenderOptsDev& o,
+                                                        const int32_t* stack, const float* stack_t) {
+  const uint32_t code = (uint32_t)(~s.ref);
+  const uint32_t first = code >> 2, cnt = (code & 3u) + 1u;
+  for (uint32_t k = 0; k < cnt; ++k) {
+    const float4* tp = m.tris + 3 * (size_t)(first + k);
+    const float4 v0 = Q3DR_MESH_LDG(tp), e1 = Q3DR_MESH_LDG(tp + 1), e2 = Q3DR_MESH_LDG(tp + 2);
+    float u, v, t;
+    if (mesh_tri_test(s.r, v0.x, v0.y, v0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z, o.near_plane, o.far_plane, u, v, t)) {
+      const uint32_t idx = (uint32_t)mesh_bits_i32(v0.w);
+      if (t < s.best_t || (t == s.best_t && idx < s.best_tri)) {
+        s.best_t = t;
+        s.best_u = u;
+        s.best_v = v;
+        s.best_tri = idx;
+        s.t_hi = fminf(s.t_hi, t + (t * kMeshSlackRel + m.pad));
       }
     }
-    if (sp == 0) break;
-    ref = stack[--sp];
   }
-  if (best_tri == 0xFFFFFFFFu) return o.clear_argb;
-  const float4* np = m.normals + 3 * (size_t)best_tri;
+  mesh_trav_pop(s, stack, stack_t);
+}
+
+__host__ __device__ __forceinline__ uint32_t mesh_trav_result(const MeshTrav& s, const MeshDev& m, const RenderOptsDev& o) {
+  if (s.best_tri == 0xFFFFFFFFu) return o.clear_argb;
+  const float4* np = m.normals + 3 * (size_t)s.best_tri;
   const float4 n0 = Q3DR_MESH_LDG(np), n1 = Q3DR_MESH_LDG(np + 1), n2 = Q3DR_MESH_LDG(np + 2);
   const float a0[3] = {n0.x, n0.y, n0.z}, a1[3] = {n1.x, n1.y, n1.z}, a2[3] = {n2.x, n2.y, n2.z};
-  return mesh_encode_normal(best_u, best_v, a0, a1, a2);
+  return mesh_encode_normal(s.best_u, s.best_v, a0, a1, a2);
+}
+
+// closest triangle of the definition in the header; returns the ARGB code.
+// "while-while" traversal: a lane first descends through inner nodes until it holds a leaf (or is done), then all
+// lanes of the warp test their leaf's triangles together.
+__host__ __device__ __forceinline__ uint32_t mesh_cast(const MeshDev& m, const RenderOptsDev& o, const MeshRay& r) {
+  int32_t stack[kMeshStack];
+  float stack_t[kMeshStack];
+  MeshTrav s;
+  mesh_trav_init(s, m, o, r);
+  while (true) {
+    while (s.ref >= 0 && s.ref != kMeshDone) mesh_trav_inner(s, m, stack, stack_t);
+    if (s.ref == kMeshDone) break;
+    mesh_trav_leaf(s, m, o, stack, stack_t);
+  }
+  return mesh_trav_result(s, m, o);
 }
 
 #ifdef __CUDACC__

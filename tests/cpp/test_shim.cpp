@@ -276,6 +276,66 @@ int main(int argc, char** argv) {
   }
   CHECK(total_hits > 5000);
 
+  // --- options_.enable_opengl = true: normals from the Poisson mesh at the kept pixel (row N2) ------------------
+  {
+    // ground top (z = 0), the wall at y = 2 and the wall at x = -2.75 as six triangles with tilted corner normals
+    std::vector<float> tv, tn;
+    auto quad = [&](const float a[3], const float b[3], const float c[3], const float d[3], float nx, float ny, float nz) {
+      const float* tri[2][3] = {{a, b, c}, {a, c, d}};
+      for (int t = 0; t < 2; ++t)
+        for (int k = 0; k < 3; ++k) {
+          for (int i = 0; i < 3; ++i) tv.push_back(tri[t][k][i]);
+          const float tilt = 0.1f * (float)(k + t);
+          const float n[3] = {nx + tilt * ny, ny + tilt * nz, nz + tilt * nx};
+          const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          for (int i = 0; i < 3; ++i) tn.push_back(n[i] / len);
+        }
+    };
+    const float g0[3] = {-6, -6, 0}, g1[3] = {6, -6, 0}, g2[3] = {6, 6, 0}, g3[3] = {-6, 6, 0};
+    const float w0[3] = {-2.5f, 2, 0}, w1[3] = {2.5f, 2, 0}, w2[3] = {2.5f, 2, 3}, w3[3] = {-2.5f, 2, 3};
+    const float x0[3] = {-2.75f, -2.5f, 0}, x1[3] = {-2.75f, 2.5f, 0}, x2[3] = {-2.75f, 2.5f, 3}, x3[3] = {-2.75f, -2.5f, 3};
+    quad(g0, g1, g2, g3, 0, 0, 1);
+    quad(w0, w1, w2, w3, 0, -1, 0);
+    quad(x0, x1, x2, x3, 1, 0, 0);
+    q3dr::PoissonMeshNormalsCuda mesh_normals(tv, tn, 0);
+    raycaster.setPoissonMeshNormals(&mesh_normals);
+    const std::size_t np = cam.w * cam.h;
+    for (const mock::Viewpoint& vp : vps) {
+      float Rt[12];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) Rt[4 * r + c] = vp.p.T.m[r][c];
+      // drawPoissonMeshNormals == the oracle's brute-force render, pixel for pixel
+      std::vector<uint32_t> image = mesh_normals.drawPoissonMeshNormals(vp);
+      std::vector<uint32_t> ref_image(np);
+      orc_mesh_render_normals(tv.data(), tn.data(), tv.size() / 9, Kf, (uint32_t)cam.w, (uint32_t)cam.h, Rt, 0.5f, 1e5f,
+                              0xFFFFFFFFu, ref_image.data());
+      CHECK(image == ref_image);
+      float nrm[3], ref_nrm[3];
+      mesh_normals.computePoissonMeshNormalVector(vp, 17, 40, nrm);
+      orc_decode_normal(ref_image[40 * cam.w + 17], ref_nrm);
+      CHECK(nrm[0] == ref_nrm[0] && nrm[1] == ref_nrm[1] && nrm[2] == ref_nrm[2]);
+      // scoring with those normals
+      auto scored = raycaster.getRaycastHitVoxelsWithInformationScore(vp, true);
+      std::vector<int32_t> o_leaf(np);
+      std::vector<float> o_info(np);
+      uint32_t hc = 0;
+      float tot = 0;
+      const size_t k = orc_score_viewpoint_image_normals(oracle, weights.data(), ref_image.data(), (uint32_t)cam.h, Kf,
+                                                         (uint32_t)cam.w, Rt, 0, cam.w, 0, cam.h, &oo, np, o_leaf.data(),
+                                                         o_info.data(), nullptr, nullptr, &hc, &tot);
+      CHECK(scored.first.size() == k);
+      std::unordered_map<const mock::Node*, float> by_voxel;
+      for (const auto& vi : scored.first) by_voxel[vi.voxel] = vi.information;
+      for (size_t i = 0; i < k; ++i) {
+        auto it = by_voxel.find(leaves[o_leaf[i]].node);
+        CHECK(it != by_voxel.end());
+        CHECK(std::fabs(it->second - o_info[i]) <= 1e-5f * std::fabs(o_info[i]));
+      }
+      CHECK(std::fabs(scored.second - tot) <= 1e-5f * std::fabs(tot));
+    }
+    raycaster.setPoissonMeshNormals(nullptr);
+  }
+
   // bvh::Tree::intersectsCuda
   std::vector<Tree::Ray> rays;
   for (int i = 0; i < 257; ++i) {

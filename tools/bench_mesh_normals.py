@@ -56,7 +56,7 @@ img = mesh.render_normals(cam.K, w, h, vps[:nr])
 render_ms = mesh.info().last_render_ms
 # parity on a sample against the oracle: brute force over all triangles only at the kept pixels of 2 viewpoints
 tree = O.OracleTree(leaves.boxes)
-ns = 2
+ns = int(os.environ.get("PARITY_VIEWPOINTS", "1"))
 t = time.perf_counter()
 ok = True
 max_rel = 0.0
