@@ -305,13 +305,43 @@ def run_ours(args):
         return qdist.gather_results(off, tot, leaf, info, nvp)
 
     def step_device():
+        if pg is not None:
+            pg.begin_step()
+        res = _score_device()
+        if pg is not None:
+            pg.end_step(nvp, stream)
+        else:
+            gather(res)
+        return res
+
+    def _score_device():
         if mesh is not None:
             res = gmap.score_viewpoints_mesh_normals_device(mesh, cam.K, w, h, window, d_rt.data_ptr(), nvp, opts,
                                                             stream=stream.cuda_stream)
         else:
             res = gmap.score_viewpoints_device(cam.K, w, window, d_rt.data_ptr(), nvp, opts, stream=stream.cuda_stream)
-        gather(res)
         return res
+
+    # N > 1: the result exchange.  Default: every finished chunk is pushed into all ranks' HBM by the copy engines while
+    # the next chunk is cast (quad3dr_b200/dist.py PeerGather); Q3DR_GATHER=nccl: one all_gather after the last kernel.
+    pg = None
+    gather_note = "single GPU: nothing to exchange"
+    if dist is not None:
+        gather_note = "NCCL all_gather of headers + padded hit lists after the last kernel"
+        if os.environ.get("Q3DR_GATHER", "peer") == "peer":
+            from quad3dr_b200 import dist as qdist
+
+            try:
+                probe = _score_device()  # sizes the receive slots (the result of fixed inputs is deterministic)
+                e_max = torch.tensor([probe.n_entries], dtype=torch.int64, device=dev)
+                dist.all_reduce(e_max, op=dist.ReduceOp.MAX)
+                pg = qdist.PeerGather(dev, nvp, int(int(e_max.item()) * 1.25) + 4096)
+                gmap.set_chunk_callback(lambda a, b, c, d, part: pg.on_chunk(a, b, c, d, part, stream))
+                gather_note = ("per chunk: copy-engine pushes (cudaMemcpyAsync into CUDA-IPC-mapped peer HBM over NVLink) on a "
+                               "side stream while the next chunk is cast; one NCCL all_reduce as the closing barrier")
+            except Exception as e:  # e.g. CUDA IPC not permitted in this container
+                pg = None
+                gather_note += f" (peer push unavailable: {type(e).__name__}: {e})"
 
     def step_host():
         if mesh is not None:
@@ -346,6 +376,9 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     n_entries = res.n_entries
+
+    if pg is not None:
+        gmap.set_chunk_callback(None)
 
     # ---- end-to-end arm (host buffers through the C ABI) ----
     for _ in range(max(1, args.warmup - 1)):
@@ -415,6 +448,7 @@ def run_ours(args):
             },
             "result_entries": int(n_entries),
         }
+        line["config"]["gather"] = gather_note
         if mesh is not None:
             mi = mesh.info()
             line["config"]["normals"] = (f"image-space (enable_opengl branch): surface mesh of {int(mi.n_triangles)} triangles, "
@@ -444,6 +478,8 @@ def run_ours(args):
                                              "voxel set, total within 1e-5 relative of the oracle"}
             line["cpu_baseline"] = cb
         emit(line)
+    if pg is not None:
+        pg.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

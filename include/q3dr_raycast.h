@@ -208,6 +208,18 @@ int q3dr_score_viewpoints_device(q3dr_map* map, const float K[4], uint32_t image
                                  uint32_t y0, uint32_t y1, const float* d_Rt, size_t n,
                                  const q3dr_score_opts* opts, void* stream, q3dr_result* result);
 
+/* Chunk notification.  A scoring call works through its viewpoints in chunks; as soon as the kernels that finish a
+ * chunk have been ISSUED on the call's stream, `cb` is invoked on the calling host thread with the viewpoint range and
+ * the entry range of the chunk and the device pointers of the partial CSR result (offsets[0 .. first + n], total,
+ * hit_count, leaf / information / first_pixel / dist_sq [0 .. first_entry + n_entries) are final once the work issued
+ * so far on the stream has run).  A consumer orders its own work after an event recorded on that stream -- e.g.
+ * copy-engine pushes of the chunk into the other GPUs' memory while the next chunk is being cast
+ * (quad3dr_b200/dist.py: PeerGather).  The pointers may change between calls (pools grow), not between the chunks of
+ * a call whose pools already have the needed capacity.  cb == NULL removes the callback. */
+typedef void (*q3dr_chunk_callback)(void* user, uint64_t first_viewpoint, uint64_t n_viewpoints, uint64_t first_entry,
+                                    uint64_t n_entries, const q3dr_result* partial_device_result);
+int q3dr_map_set_chunk_callback(q3dr_map* map, q3dr_chunk_callback cb, void* user);
+
 /* Copies the device-resident result of the last q3dr_score_viewpoints_device call to host memory
  * owned by the map. */
 int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);

@@ -376,6 +376,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaMemcpyAsync(m->h_scalar.p, m->d_offsets.p + v0 + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     Q3DR_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t chunk_first_entry = total_entries;
     total_entries = m->h_scalar.p[0];
     const size_t want = std::max<uint64_t>(total_entries, 1);
     Q3DR_TRY(m->r_leaf.ensure(want, true, stream));
@@ -400,6 +401,19 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     pp.out_dsq = m->r_dsq.p;
     q3dr::pack_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(pp);
     Q3DR_CUDA(cudaGetLastError());
+    if (m->chunk_cb) {
+      q3dr_result part;
+      part.n_viewpoints = v0 + nb;
+      part.n_entries = total_entries;
+      part.offsets = m->d_offsets.p;
+      part.leaf = m->r_leaf.p;
+      part.information = m->r_info.p;
+      part.first_pixel = m->r_pix.p;
+      part.dist_sq = m->r_dsq.p;
+      part.total = m->d_total.p;
+      part.hit_count = m->d_hit_count.p;
+      m->chunk_cb(m->chunk_cb_user, v0, nb, chunk_first_entry, total_entries - chunk_first_entry, &part);
+    }
     if (stream_to_host && total_entries > copied_entries) {
       // this chunk's slice of the CSR pool is final: ship it while the next chunk is being cast
       if (total_entries > m->h_leaf.cap) {
@@ -865,6 +879,13 @@ int q3dr_score_viewpoints_device(q3dr_map* m, const float K[4], uint32_t image_w
     d_Rt = m->d_rt.p;
   }
   return score_device_impl(m, K, image_width, x0, x1, y0, y1, d_Rt, n, opts, (cudaStream_t)stream, result, false);
+}
+
+int q3dr_map_set_chunk_callback(q3dr_map* m, q3dr_chunk_callback cb, void* user) {
+  if (!m) return fail(Q3DR_ERR_INVALID_ARG, "map is NULL");
+  m->chunk_cb = cb;
+  m->chunk_cb_user = cb ? user : nullptr;
+  return Q3DR_OK;
 }
 
 int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {

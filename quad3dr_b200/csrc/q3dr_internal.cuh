@@ -194,6 +194,8 @@ struct q3dr_map {
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
   cudaEvent_t ev_packed = nullptr;
   bool host_result_valid = false;      // the host pools already hold the entries of the last call
+  q3dr_chunk_callback chunk_cb = nullptr;
+  void* chunk_cb_user = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int grid_rays_ctas = 0;
   int grid2_ctas[2] = {0, 0};

@@ -86,3 +86,185 @@ def device_result_tensors(res, device) -> Tuple[torch.Tensor, torch.Tensor, torc
         leaf = torch.empty(0, dtype=torch.int32, device=device)
         info = torch.empty(0, dtype=torch.float32, device=device)
     return offsets, total, leaf, info
+
+
+class PeerGather:
+    """The result exchange of SURVEY.md section 8e, overlapped with the compute.
+
+    Instead of one all_gather after the last kernel, every finished chunk of a scoring call (q3dr_map_set_chunk_callback)
+    is PUSHED into all ranks' HBM by the copy engines -- cudaMemcpyAsync into CUDA-IPC-mapped peer buffers over
+    NVLink / NVSwitch, on a side stream, issued by a helper thread -- while the SMs cast the next chunk.  The pushes use
+    no SM, so they do not compete with the issue-bound raycast kernel; only the last chunk's push and one tiny NCCL
+    all_reduce (the barrier that tells every rank that all pushes into its memory have landed) stay exposed.
+
+    Every rank ends a step with the results of ALL ranks in its own receive buffer, one slot per source rank:
+        offsets int64 [n_max + 1] | total f32 [n_max] | leaf i32 [cap] | information f32 [cap]
+    Two receive buffers alternate between steps, so a fast rank's pushes of step s+1 never touch what a slow rank
+    still reads from step s.  Memory: 2 * world * (8 * cap + 12 * n_max) bytes per GPU, sized for the worst case.
+    """
+
+    def __init__(self, device: torch.device, n_local_max: int, cap_entries: int, group=None):
+        from cuda.bindings import runtime as rt
+        import queue
+        import threading
+
+        self.rt = rt
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        self.n_max = int(n_local_max)
+        self.cap = int(cap_entries)
+
+        def up(x, a=256):
+            return (x + a - 1) // a * a
+
+        self.tot_off = up(8 * (self.n_max + 1))
+        self.leaf_off = up(self.tot_off + 4 * self.n_max)
+        self.info_off = up(self.leaf_off + 4 * self.cap)
+        self.slot_bytes = up(self.info_off + 4 * self.cap)
+        torch.cuda.set_device(self.device)
+        self.base: List[int] = []
+        self.peer = [[0] * self.world for _ in range(2)]
+        handles = []
+        failure = None
+        try:
+            for _ in range(2):
+                ptr = self._ok(rt.cudaMalloc(self.world * self.slot_bytes))
+                self.base.append(int(ptr))
+                h = self._ok(rt.cudaIpcGetMemHandle(ptr))
+                handles.append(bytes(h.reserved))
+        except Exception as e:
+            failure = e
+            handles = [b"", b""]
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=group)
+        if failure is None and all(len(g[0]) and len(g[1]) for g in gathered):
+            try:
+                for b in range(2):
+                    for p in range(self.world):
+                        if p == self.rank:
+                            self.peer[b][p] = self.base[b]
+                        else:
+                            h = rt.cudaIpcMemHandle_t()
+                            h.reserved = gathered[p][b]
+                            self.peer[b][p] = int(self._ok(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
+            except Exception as e:
+                failure = e
+        elif failure is None:
+            failure = RuntimeError("another rank could not export its receive buffer")
+        # all ranks agree on success before anybody relies on it (a one-sided failure must not desynchronise collectives)
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            for ptr in self.base:
+                rt.cudaFree(ptr)
+            self.base = []
+            raise RuntimeError(f"PeerGather unavailable: {failure or 'failed on another rank'}")
+        self.side = torch.cuda.Stream(device=self.device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.cur = 1
+        self.error = None
+        self._last = None
+        self._q: "queue.Queue" = queue.Queue()
+        self._worker = threading.Thread(target=self._run, daemon=True)
+        self._worker.start()
+        dist.barrier(group=group)  # every rank has mapped every buffer before anybody pushes
+
+    def _ok(self, ret):
+        err = ret[0]
+        if int(err) != 0:
+            raise RuntimeError(f"CUDA runtime error {err} in PeerGather")
+        return ret[1] if len(ret) == 2 else ret[1:]
+
+    def _push(self, dst_off: int, src_ptr: int, nbytes: int):
+        """the same bytes into this rank's slot on every rank (copy engines, side stream)"""
+        if nbytes <= 0:
+            return
+        rt = self.rt
+        s = self.side.cuda_stream
+        for k in range(self.world):
+            p = (self.rank + k) % self.world  # start with different targets on different ranks
+            dst = self.peer[self.cur][p] + self.rank * self.slot_bytes + dst_off
+            (err,) = rt.cudaMemcpyAsync(dst, src_ptr, nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice, s)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaMemcpyAsync to rank {p}: {err}")
+
+    def _run(self):
+        self.rt.cudaSetDevice(self.device.index)
+        while True:
+            job = self._q.get()
+            try:
+                if job is None:
+                    return
+                ev, first_entry, n_entries, leaf_ptr, info_ptr = job
+                self.side.wait_event(ev)
+                self._push(self.leaf_off + 4 * first_entry, leaf_ptr + 4 * first_entry, 4 * n_entries)
+                self._push(self.info_off + 4 * first_entry, info_ptr + 4 * first_entry, 4 * n_entries)
+            except Exception as e:  # surfaced by end_step
+                self.error = e
+            finally:
+                self._q.task_done()
+
+    def begin_step(self):
+        self.cur ^= 1
+        self._last = None
+
+    def on_chunk(self, first_vp: int, n_vp: int, first_entry: int, n_entries: int, res, stream: torch.cuda.Stream):
+        """chunk callback: order the push after the work issued so far, hand it to the helper thread, return at once
+        (the calling thread goes on to launch the next chunk's raycast)"""
+        if first_entry + n_entries > self.cap or first_vp + n_vp > self.n_max:
+            self.error = RuntimeError("PeerGather: result larger than the receive slot")
+            return
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._last = res
+        self._q.put((ev, first_entry, n_entries, int(res.leaf or 0), int(res.information or 0)))
+
+    def end_step(self, n_local: int, stream: torch.cuda.Stream):
+        """headers of all local viewpoints, then the barrier; `stream` continues when every rank's pushes have landed"""
+        self._q.join()
+        if self.error is not None:
+            raise self.error
+        with torch.cuda.stream(self.side):
+            if self._last is not None and n_local > 0:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self.side.wait_event(ev)
+                self._push(0, int(self._last.offsets), 8 * (n_local + 1))
+                self._push(self.tot_off, int(self._last.total), 4 * n_local)
+            dist.all_reduce(self.token, group=self.group)
+        stream.wait_stream(self.side)
+
+    def views(self, n_per_rank: List[int]):
+        """per source rank: (offsets int64 (n+1,), total f32 (n,), leaf i32 (e,), info f32 (e,)) -- zero-copy views of
+        this rank's receive buffer of the step that just ended (valid until the step after the next one begins)"""
+        out = []
+        for r in range(self.world):
+            slot = self.base[self.cur] + r * self.slot_bytes
+            n = int(n_per_rank[r])
+            off = torch.as_tensor(CudaArrayView(slot, n + 1, "<i8"), device=self.device)
+            tot = torch.as_tensor(CudaArrayView(slot + self.tot_off, max(n, 1), "<f4"), device=self.device)[:n]
+            e = int(off[n].item()) if n else 0
+            if e:
+                leaf = torch.as_tensor(CudaArrayView(slot + self.leaf_off, e, "<i4"), device=self.device)
+                info = torch.as_tensor(CudaArrayView(slot + self.info_off, e, "<f4"), device=self.device)
+            else:
+                leaf = torch.empty(0, dtype=torch.int32, device=self.device)
+                info = torch.empty(0, dtype=torch.float32, device=self.device)
+            out.append((off, tot, leaf, info))
+        return out
+
+    def close(self):
+        self._q.put(None)
+        self._worker.join(timeout=5)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # nobody unmaps while somebody may still push
+        for b in range(2):
+            for p in range(self.world):
+                if p != self.rank and self.peer[b][p]:
+                    self.rt.cudaIpcCloseMemHandle(self.peer[b][p])
+        dist.barrier(group=self.group)
+        for ptr in self.base:
+            self.rt.cudaFree(ptr)
+        self.base = []

@@ -66,6 +66,10 @@ class _MultiResult(C.Structure):
     _fields_ = [("n_parts", C.c_uint32), ("n_viewpoints", C.c_uint64), ("first_viewpoint", C.c_void_p), ("parts", C.c_void_p)]
 
 
+# q3dr_chunk_callback(user, first_viewpoint, n_viewpoints, first_entry, n_entries, partial_device_result)
+CHUNK_CALLBACK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_Result))
+
+
 class RenderOpts(C.Structure):
     """q3dr_render_opts: clip planes and clear colour of the reference's off-screen renderer."""
 
@@ -168,6 +172,7 @@ def load_library() -> C.CDLL:
         [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [vp, C.c_size_t, C.POINTER(ScoreOpts), vp, C.POINTER(_Result)]
     )
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
+    L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_overlap_boxes.argtypes = [vp, fp, C.c_size_t, C.POINTER(_OverlapResult)]
     L.q3dr_valid_object_positions.argtypes = [vp, fp, C.c_size_t, fp, fp, C.c_float, C.POINTER(C.c_uint8)]
     L.q3dr_octree_leaves_to_boxes.argtypes = [fp, fp, fp, u32p, C.c_size_t, fp, C.c_float, C.c_float, C.c_uint32, C.c_int,
@@ -518,6 +523,20 @@ class OccupancyMap:
             )
         )
         return ScoreResult(r, copy=copy)
+
+    def set_chunk_callback(self, fn=None):
+        """fn(first_viewpoint, n_viewpoints, first_entry, n_entries, DeviceResult) is called on the host as soon as the
+        kernels finishing a chunk have been issued on the call's stream (q3dr_map_set_chunk_callback); None removes it."""
+        if fn is None:
+            self._chunk_cb = None
+            _check(load_library().q3dr_map_set_chunk_callback(self._h, C.cast(None, CHUNK_CALLBACK), None))
+            return
+
+        def tramp(_user, first_vp, n_vp, first_entry, n_entries, partial):
+            fn(int(first_vp), int(n_vp), int(first_entry), int(n_entries), DeviceResult(partial.contents))
+
+        self._chunk_cb = CHUNK_CALLBACK(tramp)  # keep the thunk alive as long as it is installed
+        _check(load_library().q3dr_map_set_chunk_callback(self._h, self._chunk_cb, None))
 
     def update_weights_from_grid(self, grid_origin, grid_increment: float, grid_dim, grid_weight, lam: float,
                                  observation_count) -> np.ndarray:
