@@ -47,6 +47,8 @@ void release_device(q3dr_map* m) {
   m->t_info.release();
   m->t_dsq.release();
   m->t_pix.release();
+  m->t_code.release();
+  m->d_nimg.release();
   m->tmp_cap = 0;
   m->d_offsets.release();
   m->d_total.release();
