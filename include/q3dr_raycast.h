@@ -391,6 +391,11 @@ int q3dr_multi_update_weights(q3dr_multi* multi, const float* weights);
 int q3dr_multi_score_viewpoints(q3dr_multi* multi, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
                                 uint32_t y0, uint32_t y1, const float* Rt, size_t n, const q3dr_score_opts* opts,
                                 q3dr_multi_result* result);
+/* Image-space normals (row N2) for q3dr_multi_score_viewpoints: the mesh is uploaded to every device of `multi`
+ * (q3dr_mesh_create per GPU) and every following scoring call takes the normals from it at the kept pixels, with
+ * render target image_width (of the call) x image_height.  tri_vertices == NULL switches back to the voxel normals. */
+int q3dr_multi_set_normal_mesh(q3dr_multi* multi, const float* tri_vertices, const float* tri_normals, size_t nf,
+                               uint32_t image_height, const q3dr_render_opts* ropts);
 
 #ifdef __cplusplus
 }

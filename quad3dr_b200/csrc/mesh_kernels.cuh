@@ -20,10 +20,11 @@
 //
 // Kernels:
 //   mesh_render_kernel        one thread per pixel of an n x H x W image batch (8x4 pixel footprints per warp)
-//   mesh_kept_normals_kernel  one thread per entry of the chunk's hit lists: the code of the entry's kept pixel only
-//                             (~7 % of the pixels of a viewpoint), written next to the list for score_blocks_kernel
-// Both walk a binary BVH over the triangles (64-byte nodes holding both children's boxes, built on the host in
-// q3dr_mesh.cu).  The result is independent of the tree: boxes are padded and a subtree is skipped only when it lies
+//   mesh_kept_normals_kernel  (score_kernels.cuh) one thread per entry of the chunk's hit lists: the code of the
+//                             entry's kept pixel only (~7 % of the pixels of a viewpoint), written next to the list
+//                             for score_blocks_kernel
+// Both walk a binary BVH over the triangles (64-byte nodes holding both children's boxes, built on the host by
+// mesh_build.h).  The result is independent of the tree: boxes are padded and a subtree is skipped only when it lies
 // beyond the best t by more than kMeshSlack, far above the rounding error of t.
 #pragma once
 
@@ -40,7 +41,7 @@ constexpr float kMeshSlackRel = 1e-3f;    // subtree skipped iff entry t > best 
 constexpr uint32_t kMeshLeafMaxTris = 4;
 
 struct MeshDev {
-  const float4* __restrict__ nodes;    // [n_nodes][4]: see MeshNode in q3dr_mesh.cu
+  const float4* __restrict__ nodes;    // [n_nodes][4]: layout in mesh_build.h
   const float4* __restrict__ tris;     // [nf][3] in BVH order: {v0 xyz, bits(original index)}, {e1 xyz, 0}, {e2 xyz, 0}
   const float4* __restrict__ normals;  // [nf][3] by ORIGINAL index: n0, n1, n2
   uint32_t n_tris;

@@ -51,6 +51,7 @@ int q3dr_mesh_create(const float* tri_vertices, const float* tri_normals, size_t
   q3dr::MeshHost hm;
   q3dr::build_mesh_host(tri_vertices, tri_normals, nf, &hm);
   const std::vector<float4>&nodes = hm.nodes, &tris = hm.tris, &normals = hm.normals;
+  if (hm.depth + 2 > (uint32_t)q3dr::kMeshStack) return fail(Q3DR_ERR_INTERNAL, "mesh tree deeper than the traversal stack");
 
   std::unique_ptr<q3dr_mesh> m(new (std::nothrow) q3dr_mesh());
   if (!m) return fail(Q3DR_ERR_OUT_OF_MEMORY, "host allocation failed");

@@ -422,7 +422,15 @@ struct q3dr_multi {
   std::vector<int> devices;
   std::vector<q3dr_result> parts;
   std::vector<uint64_t> first;
+  std::vector<q3dr_mesh*> meshes;  // one per device when image-space normals are on (row N2)
+  uint32_t mesh_image_height = 0;
+  q3dr_render_opts mesh_ropts{};
 };
+
+static void multi_drop_meshes(q3dr_multi* mm) {
+  for (q3dr_mesh* me : mm->meshes) q3dr_mesh_destroy(me);
+  mm->meshes.clear();
+}
 
 extern "C" {
 
@@ -461,8 +469,30 @@ int q3dr_multi_create(const float* boxes, const float* weights, const float* nor
   return Q3DR_OK;
 }
 
+int q3dr_multi_set_normal_mesh(q3dr_multi* mm, const float* tri_vertices, const float* tri_normals, size_t nf,
+                               uint32_t image_height, const q3dr_render_opts* ropts) {
+  if (!mm) return fail(Q3DR_ERR_INVALID_ARG, "multi is NULL");
+  multi_drop_meshes(mm);
+  if (!tri_vertices) return Q3DR_OK;
+  if (!ropts || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "render options / image height missing");
+  for (int dev : mm->devices) {
+    q3dr_mesh* me = nullptr;
+    const int st = q3dr_mesh_create(tri_vertices, tri_normals, nf, dev, &me);
+    if (st != Q3DR_OK) {
+      const std::string msg = q3dr_detail::last_error();
+      multi_drop_meshes(mm);
+      return fail(st, msg);
+    }
+    mm->meshes.push_back(me);
+  }
+  mm->mesh_image_height = image_height;
+  mm->mesh_ropts = *ropts;
+  return Q3DR_OK;
+}
+
 int q3dr_multi_destroy(q3dr_multi* mm) {
   if (!mm) return Q3DR_OK;
+  multi_drop_meshes(mm);
   for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
   delete mm;
   return Q3DR_OK;
@@ -494,7 +524,13 @@ int q3dr_multi_score_viewpoints(q3dr_multi* mm, const float K[4], uint32_t image
   for (size_t g = 0; g < G; ++g) {
     workers.emplace_back([&, g]() {
       const size_t lo = (size_t)mm->first[g], hi = (size_t)mm->first[g + 1];
-      status[g] = q3dr_score_viewpoints(mm->maps[g], K, image_width, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts, &mm->parts[g]);
+      if (!mm->meshes.empty()) {
+        status[g] = q3dr_score_viewpoints_mesh_normals(mm->maps[g], mm->meshes[g], &mm->mesh_ropts, K, image_width,
+                                                       mm->mesh_image_height, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts,
+                                                       &mm->parts[g]);
+      } else {
+        status[g] = q3dr_score_viewpoints(mm->maps[g], K, image_width, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts, &mm->parts[g]);
+      }
       if (status[g] != Q3DR_OK) message[g] = q3dr_last_error();  // thread-local: carry it out of the worker
     });
   }

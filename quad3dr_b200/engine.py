@@ -184,6 +184,7 @@ def load_library() -> C.CDLL:
     L.q3dr_multi_map.argtypes = [vp, C.c_int]
     L.q3dr_multi_map.restype = vp
     L.q3dr_multi_update_weights.argtypes = [vp, fp]
+    L.q3dr_multi_set_normal_mesh.argtypes = [vp, fp, fp, C.c_size_t, C.c_uint32, C.POINTER(RenderOpts)]
     L.q3dr_multi_score_viewpoints.argtypes = (
         [vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_MultiResult)]
     )
@@ -734,6 +735,17 @@ class MultiGpuMap:
             self.close()
         except Exception:
             pass
+
+    def set_normal_mesh(self, tri_vertices, tri_normals, image_height: int, ropts: Optional[RenderOpts] = None):
+        """image-space normals for the following score_viewpoints calls (tri_vertices None: back to voxel normals)"""
+        if tri_vertices is None:
+            _check(load_library().q3dr_multi_set_normal_mesh(self._h, None, None, 0, 0, None))
+            return
+        v = _f32(tri_vertices).reshape(-1, 9)
+        nr = _f32(tri_normals).reshape(-1, 9) if tri_normals is not None else None
+        ropts = ropts or default_render_opts()
+        _check(load_library().q3dr_multi_set_normal_mesh(self._h, _fp(v), _fp(nr) if nr is not None else None, v.shape[0],
+                                                         image_height, C.byref(ropts)))
 
     def update_weights(self, weights):
         _check(load_library().q3dr_multi_update_weights(self._h, _fp(_f32(weights))))
