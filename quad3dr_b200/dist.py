@@ -88,6 +88,83 @@ def device_result_tensors(res, device) -> Tuple[torch.Tensor, torch.Tensor, torc
     return offsets, total, leaf, info
 
 
+class CudaIpcTransport:
+    """What PeerGather needs from the machine: buffers other ranks can write into, asynchronous copies into them and
+    ordering.  This one is the product's: cudaMalloc + CUDA IPC handles, cudaMemcpyAsync on a side stream (copy engines
+    over NVLink / NVSwitch), CUDA events, one NCCL all_reduce as the barrier.  (tests/test_dist_cpu.py drives the same
+    PeerGather logic at world_size 2 on gloo with a shared-memory stand-in.)"""
+
+    def __init__(self, device: torch.device, group=None):
+        from cuda.bindings import runtime as rt
+
+        self.rt = rt
+        self.device = torch.device(device)
+        self.group = group
+        torch.cuda.set_device(self.device)
+        self.side = torch.cuda.Stream(device=self.device)
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _ok(self, ret):
+        if int(ret[0]) != 0:
+            raise RuntimeError(f"CUDA runtime error {ret[0]} in PeerGather")
+        return ret[1] if len(ret) == 2 else ret[1:]
+
+    def alloc(self, nbytes: int) -> Tuple[int, bytes]:
+        ptr = self._ok(self.rt.cudaMalloc(nbytes))
+        try:
+            h = self._ok(self.rt.cudaIpcGetMemHandle(ptr))
+        except Exception:
+            self.rt.cudaFree(ptr)
+            raise
+        return int(ptr), bytes(h.reserved)
+
+    def open(self, handle: bytes) -> int:
+        h = self.rt.cudaIpcMemHandle_t()
+        h.reserved = handle
+        return int(self._ok(self.rt.cudaIpcOpenMemHandle(h, self.rt.cudaIpcMemLazyEnablePeerAccess)))
+
+    def close(self, ptr: int):
+        self.rt.cudaIpcCloseMemHandle(ptr)
+
+    def free(self, ptr: int):
+        self.rt.cudaFree(ptr)
+
+    def agree(self, ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def thread_init(self):
+        self.rt.cudaSetDevice(self.device.index)
+
+    def mark(self, stream):
+        """a point in `stream` (the scoring call's stream) that later copies can be ordered after"""
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def after(self, mark):
+        self.side.wait_event(mark)
+
+    def copy(self, dst: int, src: int, nbytes: int):
+        (err,) = self.rt.cudaMemcpyAsync(dst, src, nbytes, self.rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice,
+                                         self.side.cuda_stream)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaMemcpyAsync: {err}")
+
+    def barrier(self, stream):
+        """every rank's copies issued so far have landed everywhere; `stream` continues after that"""
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(self.token, group=self.group)
+        stream.wait_stream(self.side)
+
+    def view(self, ptr: int, n: int, typestr: str) -> torch.Tensor:
+        return torch.as_tensor(CudaArrayView(ptr, max(n, 1), typestr), device=self.device)[:n]
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+
 class PeerGather:
     """The result exchange of SURVEY.md section 8e, overlapped with the compute.
 
@@ -103,18 +180,16 @@ class PeerGather:
     still reads from step s.  Memory: 2 * world * (8 * cap + 12 * n_max) bytes per GPU, sized for the worst case.
     """
 
-    def __init__(self, device: torch.device, n_local_max: int, cap_entries: int, group=None):
-        from cuda.bindings import runtime as rt
+    def __init__(self, device, n_local_max: int, cap_entries: int, group=None, transport=None):
         import queue
         import threading
 
-        self.rt = rt
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.device = torch.device(device)
         self.n_max = int(n_local_max)
         self.cap = int(cap_entries)
+        self.tr = transport if transport is not None else CudaIpcTransport(device, group)
 
         def up(x, a=256):
             return (x + a - 1) // a * a
@@ -123,17 +198,15 @@ class PeerGather:
         self.leaf_off = up(self.tot_off + 4 * self.n_max)
         self.info_off = up(self.leaf_off + 4 * self.cap)
         self.slot_bytes = up(self.info_off + 4 * self.cap)
-        torch.cuda.set_device(self.device)
         self.base: List[int] = []
         self.peer = [[0] * self.world for _ in range(2)]
         handles = []
         failure = None
         try:
             for _ in range(2):
-                ptr = self._ok(rt.cudaMalloc(self.world * self.slot_bytes))
-                self.base.append(int(ptr))
-                h = self._ok(rt.cudaIpcGetMemHandle(ptr))
-                handles.append(bytes(h.reserved))
+                ptr, handle = self.tr.alloc(self.world * self.slot_bytes)
+                self.base.append(ptr)
+                handles.append(handle)
         except Exception as e:
             failure = e
             handles = [b"", b""]
@@ -143,26 +216,17 @@ class PeerGather:
             try:
                 for b in range(2):
                     for p in range(self.world):
-                        if p == self.rank:
-                            self.peer[b][p] = self.base[b]
-                        else:
-                            h = rt.cudaIpcMemHandle_t()
-                            h.reserved = gathered[p][b]
-                            self.peer[b][p] = int(self._ok(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)))
+                        self.peer[b][p] = self.base[b] if p == self.rank else self.tr.open(gathered[p][b])
             except Exception as e:
                 failure = e
         elif failure is None:
             failure = RuntimeError("another rank could not export its receive buffer")
         # all ranks agree on success before anybody relies on it (a one-sided failure must not desynchronise collectives)
-        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=self.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
+        if not self.tr.agree(failure is None):
             for ptr in self.base:
-                rt.cudaFree(ptr)
+                self.tr.free(ptr)
             self.base = []
             raise RuntimeError(f"PeerGather unavailable: {failure or 'failed on another rank'}")
-        self.side = torch.cuda.Stream(device=self.device)
-        self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.cur = 1
         self.error = None
         self._last = None
@@ -171,34 +235,23 @@ class PeerGather:
         self._worker.start()
         dist.barrier(group=group)  # every rank has mapped every buffer before anybody pushes
 
-    def _ok(self, ret):
-        err = ret[0]
-        if int(err) != 0:
-            raise RuntimeError(f"CUDA runtime error {err} in PeerGather")
-        return ret[1] if len(ret) == 2 else ret[1:]
-
     def _push(self, dst_off: int, src_ptr: int, nbytes: int):
-        """the same bytes into this rank's slot on every rank (copy engines, side stream)"""
+        """the same bytes into this rank's slot on every rank"""
         if nbytes <= 0:
             return
-        rt = self.rt
-        s = self.side.cuda_stream
         for k in range(self.world):
             p = (self.rank + k) % self.world  # start with different targets on different ranks
-            dst = self.peer[self.cur][p] + self.rank * self.slot_bytes + dst_off
-            (err,) = rt.cudaMemcpyAsync(dst, src_ptr, nbytes, rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice, s)
-            if int(err) != 0:
-                raise RuntimeError(f"cudaMemcpyAsync to rank {p}: {err}")
+            self.tr.copy(self.peer[self.cur][p] + self.rank * self.slot_bytes + dst_off, src_ptr, nbytes)
 
     def _run(self):
-        self.rt.cudaSetDevice(self.device.index)
+        self.tr.thread_init()
         while True:
             job = self._q.get()
             try:
                 if job is None:
                     return
-                ev, first_entry, n_entries, leaf_ptr, info_ptr = job
-                self.side.wait_event(ev)
+                mark, first_entry, n_entries, leaf_ptr, info_ptr = job
+                self.tr.after(mark)
                 self._push(self.leaf_off + 4 * first_entry, leaf_ptr + 4 * first_entry, 4 * n_entries)
                 self._push(self.info_off + 4 * first_entry, info_ptr + 4 * first_entry, 4 * n_entries)
             except Exception as e:  # surfaced by end_step
@@ -210,31 +263,25 @@ class PeerGather:
         self.cur ^= 1
         self._last = None
 
-    def on_chunk(self, first_vp: int, n_vp: int, first_entry: int, n_entries: int, res, stream: torch.cuda.Stream):
+    def on_chunk(self, first_vp: int, n_vp: int, first_entry: int, n_entries: int, res, stream):
         """chunk callback: order the push after the work issued so far, hand it to the helper thread, return at once
         (the calling thread goes on to launch the next chunk's raycast)"""
         if first_entry + n_entries > self.cap or first_vp + n_vp > self.n_max:
             self.error = RuntimeError("PeerGather: result larger than the receive slot")
             return
-        ev = torch.cuda.Event()
-        ev.record(stream)
         self._last = res
-        self._q.put((ev, first_entry, n_entries, int(res.leaf or 0), int(res.information or 0)))
+        self._q.put((self.tr.mark(stream), first_entry, n_entries, int(res.leaf or 0), int(res.information or 0)))
 
-    def end_step(self, n_local: int, stream: torch.cuda.Stream):
+    def end_step(self, n_local: int, stream):
         """headers of all local viewpoints, then the barrier; `stream` continues when every rank's pushes have landed"""
         self._q.join()
         if self.error is not None:
             raise self.error
-        with torch.cuda.stream(self.side):
-            if self._last is not None and n_local > 0:
-                ev = torch.cuda.Event()
-                ev.record(stream)
-                self.side.wait_event(ev)
-                self._push(0, int(self._last.offsets), 8 * (n_local + 1))
-                self._push(self.tot_off, int(self._last.total), 4 * n_local)
-            dist.all_reduce(self.token, group=self.group)
-        stream.wait_stream(self.side)
+        if self._last is not None and n_local > 0:
+            self.tr.after(self.tr.mark(stream))
+            self._push(0, int(self._last.offsets), 8 * (n_local + 1))
+            self._push(self.tot_off, int(self._last.total), 4 * n_local)
+        self.tr.barrier(stream)
 
     def views(self, n_per_rank: List[int]):
         """per source rank: (offsets int64 (n+1,), total f32 (n,), leaf i32 (e,), info f32 (e,)) -- zero-copy views of
@@ -243,28 +290,24 @@ class PeerGather:
         for r in range(self.world):
             slot = self.base[self.cur] + r * self.slot_bytes
             n = int(n_per_rank[r])
-            off = torch.as_tensor(CudaArrayView(slot, n + 1, "<i8"), device=self.device)
-            tot = torch.as_tensor(CudaArrayView(slot + self.tot_off, max(n, 1), "<f4"), device=self.device)[:n]
+            off = self.tr.view(slot, n + 1, "<i8")
+            tot = self.tr.view(slot + self.tot_off, n, "<f4")
             e = int(off[n].item()) if n else 0
-            if e:
-                leaf = torch.as_tensor(CudaArrayView(slot + self.leaf_off, e, "<i4"), device=self.device)
-                info = torch.as_tensor(CudaArrayView(slot + self.info_off, e, "<f4"), device=self.device)
-            else:
-                leaf = torch.empty(0, dtype=torch.int32, device=self.device)
-                info = torch.empty(0, dtype=torch.float32, device=self.device)
+            leaf = self.tr.view(slot + self.leaf_off, e, "<i4")
+            info = self.tr.view(slot + self.info_off, e, "<f4")
             out.append((off, tot, leaf, info))
         return out
 
     def close(self):
         self._q.put(None)
         self._worker.join(timeout=5)
-        torch.cuda.synchronize(self.device)
+        self.tr.sync()
         dist.barrier(group=self.group)  # nobody unmaps while somebody may still push
         for b in range(2):
             for p in range(self.world):
                 if p != self.rank and self.peer[b][p]:
-                    self.rt.cudaIpcCloseMemHandle(self.peer[b][p])
+                    self.tr.close(self.peer[b][p])
         dist.barrier(group=self.group)
         for ptr in self.base:
-            self.rt.cudaFree(ptr)
+            self.tr.free(ptr)
         self.base = []
