@@ -372,3 +372,82 @@ def test_gpu_full_size_fused_equals_render_then_lookup():
         pick = rng.choice(pix, size=min(400, pix.shape[0]), replace=False)
         ref = O.mesh_cast_pixels(tv, tn, cam.K, 640, 480, vps[v], pick % 640, pick // 640)
         assert np.array_equal(images[v][pick // 640, pick % 640], ref)
+
+
+# --------------------------------------------------- CPU: the conventions, derived a second way from the reference
+
+def _gl_style_render(tv, tn, K, W, H, Rt, near=0.5, far=1e5):
+    """The reference's OpenGL pipeline in float64 numpy, matrix by matrix as viewpoint_offscreen_renderer.cpp builds
+    them: view = world-to-image of the pose rotated by pi about x (:303-321), proj (:283-289), clip -> NDC -> window,
+    samples at pixel centres, depth test GL_LESS, perspective-correct interpolation, shader 0.5 n + 0.5, 8-bit target,
+    QOpenGLFramebufferObject::toImage() flipping the rows.  Triangles are rasterised in homogeneous coordinates
+    (no explicit clipping).  Independent of the ray formula of mesh_kernels.cuh / the oracle."""
+    fx, fy, cx, cy = [float(v) for v in K]
+    M = np.asarray(Rt, np.float64).reshape(3, 4)
+    R, t = M[:, :3], M[:, 3]
+    Rv = R @ np.diag([1.0, -1.0, -1.0])                       # quaternion * AngleAxis(pi, UnitX)
+    V = np.eye(4)
+    V[:3, :3] = Rv.T                                            # getTransformationWorldToImage
+    V[:3, 3] = -Rv.T @ t
+    P = np.zeros((4, 4))
+    P[0, 0], P[1, 1] = fx / cx, fy / cy
+    P[2, 2] = -(far + near) / (far - near)
+    P[2, 3] = -2 * far * near / (far - near)
+    P[3, 2] = -1
+    PV = P @ V
+    jj, ii = np.mgrid[0:H, 0:W]                                 # window pixel (ii, jj), jj counted from the BOTTOM
+    px = (ii + 0.5) / W * 2 - 1
+    py = (jj + 0.5) / H * 2 - 1
+    depth = np.full((H, W), np.inf)
+    color = np.full((H, W, 3), 255, np.int64)                   # clear colour (1,1,1,1)
+    rhs = np.stack([px.ravel(), py.ravel(), np.ones(W * H)])
+    for f in range(tv.shape[0]):
+        c = (PV @ np.concatenate([tv[f].astype(np.float64), np.ones((3, 1))], axis=1).T)   # columns = corners
+        A = np.stack([c[0], c[1], c[3]])                        # x_clip, y_clip, w_clip of the three corners
+        if abs(np.linalg.det(A)) < 1e-30:
+            continue
+        lam = np.linalg.solve(A, rhs)                           # b_i / w at every pixel centre
+        s = lam.sum(0)
+        inside = (lam >= 0).all(0) & (s > 0)
+        if not inside.any():
+            continue
+        wclip = 1.0 / np.where(inside, s, 1.0)                  # = camera depth (w_clip = -z_eye)
+        ok = inside & (wclip >= near) & (wclip <= far) & (wclip < depth.ravel())
+        if not ok.any():
+            continue
+        b = lam * wclip                                         # perspective-correct barycentrics
+        n = b.T @ tn[f].astype(np.float64)
+        col = np.rint(np.clip(0.5 * n + 0.5, 0, 1) * 255).astype(np.int64)
+        d = depth.ravel()
+        d[ok] = wclip[ok]
+        depth = d.reshape(H, W)
+        cflat = color.reshape(-1, 3)
+        cflat[ok] = col[ok]
+        color = cflat.reshape(H, W, 3)
+    color = color[::-1]                                         # toImage(): row 0 on top
+    return (0xFF000000 | (color[..., 0] << 16) | (color[..., 1] << 8) | color[..., 2]).astype(np.uint32)
+
+
+def test_ray_cast_definition_agrees_with_a_gl_style_pipeline():
+    """The image definition (pixel-centre rays, camera axes, row order, depth, interpolation, encoding) against the
+    reference's own matrices pushed through a rasteriser-style pipeline: identical except where float32 vs float64
+    rounding flips an edge / tie / 8-bit boundary."""
+    g = np.load(GOLDEN)
+    W, H = int(g["width"]), int(g["height"])
+    tv, tn = g["tri_vertices"], g["tri_normals"]
+    total = exact = close = same_cover = 0
+    for v in range(g["Rt"].shape[0]):
+        ref = _gl_style_render(tv, tn, g["K"], W, H, g["Rt"][v])
+        got = g["images"][v]
+        ch = lambda a: np.stack([(a >> 16) & 255, (a >> 8) & 255, a & 255], -1).astype(np.int64)
+        diff = np.abs(ch(ref) - ch(got)).max(-1)
+        total += W * H
+        exact += int((diff == 0).sum())
+        close += int((diff <= 1).sum())
+        same_cover += int(((ref == CLEAR) == (got == CLEAR)).sum())
+    assert same_cover >= 0.995 * total, (same_cover, total)      # hit / background: silhouette pixels only
+    assert close >= 0.985 * total and exact >= 0.95 * total, (exact, close, total)
+    # an upside-down or mirrored convention would agree on a few per cent of the pixels only
+    flipped = g["images"][0][::-1]
+    ref0 = _gl_style_render(tv, tn, g["K"], W, H, g["Rt"][0])
+    assert (flipped == ref0).mean() < 0.6
