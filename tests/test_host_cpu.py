@@ -37,6 +37,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(E._Result) == 9 * 8
     assert ctypes.sizeof(E.MapInfo) == 48
     assert ctypes.sizeof(E.Stats) == 40
+    assert ctypes.sizeof(E.RenderOpts) == 12   # q3dr_render_opts
+    assert ctypes.sizeof(E.MeshInfo) == 40     # q3dr_mesh_info
 
 
 def test_score_opts_defaults_match_reference_defaults():
@@ -119,6 +121,10 @@ def test_no_gpu_means_loud_failure_not_fallback():
     leaves = synth.map_tiny()
     with pytest.raises(E.Q3drError) as ei:
         E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal)
+    assert ei.value.status == E.Q3DR_ERR_NO_DEVICE
+    # the mesh of the image-space normals has no CPU path either
+    with pytest.raises(E.Q3drError) as ei:
+        E.NormalMesh(np.array([[[0, 0, 5], [1, 0, 5], [0, 1, 5]]], np.float32))
     assert ei.value.status == E.Q3DR_ERR_NO_DEVICE
 
 
