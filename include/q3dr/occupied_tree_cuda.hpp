@@ -16,6 +16,8 @@
 //                                            <- ViewpointPlanner::getRaycastHitVoxelsWithInformationScore
 //                                               viewpoint_planner/src/planner/viewpoint_planner_raycast.cpp:89-148
 //   q3dr::VoxelWithInformation / VoxelWithInformationSet  <- planner/occupied_tree.h:62-92
+//   q3dr::VoxelWithInformationSetView        <- the same container contract (iterate / size / find / move) as a
+//                                               window into the engine's CSR result
 //   ...::intersects(bbox) / isValidObjectPositionBatch    <- bvh.h:544-554 ; viewpoint_planner_data.cpp:209-235
 //   q3dr::ObservedVoxelMapCuda<NodeT>        <- ViewpointPath::observed_voxel_map + computeNewInformation /
 //                                               addObservedVoxelsToViewpointPath / the stereo overlap sum
@@ -26,8 +28,12 @@
 #ifndef Q3DR_OCCUPIED_TREE_CUDA_HPP_
 #define Q3DR_OCCUPIED_TREE_CUDA_HPP_
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
+#include <iterator>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -56,6 +62,113 @@ struct VoxelWithInformation {
 template <typename NodeT>
 using VoxelWithInformationSet =
     std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash>;
+
+/// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.
+template <typename NodeT>
+struct VoxelSetBlock {
+  std::vector<std::int32_t> leaf;     // ascending leaf index inside every viewpoint's range
+  std::vector<float> information;
+  std::vector<NodeT*> const* nodes;   // leaf index -> host node (owned by the OccupiedTreeCuda, which must outlive the views)
+  std::unordered_map<const NodeT*, std::int32_t> const* (*leaf_of)(const void*);  // host node -> leaf index, built on first find()
+  const void* tree;
+};
+
+/// A VoxelWithInformationSet (planner/occupied_tree.h:62-92) that is a window into the engine's CSR result instead of
+/// a hash table of heap nodes: what the reference's consumers do with a voxel set -- range-for
+/// (viewpoint_planner_graph.cpp:46-52, viewpoint_planner_path.cpp:208,456,841), size() / empty()
+/// (viewpoint_planner_graph.cpp:29,53, viewpoint_planner_path.cpp:791), find() against end()
+/// (viewpoint_planner_path.cpp:842-843), begin() / end() (:985-986), move into a ViewpointEntry -- works unchanged,
+/// building it costs nothing per voxel.  Immutable; toUnorderedSet() gives the reference's own container.
+/// Iteration order is ascending leaf index (the reference's is hash order, i.e. unspecified).
+template <typename NodeT>
+class VoxelWithInformationSetView {
+ public:
+  typedef VoxelWithInformation<NodeT> value_type;
+  typedef std::size_t size_type;
+
+  class const_iterator {
+   public:
+    typedef std::random_access_iterator_tag iterator_category;
+    typedef VoxelWithInformation<NodeT> value_type;
+    typedef std::ptrdiff_t difference_type;
+    struct pointer {  // arrow proxy: it->voxel, it->information
+      value_type v;
+      const value_type* operator->() const { return &v; }
+    };
+    typedef value_type reference;  // by value: elements are assembled from (leaf, information) on the fly
+
+    const_iterator() : block_(nullptr), i_(0) {}
+    const_iterator(const VoxelSetBlock<NodeT>* block, std::size_t i) : block_(block), i_(i) {}
+    value_type operator*() const {
+      return value_type((*block_->nodes)[static_cast<std::size_t>(block_->leaf[i_])], block_->information[i_]);
+    }
+    pointer operator->() const { return pointer{**this}; }
+    value_type operator[](difference_type k) const { return *(*this + k); }
+    const_iterator& operator++() { ++i_; return *this; }
+    const_iterator operator++(int) { const_iterator t(*this); ++i_; return t; }
+    const_iterator& operator--() { --i_; return *this; }
+    const_iterator operator--(int) { const_iterator t(*this); --i_; return t; }
+    const_iterator& operator+=(difference_type k) { i_ += k; return *this; }
+    const_iterator& operator-=(difference_type k) { i_ -= k; return *this; }
+    const_iterator operator+(difference_type k) const { return const_iterator(block_, i_ + k); }
+    const_iterator operator-(difference_type k) const { return const_iterator(block_, i_ - k); }
+    difference_type operator-(const const_iterator& o) const {
+      return static_cast<difference_type>(i_) - static_cast<difference_type>(o.i_);
+    }
+    bool operator==(const const_iterator& o) const { return i_ == o.i_; }
+    bool operator!=(const const_iterator& o) const { return i_ != o.i_; }
+    bool operator<(const const_iterator& o) const { return i_ < o.i_; }
+    std::int32_t leaf() const { return block_->leaf[i_]; }
+
+   private:
+    const VoxelSetBlock<NodeT>* block_;
+    std::size_t i_;
+  };
+  typedef const_iterator iterator;
+
+  VoxelWithInformationSetView() : begin_(0), end_(0) {}
+  VoxelWithInformationSetView(std::shared_ptr<const VoxelSetBlock<NodeT> > block, std::size_t begin, std::size_t end)
+      : block_(std::move(block)), begin_(begin), end_(end) {}
+
+  size_type size() const { return end_ - begin_; }
+  bool empty() const { return end_ == begin_; }
+  const_iterator begin() const { return const_iterator(block_.get(), begin_); }
+  const_iterator end() const { return const_iterator(block_.get(), end_); }
+  const_iterator cbegin() const { return begin(); }
+  const_iterator cend() const { return end(); }
+
+  /// Like the reference's unordered_set::find with VoxelWithInformation::operator== : the voxel must be in the set
+  /// AND carry the same information (occupied_tree.h:73-79).
+  const_iterator find(const value_type& vi) const {
+    if (empty()) return end();
+    const std::unordered_map<const NodeT*, std::int32_t>* table = block_->leaf_of(block_->tree);
+    typename std::unordered_map<const NodeT*, std::int32_t>::const_iterator it = table->find(vi.voxel);
+    if (it == table->end()) return end();
+    const std::int32_t* first = block_->leaf.data() + begin_;
+    const std::int32_t* last = block_->leaf.data() + end_;
+    const std::int32_t* p = std::lower_bound(first, last, it->second);
+    if (p == last || *p != it->second) return end();
+    const std::size_t i = static_cast<std::size_t>(p - block_->leaf.data());
+    return block_->information[i] == vi.information ? const_iterator(block_.get(), i) : end();
+  }
+  size_type count(const value_type& vi) const { return find(vi) == end() ? 0 : 1; }
+
+  /// the engine's view of the set: ascending leaf indices and their informations
+  const std::int32_t* leafData() const { return block_ ? block_->leaf.data() + begin_ : nullptr; }
+  const float* informationData() const { return block_ ? block_->information.data() + begin_ : nullptr; }
+
+  /// the reference's own container (one hash-node allocation per voxel)
+  VoxelWithInformationSet<NodeT> toUnorderedSet() const {
+    VoxelWithInformationSet<NodeT> set;
+    set.reserve(size());
+    for (const_iterator it = begin(); it != end(); ++it) set.insert(*it);
+    return set;
+  }
+
+ private:
+  std::shared_ptr<const VoxelSetBlock<NodeT> > block_;
+  std::size_t begin_, end_;
+};
 
 /// One BVH leaf as generateBVHTree emits it (viewpoint_planner_data.cpp:820-897) plus its host node.
 template <typename NodeT>
@@ -187,6 +300,15 @@ class OccupiedTreeCuda {
     return it == leaf_of_.end() ? -1 : it->second;
   }
   NodeT* leafNode(std::int32_t leaf) const { return leaf < 0 ? nullptr : nodes_[static_cast<std::size_t>(leaf)]; }
+  const std::vector<NodeT*>& leafNodes() const { return nodes_; }
+  /// host node -> leaf index for all leaves (built once, on first use)
+  const std::unordered_map<const NodeT*, std::int32_t>& leafIndexTable() const {
+    leafIndex(nullptr);
+    return leaf_of_;
+  }
+  static const std::unordered_map<const NodeT*, std::int32_t>* leafIndexTableOf(const void* tree) {
+    return &static_cast<const OccupiedTreeCuda*>(tree)->leafIndexTable();
+  }
   q3dr_map* handle() const { return map_; }
 
   /// bvh.h:396-451.  intrinsics: 4x4 (fx, fy, cx, cy are read, bvh.cu:329-330); extrinsics: 3x4 [R|t] image-to-world.
@@ -506,13 +628,74 @@ class ViewpointRaycastCuda {
                                                    viewpoint.camera().height(), ignore_voxels_with_zero_information);
   }
 
-  /// Batched form: all candidates of one graph-building round in one call (one camera for all viewpoints).
+  typedef VoxelWithInformationSetView<NodeT> VoxelSetView;
+
+  /// Batched form: all candidates of one graph-building round in one call (one camera for all viewpoints), the
+  /// reference's own container per viewpoint.  The sets are filled by all host threads (OpenMP over viewpoints, like the
+  /// reference's result conversion, bvh.h:430,487); for 10^3 viewpoints x 10^4 voxels this conversion, not the GPU, is
+  /// what the call costs -- consumers that only read the sets take ...BatchView below.
   template <typename ViewpointT>
   std::vector<std::pair<VoxelSet, float>> getRaycastHitVoxelsWithInformationScoreBatch(
       const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end, std::size_t y_start,
       std::size_t y_end, bool ignore_voxels_with_zero_information = false) const {
     std::vector<std::pair<VoxelSet, float>> out(viewpoints.size());
     if (viewpoints.empty()) return out;
+    const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
+    const std::vector<NodeT*>& nodes = bvh_tree_->leafNodes();
+    const std::ptrdiff_t nv = static_cast<std::ptrdiff_t>(viewpoints.size());
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (std::ptrdiff_t v = 0; v < nv; ++v) {
+      VoxelSet& set = out[static_cast<std::size_t>(v)].first;
+      set.reserve(static_cast<std::size_t>(r.offsets[v + 1] - r.offsets[v]));
+      for (std::uint64_t i = r.offsets[v]; i < r.offsets[v + 1]; ++i) {
+        set.insert(VoxelWithInformation<NodeT>(nodes[static_cast<std::size_t>(r.leaf[i])], r.information[i]));
+      }
+      out[static_cast<std::size_t>(v)].second = r.total[v];
+    }
+    return out;
+  }
+
+  /// Batched form returning views into one shared copy of the CSR result: no per-voxel work on the host at all.
+  template <typename ViewpointT>
+  std::vector<std::pair<VoxelSetView, float>> getRaycastHitVoxelsWithInformationScoreBatchView(
+      const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end, std::size_t y_start,
+      std::size_t y_end, bool ignore_voxels_with_zero_information = false) const {
+    std::vector<std::pair<VoxelSetView, float>> out(viewpoints.size());
+    if (viewpoints.empty()) return out;
+    const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
+    std::shared_ptr<VoxelSetBlock<NodeT> > block = std::make_shared<VoxelSetBlock<NodeT> >();
+    const std::size_t ne = static_cast<std::size_t>(r.n_entries);
+    block->leaf.resize(ne);
+    block->information.resize(ne);
+    block->nodes = &bvh_tree_->leafNodes();
+    block->leaf_of = &TreeType::leafIndexTableOf;
+    block->tree = bvh_tree_;
+    // the map-owned host arrays are overwritten by the next scoring call: one parallel copy into the shared block
+    const std::ptrdiff_t pieces = static_cast<std::ptrdiff_t>((ne + kCopyPiece - 1) / kCopyPiece);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (std::ptrdiff_t p = 0; p < pieces; ++p) {
+      const std::size_t a = static_cast<std::size_t>(p) * kCopyPiece, n = std::min(kCopyPiece, ne - a);
+      std::memcpy(block->leaf.data() + a, r.leaf + a, n * sizeof(std::int32_t));
+      std::memcpy(block->information.data() + a, r.information + a, n * sizeof(float));
+    }
+    for (std::size_t v = 0; v < viewpoints.size(); ++v) {
+      out[v].first = VoxelSetView(block, static_cast<std::size_t>(r.offsets[v]), static_cast<std::size_t>(r.offsets[v + 1]));
+      out[v].second = r.total[v];
+    }
+    return out;
+  }
+
+ private:
+  static const std::size_t kCopyPiece = 1u << 20;
+
+  /// the engine call behind both batch forms; only (leaf, information) travel back (8 bytes per voxel)
+  template <typename ViewpointT>
+  q3dr_result scoreBatch(const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end,
+                         std::size_t y_start, std::size_t y_end, bool ignore_voxels_with_zero_information) const {
     bvh_tree_->requireMap();
     float K[4];
     std::vector<float> Rt(12 * viewpoints.size());
@@ -523,32 +706,26 @@ class ViewpointRaycastCuda {
     q3dr_score_opts o = opts_;
     o.ignore_voxels_with_zero_information = ignore_voxels_with_zero_information ? 1 : 0;
     q3dr_result r;
+    bvh_tree_->check(q3dr_map_set_result_fields(bvh_tree_->handle(), 0u));
+    int st;
     if (mesh_normals_ != nullptr) {
-      bvh_tree_->check(q3dr_score_viewpoints_mesh_normals(
+      st = q3dr_score_viewpoints_mesh_normals(
           bvh_tree_->handle(), mesh_normals_->handle(), &mesh_normals_->renderOptions(), K,
           static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
           static_cast<std::uint32_t>(viewpoints[0]->camera().height()), static_cast<std::uint32_t>(x_start),
           static_cast<std::uint32_t>(x_end), static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
-          Rt.data(), viewpoints.size(), &o, &r));
+          Rt.data(), viewpoints.size(), &o, &r);
     } else {
-      bvh_tree_->check(q3dr_score_viewpoints(bvh_tree_->handle(), K,
-                                             static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
-                                             static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
-                                             static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end),
-                                             Rt.data(), viewpoints.size(), &o, &r));
+      st = q3dr_score_viewpoints(bvh_tree_->handle(), K, static_cast<std::uint32_t>(viewpoints[0]->camera().width()),
+                                 static_cast<std::uint32_t>(x_start), static_cast<std::uint32_t>(x_end),
+                                 static_cast<std::uint32_t>(y_start), static_cast<std::uint32_t>(y_end), Rt.data(),
+                                 viewpoints.size(), &o, &r);
     }
-    for (std::size_t v = 0; v < viewpoints.size(); ++v) {
-      VoxelSet& set = out[v].first;
-      set.reserve(static_cast<std::size_t>(r.offsets[v + 1] - r.offsets[v]));
-      for (std::uint64_t i = r.offsets[v]; i < r.offsets[v + 1]; ++i) {
-        set.insert(VoxelWithInformation<NodeT>(bvh_tree_->leafNode(r.leaf[i]), r.information[i]));
-      }
-      out[v].second = r.total[v];
-    }
-    return out;
+    q3dr_map_set_result_fields(bvh_tree_->handle(), Q3DR_RESULT_FIRST_PIXEL | Q3DR_RESULT_DIST_SQ);
+    bvh_tree_->check(st);
+    return r;
   }
 
- private:
   TreeType* bvh_tree_;
   float min_range_;
   float max_range_;
@@ -587,6 +764,9 @@ class ObservedVoxelMapCuda {
   /// computeNewInformation / addObservedVoxelsToViewpointPath for a stored ViewpointEntry::voxel_set
   float computeNewInformation(const VoxelWithInformationSet<NodeT>& voxel_set) const { return voxelSet(voxel_set, 0); }
   float addObservedVoxels(const VoxelWithInformationSet<NodeT>& voxel_set) { return voxelSet(voxel_set, 1); }
+  /// ... and for a view (its leaf / information arrays go to the device as they are)
+  float computeNewInformation(const VoxelWithInformationSetView<NodeT>& voxel_set) const { return voxelView(voxel_set, 0); }
+  float addObservedVoxels(const VoxelWithInformationSetView<NodeT>& voxel_set) { return voxelView(voxel_set, 1); }
 
   /// compute_overlap_information_lambda(set1 = others[i], set2 = ref)
   std::vector<float> computeOverlapInformation(std::uint32_t ref, const std::vector<std::uint32_t>& others) const {
@@ -607,6 +787,12 @@ class ObservedVoxelMapCuda {
     }
     float v = 0;
     check(q3dr_observed_voxel_set(tree_->handle(), obs_, factor_, leaf.data(), info.data(), leaf.size(), add, &v));
+    return v;
+  }
+  float voxelView(const VoxelWithInformationSetView<NodeT>& voxel_set, int add) const {
+    float v = 0;
+    check(q3dr_observed_voxel_set(tree_->handle(), obs_, factor_, voxel_set.leafData(), voxel_set.informationData(),
+                                  voxel_set.size(), add, &v));
     return v;
   }
   void check(int status) const {

@@ -34,6 +34,9 @@
  *        ViewpointOffscreenRenderer::uploadPoissonMesh, drawPoissonMeshNormals, computePoissonMeshNormalVector
  *        viewpoint_planner/src/planner/viewpoint_offscreen_renderer.cpp:138-200,276-293,361-397,499-527 ;
  *        viewpoint_planner/src/shaders/triangles_normals.{v,f}.glsl
+ *   q3dr_exchange_* / q3dr_multi_enable_gather
+ *        no counterpart (the reference is single-GPU, viewpoint_planner_data.cpp:328-335): the gather of the sharded
+ *        candidate set, SURVEY.md section 8e
  *   q3dr_score_viewpoints_mesh_normals / q3dr_score_viewpoints_normal_images
  *        getRaycastHitVoxelsWithInformationScore with options_.enable_opengl = true: computeNormalVector takes the
  *        normal from the mesh-normal image at the voxel's kept pixel
@@ -56,7 +59,7 @@
 extern "C" {
 #endif
 
-#define Q3DR_ABI_VERSION 3
+#define Q3DR_ABI_VERSION 4
 
 enum q3dr_status {
   Q3DR_OK = 0,
@@ -215,7 +218,9 @@ int q3dr_score_viewpoints_device(q3dr_map* map, const float K[4], uint32_t image
  * so far on the stream has run).  A consumer orders its own work after an event recorded on that stream -- e.g.
  * copy-engine pushes of the chunk into the other GPUs' memory while the next chunk is being cast
  * (quad3dr_b200/dist.py: PeerGather).  The pointers may change between calls (pools grow), not between the chunks of
- * a call whose pools already have the needed capacity.  cb == NULL removes the callback. */
+ * a call whose pools already have the needed capacity; a pool that had to grow is REPLACED, and the replaced block
+ * stays allocated and intact until the next scoring call on the map begins, so work a consumer enqueued on an earlier
+ * chunk's pointers remains valid for the whole call.  cb == NULL removes the callback. */
 typedef void (*q3dr_chunk_callback)(void* user, uint64_t first_viewpoint, uint64_t n_viewpoints, uint64_t first_entry,
                                     uint64_t n_entries, const q3dr_result* partial_device_result);
 int q3dr_map_set_chunk_callback(q3dr_map* map, q3dr_chunk_callback cb, void* user);
@@ -223,6 +228,14 @@ int q3dr_map_set_chunk_callback(q3dr_map* map, q3dr_chunk_callback cb, void* use
 /* Copies the device-resident result of the last q3dr_score_viewpoints_device call to host memory
  * owned by the map. */
 int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);
+
+/* Which per-entry arrays the scoring calls on this map deliver besides (leaf, information).  The reference's facade
+ * (getRaycastHitVoxelsWithInformationScore -> VoxelWithInformationSet, viewpoint_planner_raycast.cpp:116-148) consumes
+ * voxel + information only: with fields == 0 a result entry costs 8 instead of 16 bytes of D2H / peer traffic and the
+ * kept pixel's dist_sq is not recomputed.  Arrays that are switched off come back as NULL.  Default: both on. */
+#define Q3DR_RESULT_FIRST_PIXEL 1u
+#define Q3DR_RESULT_DIST_SQ 2u
+int q3dr_map_set_result_fields(q3dr_map* map, uint32_t fields);
 
 /* ---- consumers of the voxel sets: the planner's path search ----
  *
@@ -396,6 +409,61 @@ int q3dr_multi_score_viewpoints(q3dr_multi* multi, const float K[4], uint32_t im
  * render target image_width (of the call) x image_height.  tri_vertices == NULL switches back to the voxel normals. */
 int q3dr_multi_set_normal_mesh(q3dr_multi* multi, const float* tri_vertices, const float* tri_normals, size_t nf,
                                uint32_t image_height, const q3dr_render_opts* ropts);
+
+/* ---- result exchange between GPUs ("per-viewpoint hit sets and scores are gathered") ----
+ *
+ * Every rank (one GPU each; ranks may be threads of one process or separate processes) owns a RECEIVE BUFFER in its
+ * own HBM with one slot per source rank.  While a scoring call runs, every finished chunk of its CSR result is pushed
+ * into this rank's slot on every rank by the copy engines (cudaMemcpyAsync into peer memory over NVLink / NVSwitch, on
+ * a side stream, no SM involved) while the SMs cast the next chunk; q3dr_exchange_end_step pushes the per-viewpoint
+ * headers and a completion flag behind them and then waits -- on the device, in `stream` -- for the flags of all
+ * ranks.  After it returns every rank holds the results of ALL ranks (the all-gather of the reference's single-GPU
+ * result, viewpoint_planner_data.cpp:328-335 selects one device; here the candidate set is sharded).
+ * Two buffers alternate between steps: a view of step s stays valid until this rank's next q3dr_exchange_begin_step.
+ *
+ * Same process:       q3dr_exchange_create on every map, then q3dr_exchange_connect(all exchanges).
+ * Separate processes: q3dr_exchange_create, q3dr_exchange_export (2 x 64-byte CUDA IPC handles), ship the handles of
+ *                     all ranks to all ranks by any means (MPI, torch.distributed ...), q3dr_exchange_import. */
+typedef struct q3dr_exchange q3dr_exchange;
+
+#define Q3DR_IPC_HANDLE_BYTES 64
+
+/* byte offsets inside one receive buffer (host-only arithmetic; what tests and foreign readers of the buffer need) */
+typedef struct q3dr_exchange_layout {
+  uint64_t header_off;   /* per slot: {u64 n_viewpoints, u64 n_entries, u64 step, u64 status} */
+  uint64_t offsets_off;  /* u64 [max_viewpoints + 1] */
+  uint64_t total_off;    /* f32 [max_viewpoints] */
+  uint64_t leaf_off;     /* i32 [max_entries] */
+  uint64_t info_off;     /* f32 [max_entries] */
+  uint64_t slot_bytes;   /* one slot; slot of source rank r starts at r * slot_bytes */
+  uint64_t flags_off;    /* u64 [n_ranks] completion flags behind the slots: (step << 1) | failed */
+  uint64_t buffer_bytes;
+} q3dr_exchange_layout;
+
+int q3dr_exchange_layout_of(uint32_t n_ranks, uint64_t max_viewpoints, uint64_t max_entries, q3dr_exchange_layout* out);
+
+/* max_viewpoints / max_entries: the largest per-rank viewpoint count / result size of any step (same on all ranks). */
+int q3dr_exchange_create(q3dr_map* map, uint32_t n_ranks, uint32_t rank, uint64_t max_viewpoints, uint64_t max_entries,
+                         q3dr_exchange** out);
+/* Unmaps the peers' buffers (no more pushes from this rank).  Across processes: every rank disconnects, the ranks meet
+ * at a barrier of their own, then every rank destroys -- so nobody frees memory a peer still has mapped. */
+int q3dr_exchange_disconnect(q3dr_exchange* ex);
+int q3dr_exchange_destroy(q3dr_exchange* ex); /* disconnects first if need be */
+int q3dr_exchange_export(q3dr_exchange* ex, void* handles_out /* 2 x Q3DR_IPC_HANDLE_BYTES */);
+int q3dr_exchange_import(q3dr_exchange* ex, const void* all_handles /* n_ranks x 2 x Q3DR_IPC_HANDLE_BYTES, by rank */);
+int q3dr_exchange_connect(q3dr_exchange* const* all, uint32_t n_ranks);
+/* Arms the exchange: the next scoring call on the map pushes its chunks.  Call it on every rank, every step. */
+int q3dr_exchange_begin_step(q3dr_exchange* ex);
+/* local_status: status of this rank's scoring call; a non-zero value is forwarded so that all ranks fail together
+ * instead of waiting for data that never comes.  stream: a cudaStream_t the wait is enqueued on (and synchronised). */
+int q3dr_exchange_end_step(q3dr_exchange* ex, int local_status, void* stream);
+/* Result of source rank `src` in this rank's receive buffer (DEVICE pointers; first_pixel, dist_sq, hit_count NULL). */
+int q3dr_exchange_view(const q3dr_exchange* ex, uint32_t src, q3dr_result* out);
+
+/* q3dr_multi with the exchange switched on: after q3dr_multi_score_viewpoints every GPU of `multi` holds the results
+ * of all GPUs; q3dr_multi_gathered returns the part scored by GPU `src` as GPU `on` holds it (device pointers). */
+int q3dr_multi_enable_gather(q3dr_multi* multi, uint64_t max_viewpoints_per_gpu, uint64_t max_entries_per_gpu);
+int q3dr_multi_gathered(q3dr_multi* multi, uint32_t on, uint32_t src, q3dr_result* out);
 
 #ifdef __cplusplus
 }

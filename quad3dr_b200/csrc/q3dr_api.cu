@@ -62,6 +62,10 @@ void release_device(q3dr_map* m) {
   m->d_ray_d.release();
   m->d_pixels.release();
   m->last_n_vp = m->last_n_entries = 0;
+  m->free_retired();
+  m->fp_epoch = 0;
+  m->fp_tagged_garbage = false;
+  m->scratch_dirty = false;
 }
 
 int configure_rays_kernel(q3dr_map* m) {
@@ -132,23 +136,28 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
     Q3DR_TRY(m->d_bitmap.ensure(slots * word_stride));
     Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), m->stream));
     Q3DR_CUDA(cudaMemsetAsync(m->d_bitmap.p, 0, m->d_bitmap.bytes(), m->stream));
+    m->fp_epoch = 0;
+    m->fp_tagged_garbage = false;
     Q3DR_TRY(m->d_kept.ensure(slots));
     m->slots = slots;
     m->leaf_stride = leaf_stride;
     m->word_stride = word_stride;
+    m->max_blocks = 0;  // the block tables below are laid out with m->slots: lay them out again
   }
   {
-    const size_t sl = std::max<size_t>(slots, m->slots);
-    const size_t max_blocks = sl * ((cap + q3dr::kSegThreads - 1) / q3dr::kSegThreads + 1);
-    if (max_blocks > m->max_blocks || m->d_blk_u32.cap < sl + 1 + 2 * max_blocks) {
+    // block tables: [m->slots + 1] blk_off | [m->max_blocks] blk_kept | [m->max_blocks] blk_koff.  Allocation and
+    // layout both derive from the stored pair (m->slots, m->max_blocks), which only ever grows together with the buffer.
+    const size_t want_blocks = m->slots * ((cap + q3dr::kSegThreads - 1) / q3dr::kSegThreads + 1);
+    if (want_blocks > m->max_blocks) {
       m->d_blk_u32.release();
       m->d_seg_f64.release();
-      Q3DR_TRY(m->d_blk_u32.ensure(sl + 1 + 2 * max_blocks));
-      Q3DR_TRY(m->d_seg_f64.ensure(max_blocks));
-      m->max_blocks = max_blocks;
+      Q3DR_TRY(m->d_blk_u32.ensure(m->slots + 1 + 2 * want_blocks));
+      Q3DR_TRY(m->d_seg_f64.ensure(want_blocks));
+      m->max_blocks = want_blocks;
     }
+    if (m->slots + 1 + 2 * m->max_blocks > m->d_blk_u32.cap) return fail(Q3DR_ERR_INTERNAL, "block table layout exceeds its buffer");
   }
-  const size_t need = std::max<size_t>(slots, m->slots) * cap;
+  const size_t need = m->slots * cap;
   if (need > m->t_leaf.cap || cap != m->tmp_cap) {
     Q3DR_TRY(m->t_leaf.ensure(need));
     Q3DR_TRY(m->t_info.ensure(need));
@@ -167,7 +176,9 @@ size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint6
   // that the D2H copy of a finished chunk overlaps the next one (measured on C2: 150 / 296 / 500 / 1000 viewpoints per
   // chunk -> 26.6 / 26.0 / 28.2 / 29.5 ms end to end)
   want = std::max<size_t>(want, 2 * (size_t)m->sm_count);
-  if (const char* e = std::getenv("Q3DR_CHUNK")) want = (size_t)std::max(1, atoi(e));
+  if (const char* e = std::getenv("Q3DR_CHUNK")) {
+    want = (size_t)std::min<long>(std::max<long>(1, std::strtol(e, nullptr, 10)), (long)q3dr::kMaxChunkViewpoints);
+  }
   // ... bounded by scratch memory (first-pixel tables + temporary lists)
   const uint64_t per_slot = ((m->n + q3dr::kSegLeaves - 1) / q3dr::kSegLeaves * q3dr::kSegLeaves) * 4 + cap * 16;
   const uint64_t budget = 8ull << 30;
@@ -221,6 +232,16 @@ int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
   return Q3DR_OK;
 }
 
+// One scoring call.  The chunks of a call are software-pipelined on ONE stream so that the SMs never wait for the host:
+//
+//   stream:  R(0) S(0) c(0) R(1) | P(0) S(1) c(1) R(2) | P(1) S(2) c(2) ...        R = raycast, S = score, P = pack
+//   host  :  ........ issue R(1), then wait for c(0) (the chunk's entry count), size the pools, issue P(0), S(1) ...
+//
+// The host needs the entry count of chunk k only to make sure the CSR pools are large enough before P(k) is issued; by
+// then R(k+1) is already queued, so the wait costs nothing on the device.  R(k+1) touches the dedup tables only (left
+// clean by S(k)), P(k) the temporary lists of chunk k (rewritten by S(k+1), which is issued after P(k)).  Pools that
+// have to grow are replaced, never freed inside the call (q3dr_map::retired): pointers handed to a chunk consumer and
+// D2H copies in flight stay valid.  Timing events are read once, after the final synchronisation.
 int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
                       uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
                       q3dr_result* result, bool stream_to_host, const NormalSource* ns = nullptr) {
@@ -237,6 +258,9 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   }
   m->stream = stream;
   m->host_result_valid = false;
+  m->free_retired();  // the previous call is complete and its consumers have been told so (see q3dr_raycast.h)
+  const bool want_pix = (m->result_fields & Q3DR_RESULT_FIRST_PIXEL) != 0;
+  const bool want_dsq = (m->result_fields & Q3DR_RESULT_DIST_SQ) != 0;
   uint64_t copied_entries = 0;
   q3dr::RaycastParams rp;
   fill_raycast_params(m, K, x0, x1, y0, y1, opts->raycast_max_range, &rp);
@@ -244,21 +268,31 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   const size_t B = choose_chunk(m, rp.tiles_per_vp, n_vp, cap);
   if ((uint64_t)B * rp.tiles_per_vp >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "chunk too large");
   Q3DR_TRY(ensure_scratch(m, B, cap));
-  if (nmode == q3dr::kNormalCode) Q3DR_TRY(m->t_code.ensure(std::max<size_t>(B, m->slots) * cap));
+  if (nmode == q3dr::kNormalCode) Q3DR_TRY(m->t_code.ensure(m->slots * cap));
   if (nmode == q3dr::kNormalImage && !ns->images_on_device) {
     Q3DR_TRY(m->d_nimg.ensure(B * (size_t)image_width * ns->img_h));
   }
-  if (m->scratch_dirty) {
-    // the kernels leave the dedup tables clean themselves; after a failed call they may not have
+  const bool tagged = (uint64_t)rp.w * rp.h <= (uint64_t)q3dr::kPixIndexMask + 1u;
+  if (m->scratch_dirty || (!tagged && m->fp_tagged_garbage)) {
+    // the kernels leave the dedup tables clean themselves; after a failed call they may not have, and an untagged call
+    // cannot read past the tagged entries earlier calls left behind
     Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), stream));
     Q3DR_CUDA(cudaMemsetAsync(m->d_bitmap.p, 0, m->d_bitmap.bytes(), stream));
     Q3DR_CUDA(cudaMemsetAsync(m->d_seg_u32.p, 0, m->d_seg_u32.bytes(), stream));
     m->scratch_dirty = false;
+    m->fp_epoch = 0;
+    m->fp_tagged_garbage = false;
   }
   Q3DR_TRY(m->d_offsets.ensure(n_vp + 1));
   Q3DR_TRY(m->d_total.ensure(std::max<size_t>(n_vp, 1)));
   Q3DR_TRY(m->d_hit_count.ensure(std::max<size_t>(n_vp, 1)));
   Q3DR_CUDA(cudaMemsetAsync(m->d_offsets.p, 0, sizeof(uint64_t), stream));
+  const size_t n_chunks = (n_vp + B - 1) / B;
+  while (m->ev_chunk.size() < 5 * n_chunks) {
+    cudaEvent_t e = nullptr;
+    Q3DR_CUDA(cudaEventCreate(&e));
+    m->ev_chunk.push_back(e);
+  }
 
   const Derived dv = derive(*opts);
   const uint32_t S = m->n_segs;
@@ -306,6 +340,9 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   sp.tmp_code = m->t_code.p;
   sp.img_w = image_width;
   sp.img_h = ns ? ns->img_h : 0;
+  sp.pix_mask = tagged ? q3dr::kPixIndexMask : 0xFFFFFFFFu;
+  sp.reset_fp = tagged ? 0 : 1;
+  sp.want_dsq = want_dsq ? 1 : 0;
   q3dr::MeshDev mesh_dev{};
   q3dr::RenderOptsDev ropts_dev{};
   if (nmode == q3dr::kNormalCode) {
@@ -330,19 +367,38 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   q3dr_stats st{};
   st.viewpoints_per_chunk = (uint32_t)B;
   Q3DR_CUDA(cudaEventRecord(m->ev[3], stream));
-  uint64_t total_entries = 0;
-  for (size_t v0 = 0; v0 < n_vp; v0 += B) {
-    const size_t nb = std::min(B, n_vp - v0);
+
+  auto issue_raycast = [&](size_t c) -> int {
+    const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
+    if (tagged) {
+      if (m->fp_epoch >= q3dr::kPixEpochs - 1u) {  // tags used up (once per 1022 chunks): start over from a clean table
+        Q3DR_CUDA(cudaMemsetAsync(m->d_first_pix.p, 0xFF, m->d_first_pix.bytes(), stream));
+        m->fp_epoch = 0;
+      }
+      ++m->fp_epoch;
+      rp.pix_tag = (q3dr::kPixEpochs - m->fp_epoch) << q3dr::kPixTagShift;
+      rp.pix_limit = rp.pix_tag | q3dr::kPixIndexMask;
+      m->fp_tagged_garbage = true;
+    } else {
+      rp.pix_tag = 0u;
+      rp.pix_limit = 0xFFFFFFFEu;
+    }
     rp.rt = d_Rt + 12 * v0;
     rp.total_tiles = (uint32_t)(nb * rp.tiles_per_vp);
     Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), stream));
-    Q3DR_CUDA(cudaEventRecord(m->ev[0], stream));
+    Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 0], stream));
     m->scratch_dirty = true;  // cleared when this chunk's scoring kernels have been issued
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore],
                                             ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
     q3dr::raycast2_kernel<q3dr::kModeScore><<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
     Q3DR_CUDA(cudaGetLastError());
-    Q3DR_CUDA(cudaEventRecord(m->ev[1], stream));
+    Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
+    st.kernel_launches += 1;
+    return Q3DR_OK;
+  };
+
+  auto issue_score = [&](size_t c) -> int {
+    const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
     sp.rt = d_Rt + 12 * v0;
     sp.hit_count = m->d_hit_count.p + v0;
     sp.total = m->d_total.p + v0;
@@ -373,23 +429,39 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     q3dr::finalize_viewpoints_kernel<<<(unsigned)nb, q3dr::kSegThreads, 0, stream>>>(sp);
     Q3DR_CUDA(cudaGetLastError());
-    m->scratch_dirty = false;  // emit_list cleared the bitmap and the segment counters, score_blocks reset first_pix
+    m->scratch_dirty = false;  // emit_list cleared the bitmap and the segment counters; first_pix is tagged or was reset
     q3dr::csr_offsets_kernel<<<1, q3dr::kSegThreads, 0, stream>>>(m->d_kept.p, (uint32_t)nb, m->d_offsets.p + v0);
     Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 2], stream));
     Q3DR_CUDA(cudaMemcpyAsync(m->h_scalar.p, m->d_offsets.p + v0 + nb, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-    Q3DR_CUDA(cudaStreamSynchronize(stream));
+    Q3DR_CUDA(cudaEventRecord(m->ev_count, stream));
+    st.kernel_launches += 6;
+    return Q3DR_OK;
+  };
+
+  uint64_t total_entries = 0;
+  if (n_chunks > 0) Q3DR_TRY(issue_raycast(0));
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
+    Q3DR_TRY(issue_score(c));
+    if (c + 1 < n_chunks) Q3DR_TRY(issue_raycast(c + 1));  // keeps the SMs busy while the host waits below
+    Q3DR_CUDA(cudaEventSynchronize(m->ev_count));
     const uint64_t chunk_first_entry = total_entries;
     total_entries = m->h_scalar.p[0];
-    const size_t want = std::max<uint64_t>(total_entries, 1);
-    Q3DR_TRY(m->r_leaf.ensure(want, true, stream));
-    Q3DR_TRY(m->r_info.ensure(want, true, stream));
-    Q3DR_TRY(m->r_pix.ensure(want, true, stream));
-    Q3DR_TRY(m->r_dsq.ensure(want, true, stream));
+    if (total_entries > m->r_leaf.cap) {
+      // project the call's total from what the viewpoints so far produced, so that a call grows its pools about once
+      const double per_vp = (double)total_entries / (double)(v0 + nb);
+      const size_t want = (size_t)std::max<double>((double)total_entries, per_vp * (double)n_vp * 1.15 + 4096.0);
+      Q3DR_TRY(m->r_leaf.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+      Q3DR_TRY(m->r_info.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+    }
+    if (want_pix) Q3DR_TRY(m->r_pix.grow_deferred(m->r_leaf.cap, chunk_first_entry, stream, &m->retired));
+    if (want_dsq) Q3DR_TRY(m->r_dsq.grow_deferred(m->r_leaf.cap, chunk_first_entry, stream, &m->retired));
     q3dr::PackParams2 pp;
     pp.offsets = m->d_offsets.p + v0;
     pp.blk_off = blk_off;
     pp.blk_koff = blk_koff;
-    pp.hit_count = sp.hit_count;
+    pp.hit_count = m->d_hit_count.p + v0;
     pp.n_vp = (uint32_t)nb;
     pp.ignore_zero = sp.ignore_zero;
     pp.cap = cap;
@@ -399,10 +471,16 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     pp.tmp_dsq = m->t_dsq.p;
     pp.out_leaf = m->r_leaf.p;
     pp.out_info = m->r_info.p;
-    pp.out_pix = m->r_pix.p;
-    pp.out_dsq = m->r_dsq.p;
+    pp.out_pix = want_pix ? m->r_pix.p : nullptr;
+    pp.out_dsq = want_dsq ? m->r_dsq.p : nullptr;
+    Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 3], stream));
     q3dr::pack_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(pp);
     Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 4], stream));
+    st.kernel_launches += 1;
+    st.chunks += 1;
+    const bool consumers = m->chunk_cb != nullptr || m->exchange != nullptr || (stream_to_host && total_entries > copied_entries);
+    if (consumers) Q3DR_CUDA(cudaEventRecord(m->ev_packed, stream));
     if (m->chunk_cb) {
       q3dr_result part;
       part.n_viewpoints = v0 + nb;
@@ -410,55 +488,68 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
       part.offsets = m->d_offsets.p;
       part.leaf = m->r_leaf.p;
       part.information = m->r_info.p;
-      part.first_pixel = m->r_pix.p;
-      part.dist_sq = m->r_dsq.p;
+      part.first_pixel = want_pix ? m->r_pix.p : nullptr;
+      part.dist_sq = want_dsq ? m->r_dsq.p : nullptr;
       part.total = m->d_total.p;
       part.hit_count = m->d_hit_count.p;
       m->chunk_cb(m->chunk_cb_user, v0, nb, chunk_first_entry, total_entries - chunk_first_entry, &part);
+    }
+    if (m->exchange) {
+      Q3DR_TRY(q3dr_detail::exchange_push_chunk(m->exchange, m->ev_packed, m->r_leaf.p, m->r_info.p, chunk_first_entry,
+                                                total_entries - chunk_first_entry));
     }
     if (stream_to_host && total_entries > copied_entries) {
       // this chunk's slice of the CSR pool is final: ship it while the next chunk is being cast
       if (total_entries > m->h_leaf.cap) {
         Q3DR_CUDA(cudaStreamSynchronize(m->copy_stream));
-        Q3DR_TRY(m->h_leaf.grow_keep(total_entries, copied_entries));
-        Q3DR_TRY(m->h_info.grow_keep(total_entries, copied_entries));
-        Q3DR_TRY(m->h_pix.grow_keep(total_entries, copied_entries));
-        Q3DR_TRY(m->h_dsq.grow_keep(total_entries, copied_entries));
+        const double per_vp = (double)total_entries / (double)(v0 + nb);
+        const size_t want = (size_t)std::max<double>((double)total_entries, per_vp * (double)n_vp * 1.15 + 4096.0);
+        Q3DR_TRY(m->h_leaf.grow_keep(want, copied_entries));
+        Q3DR_TRY(m->h_info.grow_keep(want, copied_entries));
       }
+      if (want_pix) Q3DR_TRY(m->h_pix.grow_keep(m->h_leaf.cap, copied_entries));
+      if (want_dsq) Q3DR_TRY(m->h_dsq.grow_keep(m->h_leaf.cap, copied_entries));
       const size_t c0 = copied_entries, cn = total_entries - copied_entries;
-      Q3DR_CUDA(cudaEventRecord(m->ev_packed, stream));
       Q3DR_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_packed, 0));
       Q3DR_CUDA(cudaMemcpyAsync(m->h_leaf.p + c0, m->r_leaf.p + c0, cn * sizeof(int32_t), cudaMemcpyDeviceToHost, m->copy_stream));
       Q3DR_CUDA(cudaMemcpyAsync(m->h_info.p + c0, m->r_info.p + c0, cn * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
-      Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p + c0, m->r_pix.p + c0, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->copy_stream));
-      Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p + c0, m->r_dsq.p + c0, cn * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+      if (want_pix) {
+        Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p + c0, m->r_pix.p + c0, cn * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->copy_stream));
+      }
+      if (want_dsq) {
+        Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p + c0, m->r_dsq.p + c0, cn * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+      }
       copied_entries = total_entries;
     }
-    Q3DR_CUDA(cudaEventRecord(m->ev[2], stream));
-    Q3DR_CUDA(cudaEventSynchronize(m->ev[2]));
-    st.raycast_ms += elapsed_ms(m->ev[0], m->ev[1]);
-    st.score_ms += elapsed_ms(m->ev[1], m->ev[2]);
-    st.kernel_launches += 8;
-    st.chunks += 1;
   }
+  Q3DR_CUDA(cudaEventRecord(m->ev[2], stream));
   Q3DR_CUDA(cudaStreamSynchronize(stream));
   if (stream_to_host) {
     Q3DR_CUDA(cudaStreamSynchronize(m->copy_stream));
     m->host_result_valid = true;
   }
+  for (size_t c = 0; c < n_chunks; ++c) {
+    st.raycast_ms += elapsed_ms(m->ev_chunk[5 * c + 0], m->ev_chunk[5 * c + 1]);
+    st.score_ms += elapsed_ms(m->ev_chunk[5 * c + 1], m->ev_chunk[5 * c + 2]);
+    st.score_ms += elapsed_ms(m->ev_chunk[5 * c + 3], m->ev_chunk[5 * c + 4]);
+  }
+  // S(c) is bracketed by the end of R(c) and its own end event; R(c+1) is issued after that event, so the brackets
+  // do not overlap
   if (n_vp > 0) st.total_ms = elapsed_ms(m->ev[3], m->ev[2]);
   st.rays = (uint64_t)n_vp * rp.w * rp.h;
   m->stats = st;
   m->last_n_vp = n_vp;
   m->last_n_entries = total_entries;
+  m->stream = nullptr;  // everything is complete: follow-up calls (q3dr_result_to_host, set consumers, overlap queries)
+                        // run on the default stream and never touch the caller's stream handle again
   if (result) {
     result->n_viewpoints = n_vp;
     result->n_entries = total_entries;
     result->offsets = m->d_offsets.p;
     result->leaf = m->r_leaf.p;
     result->information = m->r_info.p;
-    result->first_pixel = m->r_pix.p;
-    result->dist_sq = m->r_dsq.p;
+    result->first_pixel = want_pix ? m->r_pix.p : nullptr;
+    result->dist_sq = want_dsq ? m->r_dsq.p : nullptr;
     result->total = m->d_total.p;
     result->hit_count = m->d_hit_count.p;
   }
@@ -703,7 +794,9 @@ int map_create_impl(const float* boxes, const float* weights, const float* norma
     cudaError_t e = cudaSetDevice(device);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_packed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_count, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) st = fail(Q3DR_ERR_CUDA, std::string("event setup: ") + cudaGetErrorString(e));
   }
   if (st == Q3DR_OK) st = upload_map(m);
@@ -789,7 +882,11 @@ int q3dr_map_destroy(q3dr_map* m) {
     if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   }
   if (m->ev_packed) cudaEventDestroy(m->ev_packed);
+  if (m->ev_count) cudaEventDestroy(m->ev_count);
+  for (cudaEvent_t e : m->ev_chunk) cudaEventDestroy(e);
+  m->free_retired();
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
   cudaGetLastError();
   delete m;
   return Q3DR_OK;
@@ -894,15 +991,17 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
   Q3DR_TRY(check_map(m));
   if (!result) return fail(Q3DR_ERR_INVALID_ARG, "result is NULL");
   Q3DR_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = m->stream;
+  cudaStream_t s = m->own_stream;  // the scoring call returned synchronised; nothing of the caller's stream is touched
   const size_t nv = m->last_n_vp, ne = m->last_n_entries;
+  const bool want_pix = (m->result_fields & Q3DR_RESULT_FIRST_PIXEL) != 0 && (m->r_pix.p != nullptr || ne == 0);
+  const bool want_dsq = (m->result_fields & Q3DR_RESULT_DIST_SQ) != 0 && (m->r_dsq.p != nullptr || ne == 0);
   Q3DR_TRY(m->h_offsets.ensure(nv + 1));
   Q3DR_TRY(m->h_total.ensure(std::max<size_t>(nv, 1)));
   Q3DR_TRY(m->h_hit_count.ensure(std::max<size_t>(nv, 1)));
   Q3DR_TRY(m->h_leaf.ensure(std::max<size_t>(ne, 1)));
   Q3DR_TRY(m->h_info.ensure(std::max<size_t>(ne, 1)));
-  Q3DR_TRY(m->h_pix.ensure(std::max<size_t>(ne, 1)));
-  Q3DR_TRY(m->h_dsq.ensure(std::max<size_t>(ne, 1)));
+  if (want_pix) Q3DR_TRY(m->h_pix.ensure(std::max<size_t>(ne, 1)));
+  if (want_dsq) Q3DR_TRY(m->h_dsq.ensure(std::max<size_t>(ne, 1)));
   Q3DR_CUDA(cudaMemcpyAsync(m->h_offsets.p, m->d_offsets.p, (nv + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
   if (nv) {
     Q3DR_CUDA(cudaMemcpyAsync(m->h_total.p, m->d_total.p, nv * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -911,8 +1010,8 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
   if (ne && !m->host_result_valid) {
     Q3DR_CUDA(cudaMemcpyAsync(m->h_leaf.p, m->r_leaf.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     Q3DR_CUDA(cudaMemcpyAsync(m->h_info.p, m->r_info.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
-    Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p, m->r_pix.p, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p, m->r_dsq.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (want_pix) Q3DR_CUDA(cudaMemcpyAsync(m->h_pix.p, m->r_pix.p, ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (want_dsq) Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p, m->r_dsq.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   Q3DR_CUDA(cudaStreamSynchronize(s));
   result->n_viewpoints = nv;
@@ -920,10 +1019,17 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
   result->offsets = m->h_offsets.p;
   result->leaf = m->h_leaf.p;
   result->information = m->h_info.p;
-  result->first_pixel = m->h_pix.p;
-  result->dist_sq = m->h_dsq.p;
+  result->first_pixel = want_pix ? m->h_pix.p : nullptr;
+  result->dist_sq = want_dsq ? m->h_dsq.p : nullptr;
   result->total = m->h_total.p;
   result->hit_count = m->h_hit_count.p;
+  return Q3DR_OK;
+}
+
+int q3dr_map_set_result_fields(q3dr_map* m, uint32_t fields) {
+  if (!m) return fail(Q3DR_ERR_INVALID_ARG, "map is NULL");
+  if (fields & ~(uint32_t)(Q3DR_RESULT_FIRST_PIXEL | Q3DR_RESULT_DIST_SQ)) return fail(Q3DR_ERR_INVALID_ARG, "unknown result field");
+  m->result_fields = fields;
   return Q3DR_OK;
 }
 
@@ -934,7 +1040,7 @@ int q3dr_score_viewpoints(q3dr_map* m, const float K[4], uint32_t image_width, u
   Q3DR_TRY(check_window(x0, x1, y0, y1));
   if (image_width == 0) return fail(Q3DR_ERR_INVALID_ARG, "image_width is 0");
   Q3DR_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = nullptr;
+  cudaStream_t s = m->own_stream;
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
   Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true));
@@ -975,7 +1081,7 @@ int q3dr_score_viewpoints_mesh_normals(q3dr_map* m, const q3dr_mesh* mesh, const
   Q3DR_TRY(check_window(x0, x1, y0, y1));
   if (image_width == 0 || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "empty image");
   Q3DR_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = nullptr;
+  cudaStream_t s = m->own_stream;
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
   NormalSource ns;
@@ -996,7 +1102,7 @@ int q3dr_score_viewpoints_normal_images(q3dr_map* m, const uint32_t* normal_imag
   Q3DR_TRY(check_window(x0, x1, y0, y1));
   if (image_width == 0 || image_height == 0) return fail(Q3DR_ERR_INVALID_ARG, "empty image");
   Q3DR_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = nullptr;
+  cudaStream_t s = m->own_stream;
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
   NormalSource ns;
@@ -1020,7 +1126,11 @@ int q3dr_raycast_unique(q3dr_map* m, const float K[4], const float Rt[12], uint3
   o.raycast_min_range = min_range;
   o.raycast_max_range = max_range;
   q3dr_result r;
-  Q3DR_TRY(q3dr_score_viewpoints(m, K, x1 > x0 ? x1 - x0 : 1, x0, x1, y0, y1, Rt, 1, &o, &r));
+  const uint32_t saved_fields = m->result_fields;
+  m->result_fields = Q3DR_RESULT_FIRST_PIXEL;  // the second pass below re-casts exactly the kept pixels
+  const int st_score = q3dr_score_viewpoints(m, K, x1 > x0 ? x1 - x0 : 1, x0, x1, y0, y1, Rt, 1, &o, &r);
+  m->result_fields = saved_fields;
+  Q3DR_TRY(st_score);
   *count = (size_t)r.n_entries;
   if (r.n_entries > cap) return fail(Q3DR_ERR_INVALID_ARG, "output capacity too small");
   if (r.n_entries == 0) return Q3DR_OK;

@@ -71,6 +71,25 @@ struct DevBuf {
     cap = want;
     return Q3DR_OK;
   }
+  // Grows WITHOUT freeing the old block: the first `used` elements are copied on `s` (stream ordered, no host sync) and
+  // the old block is handed to `retired`, to be freed when nothing can refer to it any more (q3dr_map::free_retired).
+  // Pointers given out earlier -- chunk callbacks, D2H copies in flight on another stream -- stay valid meanwhile.
+  int grow_deferred(size_t n, size_t used, cudaStream_t s, std::vector<void*>* retired) {
+    if (n <= cap) return Q3DR_OK;
+    T* q = nullptr;
+    Q3DR_CUDA(cudaMalloc(&q, n * sizeof(T)));
+    if (p && used) {
+      cudaError_t e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) {
+        cudaFree(q);
+        return fail(Q3DR_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(e));
+      }
+    }
+    if (p) retired->push_back(p);
+    p = q;
+    cap = n;
+    return Q3DR_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -126,6 +145,8 @@ inline Derived derive(const q3dr_score_opts& o) {
   return d;
 }
 
+
+struct q3dr_exchange;
 
 struct q3dr_map {
   int device = 0;
@@ -192,15 +213,34 @@ struct q3dr_map {
   std::vector<int32_t> h_q_leaf;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
+  cudaStream_t own_stream = nullptr;   // non-blocking; the host-buffer entry points work on it (they return synchronised),
+                                       // so two maps driven by two host threads never serialise on the legacy stream
   cudaEvent_t ev_packed = nullptr;
   bool host_result_valid = false;      // the host pools already hold the entries of the last call
   q3dr_chunk_callback chunk_cb = nullptr;
   void* chunk_cb_user = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // per-chunk timing events of a scoring call (5 per chunk: raycast begin / end, scoring end, pack begin / end); read
+  // once after the call's final synchronisation, never waited on inside the chunk loop
+  std::vector<cudaEvent_t> ev_chunk;
+  cudaEvent_t ev_count = nullptr;      // "the entry count of the chunk is in h_scalar"
+  std::vector<void*> retired;          // result pools replaced while growing; freed at the start of the next call
+  uint32_t result_fields = 3u;         // Q3DR_RESULT_* the scoring calls deliver besides (leaf, information)
+  // first-pixel table: values are (tag << 22 | pixel) with a tag that DEcreases from chunk to chunk, so entries of earlier
+  // chunks read as "not hit" and the table never needs a reset pass (windows of up to 2^22 pixels; larger ones run
+  // untagged and the scoring kernel resets what it read)
+  uint32_t fp_epoch = 0;
+  bool fp_tagged_garbage = false;      // the table holds tagged entries of earlier chunks
+  q3dr_exchange* exchange = nullptr;   // pushes every finished chunk to the peers (q3dr_exchange_begin_step)
   int grid_rays_ctas = 0;
   int grid2_ctas[2] = {0, 0};
   size_t smem_bytes = 0;
   q3dr_stats stats{};
+
+  void free_retired() {
+    for (void* q : retired) cudaFree(q);
+    retired.clear();
+  }
 
   uint64_t device_bytes() const {
     return d_nodes.bytes() + d_leaf_rec.bytes() + d_depth.bytes() + d_seg_u32.bytes() + d_blk_u32.bytes() + d_seg_f64.bytes() +
@@ -241,6 +281,10 @@ struct NormalSource {
 
 namespace q3dr_detail {
 int check_map(const q3dr_map* m);
+// q3dr_exchange.cu: pushes entries [first_entry, first_entry + n_entries) of the chunk just packed (ready when `ready`
+// has fired) into this rank's slot on every peer; called by the scoring call for each finished chunk
+int exchange_push_chunk(q3dr_exchange* ex, cudaEvent_t ready, const int32_t* d_leaf, const float* d_info,
+                        uint64_t first_entry, uint64_t n_entries);
 int map_create_impl(const float* boxes, const float* weights, const float* normals, const uint32_t* depth, size_t n,
                     int device, std::shared_ptr<const q3dr::FlatTree> shared_tree, q3dr_map** out);
 }  // namespace q3dr_detail

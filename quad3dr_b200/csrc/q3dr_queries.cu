@@ -422,6 +422,7 @@ struct q3dr_multi {
   std::vector<int> devices;
   std::vector<q3dr_result> parts;
   std::vector<uint64_t> first;
+  std::vector<q3dr_exchange*> exchanges;  // one per device once q3dr_multi_enable_gather was called
   std::vector<q3dr_mesh*> meshes;  // one per device when image-space normals are on (row N2)
   uint32_t mesh_image_height = 0;
   q3dr_render_opts mesh_ropts{};
@@ -490,8 +491,39 @@ int q3dr_multi_set_normal_mesh(q3dr_multi* mm, const float* tri_vertices, const 
   return Q3DR_OK;
 }
 
+int q3dr_multi_enable_gather(q3dr_multi* mm, uint64_t max_viewpoints_per_gpu, uint64_t max_entries_per_gpu) {
+  if (!mm) return fail(Q3DR_ERR_INVALID_ARG, "multi is NULL");
+  for (q3dr_exchange* ex : mm->exchanges) q3dr_exchange_destroy(ex);
+  mm->exchanges.clear();
+  if (max_viewpoints_per_gpu == 0) return Q3DR_OK;  // switched off
+  const uint32_t G = (uint32_t)mm->maps.size();
+  int st = Q3DR_OK;
+  for (uint32_t g = 0; g < G && st == Q3DR_OK; ++g) {
+    q3dr_exchange* ex = nullptr;
+    st = q3dr_exchange_create(mm->maps[g], G, g, max_viewpoints_per_gpu, max_entries_per_gpu, &ex);
+    if (st == Q3DR_OK) mm->exchanges.push_back(ex);
+  }
+  if (st == Q3DR_OK) st = q3dr_exchange_connect(mm->exchanges.data(), G);
+  if (st != Q3DR_OK) {
+    const std::string msg = q3dr_detail::last_error();
+    for (q3dr_exchange* ex : mm->exchanges) q3dr_exchange_destroy(ex);
+    mm->exchanges.clear();
+    return fail(st, msg);
+  }
+  return Q3DR_OK;
+}
+
+int q3dr_multi_gathered(q3dr_multi* mm, uint32_t on, uint32_t src, q3dr_result* out) {
+  if (!mm || !out) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (mm->exchanges.empty()) return fail(Q3DR_ERR_INVALID_ARG, "q3dr_multi_enable_gather was not called");
+  if (on >= mm->exchanges.size()) return fail(Q3DR_ERR_INVALID_ARG, "device index out of range");
+  return q3dr_exchange_view(mm->exchanges[on], src, out);
+}
+
 int q3dr_multi_destroy(q3dr_multi* mm) {
   if (!mm) return Q3DR_OK;
+  for (q3dr_exchange* ex : mm->exchanges) q3dr_exchange_destroy(ex);
+  mm->exchanges.clear();
   multi_drop_meshes(mm);
   for (q3dr_map* m : mm->maps) q3dr_map_destroy(m);
   delete mm;
@@ -524,6 +556,8 @@ int q3dr_multi_score_viewpoints(q3dr_multi* mm, const float K[4], uint32_t image
   for (size_t g = 0; g < G; ++g) {
     workers.emplace_back([&, g]() {
       const size_t lo = (size_t)mm->first[g], hi = (size_t)mm->first[g + 1];
+      q3dr_exchange* ex = mm->exchanges.empty() ? nullptr : mm->exchanges[g];
+      if (ex && q3dr_exchange_begin_step(ex) != Q3DR_OK) ex = nullptr;  // (cannot fail once connected)
       if (!mm->meshes.empty()) {
         status[g] = q3dr_score_viewpoints_mesh_normals(mm->maps[g], mm->meshes[g], &mm->mesh_ropts, K, image_width,
                                                        mm->mesh_image_height, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts,
@@ -532,6 +566,14 @@ int q3dr_multi_score_viewpoints(q3dr_multi* mm, const float K[4], uint32_t image
         status[g] = q3dr_score_viewpoints(mm->maps[g], K, image_width, x0, x1, y0, y1, Rt + 12 * lo, hi - lo, opts, &mm->parts[g]);
       }
       if (status[g] != Q3DR_OK) message[g] = q3dr_last_error();  // thread-local: carry it out of the worker
+      if (ex) {
+        // every worker takes part, failed or not, so that nobody waits for flags that never come
+        const int est = q3dr_exchange_end_step(ex, status[g], mm->maps[g]->own_stream);
+        if (status[g] == Q3DR_OK && est != Q3DR_OK) {
+          status[g] = est;
+          message[g] = q3dr_last_error();
+        }
+      }
     });
   }
   for (std::thread& t : workers) t.join();

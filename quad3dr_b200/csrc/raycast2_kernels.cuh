@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
         const uint32_t grp = __match_any_sync(Q3DR_FULL_MASK, leaf);
         const bool leader = (leaf >= 0) && ((__ffs(grp) - 1) == lane);
         if (leader) {
-          const uint32_t old = atomicMin(fpv + (uint32_t)leaf, pix);
-          if (old == kEmptyPixel) {
+          const uint32_t old = atomicMin(fpv + (uint32_t)leaf, p.pix_tag | pix);
+          if (old > p.pix_limit) {  // nothing of THIS chunk was there yet: first toucher
             atomicOr(bmv + ((uint32_t)leaf >> 5), 1u << (leaf & 31));
             atomicAdd(p.seg_hits + (size_t)vp * p.n_segs + ((uint32_t)leaf >> 15), 1u);
           }

@@ -23,6 +23,9 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kStackEntries = 64;
 constexpr uint32_t kEmptyPixel = 0xFFFFFFFFu;
+constexpr uint32_t kPixTagShift = 22;                       // tagged first-pixel entries: windows of up to 2^22 pixels
+constexpr uint32_t kPixIndexMask = (1u << kPixTagShift) - 1u;
+constexpr uint32_t kPixEpochs = (1u << (32 - kPixTagShift)) - 1u;  // tags 1022 .. 0 are usable, 1023 = never written
 constexpr int kScoreThreads = 512;
 #ifndef Q3DR_SMEM_TOP
 #define Q3DR_SMEM_TOP 1
@@ -50,6 +53,11 @@ struct RaycastParams {
   uint64_t word_stride;
   uint32_t* seg_hits;   // [slot][n_segs]: set bits per 32768-leaf segment of the bitmap (score_kernels.cuh)
   uint32_t n_segs;
+  // first_pix entries are (pix_tag | pixel); the tag decreases from chunk to chunk, so whatever an earlier chunk left
+  // behind compares greater than pix_limit = pix_tag | (largest pixel index) and reads as "not hit yet".  Untagged mode
+  // (huge windows): pix_tag = 0, pix_limit = 0xFFFFFFFE and the table is kept at 0xFFFFFFFF between chunks.
+  uint32_t pix_tag;
+  uint32_t pix_limit;
   // kModePixels / raycast_rays_kernel
   q3dr_pixel_hit* pixels;
   const uint8_t* __restrict__ leaf_depth;

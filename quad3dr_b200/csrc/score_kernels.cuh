@@ -70,6 +70,9 @@ struct ScoreParams2 {
   uint32_t* hit_count;   // [n_vp_total] (already offset to the chunk)
   float* total;          // [n_vp_total] (already offset to the chunk)
   // image-space normals (row N2)
+  uint32_t pix_mask;   // first_pix entry & pix_mask = pixel index (tagged entries, see RaycastParams::pix_tag)
+  int32_t reset_fp;    // untagged mode: write kEmptyPixel back after reading an entry
+  int32_t want_dsq;    // compute dist_sq of the kept pixel (Q3DR_RESULT_DIST_SQ)
   const uint32_t* normal_images;  // kNormalImage: [B][img_h][img_w] ARGB32 of the chunk's viewpoints
   uint32_t* tmp_code;             // kNormalCode: [B][cap] next to tmp_leaf
   uint32_t img_w, img_h;
@@ -285,8 +288,8 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
       ra[u] = rb[u] = rc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid[u]) {
         uint32_t* fp = p.first_pix + (size_t)vp[u] * p.leaf_stride + (uint32_t)leaf[u];
-        pix[u] = *fp;
-        *fp = kEmptyPixel;
+        pix[u] = *fp & p.pix_mask;
+        if (p.reset_fp) *fp = kEmptyPixel;
         const float4* rec = p.leaf_rec + kLeafRecStride * (size_t)leaf[u];
         ra[u] = __ldg(rec);
         rb[u] = __ldg(rec + 1);
@@ -314,7 +317,7 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
                                      __ldg(rt + 11));
         keep = !p.ignore_zero || info > 0.0f;
         float dsq = 0.0f;
-        if (keep) {
+        if (keep && p.want_dsq) {
           // dist_sq of the kept pixel: the reference's own test of that pixel's ray against the voxel
           const uint32_t py = pix[u] / p.w, px = pix[u] - py * p.w;
           Ray ray;
@@ -365,7 +368,7 @@ static __global__ void __launch_bounds__(kSegThreads) mesh_kept_normals_kernel(c
     if (i >= p.hit_count[vp]) continue;
     const size_t at = (size_t)vp * p.cap + i;
     const int32_t leaf = p.tmp_leaf[at];
-    const uint32_t pix = p.first_pix[(size_t)vp * p.leaf_stride + (uint32_t)leaf];
+    const uint32_t pix = p.first_pix[(size_t)vp * p.leaf_stride + (uint32_t)leaf] & p.pix_mask;
     const uint32_t py = pix / p.w, px = pix - py * p.w;
     const float* rt = p.rt + 12 * (size_t)vp;
     float m[12];
@@ -418,7 +421,7 @@ struct PackParams2 {
   const float* __restrict__ tmp_dsq;
   int32_t* out_leaf;
   float* out_info;
-  uint32_t* out_pix;
+  uint32_t* out_pix;  // nullptr: field not requested (q3dr_map_set_result_fields)
   float* out_dsq;
 };
 
@@ -446,8 +449,8 @@ static __global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const P
       const uint64_t dst = p.offsets[vp] + p.blk_koff[blk] + rank;
       p.out_leaf[dst] = p.tmp_leaf[at];
       p.out_info[dst] = info;
-      p.out_pix[dst] = p.tmp_pix[at];
-      p.out_dsq[dst] = p.tmp_dsq[at];
+      if (p.out_pix != nullptr) p.out_pix[dst] = p.tmp_pix[at];
+      if (p.out_dsq != nullptr) p.out_dsq[dst] = p.tmp_dsq[at];
     }
     __syncthreads();
   }

@@ -38,6 +38,16 @@ def gather_results(offsets: torch.Tensor, total: torch.Tensor, leaf: torch.Tenso
     dev = offsets.device
     n_local = total.numel()
     e_local = int(leaf.numel())
+    # n_local_max must be the same on every rank and cover every rank's slice; checked collectively BEFORE the first
+    # sized collective, so that a bad argument raises on all ranks instead of hanging or corrupting some
+    chk = torch.tensor([n_local_max, -n_local_max, n_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=group)
+    if int(chk[0]) != -int(chk[1]):
+        raise ValueError("gather_results: n_local_max differs between ranks")
+    if int(chk[2]) > n_local_max:
+        raise ValueError(f"gather_results: a rank holds {int(chk[2])} viewpoints, more than n_local_max = {n_local_max}")
+    if offsets.numel() != n_local + 1 or info.numel() != e_local:
+        raise ValueError("gather_results: inconsistent CSR arrays")
     # header: [n_local, e_local, counts (n_local_max), totals bits (n_local_max)] as int64
     head = torch.zeros(2 + 2 * n_local_max, dtype=torch.int64, device=dev)
     head[0] = n_local
@@ -88,226 +98,95 @@ def device_result_tensors(res, device) -> Tuple[torch.Tensor, torch.Tensor, torc
     return offsets, total, leaf, info
 
 
-class CudaIpcTransport:
-    """What PeerGather needs from the machine: buffers other ranks can write into, asynchronous copies into them and
-    ordering.  This one is the product's: cudaMalloc + CUDA IPC handles, cudaMemcpyAsync on a side stream (copy engines
-    over NVLink / NVSwitch), CUDA events, one NCCL all_reduce as the barrier.  (tests/test_dist_cpu.py drives the same
-    PeerGather logic at world_size 2 on gloo with a shared-memory stand-in.)"""
-
-    def __init__(self, device: torch.device, group=None):
-        from cuda.bindings import runtime as rt
-
-        self.rt = rt
-        self.device = torch.device(device)
-        self.group = group
-        torch.cuda.set_device(self.device)
-        self.side = torch.cuda.Stream(device=self.device)
-        self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
-
-    def _ok(self, ret):
-        if int(ret[0]) != 0:
-            raise RuntimeError(f"CUDA runtime error {ret[0]} in PeerGather")
-        return ret[1] if len(ret) == 2 else ret[1:]
-
-    def alloc(self, nbytes: int) -> Tuple[int, bytes]:
-        ptr = self._ok(self.rt.cudaMalloc(nbytes))
-        try:
-            h = self._ok(self.rt.cudaIpcGetMemHandle(ptr))
-        except Exception:
-            self.rt.cudaFree(ptr)
-            raise
-        return int(ptr), bytes(h.reserved)
-
-    def open(self, handle: bytes) -> int:
-        h = self.rt.cudaIpcMemHandle_t()
-        h.reserved = handle
-        return int(self._ok(self.rt.cudaIpcOpenMemHandle(h, self.rt.cudaIpcMemLazyEnablePeerAccess)))
-
-    def close(self, ptr: int):
-        self.rt.cudaIpcCloseMemHandle(ptr)
-
-    def free(self, ptr: int):
-        self.rt.cudaFree(ptr)
-
-    def agree(self, ok: bool) -> bool:
-        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        return bool(int(t.item()))
-
-    def thread_init(self):
-        self.rt.cudaSetDevice(self.device.index)
-
-    def mark(self, stream):
-        """a point in `stream` (the scoring call's stream) that later copies can be ordered after"""
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        return ev
-
-    def after(self, mark):
-        self.side.wait_event(mark)
-
-    def copy(self, dst: int, src: int, nbytes: int):
-        (err,) = self.rt.cudaMemcpyAsync(dst, src, nbytes, self.rt.cudaMemcpyKind.cudaMemcpyDeviceToDevice,
-                                         self.side.cuda_stream)
-        if int(err) != 0:
-            raise RuntimeError(f"cudaMemcpyAsync: {err}")
-
-    def barrier(self, stream):
-        """every rank's copies issued so far have landed everywhere; `stream` continues after that"""
-        with torch.cuda.stream(self.side):
-            dist.all_reduce(self.token, group=self.group)
-        stream.wait_stream(self.side)
-
-    def view(self, ptr: int, n: int, typestr: str) -> torch.Tensor:
-        return torch.as_tensor(CudaArrayView(ptr, max(n, 1), typestr), device=self.device)[:n]
-
-    def sync(self):
-        torch.cuda.synchronize(self.device)
+def all_gather_bytes(blob: bytes, group=None) -> List[bytes]:
+    """Every rank's blob on every rank, in rank order (object collective: works on gloo and nccl groups alike)."""
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, bytes(blob), group=group)
+    return [bytes(b) for b in out]
 
 
-class PeerGather:
-    """The result exchange of SURVEY.md section 8e, overlapped with the compute.
+def agree(ok: bool, device=None, group=None) -> bool:
+    """True iff every rank passes True; all ranks get the same answer (no one-sided failure may desynchronise the
+    collectives that follow)."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()))
 
-    Instead of one all_gather after the last kernel, every finished chunk of a scoring call (q3dr_map_set_chunk_callback)
-    is PUSHED into all ranks' HBM by the copy engines -- cudaMemcpyAsync into CUDA-IPC-mapped peer buffers over
-    NVLink / NVSwitch, on a side stream, issued by a helper thread -- while the SMs cast the next chunk.  The pushes use
-    no SM, so they do not compete with the issue-bound raycast kernel; only the last chunk's push and one tiny NCCL
-    all_reduce (the barrier that tells every rank that all pushes into its memory have landed) stay exposed.
 
-    Every rank ends a step with the results of ALL ranks in its own receive buffer, one slot per source rank:
-        offsets int64 [n_max + 1] | total f32 [n_max] | leaf i32 [cap] | information f32 [cap]
-    Two receive buffers alternate between steps, so a fast rank's pushes of step s+1 never touch what a slow rank
-    still reads from step s.  Memory: 2 * world * (8 * cap + 12 * n_max) bytes per GPU, sized for the worst case.
-    """
+class PeerExchange:
+    """The result exchange of SURVEY.md section 8e for one process per GPU: torch.distributed plumbing around the C
+    ABI's q3dr_exchange (quad3dr_b200/csrc/q3dr_exchange.cu), which does the work.
 
-    def __init__(self, device, n_local_max: int, cap_entries: int, group=None, transport=None):
-        import queue
-        import threading
+    Instead of one all_gather after the last kernel, every finished chunk of a scoring call is pushed into all ranks'
+    HBM by the copy engines -- cudaMemcpyAsync into CUDA-IPC-mapped peer buffers over NVLink / NVSwitch, on a side
+    stream, issued by the scoring call itself -- while the SMs cast the next chunk; completion travels as flags behind
+    the data, and end_step waits for them on the device.  torch.distributed is used ONCE, to ship the IPC handles (and
+    for the agreement / teardown barriers); there is no collective in a step.
+
+    Every rank ends a step holding the results of ALL ranks: views() gives zero-copy tensors per source rank."""
+
+    def __init__(self, gmap, device, n_local_max: int, cap_entries: int, group=None):
+        from . import engine as E
 
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.n_max = int(n_local_max)
-        self.cap = int(cap_entries)
-        self.tr = transport if transport is not None else CudaIpcTransport(device, group)
-
-        def up(x, a=256):
-            return (x + a - 1) // a * a
-
-        self.tot_off = up(8 * (self.n_max + 1))
-        self.leaf_off = up(self.tot_off + 4 * self.n_max)
-        self.info_off = up(self.leaf_off + 4 * self.cap)
-        self.slot_bytes = up(self.info_off + 4 * self.cap)
-        self.base: List[int] = []
-        self.peer = [[0] * self.world for _ in range(2)]
-        handles = []
+        self.device = torch.device(device)
+        self.ex = None
         failure = None
+        handles = b""
         try:
-            for _ in range(2):
-                ptr, handle = self.tr.alloc(self.world * self.slot_bytes)
-                self.base.append(ptr)
-                handles.append(handle)
-        except Exception as e:
+            self.ex = E.Exchange(gmap, self.world, self.rank, int(n_local_max), int(cap_entries))
+            handles = self.ex.export_handles()
+        except Exception as e:  # e.g. CUDA IPC not permitted in this container
             failure = e
-            handles = [b"", b""]
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, handles, group=group)
-        if failure is None and all(len(g[0]) and len(g[1]) for g in gathered):
-            try:
-                for b in range(2):
-                    for p in range(self.world):
-                        self.peer[b][p] = self.base[b] if p == self.rank else self.tr.open(gathered[p][b])
-            except Exception as e:
-                failure = e
-        elif failure is None:
-            failure = RuntimeError("another rank could not export its receive buffer")
-        # all ranks agree on success before anybody relies on it (a one-sided failure must not desynchronise collectives)
-        if not self.tr.agree(failure is None):
-            for ptr in self.base:
-                self.tr.free(ptr)
-            self.base = []
-            raise RuntimeError(f"PeerGather unavailable: {failure or 'failed on another rank'}")
-        self.cur = 1
-        self.error = None
-        self._last = None
-        self._q: "queue.Queue" = queue.Queue()
-        self._worker = threading.Thread(target=self._run, daemon=True)
-        self._worker.start()
+        gathered = all_gather_bytes(handles, group)
+        if failure is None:
+            if all(len(h) == 2 * E.IPC_HANDLE_BYTES for h in gathered):
+                try:
+                    self.ex.import_handles(gathered)
+                except Exception as e:
+                    failure = e
+            else:
+                failure = RuntimeError("another rank could not export its receive buffer")
+        if not agree(failure is None, self.device, group):
+            if self.ex is not None:
+                self.ex.close()
+                self.ex = None
+            raise RuntimeError(f"PeerExchange unavailable: {failure or 'failed on another rank'}")
         dist.barrier(group=group)  # every rank has mapped every buffer before anybody pushes
 
-    def _push(self, dst_off: int, src_ptr: int, nbytes: int):
-        """the same bytes into this rank's slot on every rank"""
-        if nbytes <= 0:
-            return
-        for k in range(self.world):
-            p = (self.rank + k) % self.world  # start with different targets on different ranks
-            self.tr.copy(self.peer[self.cur][p] + self.rank * self.slot_bytes + dst_off, src_ptr, nbytes)
-
-    def _run(self):
-        self.tr.thread_init()
-        while True:
-            job = self._q.get()
-            try:
-                if job is None:
-                    return
-                mark, first_entry, n_entries, leaf_ptr, info_ptr = job
-                self.tr.after(mark)
-                self._push(self.leaf_off + 4 * first_entry, leaf_ptr + 4 * first_entry, 4 * n_entries)
-                self._push(self.info_off + 4 * first_entry, info_ptr + 4 * first_entry, 4 * n_entries)
-            except Exception as e:  # surfaced by end_step
-                self.error = e
-            finally:
-                self._q.task_done()
-
     def begin_step(self):
-        self.cur ^= 1
-        self._last = None
+        self.ex.begin_step()
 
-    def on_chunk(self, first_vp: int, n_vp: int, first_entry: int, n_entries: int, res, stream):
-        """chunk callback: order the push after the work issued so far, hand it to the helper thread, return at once
-        (the calling thread goes on to launch the next chunk's raycast)"""
-        if first_entry + n_entries > self.cap or first_vp + n_vp > self.n_max:
-            self.error = RuntimeError("PeerGather: result larger than the receive slot")
-            return
-        self._last = res
-        self._q.put((self.tr.mark(stream), first_entry, n_entries, int(res.leaf or 0), int(res.information or 0)))
+    def end_step(self, local_status: int = 0, stream: int = 0):
+        """raises on ALL ranks if any rank failed in this step (the failure flag travels with the completion flags)"""
+        self.ex.end_step(local_status, stream)
 
-    def end_step(self, n_local: int, stream):
-        """headers of all local viewpoints, then the barrier; `stream` continues when every rank's pushes have landed"""
-        self._q.join()
-        if self.error is not None:
-            raise self.error
-        if self._last is not None and n_local > 0:
-            self.tr.after(self.tr.mark(stream))
-            self._push(0, int(self._last.offsets), 8 * (n_local + 1))
-            self._push(self.tot_off, int(self._last.total), 4 * n_local)
-        self.tr.barrier(stream)
-
-    def views(self, n_per_rank: List[int]):
+    def views(self):
         """per source rank: (offsets int64 (n+1,), total f32 (n,), leaf i32 (e,), info f32 (e,)) -- zero-copy views of
-        this rank's receive buffer of the step that just ended (valid until the step after the next one begins)"""
+        this rank's receive buffer of the step that just ended (valid until this rank's next begin_step)"""
         out = []
         for r in range(self.world):
-            slot = self.base[self.cur] + r * self.slot_bytes
-            n = int(n_per_rank[r])
-            off = self.tr.view(slot, n + 1, "<i8")
-            tot = self.tr.view(slot + self.tot_off, n, "<f4")
-            e = int(off[n].item()) if n else 0
-            leaf = self.tr.view(slot + self.leaf_off, e, "<i4")
-            info = self.tr.view(slot + self.info_off, e, "<f4")
-            out.append((off, tot, leaf, info))
+            v = self.ex.view(r)
+            n, e = v.n_viewpoints, v.n_entries
+
+            def t(ptr, cnt, typestr):
+                if cnt == 0:
+                    return torch.empty(0, dtype={"<i8": torch.int64, "<f4": torch.float32, "<i4": torch.int32}[typestr],
+                                       device=self.device)
+                return torch.as_tensor(CudaArrayView(ptr, cnt, typestr), device=self.device)
+
+            off = t(v.offsets, n + 1, "<i8") if n else torch.zeros(1, dtype=torch.int64, device=self.device)
+            out.append((off, t(v.total, n, "<f4"), t(v.leaf, e, "<i4"), t(v.information, e, "<f4")))
         return out
 
     def close(self):
-        self._q.put(None)
-        self._worker.join(timeout=5)
-        self.tr.sync()
+        if self.ex is None:
+            return
+        torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)  # nobody unmaps while somebody may still push
-        for b in range(2):
-            for p in range(self.world):
-                if p != self.rank and self.peer[b][p]:
-                    self.tr.close(self.peer[b][p])
-        dist.barrier(group=self.group)
-        for ptr in self.base:
-            self.tr.free(ptr)
-        self.base = []
+        self.ex.disconnect()
+        dist.barrier(group=self.group)  # nobody frees while somebody still has it mapped
+        self.ex.close()
+        self.ex = None

@@ -62,6 +62,18 @@ class _OverlapResult(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
 
 
+class ExchangeLayout(C.Structure):
+    """q3dr_exchange_layout: byte offsets inside one receive buffer of the result exchange."""
+
+    _fields_ = [(n, C.c_uint64) for n in ("header_off", "offsets_off", "total_off", "leaf_off", "info_off", "slot_bytes",
+                                          "flags_off", "buffer_bytes")]
+
+
+IPC_HANDLE_BYTES = 64
+RESULT_FIRST_PIXEL = 1
+RESULT_DIST_SQ = 2
+
+
 class _MultiResult(C.Structure):
     _fields_ = [("n_parts", C.c_uint32), ("n_viewpoints", C.c_uint64), ("first_viewpoint", C.c_void_p), ("parts", C.c_void_p)]
 
@@ -173,6 +185,19 @@ def load_library() -> C.CDLL:
     )
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
+    L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_exchange_layout_of.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(ExchangeLayout)]
+    L.q3dr_exchange_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    L.q3dr_exchange_destroy.argtypes = [vp]
+    L.q3dr_exchange_disconnect.argtypes = [vp]
+    L.q3dr_exchange_export.argtypes = [vp, vp]
+    L.q3dr_exchange_import.argtypes = [vp, vp]
+    L.q3dr_exchange_connect.argtypes = [C.POINTER(vp), C.c_uint32]
+    L.q3dr_exchange_begin_step.argtypes = [vp]
+    L.q3dr_exchange_end_step.argtypes = [vp, C.c_int, vp]
+    L.q3dr_exchange_view.argtypes = [vp, C.c_uint32, C.POINTER(_Result)]
+    L.q3dr_multi_enable_gather.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.q3dr_multi_gathered.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(_Result)]
     L.q3dr_overlap_boxes.argtypes = [vp, fp, C.c_size_t, C.POINTER(_OverlapResult)]
     L.q3dr_valid_object_positions.argtypes = [vp, fp, C.c_size_t, fp, fp, C.c_float, C.POINTER(C.c_uint8)]
     L.q3dr_octree_leaves_to_boxes.argtypes = [fp, fp, fp, u32p, C.c_size_t, fp, C.c_float, C.c_float, C.c_uint32, C.c_int,
@@ -212,8 +237,6 @@ def load_library() -> C.CDLL:
     L.q3dr_score_viewpoints_normal_images.argtypes = (
         [vp, u32p, fp] + [C.c_uint32] * 6 + [fp, C.c_size_t, C.POINTER(ScoreOpts), C.POINTER(_Result)]
     )
-    for name in dir(L):
-        pass
     _lib = L
     return L
 
@@ -525,6 +548,11 @@ class OccupancyMap:
         )
         return ScoreResult(r, copy=copy)
 
+    def set_result_fields(self, first_pixel: bool = True, dist_sq: bool = True):
+        """Which per-entry arrays scoring calls deliver besides (leaf, information); see q3dr_map_set_result_fields."""
+        f = (RESULT_FIRST_PIXEL if first_pixel else 0) | (RESULT_DIST_SQ if dist_sq else 0)
+        _check(load_library().q3dr_map_set_result_fields(self._h, f))
+
     def set_chunk_callback(self, fn=None):
         """fn(first_viewpoint, n_viewpoints, first_entry, n_entries, DeviceResult) is called on the host as soon as the
         kernels finishing a chunk have been issued on the call's stream (q3dr_map_set_chunk_callback); None removes it."""
@@ -579,6 +607,69 @@ class OccupancyMap:
         r = _Result()
         _check(load_library().q3dr_result_to_host(self._h, C.byref(r)))
         return ScoreResult(r, copy=copy)
+
+
+def exchange_layout(n_ranks: int, max_viewpoints: int, max_entries: int) -> ExchangeLayout:
+    lay = ExchangeLayout()
+    _check(load_library().q3dr_exchange_layout_of(n_ranks, max_viewpoints, max_entries, C.byref(lay)))
+    return lay
+
+
+class Exchange:
+    """q3dr_exchange: this rank's end of the result exchange between GPUs (copy-engine pushes into peer HBM per finished
+    chunk, completion flags instead of a barrier).  One per map.  Separate processes: export_handles() on every rank,
+    ship all handles to all ranks (any transport), import_handles(); threads of one process: Exchange.connect(all)."""
+
+    def __init__(self, gmap: "OccupancyMap", n_ranks: int, rank: int, max_viewpoints: int, max_entries: int):
+        h = C.c_void_p()
+        _check(load_library().q3dr_exchange_create(gmap._h, n_ranks, rank, max_viewpoints, max_entries, C.byref(h)))
+        self._h = h
+        self.map = gmap
+        self.n_ranks = n_ranks
+        self.rank = rank
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().q3dr_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def disconnect(self):
+        if getattr(self, "_h", None):
+            _check(load_library().q3dr_exchange_disconnect(self._h))
+
+    def export_handles(self) -> bytes:
+        buf = C.create_string_buffer(2 * IPC_HANDLE_BYTES)
+        _check(load_library().q3dr_exchange_export(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def import_handles(self, all_handles: Sequence[bytes]):
+        blob = b"".join(all_handles)
+        if len(blob) != self.n_ranks * 2 * IPC_HANDLE_BYTES:
+            raise ValueError("need 2 handles of 64 bytes from every rank, in rank order")
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(load_library().q3dr_exchange_import(self._h, C.cast(buf, C.c_void_p)))
+
+    @staticmethod
+    def connect(exchanges: Sequence["Exchange"]):
+        arr = (C.c_void_p * len(exchanges))(*[e._h for e in exchanges])
+        _check(load_library().q3dr_exchange_connect(arr, len(exchanges)))
+
+    def begin_step(self):
+        _check(load_library().q3dr_exchange_begin_step(self._h))
+
+    def end_step(self, local_status: int = 0, stream: int = 0):
+        _check(load_library().q3dr_exchange_end_step(self._h, int(local_status), C.c_void_p(stream)))
+
+    def view(self, src: int) -> DeviceResult:
+        r = _Result()
+        _check(load_library().q3dr_exchange_view(self._h, src, C.byref(r)))
+        return DeviceResult(r)
 
 
 def default_render_opts(**kw) -> RenderOpts:
@@ -749,6 +840,16 @@ class MultiGpuMap:
 
     def update_weights(self, weights):
         _check(load_library().q3dr_multi_update_weights(self._h, _fp(_f32(weights))))
+
+    def enable_gather(self, max_viewpoints_per_gpu: int, max_entries_per_gpu: int):
+        """after this every score_viewpoints call leaves the results of ALL GPUs on every GPU (0, 0 switches it off)"""
+        _check(load_library().q3dr_multi_enable_gather(self._h, max_viewpoints_per_gpu, max_entries_per_gpu))
+
+    def gathered(self, on: int, src: int) -> DeviceResult:
+        """the part scored by GPU `src` as GPU `on` holds it after the last call (device pointers on GPU `on`)"""
+        r = _Result()
+        _check(load_library().q3dr_multi_gathered(self._h, on, src, C.byref(r)))
+        return DeviceResult(r)
 
     def score_viewpoints(self, K, image_width: int, window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None):
         """Returns [(first_viewpoint, ScoreResult)] per GPU; viewpoint v of part g is viewpoint first + v of the call."""

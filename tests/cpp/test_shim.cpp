@@ -255,6 +255,34 @@ int main(int argc, char** argv) {
     std::size_t nh = 0;
     for (std::size_t i = 0; i < np; ++i) nh += leaf[i] >= 0;
     CHECK(nodup.size() == nh);
+    {
+      // remove_duplicates = false (the reference's updateWeightsWithRealViewpoints mode, viewpoint_planner_data.cpp:522):
+      // every hit pixel in scan order, misses dropped -- the properly compacted list the reference's buggy
+      // removeInvalidRaycastHitVoxels (viewpoint_raycast.cpp:287-303) was meant to produce
+      std::size_t j = 0;
+      for (std::size_t i = 0; i < np; ++i) {
+        if (leaf[i] < 0) continue;
+        const auto& r = nodup[j].intersection_result;
+        CHECK(r.node == leaves[leaf[i]].node && r.dist_sq == dsq[i] && r.depth == depth[i]);
+        CHECK(r.intersection[0] == xyz[3 * i] && r.intersection[1] == xyz[3 * i + 1] && r.intersection[2] == xyz[3 * i + 2]);
+        CHECK(nodup[j].screen_coordinates[0] == (float)(i % cam.w) && nodup[j].screen_coordinates[1] == (float)(i / cam.w));
+        ++j;
+      }
+      CHECK(j == nh);
+      // ... also on a sub-window
+      auto sub = raycaster.getRaycastHitVoxelsWithScreenCoordinates(vp, 8, 40, 4, 20, false);
+      j = 0;
+      for (std::size_t y = 4; y < 20; ++y)
+        for (std::size_t x = 8; x < 40; ++x) {
+          const std::size_t i = y * cam.w + x;
+          if (leaf[i] < 0) continue;
+          CHECK(j < sub.size());
+          CHECK(sub[j].intersection_result.node == leaves[leaf[i]].node && sub[j].intersection_result.dist_sq == dsq[i]);
+          CHECK(sub[j].screen_coordinates[0] == (float)x && sub[j].screen_coordinates[1] == (float)y);
+          ++j;
+        }
+      CHECK(j == sub.size());
+    }
 
     // ViewpointPlanner::getRaycastHitVoxelsWithInformationScore(viewpoint, ignore_zero = true)
     auto scored = raycaster.getRaycastHitVoxelsWithInformationScore(vp, true);
@@ -446,6 +474,68 @@ int main(int argc, char** argv) {
         const float a2 = by_index.addObservedVoxels(v);
         CHECK(std::fabs(a1 - a2) <= 1e-6f * std::fabs(a2));
       }
+    }
+  }
+
+  // the CSR-backed voxel sets: same container contract as the reference's unordered_set, no per-voxel host work
+  {
+    std::vector<const mock::Viewpoint*> batch;
+    for (const mock::Viewpoint& vp : vps) batch.push_back(&vp);
+    for (int ignore_zero = 0; ignore_zero < 2; ++ignore_zero) {
+      auto sets = raycaster.getRaycastHitVoxelsWithInformationScoreBatch(batch, 0, cam.w, 0, cam.h, ignore_zero != 0);
+      auto views = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(batch, 0, cam.w, 0, cam.h, ignore_zero != 0);
+      CHECK(sets.size() == batch.size() && views.size() == batch.size());
+      for (std::size_t v = 0; v < batch.size(); ++v) {
+        const auto& set = sets[v].first;
+        const auto& view = views[v].first;
+        CHECK(view.size() == set.size() && view.empty() == set.empty() && view.size() > 100);
+        CHECK(views[v].second == sets[v].second);
+        std::size_t cnt = 0;
+        int32_t prev = -1;
+        float sum = 0;
+        for (const q3dr::VoxelWithInformation<mock::Node>& vi : view) {  // the reference's loop, verbatim
+          CHECK(set.find(vi) != set.end());
+          sum += vi.information;
+          ++cnt;
+        }
+        CHECK(cnt == set.size());
+        for (auto it = view.begin(); it != view.end(); ++it) {
+          CHECK(it.leaf() > prev);
+          prev = it.leaf();
+          CHECK(it->voxel == leaves[(std::size_t)it.leaf()].node && it->information == (*it).information);
+        }
+        for (const auto& vi : set) {
+          const auto it = view.find(vi);  // viewpoint_planner_path.cpp:842-843
+          CHECK(it != view.end());
+          CHECK(it->voxel == vi.voxel && it->information == vi.information);
+          CHECK(view.count(vi) == 1);
+        }
+        // same voxel, other information: not "in" the set (VoxelWithInformation::operator==, occupied_tree.h:73-79)
+        const q3dr::VoxelWithInformation<mock::Node> first = *view.begin();
+        CHECK(view.find(q3dr::VoxelWithInformation<mock::Node>(first.voxel, first.information + 1.0f)) == view.end());
+        mock::Node stranger;
+        CHECK(view.find(q3dr::VoxelWithInformation<mock::Node>(&stranger, first.information)) == view.end());
+        CHECK(view.toUnorderedSet() == set);
+        CHECK((std::size_t)(view.end() - view.begin()) == view.size());
+        // ViewpointEntry keeps the set by value: moving the view keeps it valid after the batch vector is gone
+        q3dr::VoxelWithInformationSetView<mock::Node> kept = std::move(views[v].first);
+        CHECK(kept.size() == set.size() && kept.find(first) != kept.end());
+      }
+      // views of an earlier call stay intact when the map's host buffers are reused by the next call
+      auto again = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(batch, 0, cam.w, 0, cam.h, ignore_zero != 0);
+      auto other = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(batch, 8, 40, 4, 20, ignore_zero != 0);
+      for (std::size_t v = 0; v < batch.size(); ++v) {
+        CHECK(again[v].first.toUnorderedSet() == sets[v].first);
+        CHECK(other[v].first.size() < again[v].first.size());
+      }
+    }
+    // the set consumers take a view as well
+    auto views = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(batch, 0, cam.w, 0, cam.h, true);
+    auto sets = raycaster.getRaycastHitVoxelsWithInformationScoreBatch(batch, 0, cam.w, 0, cam.h, true);
+    q3dr::ObservedVoxelMapCuda<mock::Node> a(&tree), b(&tree);
+    for (std::size_t v = 0; v < batch.size(); ++v) {
+      CHECK(a.computeNewInformation(views[v].first) == b.computeNewInformation(sets[v].first));
+      CHECK(a.addObservedVoxels(views[v].first) == b.addObservedVoxels(sets[v].first));
     }
   }
 

@@ -1,5 +1,6 @@
 """q3dr_map_set_chunk_callback: the chunk reports of a scoring call tile its viewpoints and its entries, in order, and
-agree with the final CSR offsets (the multi-GPU exchange of quad3dr_b200/dist.py PeerGather is driven by them)."""
+agree with the final CSR offsets (external consumers of finished chunks hang on them; the library's own multi-GPU
+exchange, q3dr_exchange, is fed from the same place in the scoring call)."""
 import os
 
 import numpy as np

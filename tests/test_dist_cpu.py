@@ -79,123 +79,49 @@ def test_gather_results_world2_gloo(n):
     assert got == {0: True, 1: True}
 
 
-# ---- PeerGather (the overlapped exchange) at world_size 2 on gloo: same logic, shared memory instead of CUDA IPC ----
+# ---- the torch.distributed plumbing around the C ABI's exchange (quad3dr_b200/dist.py PeerExchange) at world_size 2 ----
 
-class ShmTransport:
-    """Stand-in for quad3dr_b200.dist.CudaIpcTransport on a machine without GPUs: receive buffers are POSIX shared
-    memory segments ("IPC handle" = the segment name), a copy is a memmove, ordering is immediate, the barrier is
-    gloo's.  Everything above the transport -- slot layout, per-chunk pushes from the helper thread, header push, double
-    buffering, views -- is PeerGather's own code."""
-
-    def __init__(self):
-        import ctypes
-        from multiprocessing import shared_memory
-
-        self.ctypes = ctypes
-        self.shared_memory = shared_memory
-        self.segs = {}
-
-    def _map(self, shm):
-        anchor = self.ctypes.c_char.from_buffer(shm.buf)
-        ptr = self.ctypes.addressof(anchor)
-        self.segs[ptr] = [shm, anchor]
-        return ptr
-
-    def alloc(self, nbytes):
-        shm = self.shared_memory.SharedMemory(create=True, size=nbytes)
-        return self._map(shm), shm.name.encode()
-
-    def open(self, handle):
-        return self._map(self.shared_memory.SharedMemory(name=handle.decode()))
-
-    def close(self, ptr):
-        entry = self.segs.pop(ptr)
-        shm = entry[0]
-        entry.clear()  # drops the anchor: a segment with an exported buffer cannot be closed
-        shm.close()
-
-    def free(self, ptr):
-        entry = self.segs.pop(ptr)
-        shm = entry[0]
-        entry.clear()
-        shm.close()
-        shm.unlink()
-
-    def agree(self, ok):
-        t = torch.tensor([1 if ok else 0], dtype=torch.int32)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return bool(int(t.item()))
-
-    def thread_init(self):
-        pass
-
-    def mark(self, stream):
-        return None
-
-    def after(self, mark):
-        pass
-
-    def copy(self, dst, src, nbytes):
-        self.ctypes.memmove(dst, src, nbytes)
-
-    def barrier(self, stream):
-        dist.barrier()
-
-    def view(self, ptr, n, typestr):
-        dt = np.dtype(typestr)
-        if n == 0:
-            return torch.empty(0, dtype=torch.from_numpy(np.empty(0, dt)).dtype)
-        raw = (self.ctypes.c_char * (n * dt.itemsize)).from_address(ptr)
-        return torch.from_numpy(np.frombuffer(raw, dtype=dt, count=n).copy())
-
-    def sync(self):
-        pass
-
-
-def _peer_worker(rank, world, port, n, q):
-    from types import SimpleNamespace
-
+def _plumbing_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ok = True
     try:
-        lo, hi = qdist.shard_range(n, rank, world)
-        n_per = [qdist.shard_range(n, r, world)[1] - qdist.shard_range(n, r, world)[0] for r in range(world)]
-        pg = qdist.PeerGather(None, max(n_per), 40 * max(n_per) + 8, transport=ShmTransport())
-        for step in range(4):
-            seed = 1000 * step
-            drop = 1 if step == 2 and hi - lo > 0 else 0            # a smaller result in the middle
-            o, t, l, i = _fake_result(lo, hi - drop, seed)
-            res = SimpleNamespace(offsets=o.ctypes.data, total=t.ctypes.data if t.size else 0,
-                                  leaf=l.ctypes.data if l.size else 0, information=i.ctypes.data if i.size else 0)
-            pg.begin_step()
-            n_local = hi - lo - drop
-            for v0 in range(0, n_local, 3):                          # the engine reports chunk after chunk
-                nv = min(3, n_local - v0)
-                pg.on_chunk(v0, nv, int(o[v0]), int(o[v0 + nv] - o[v0]), res, None)
-            pg.end_step(n_local, None)
-            n_use = [n_per[r] - (1 if step == 2 and n_per[r] > 0 else 0) for r in range(world)]
-            got = pg.views(n_use)
-            for r in range(world):
-                rlo, rhi = qdist.shard_range(n, r, world)
-                eo, et, el, ei = _fake_result(rlo, rlo + n_use[r], seed)
-                go, gt, gl, gi = got[r]
-                ok &= bool(np.array_equal(go.numpy(), eo) and np.array_equal(gt.numpy().view(np.uint32), et.view(np.uint32))
-                           and np.array_equal(gl.numpy(), el) and np.array_equal(gi.numpy().view(np.uint32), ei.view(np.uint32)))
-        pg.close()
+        # IPC handles travel as opaque 128-byte blobs, rank order preserved
+        blob = bytes([rank]) * 128
+        got = qdist.all_gather_bytes(blob)
+        ok &= got == [bytes([r]) * 128 for r in range(world)]
+        # a rank that failed locally ships an empty blob; everybody sees it and everybody agrees on the outcome
+        got = qdist.all_gather_bytes(b"" if rank == 1 else blob)
+        ok &= [len(g) for g in got] == [128 if r != 1 else 0 for r in range(world)]
+        ok &= qdist.agree(True) is True
+        ok &= qdist.agree(rank != 1) is False
+        # gather_results refuses a slice larger than n_local_max on ALL ranks (no hang, no corruption)
+        lo, hi = qdist.shard_range(7, rank, world)
+        o, t, l, i = [torch.from_numpy(x) for x in _fake_result(lo, hi)]
+        try:
+            qdist.gather_results(o, t, l, i, 3)  # rank 0 holds 4 viewpoints
+            ok = False
+        except ValueError:
+            pass
+        try:
+            qdist.gather_results(o, t, l, i, 4 + rank)  # n_local_max differs between ranks
+            ok = False
+        except ValueError:
+            pass
+        O_, _, _, _ = qdist.gather_results(o, t, l, i, 4)  # and works right after
+        ok &= int(O_.numel()) == 8
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [11, 2, 1])
-def test_peer_gather_protocol_world2_gloo(n):
+def test_exchange_plumbing_world2_gloo():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_plumbing_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/q3dr_raycast.h but not exported"
-    assert lib.q3dr_abi_version() == 3
+    assert lib.q3dr_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
@@ -39,6 +39,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(E.Stats) == 40
     assert ctypes.sizeof(E.RenderOpts) == 12   # q3dr_render_opts
     assert ctypes.sizeof(E.MeshInfo) == 40     # q3dr_mesh_info
+    assert ctypes.sizeof(E.ExchangeLayout) == 64  # q3dr_exchange_layout
 
 
 def test_score_opts_defaults_match_reference_defaults():

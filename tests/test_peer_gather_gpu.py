@@ -1,4 +1,4 @@
-"""Copy-engine push exchange between GPUs (PeerGather) against the NCCL all_gather path; needs >= 2 GPUs."""
+"""Copy-engine push exchange between GPUs (q3dr_exchange across processes, CUDA IPC) against the NCCL all_gather path; needs >= 2 GPUs."""
 import os
 import subprocess
 import sys
