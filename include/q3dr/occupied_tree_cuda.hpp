@@ -66,8 +66,11 @@ using VoxelWithInformationSet =
 /// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.
 template <typename NodeT>
 struct VoxelSetBlock {
-  std::vector<std::int32_t> leaf;     // ascending leaf index inside every viewpoint's range
-  std::vector<float> information;
+  // plain arrays, deliberately NOT value-initialised: the parallel copy that fills them is also their first touch, so
+  // the page faults of a fresh 10^8-byte block are spread over all host threads instead of serialised in a resize()
+  std::unique_ptr<std::int32_t[]> leaf;     // ascending leaf index inside every viewpoint's range
+  std::unique_ptr<float[]> information;
+  std::size_t n_entries;
   std::vector<NodeT*> const* nodes;   // leaf index -> host node (owned by the OccupiedTreeCuda, which must outlive the views)
   std::unordered_map<const NodeT*, std::int32_t> const* (*leaf_of)(const void*);  // host node -> leaf index, built on first find()
   const void* tree;
@@ -144,18 +147,18 @@ class VoxelWithInformationSetView {
     const std::unordered_map<const NodeT*, std::int32_t>* table = block_->leaf_of(block_->tree);
     typename std::unordered_map<const NodeT*, std::int32_t>::const_iterator it = table->find(vi.voxel);
     if (it == table->end()) return end();
-    const std::int32_t* first = block_->leaf.data() + begin_;
-    const std::int32_t* last = block_->leaf.data() + end_;
+    const std::int32_t* first = block_->leaf.get() + begin_;
+    const std::int32_t* last = block_->leaf.get() + end_;
     const std::int32_t* p = std::lower_bound(first, last, it->second);
     if (p == last || *p != it->second) return end();
-    const std::size_t i = static_cast<std::size_t>(p - block_->leaf.data());
+    const std::size_t i = static_cast<std::size_t>(p - block_->leaf.get());
     return block_->information[i] == vi.information ? const_iterator(block_.get(), i) : end();
   }
   size_type count(const value_type& vi) const { return find(vi) == end() ? 0 : 1; }
 
   /// the engine's view of the set: ascending leaf indices and their informations
-  const std::int32_t* leafData() const { return block_ ? block_->leaf.data() + begin_ : nullptr; }
-  const float* informationData() const { return block_ ? block_->information.data() + begin_ : nullptr; }
+  const std::int32_t* leafData() const { return block_ ? block_->leaf.get() + begin_ : nullptr; }
+  const float* informationData() const { return block_ ? block_->information.get() + begin_ : nullptr; }
 
   /// the reference's own container (one hash-node allocation per voxel)
   VoxelWithInformationSet<NodeT> toUnorderedSet() const {
@@ -667,8 +670,9 @@ class ViewpointRaycastCuda {
     const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
     std::shared_ptr<VoxelSetBlock<NodeT> > block = std::make_shared<VoxelSetBlock<NodeT> >();
     const std::size_t ne = static_cast<std::size_t>(r.n_entries);
-    block->leaf.resize(ne);
-    block->information.resize(ne);
+    block->leaf.reset(new std::int32_t[ne > 0 ? ne : 1]);
+    block->information.reset(new float[ne > 0 ? ne : 1]);
+    block->n_entries = ne;
     block->nodes = &bvh_tree_->leafNodes();
     block->leaf_of = &TreeType::leafIndexTableOf;
     block->tree = bvh_tree_;
@@ -679,8 +683,8 @@ class ViewpointRaycastCuda {
 #endif
     for (std::ptrdiff_t p = 0; p < pieces; ++p) {
       const std::size_t a = static_cast<std::size_t>(p) * kCopyPiece, n = std::min(kCopyPiece, ne - a);
-      std::memcpy(block->leaf.data() + a, r.leaf + a, n * sizeof(std::int32_t));
-      std::memcpy(block->information.data() + a, r.information + a, n * sizeof(float));
+      std::memcpy(block->leaf.get() + a, r.leaf + a, n * sizeof(std::int32_t));
+      std::memcpy(block->information.get() + a, r.information + a, n * sizeof(float));
     }
     for (std::size_t v = 0; v < viewpoints.size(); ++v) {
       out[v].first = VoxelSetView(block, static_cast<std::size_t>(r.offsets[v]), static_cast<std::size_t>(r.offsets[v + 1]));

@@ -81,12 +81,45 @@ int configure_rays_kernel(q3dr_map* m) {
   return Q3DR_OK;
 }
 
-template <int MODE>
+// The camera-window kernel exists in several packet shapes (raycast2_kernels.cuh): rays per lane, tile width, packed
+// binary32 arithmetic.  All compute the same results bit for bit; which one a map uses is fixed at creation
+// (Q3DR_RAY_VARIANT overrides the default, for measurements).
+typedef void (*RaycastKernel)(const q3dr::RaycastParams);
+struct RayVariant {
+  const char* name;
+  int nr, tw;
+  RaycastKernel kernel[2];  // [MODE]
+};
+#define Q3DR_VARIANT(NAME, NR, TW, PK)                                                   \
+  {NAME, NR, TW, {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK>}}
+const RayVariant kRayVariants[] = {
+    Q3DR_VARIANT("2x8x8", 2, 8, false),     // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 64 registers
+    Q3DR_VARIANT("2x8x8p", 2, 8, true),     // 1: ... with FADD2 / FMUL2
+    Q3DR_VARIANT("4x8x16", 4, 8, false),    // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
+    Q3DR_VARIANT("4x8x16p", 4, 8, true),    // 3
+    Q3DR_VARIANT("4x16x8", 4, 16, false),   // 4: four rays per lane, 16 x 8 pixel packets
+    Q3DR_VARIANT("4x16x8p", 4, 16, true),   // 5
+};
+#undef Q3DR_VARIANT
+constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
+constexpr int kDefaultRayVariant = 0;
+
+const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
+
 int configure_kernel2(q3dr_map* m) {
-  int per_sm = 0;
-  Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q3dr::raycast2_kernel<MODE>, q3dr::kThreadsPerCta, 0));
-  if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
-  m->grid2_ctas[MODE] = per_sm * m->sm_count;
+  m->ray_variant = kDefaultRayVariant;
+  if (const char* e = std::getenv("Q3DR_RAY_VARIANT")) {
+    const long v = std::strtol(e, nullptr, 10);
+    if (v < 0 || v >= kNumRayVariants) return fail(Q3DR_ERR_INVALID_ARG, "Q3DR_RAY_VARIANT out of range");
+    m->ray_variant = (int)v;
+  }
+  const RayVariant& rv = variant_of(m);
+  for (int mode = 0; mode < 2; ++mode) {
+    int per_sm = 0;
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.kernel[mode], q3dr::kThreadsPerCta, 0));
+    if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
+    m->grid2_ctas[mode] = per_sm * m->sm_count;
+  }
   return Q3DR_OK;
 }
 
@@ -115,8 +148,7 @@ int upload_map(q3dr_map* m) {
   Q3DR_TRY(m->h_scalar.ensure(8));
   m->smem_bytes = (size_t)m->tree->top_nodes * sizeof(q3dr::Node4);
   Q3DR_TRY(configure_rays_kernel(m));
-  Q3DR_TRY(configure_kernel2<q3dr::kModeScore>(m));
-  Q3DR_TRY(configure_kernel2<q3dr::kModePixels>(m));
+  Q3DR_TRY(configure_kernel2(m));
   return Q3DR_OK;
 }
 
@@ -171,7 +203,7 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
 size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint64_t cap) {
   // enough packets in flight that the persistent grid's tail is small ...
   const size_t resident_warps = (size_t)m->grid2_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
-  size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;
+  size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;  // ~64 packets per resident warp
   // ... and enough viewpoints per chunk to amortise the per-chunk host sync and the small scoring kernels, few enough
   // that the D2H copy of a finished chunk overlaps the next one (measured on C2: 150 / 296 / 500 / 1000 viewpoints per
   // chunk -> 26.6 / 26.0 / 28.2 / 29.5 ms end to end)
@@ -208,8 +240,9 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   p->y0 = y0;
   p->w = x1 - x0;
   p->h = y1 - y0;
-  p->tiles_x = (p->w + q3dr::kTile2W - 1) / q3dr::kTile2W;
-  const uint32_t tiles_y = (p->h + q3dr::kTile2H - 1) / q3dr::kTile2H;
+  const uint32_t tile_w = (uint32_t)variant_of(m).tw, tile_h = (uint32_t)(32 / variant_of(m).tw * variant_of(m).nr);
+  p->tiles_x = (p->w + tile_w - 1) / tile_w;
+  const uint32_t tiles_y = (p->h + tile_h - 1) / tile_h;
   p->tiles_per_vp = p->tiles_x * tiles_y;
   p->max_range = max_range;
   p->leaf_depth = m->d_depth.p;
@@ -234,14 +267,16 @@ int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
 
 // One scoring call.  The chunks of a call are software-pipelined on ONE stream so that the SMs never wait for the host:
 //
-//   stream:  R(0) S(0) c(0) R(1) | P(0) S(1) c(1) R(2) | P(1) S(2) c(2) ...        R = raycast, S = score, P = pack
-//   host  :  ........ issue R(1), then wait for c(0) (the chunk's entry count), size the pools, issue P(0), S(1) ...
+//   stream:  R(0) S(0) P(0) c(0) R(1) | S(1) P(1) c(1) R(2) | S(2) P(2) c(2) ...     R = raycast, S = score, P = pack
+//   host  :  ............. issue R(1), then wait for c(0) (the chunk's entry count), hand chunk 0 to its consumers ...
 //
-// The host needs the entry count of chunk k only to make sure the CSR pools are large enough before P(k) is issued; by
-// then R(k+1) is already queued, so the wait costs nothing on the device.  R(k+1) touches the dedup tables only (left
-// clean by S(k)), P(k) the temporary lists of chunk k (rewritten by S(k+1), which is issued after P(k)).  Pools that
-// have to grow are replaced, never freed inside the call (q3dr_map::retired): pointers handed to a chunk consumer and
-// D2H copies in flight stay valid.  Timing events are read once, after the final synchronisation.
+// The host needs the entry count of chunk k to know whether the CSR pools were large enough and to tell the consumers
+// (D2H copy, peer pushes, callback) which range is final; by then R(k+1) is queued, so the wait costs nothing on the
+// device, and the consumers' copies overlap R(k+1).  P(k) is issued BEFORE the count is known, into the pools as they
+// are; it skips entries beyond their capacity.  If the count then exceeds the capacity (first calls on a map only) the
+// pools are grown and P(k) is issued again -- the chunk's temporary lists are intact until S(k+1) is issued.  Pools
+// that grow are replaced, never freed inside the call (q3dr_map::retired): pointers handed to a chunk consumer and D2H
+// copies in flight stay valid.  Timing events are read once, after the final synchronisation.
 int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
                       uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
                       q3dr_result* result, bool stream_to_host, const NormalSource* ns = nullptr) {
@@ -390,7 +425,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     m->scratch_dirty = true;  // cleared when this chunk's scoring kernels have been issued
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore],
                                             ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-    q3dr::raycast2_kernel<q3dr::kModeScore><<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
+    variant_of(m).kernel[q3dr::kModeScore]<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
     st.kernel_launches += 1;
@@ -439,24 +474,8 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     return Q3DR_OK;
   };
 
-  uint64_t total_entries = 0;
-  if (n_chunks > 0) Q3DR_TRY(issue_raycast(0));
-  for (size_t c = 0; c < n_chunks; ++c) {
+  auto issue_pack = [&](size_t c) -> int {
     const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
-    Q3DR_TRY(issue_score(c));
-    if (c + 1 < n_chunks) Q3DR_TRY(issue_raycast(c + 1));  // keeps the SMs busy while the host waits below
-    Q3DR_CUDA(cudaEventSynchronize(m->ev_count));
-    const uint64_t chunk_first_entry = total_entries;
-    total_entries = m->h_scalar.p[0];
-    if (total_entries > m->r_leaf.cap) {
-      // project the call's total from what the viewpoints so far produced, so that a call grows its pools about once
-      const double per_vp = (double)total_entries / (double)(v0 + nb);
-      const size_t want = (size_t)std::max<double>((double)total_entries, per_vp * (double)n_vp * 1.15 + 4096.0);
-      Q3DR_TRY(m->r_leaf.grow_deferred(want, chunk_first_entry, stream, &m->retired));
-      Q3DR_TRY(m->r_info.grow_deferred(want, chunk_first_entry, stream, &m->retired));
-    }
-    if (want_pix) Q3DR_TRY(m->r_pix.grow_deferred(m->r_leaf.cap, chunk_first_entry, stream, &m->retired));
-    if (want_dsq) Q3DR_TRY(m->r_dsq.grow_deferred(m->r_leaf.cap, chunk_first_entry, stream, &m->retired));
     q3dr::PackParams2 pp;
     pp.offsets = m->d_offsets.p + v0;
     pp.blk_off = blk_off;
@@ -473,14 +492,46 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     pp.out_info = m->r_info.p;
     pp.out_pix = want_pix ? m->r_pix.p : nullptr;
     pp.out_dsq = want_dsq ? m->r_dsq.p : nullptr;
+    pp.pool_cap = m->r_leaf.cap;
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 3], stream));
     q3dr::pack_blocks_kernel<<<flat_grid, q3dr::kSegThreads, 0, stream>>>(pp);
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 4], stream));
+    Q3DR_CUDA(cudaEventRecord(m->ev_packed, stream));
     st.kernel_launches += 1;
+    return Q3DR_OK;
+  };
+
+  uint64_t total_entries = 0;
+  // the optional pools always match the (leaf, information) pools
+  if (want_pix && m->r_pix.cap < m->r_leaf.cap) Q3DR_TRY(m->r_pix.grow_deferred(m->r_leaf.cap, 0, stream, &m->retired));
+  if (want_dsq && m->r_dsq.cap < m->r_leaf.cap) Q3DR_TRY(m->r_dsq.grow_deferred(m->r_leaf.cap, 0, stream, &m->retired));
+  if (n_chunks > 0) Q3DR_TRY(issue_raycast(0));
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
+    Q3DR_TRY(issue_score(c));
+    // packed right away into the pools as they are (entries beyond their capacity are skipped, see below): in the steady
+    // state the chunk's result is final BEFORE the next raycast starts, so its D2H / peer pushes overlap that raycast
+    const bool packed_early = m->r_leaf.cap > 0;
+    if (packed_early) Q3DR_TRY(issue_pack(c));
+    if (c + 1 < n_chunks) Q3DR_TRY(issue_raycast(c + 1));  // keeps the SMs busy while the host waits below
+    Q3DR_CUDA(cudaEventSynchronize(m->ev_count));
+    const uint64_t chunk_first_entry = total_entries;
+    total_entries = m->h_scalar.p[0];
+    if (total_entries > m->r_leaf.cap || !packed_early) {
+      if (total_entries > m->r_leaf.cap) {
+        // project the call's total from what the viewpoints so far produced, so that a call grows its pools about once
+        const double per_vp = (double)total_entries / (double)(v0 + nb);
+        const size_t want = (size_t)std::max<double>((double)total_entries, per_vp * (double)n_vp * 1.15 + 4096.0);
+        Q3DR_TRY(m->r_leaf.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+        Q3DR_TRY(m->r_info.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+        if (want_pix) Q3DR_TRY(m->r_pix.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+        if (want_dsq) Q3DR_TRY(m->r_dsq.grow_deferred(want, chunk_first_entry, stream, &m->retired));
+      }
+      // (first calls only) the chunk's temporary lists are still intact -- S(c + 1) has not been issued: pack again
+      if (total_entries > chunk_first_entry) Q3DR_TRY(issue_pack(c));
+    }
     st.chunks += 1;
-    const bool consumers = m->chunk_cb != nullptr || m->exchange != nullptr || (stream_to_host && total_entries > copied_entries);
-    if (consumers) Q3DR_CUDA(cudaEventRecord(m->ev_packed, stream));
     if (m->chunk_cb) {
       q3dr_result part;
       part.n_viewpoints = v0 + nb;
@@ -912,7 +963,7 @@ int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint3
   const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels],
                                           ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
   Q3DR_CUDA(cudaEventRecord(m->ev[0], s));
-  q3dr::raycast2_kernel<q3dr::kModePixels><<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaEventRecord(m->ev[1], s));
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, npix * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));

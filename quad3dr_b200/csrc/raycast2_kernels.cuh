@@ -1,15 +1,15 @@
-// raycast2_kernels.cuh -- the camera-window traversal kernel: one warp = one 8x8 pixel packet, TWO rays per lane.
+// raycast2_kernels.cuh -- the camera-window traversal kernel: one warp = one pixel packet, SEVERAL rays per lane.
 //
 // Every ray of a viewpoint starts at the camera centre, so the 24 plane-minus-origin differences of a 4-wide node
-// are the same for all rays; with two rays per lane they, the node fetch and the whole scalar epilogue of a node
-// visit (candidate mask, leaf loop, descent / stack) are paid once per 64 rays instead of once per 32.  The numeric
-// contract is the one of raycast_kernels.cuh: every value that feeds a hit decision is a
-// single correctly rounded binary32 operation in the reference's order.
+// are the same for all rays; with NR rays per lane they, the node fetch and the whole scalar epilogue of a node
+// visit (candidate mask, leaf loop, descent / stack) are paid once per 32 * NR rays instead of once per 32.  The
+// numeric contract is the one of raycast_kernels.cuh: every value that feeds a hit decision
+// is a single correctly rounded binary32 operation in the reference's order.
 //
-//   traverse_packet2<false>  all 64 rays share one direction octant: near / far planes are picked by address
-//   traverse_packet2<true>   mixed octants (packets straddling an axis): lo = min(t0, t1), hi = max(t0, t1) per
-//                            axis like the reference writes it (no NaN can arise with finite inverse directions,
-//                            so fminf / fmaxf equal the reference's ternaries)
+//   traverse_packetN<NR, false, .>  all rays share one direction octant: near / far planes are picked by address
+//   traverse_packetN<NR, true, .>   mixed octants (packets straddling an axis): lo = min(t0, t1), hi = max(t0, t1)
+//                                   per axis like the reference writes it (no NaN can arise with finite inverse
+//                                   directions, so fminf / fmaxf equal the reference's ternaries)
 //   packets with a non-finite inverse direction (exactly axis-parallel rays) take traverse_packet_exact per ray.
 #pragma once
 
@@ -17,8 +17,6 @@
 
 namespace q3dr {
 
-constexpr int kTile2W = 8;
-constexpr int kTile2H = 8;
 
 struct Dir2 {
   float dx, dy, dz;
@@ -61,16 +59,24 @@ __device__ __forceinline__ float dist_sq_at2(float ox, float oy, float oz, const
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 1.0f / 2048.0f, t) + A; }
 
-// kMixed = false: all 64 rays share one direction octant, near / far planes are picked by address.
+// One warp = one packet of 32 * NR rays, NR rays per lane.  Every ray of a viewpoint starts at the camera centre, so the
+// 24 plane-minus-origin differences of a 4-wide node are the same for all rays of the packet: they, the node fetch and
+// the scalar epilogue of a node visit (candidate mask, leaf loop, descent / stack) are paid once per 32 * NR rays.
+//
+// kMixed = false: all rays of the packet share one direction octant, near / far planes are picked by address.
 // kMixed = true : lo = min(t0, t1), hi = max(t0, t1) per axis like the reference writes it.
+// kPacked       : the plane differences and the slab products of two CHILDREN at a time with sm_100's packed binary32
+//                 instructions (FADD2 / FMUL2: two independent round-to-nearest-even operations per instruction, so
+//                 every product is bit-identical to the scalar __fmul_rn; a - o is computed as a + (-o), which is the
+//                 same IEEE operation).  One LDG.128 delivers the same plane of children 0..3 in consecutive registers,
+//                 i.e. as two aligned register pairs.
 // The reference's clamp of tmax at FLT_MAX is omitted: it can only bind when all three exit parameters overflow,
 // which a normalised direction (|inv| <= 2 on some axis) cannot produce over a map bounded by 1e18 -- a packet
 // precondition as well.  The exit parameter is kept as x' = min(exit, tU): "hit and still needed" is then entry < x'.
-template <bool kMixed>
-__device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, float A, const Dir2& r0, const Dir2& r1,
-                                                 Best2& b0, Best2& b1, const float4* __restrict__ nodes, uint32_t octant) {
-  float stack_t0[kStackEntries];
-  float stack_t1[kStackEntries];
+template <int NR, bool kMixed, bool kPacked>
+__device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, float A, const Dir2 (&r)[NR], Best2 (&b)[NR],
+                                                 const float4* __restrict__ nodes, uint32_t octant) {
+  float stack_t[NR][kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
   uint32_t ref = 0;
@@ -79,70 +85,110 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, f
                  nz = (!kMixed && (octant & 4u)) ? 5u : 2u;
   const uint32_t fx = 3u - nx, fy = 5u - ny, fz = 7u - nz;
   const float kInf = __int_as_float(0x7F800000);
+  // kPacked: the per-packet constants as register pairs
+  const float2 nox = make_float2(-ox, -ox), noy = make_float2(-oy, -oy), noz = make_float2(-oz, -oz);
+  float2 iix[NR], iiy[NR], iiz[NR];
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    iix[j] = make_float2(r[j].ix, r[j].ix);
+    iiy[j] = make_float2(r[j].iy, r[j].iy);
+    iiz[j] = make_float2(r[j].iz, r[j].iz);
+  }
   while (true) {
     const float4* np = nodes + (size_t)ref * 8u;
     const float4 nrx = __ldg(np + nx), nry = __ldg(np + ny), nrz = __ldg(np + nz);
     const float4 frx = __ldg(np + fx), fry = __ldg(np + fy), frz = __ldg(np + fz);
     const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+    const uint32_t chv[4] = {ch.x, ch.y, ch.z, ch.w};
 
-    float t00, t01, t02, t03, t10, t11, t12, t13;  // entry parameter, [ray][child]
-    float x00, x01, x02, x03, x10, x11, x12, x13;  // min(exit parameter, tU)
-#define Q3DR_SLAB1(R, B, TA, XA)                                                                            \
-      {                                                                                                     \
-        float lx = __fmul_rn(anx, R.ix), hx = __fmul_rn(afx, R.ix);                                         \
-        float ly = __fmul_rn(any_, R.iy), hy = __fmul_rn(afy, R.iy);                                        \
-        float lz = __fmul_rn(anz, R.iz), hz = __fmul_rn(afz, R.iz);                                         \
-        if (kMixed) {                                                                                       \
-          const float sx = fminf(lx, hx), sy = fminf(ly, hy), sz = fminf(lz, hz);                           \
-          hx = fmaxf(lx, hx); hy = fmaxf(ly, hy); hz = fmaxf(lz, hz);                                       \
-          lx = sx; ly = sy; lz = sz;                                                                        \
-        }                                                                                                   \
-        (XA) = fminf(fminf(fminf(hx, hy), hz), B.tU);                                                       \
-        (TA) = fmaxf(fmaxf(fmaxf(lx, ly), lz), 0.0f);                                                       \
+    float t[NR][4];  // entry parameter, [ray][child]
+    float x[NR][4];  // min(exit parameter, tU)
+    if (!kPacked) {
+      const float pnx[4] = {nrx.x, nrx.y, nrx.z, nrx.w}, pny[4] = {nry.x, nry.y, nry.z, nry.w}, pnz[4] = {nrz.x, nrz.y, nrz.z, nrz.w};
+      const float pfx[4] = {frx.x, frx.y, frx.z, frx.w}, pfy[4] = {fry.x, fry.y, fry.z, fry.w}, pfz[4] = {frz.x, frz.y, frz.z, frz.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float anx = __fsub_rn(pnx[c], ox), afx = __fsub_rn(pfx[c], ox);
+        const float any_ = __fsub_rn(pny[c], oy), afy = __fsub_rn(pfy[c], oy);
+        const float anz = __fsub_rn(pnz[c], oz), afz = __fsub_rn(pfz[c], oz);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          float lx = __fmul_rn(anx, r[j].ix), hx = __fmul_rn(afx, r[j].ix);
+          float ly = __fmul_rn(any_, r[j].iy), hy = __fmul_rn(afy, r[j].iy);
+          float lz = __fmul_rn(anz, r[j].iz), hz = __fmul_rn(afz, r[j].iz);
+          if (kMixed) {
+            const float sx = fminf(lx, hx), sy = fminf(ly, hy), sz = fminf(lz, hz);
+            hx = fmaxf(lx, hx); hy = fmaxf(ly, hy); hz = fmaxf(lz, hz);
+            lx = sx; ly = sy; lz = sz;
+          }
+          x[j][c] = fminf(fminf(fminf(hx, hy), hz), b[j].tU);
+          t[j][c] = fmaxf(fmaxf(fmaxf(lx, ly), lz), 0.0f);
+        }
       }
-#define Q3DR_SLAB2(C, TA, XA, TB, XB)                                                                      \
-    {                                                                                                       \
-      const float anx = __fsub_rn(nrx.C, ox), afx = __fsub_rn(frx.C, ox);                                   \
-      const float any_ = __fsub_rn(nry.C, oy), afy = __fsub_rn(fry.C, oy);                                  \
-      const float anz = __fsub_rn(nrz.C, oz), afz = __fsub_rn(frz.C, oz);                                   \
-      Q3DR_SLAB1(r0, b0, TA, XA)                                                                            \
-      Q3DR_SLAB1(r1, b1, TB, XB)                                                                            \
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // children 2h, 2h + 1
+        const float2 anx = __fadd2_rn(h ? make_float2(nrx.z, nrx.w) : make_float2(nrx.x, nrx.y), nox);
+        const float2 afx = __fadd2_rn(h ? make_float2(frx.z, frx.w) : make_float2(frx.x, frx.y), nox);
+        const float2 any_ = __fadd2_rn(h ? make_float2(nry.z, nry.w) : make_float2(nry.x, nry.y), noy);
+        const float2 afy = __fadd2_rn(h ? make_float2(fry.z, fry.w) : make_float2(fry.x, fry.y), noy);
+        const float2 anz = __fadd2_rn(h ? make_float2(nrz.z, nrz.w) : make_float2(nrz.x, nrz.y), noz);
+        const float2 afz = __fadd2_rn(h ? make_float2(frz.z, frz.w) : make_float2(frz.x, frz.y), noz);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          float2 lx = __fmul2_rn(anx, iix[j]), hx = __fmul2_rn(afx, iix[j]);
+          float2 ly = __fmul2_rn(any_, iiy[j]), hy = __fmul2_rn(afy, iiy[j]);
+          float2 lz = __fmul2_rn(anz, iiz[j]), hz = __fmul2_rn(afz, iiz[j]);
+          if (kMixed) {
+            const float2 sx = make_float2(fminf(lx.x, hx.x), fminf(lx.y, hx.y));
+            const float2 sy = make_float2(fminf(ly.x, hy.x), fminf(ly.y, hy.y));
+            const float2 sz = make_float2(fminf(lz.x, hz.x), fminf(lz.y, hz.y));
+            hx = make_float2(fmaxf(lx.x, hx.x), fmaxf(lx.y, hx.y));
+            hy = make_float2(fmaxf(ly.x, hy.x), fmaxf(ly.y, hy.y));
+            hz = make_float2(fmaxf(lz.x, hz.x), fmaxf(lz.y, hz.y));
+            lx = sx; ly = sy; lz = sz;
+          }
+          x[j][2 * h] = fminf(fminf(fminf(hx.x, hy.x), hz.x), b[j].tU);
+          t[j][2 * h] = fmaxf(fmaxf(fmaxf(lx.x, ly.x), lz.x), 0.0f);
+          x[j][2 * h + 1] = fminf(fminf(fminf(hx.y, hy.y), hz.y), b[j].tU);
+          t[j][2 * h + 1] = fmaxf(fmaxf(fmaxf(lx.y, ly.y), lz.y), 0.0f);
+        }
+      }
     }
-    Q3DR_SLAB2(x, t00, x00, t10, x10)
-    Q3DR_SLAB2(y, t01, x01, t11, x11)
-    Q3DR_SLAB2(z, t02, x02, t12, x12)
-    Q3DR_SLAB2(w, t03, x03, t13, x13)
-#undef Q3DR_SLAB2
-#undef Q3DR_SLAB1
     // exit parameter == 0 for some child of some ray (tU > 0, so x' == 0 says exactly that): the ray's origin lies
     // on a face plane of the box, where the reference's inside / outside distinction decides -- redo this node with
     // the reference's full box test and express its verdict in the same form.  Rare.
     {
-      const float m0 = fminf(fminf(fabsf(x00), fabsf(x01)), fminf(fabsf(x02), fabsf(x03)));
-      const float m1 = fminf(fminf(fabsf(x10), fabsf(x11)), fminf(fabsf(x12), fabsf(x13)));
-      if (__any_sync(Q3DR_FULL_MASK, fminf(m0, m1) == 0.0f)) {
+      float mm = kInf;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        mm = fminf(mm, fminf(fminf(fabsf(x[j][0]), fabsf(x[j][1])), fminf(fabsf(x[j][2]), fabsf(x[j][3]))));
+      }
+      if (__any_sync(Q3DR_FULL_MASK, mm == 0.0f)) {
         const float4 mnx = np[0], mny = np[1], mnz = np[2], mxx = np[3], mxy = np[4], mxz = np[5];
         Ray q;
         float dd;
         q.ox = ox; q.oy = oy; q.oz = oz;
-        q.dx = r0.dx; q.dy = r0.dy; q.dz = r0.dz; q.ix = r0.ix; q.iy = r0.iy; q.iz = r0.iz;
-        x00 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t00) ? b0.tU : -1.0f;
-        x01 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t01) ? b0.tU : -1.0f;
-        x02 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t02) ? b0.tU : -1.0f;
-        x03 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t03) ? b0.tU : -1.0f;
-        q.dx = r1.dx; q.dy = r1.dy; q.dz = r1.dz; q.ix = r1.ix; q.iy = r1.iy; q.iz = r1.iz;
-        x10 = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t10) ? b1.tU : -1.0f;
-        x11 = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t11) ? b1.tU : -1.0f;
-        x12 = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t12) ? b1.tU : -1.0f;
-        x13 = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t13) ? b1.tU : -1.0f;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          q.dx = r[j].dx; q.dy = r[j].dy; q.dz = r[j].dz; q.ix = r[j].ix; q.iy = r[j].iy; q.iz = r[j].iz;
+          x[j][0] = box_test(q, mnx.x, mny.x, mnz.x, mxx.x, mxy.x, mxz.x, dd, t[j][0]) ? b[j].tU : -1.0f;
+          x[j][1] = box_test(q, mnx.y, mny.y, mnz.y, mxx.y, mxy.y, mxz.y, dd, t[j][1]) ? b[j].tU : -1.0f;
+          x[j][2] = box_test(q, mnx.z, mny.z, mnz.z, mxx.z, mxy.z, mxz.z, dd, t[j][2]) ? b[j].tU : -1.0f;
+          x[j][3] = box_test(q, mnx.w, mny.w, mnz.w, mxx.w, mxy.w, mxz.w, dd, t[j][3]) ? b[j].tU : -1.0f;
+        }
       }
     }
 
     // "some ray still needs child c"
-    uint32_t any = (__any_sync(Q3DR_FULL_MASK, (t00 < x00) || (t10 < x10)) ? 1u : 0u) |
-                   (__any_sync(Q3DR_FULL_MASK, (t01 < x01) || (t11 < x11)) ? 2u : 0u) |
-                   (__any_sync(Q3DR_FULL_MASK, (t02 < x02) || (t12 < x12)) ? 4u : 0u) |
-                   (__any_sync(Q3DR_FULL_MASK, (t03 < x03) || (t13 < x13)) ? 8u : 0u);
+    uint32_t any = 0u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      bool need = false;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) need = need || (t[j][c] < x[j][c]);
+      any |= __any_sync(Q3DR_FULL_MASK, need) ? (1u << c) : 0u;
+    }
     const uint32_t leaf_mask = (ch.x >> kLeafMaskShift) & 0xFu;
 
     // leaves first: they tighten the bounds before the inner children are judged.  A ray accepts a leaf on the
@@ -151,35 +197,42 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, f
     const uint32_t todo = any & leaf_mask;
     if (todo) {
       bool tightened = false;
-#define Q3DR_LEAF2(BIT, CH, TA, XA, TB, XB)                                                        \
-      if (todo & (BIT)) {                                                                           \
-        const int32_t li = (int32_t)((CH) & kPayloadMask);                                          \
-        const float d0 = dist_sq_at2(ox, oy, oz, r0, (TA));                                         \
-        const float d1 = dist_sq_at2(ox, oy, oz, r1, (TB));                                         \
-        const bool acc0 = ((XA) > (TA)) && (d0 < b0.dsq || (d0 == b0.dsq && li > b0.leaf));         \
-        const bool acc1 = ((XB) > (TB)) && (d1 < b1.dsq || (d1 == b1.dsq && li > b1.leaf));         \
-        if (__any_sync(Q3DR_FULL_MASK, acc0 || acc1)) {                                             \
-          if (acc0) {                                                                               \
-            b0.dsq = d0; b0.t = (TA); b0.leaf = li; b0.tU = bound_after((TA), A);                   \
-          }                                                                                         \
-          if (acc1) {                                                                               \
-            b1.dsq = d1; b1.t = (TB); b1.leaf = li; b1.tU = bound_after((TB), A);                   \
-          }                                                                                         \
-          tightened = true;                                                                         \
-        }                                                                                           \
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (todo & (1u << c)) {
+          const int32_t li = (int32_t)(chv[c] & kPayloadMask);
+          float d[NR];
+          bool acc[NR];
+          bool some = false;
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            d[j] = dist_sq_at2(ox, oy, oz, r[j], t[j][c]);
+            acc[j] = (x[j][c] > t[j][c]) && (d[j] < b[j].dsq || (d[j] == b[j].dsq && li > b[j].leaf));
+            some = some || acc[j];
+          }
+          if (__any_sync(Q3DR_FULL_MASK, some)) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+              if (acc[j]) {
+                b[j].dsq = d[j]; b[j].t = t[j][c]; b[j].leaf = li; b[j].tU = bound_after(t[j][c], A);
+              }
+            }
+            tightened = true;
+          }
+        }
       }
-      Q3DR_LEAF2(1u, ch.x, t00, x00, t10, x10)
-      Q3DR_LEAF2(2u, ch.y, t01, x01, t11, x11)
-      Q3DR_LEAF2(4u, ch.z, t02, x02, t12, x12)
-      Q3DR_LEAF2(8u, ch.w, t03, x03, t13, x13)
-#undef Q3DR_LEAF2
       if (tightened && (any & ~leaf_mask)) {
-        x00 = fminf(x00, b0.tU); x01 = fminf(x01, b0.tU); x02 = fminf(x02, b0.tU); x03 = fminf(x03, b0.tU);
-        x10 = fminf(x10, b1.tU); x11 = fminf(x11, b1.tU); x12 = fminf(x12, b1.tU); x13 = fminf(x13, b1.tU);
-        any = (__any_sync(Q3DR_FULL_MASK, (t00 < x00) || (t10 < x10)) ? 1u : 0u) |
-              (__any_sync(Q3DR_FULL_MASK, (t01 < x01) || (t11 < x11)) ? 2u : 0u) |
-              (__any_sync(Q3DR_FULL_MASK, (t02 < x02) || (t12 < x12)) ? 4u : 0u) |
-              (__any_sync(Q3DR_FULL_MASK, (t03 < x03) || (t13 < x13)) ? 8u : 0u);
+        any = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          bool need = false;
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            x[j][c] = fminf(x[j][c], b[j].tU);
+            need = need || (t[j][c] < x[j][c]);
+          }
+          any |= __any_sync(Q3DR_FULL_MASK, need) ? (1u << c) : 0u;
+        }
       }
     }
 
@@ -190,17 +243,17 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, f
         // more than one: nearest first; the others go on the stack, farthest first, with every ray's own entry
         // parameter (+inf for rays that do not need the child)
         const uint32_t kNone = 0xFFFFFFFFu;
-#define Q3DR_KEY(C, TA, XA, TB, XB)                                                                       \
-        ((inner & (1u << (C)))                                                                            \
-             ? __reduce_min_sync(Q3DR_FULL_MASK, min(((TA) < (XA)) ? __float_as_uint(TA) : kNone,          \
-                                                    ((TB) < (XB)) ? __float_as_uint(TB) : kNone))          \
-             : kNone)
         uint32_t key[4];
-        key[0] = Q3DR_KEY(0, t00, x00, t10, x10);
-        key[1] = Q3DR_KEY(1, t01, x01, t11, x11);
-        key[2] = Q3DR_KEY(2, t02, x02, t12, x12);
-        key[3] = Q3DR_KEY(3, t03, x03, t13, x13);
-#undef Q3DR_KEY
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          key[c] = kNone;
+          if (inner & (1u << c)) {
+            uint32_t k = kNone;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) k = min(k, (t[j][c] < x[j][c]) ? __float_as_uint(t[j][c]) : kNone);
+            key[c] = __reduce_min_sync(Q3DR_FULL_MASK, k);
+          }
+        }
         while (inner & (inner - 1u)) {
           uint32_t far = 0u, far_key = 0u;  // farthest remaining candidate (ties: higher slot)
 #pragma unroll
@@ -211,10 +264,11 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, f
             }
           }
           inner &= ~(1u << far);
-          const float T0 = pick4f(far, t00, t01, t02, t03), X0 = pick4f(far, x00, x01, x02, x03);
-          const float T1 = pick4f(far, t10, t11, t12, t13), X1 = pick4f(far, x10, x11, x12, x13);
-          stack_t0[sp] = (T0 < X0) ? T0 : kInf;  // tU only shrinks: an entry parameter >= tU now stays >= tU
-          stack_t1[sp] = (T1 < X1) ? T1 : kInf;
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            const float T = pick4f(far, t[j][0], t[j][1], t[j][2], t[j][3]), X = pick4f(far, x[j][0], x[j][1], x[j][2], x[j][3]);
+            stack_t[j][sp] = (T < X) ? T : kInf;  // tU only shrinks: an entry parameter >= tU now stays >= tU
+          }
           stack_n[sp] = pick4(far, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
           ++sp;
         }
@@ -225,9 +279,11 @@ __device__ __forceinline__ void traverse_packet2(float ox, float oy, float oz, f
     bool found = false;
     while (sp > 0) {
       --sp;
-      const float e0 = stack_t0[sp], e1 = stack_t1[sp];
+      bool need = false;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) need = need || (stack_t[j][sp] < b[j].tU);
       const uint32_t n = stack_n[sp];
-      if (__any_sync(Q3DR_FULL_MASK, e0 < b0.tU || e1 < b1.tU)) {
+      if (__any_sync(Q3DR_FULL_MASK, need)) {
         ref = n;
         found = true;
         break;
@@ -273,14 +329,25 @@ __device__ __forceinline__ void copy_dir_from_lane(Dir2& r, const Dir2& src_ray,
   }
 }
 
+// Packet geometry: a tile is TW pixels wide and (32 / TW) * NR pixels tall; lane l carries column l % TW and the NR
+// rows l / TW + (32 / TW) * j, j = 0 .. NR-1.  Within one j the lanes are in row-major pixel order.
+template <int NR, int TW>
+struct PacketShape {
+  static constexpr int kRowsPerSlab = 32 / TW;
+  static constexpr int kTileH = kRowsPerSlab * NR;
+};
+
 // MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_rays_kernel).
-template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const RaycastParams p) {
+// NR rays per lane; resident CTAs per SM chosen so that the register file is used up: 4 x 64 or 2 x 128 registers.
+template <int MODE, int NR, int TW, bool kPacked>
+__global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_kernel(const RaycastParams p) {
   __shared__ uint32_t s_tile[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
   const float kInf = __int_as_float(0x7F800000);
+  constexpr int kRows = PacketShape<NR, TW>::kRowsPerSlab;
+  constexpr int kTileH = PacketShape<NR, TW>::kTileH;
 
   while (true) {
     if (lane == 0) s_tile[warp] = atomicAdd(p.tile_counter, 1u);
@@ -293,13 +360,18 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
     const uint32_t rem = tile - vp * p.tiles_per_vp;
     const uint32_t ty = rem / p.tiles_x;
     const uint32_t tx = rem - ty * p.tiles_x;
-    const uint32_t px = tx * kTile2W + (lane & 7);
-    const uint32_t py0 = ty * kTile2H + (lane >> 3);
-    const uint32_t py1 = py0 + 4u;
-    const bool live0 = (px < p.w) && (py0 < p.h);
-    const bool live1 = (px < p.w) && (py1 < p.h);
-    const uint32_t live_mask = __ballot_sync(Q3DR_FULL_MASK, live0);
-    if (live_mask == 0u) continue;  // live1 implies live0
+    const uint32_t px = tx * TW + (lane % TW);
+    uint32_t py[NR];
+    bool live[NR];
+    bool all_live = true;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      py[j] = ty * kTileH + (lane / TW) + kRows * j;
+      live[j] = (px < p.w) && (py[j] < p.h);
+      all_live = all_live && live[j];
+    }
+    const uint32_t live_mask = __ballot_sync(Q3DR_FULL_MASK, live[0]);
+    if (live_mask == 0u) continue;  // live[j] implies live[0]
 
     float R[12];
     {
@@ -311,47 +383,55 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
     }
     const float ox = R[3], oy = R[7], oz = R[11];
     const float c0 = __fdiv_rn(__fsub_rn((float)(p.x0 + px), p.cx), p.fx);
-    Dir2 r0, r1;
-    const bool unit0 = camera_dir2(R, c0, p.fy, p.cy, p.y0 + py0, r0);
-    const bool unit1 = camera_dir2(R, c0, p.fy, p.cy, p.y0 + py1, r1);
+    Dir2 r[NR];
+    bool unit[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) unit[j] = camera_dir2(R, c0, p.fy, p.cy, p.y0 + py[j], r[j]);
     {
       // a dead ray rides along with a copy of a live one and never accepts anything (dist_sq >= 0 > -1, t >= 0 > -1)
       const int src = __ffs(live_mask) - 1;
-      if (live_mask != Q3DR_FULL_MASK || !__all_sync(Q3DR_FULL_MASK, live1)) {
-        const Dir2 s = r0;
-        copy_dir_from_lane(r0, s, src, !live0);
-        copy_dir_from_lane(r1, s, src, !live1);
+      if (!__all_sync(Q3DR_FULL_MASK, all_live)) {
+        const Dir2 s = r[0];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) copy_dir_from_lane(r[j], s, src, !live[j]);
       }
     }
-    Best2 b0, b1;
-    b0.leaf = b1.leaf = -1;
-    b0.t = b1.t = 0.0f;
-    b0.dsq = live0 ? range_sq : -1.0f;
-    b1.dsq = live1 ? range_sq : -1.0f;
+    Best2 b[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      b[j].leaf = -1;
+      b[j].t = 0.0f;
+      b[j].dsq = live[j] ? range_sq : -1.0f;
+    }
 
-    // preconditions of the fast loops (see bound_after / traverse_packet2); dead rays are copies of live ones
+    // preconditions of the fast loops (see bound_after / traverse_packetN); dead rays are copies of live ones
     const float M = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
-    const bool finite = (fabsf(r0.ix) <= FLT_MAX) && (fabsf(r0.iy) <= FLT_MAX) && (fabsf(r0.iz) <= FLT_MAX) &&
-                        (fabsf(r1.ix) <= FLT_MAX) && (fabsf(r1.iy) <= FLT_MAX) && (fabsf(r1.iz) <= FLT_MAX);
-    const bool tame = finite && (unit0 || !live0) && (unit1 || !live1) && p.bounded_map && (M <= 1e18f) &&
-                      !(p.max_range > 1e18f);
+    bool tame = p.bounded_map && (M <= 1e18f) && !(p.max_range > 1e18f);
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      tame = tame && (fabsf(r[j].ix) <= FLT_MAX) && (fabsf(r[j].iy) <= FLT_MAX) && (fabsf(r[j].iz) <= FLT_MAX) &&
+             (unit[j] || !live[j]);
+    }
     if (__all_sync(Q3DR_FULL_MASK, tame)) {
       const float A = fmaf(M, 1.0f / 1048576.0f, 1.0f / 8192.0f);
       const float u = (p.max_range > 0.0f) ? bound_after(p.max_range, A) : kInf;
-      b0.tU = live0 ? u : -1.0f;
-      b1.tU = live1 ? u : -1.0f;
       // per axis: all rays positive, all negative, or mixed
-      const uint32_t bx = __ballot_sync(Q3DR_FULL_MASK, r0.ix < 0.0f), cx = __ballot_sync(Q3DR_FULL_MASK, r1.ix < 0.0f);
-      const uint32_t by = __ballot_sync(Q3DR_FULL_MASK, r0.iy < 0.0f), cy = __ballot_sync(Q3DR_FULL_MASK, r1.iy < 0.0f);
-      const uint32_t bz = __ballot_sync(Q3DR_FULL_MASK, r0.iz < 0.0f), cz = __ballot_sync(Q3DR_FULL_MASK, r1.iz < 0.0f);
-      const bool ux = ((bx | cx) == 0u) || ((bx & cx) == Q3DR_FULL_MASK);
-      const bool uy = ((by | cy) == 0u) || ((by & cy) == Q3DR_FULL_MASK);
-      const bool uz = ((bz | cz) == 0u) || ((bz & cz) == Q3DR_FULL_MASK);
-      if (ux && uy && uz) {
-        const uint32_t octant = (bx ? 1u : 0u) | (by ? 2u : 0u) | (bz ? 4u : 0u);
-        traverse_packet2<false>(ox, oy, oz, A, r0, r1, b0, b1, p.nodes, octant);
+      bool nxa = false, nya = false, nza = false, pxa = false, pya = false, pza = false;
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        b[j].tU = live[j] ? u : -1.0f;
+        nxa = nxa || (r[j].ix < 0.0f); pxa = pxa || !(r[j].ix < 0.0f);
+        nya = nya || (r[j].iy < 0.0f); pya = pya || !(r[j].iy < 0.0f);
+        nza = nza || (r[j].iz < 0.0f); pza = pza || !(r[j].iz < 0.0f);
+      }
+      const bool anx = __any_sync(Q3DR_FULL_MASK, nxa), apx = __any_sync(Q3DR_FULL_MASK, pxa);
+      const bool any_ = __any_sync(Q3DR_FULL_MASK, nya), apy = __any_sync(Q3DR_FULL_MASK, pya);
+      const bool anz = __any_sync(Q3DR_FULL_MASK, nza), apz = __any_sync(Q3DR_FULL_MASK, pza);
+      if (!(anx && apx) && !(any_ && apy) && !(anz && apz)) {
+        const uint32_t octant = (anx ? 1u : 0u) | (any_ ? 2u : 0u) | (anz ? 4u : 0u);
+        traverse_packetN<NR, false, kPacked>(ox, oy, oz, A, r, b, p.nodes, octant);
       } else {
-        traverse_packet2<true>(ox, oy, oz, A, r0, r1, b0, b1, p.nodes, 0u);
+        traverse_packetN<NR, true, kPacked>(ox, oy, oz, A, r, b, p.nodes, 0u);
       }
     } else {
       // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge
@@ -359,26 +439,25 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
       Ray q;
       PacketHit h;
       q.ox = ox; q.oy = oy; q.oz = oz;
-      q.dx = r0.dx; q.dy = r0.dy; q.dz = r0.dz; q.ix = r0.ix; q.iy = r0.iy; q.iz = r0.iz;
-      h.dsq = b0.dsq; h.t = 0.0f; h.tU = 0.0f; h.leaf = -1;
-      traverse_packet_exact(q, h, p.nodes, p.nodes, 0u);
-      b0.dsq = h.dsq; b0.t = h.t; b0.leaf = h.leaf;
-      q.dx = r1.dx; q.dy = r1.dy; q.dz = r1.dz; q.ix = r1.ix; q.iy = r1.iy; q.iz = r1.iz;
-      h.dsq = b1.dsq; h.t = 0.0f; h.tU = 0.0f; h.leaf = -1;
-      traverse_packet_exact(q, h, p.nodes, p.nodes, 0u);
-      b1.dsq = h.dsq; b1.t = h.t; b1.leaf = h.leaf;
+#pragma unroll 1
+      for (int j = 0; j < NR; ++j) {
+        q.dx = r[j].dx; q.dy = r[j].dy; q.dz = r[j].dz; q.ix = r[j].ix; q.iy = r[j].iy; q.iz = r[j].iz;
+        h.dsq = b[j].dsq; h.t = 0.0f; h.tU = 0.0f; h.leaf = -1;
+        traverse_packet_exact(q, h, p.nodes, p.nodes, 0u);
+        b[j].dsq = h.dsq; b[j].t = h.t; b[j].leaf = h.leaf;
+      }
     }
 
     if (MODE == kModeScore) {
-      // warp-aggregated dedup: within each half of the tile lanes are in row-major pixel order, so the lowest lane
+      // warp-aggregated dedup: within each slab j of the tile lanes are in row-major pixel order, so the lowest lane
       // of each equal-leaf group owns the group's first pixel; only group leaders touch the tables (atomicMin
-      // merges the two halves and the other tiles of the viewpoint).
+      // merges the slabs and the other tiles of the viewpoint).
       uint32_t* fpv = p.first_pix + (size_t)vp * p.leaf_stride;
       uint32_t* bmv = p.bitmap + (size_t)vp * p.word_stride;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int32_t leaf = half ? b1.leaf : b0.leaf;
-        const uint32_t pix = (half ? py1 : py0) * p.w + px;
+      for (int j = 0; j < NR; ++j) {
+        const int32_t leaf = b[j].leaf;
+        const uint32_t pix = py[j] * p.w + px;
         const uint32_t grp = __match_any_sync(Q3DR_FULL_MASK, leaf);
         const bool leader = (leaf >= 0) && ((__ffs(grp) - 1) == lane);
         if (leader) {
@@ -391,22 +470,18 @@ __global__ void __launch_bounds__(kThreadsPerCta, 4) raycast2_kernel(const Rayca
       }
     } else {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const bool live = half ? live1 : live0;
-        if (!live) continue;
-        const Best2& b = half ? b1 : b0;
-        const Dir2& r = half ? r1 : r0;
-        const uint32_t py = half ? py1 : py0;
-        const bool hit = b.leaf >= 0;
+      for (int j = 0; j < NR; ++j) {
+        if (!live[j]) continue;
+        const bool hit = b[j].leaf >= 0;
         // intersection = origin + direction * t  (geometry.h:345-348); t = 0 when the origin is inside
-        const float hx = hit ? __fadd_rn(ox, __fmul_rn(r.dx, b.t)) : 0.0f;
-        const float hy = hit ? __fadd_rn(oy, __fmul_rn(r.dy, b.t)) : 0.0f;
-        const float hz = hit ? __fadd_rn(oz, __fmul_rn(r.dz, b.t)) : 0.0f;
-        const uint32_t depth = hit ? (uint32_t)__ldg(p.leaf_depth + b.leaf) : 0u;
-        const size_t oi = (size_t)vp * p.w * p.h + (size_t)py * p.w + px;
+        const float hx = hit ? __fadd_rn(ox, __fmul_rn(r[j].dx, b[j].t)) : 0.0f;
+        const float hy = hit ? __fadd_rn(oy, __fmul_rn(r[j].dy, b[j].t)) : 0.0f;
+        const float hz = hit ? __fadd_rn(oz, __fmul_rn(r[j].dz, b[j].t)) : 0.0f;
+        const uint32_t depth = hit ? (uint32_t)__ldg(p.leaf_depth + b[j].leaf) : 0u;
+        const size_t oi = (size_t)vp * p.w * p.h + (size_t)py[j] * p.w + px;
         float4* dst = reinterpret_cast<float4*>(p.pixels + oi);
-        dst[0] = make_float4(hx, hy, hz, __int_as_float(b.leaf));
-        dst[1] = make_float4(__uint_as_float(depth), hit ? b.dsq : 0.0f, (float)(p.x0 + px), (float)(p.y0 + py));
+        dst[0] = make_float4(hx, hy, hz, __int_as_float(b[j].leaf));
+        dst[1] = make_float4(__uint_as_float(depth), hit ? b[j].dsq : 0.0f, (float)(p.x0 + px), (float)(p.y0 + py[j]));
       }
     }
   }

