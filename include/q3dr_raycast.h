@@ -34,6 +34,8 @@
  *        ViewpointOffscreenRenderer::uploadPoissonMesh, drawPoissonMeshNormals, computePoissonMeshNormalVector
  *        viewpoint_planner/src/planner/viewpoint_offscreen_renderer.cpp:138-200,276-293,361-397,499-527 ;
  *        viewpoint_planner/src/shaders/triangles_normals.{v,f}.glsl
+ *   q3dr_map_downweight_real_viewpoints
+ *        ViewpointPlannerData::updateWeightsWithRealViewpoints        viewpoint_planner_data.cpp:498-571
  *   q3dr_exchange_* / q3dr_multi_enable_gather
  *        no counterpart (the reference is single-GPU, viewpoint_planner_data.cpp:328-335): the gather of the sharded
  *        candidate set, SURVEY.md section 8e
@@ -380,6 +382,26 @@ int q3dr_score_viewpoints_normal_images(q3dr_map* map, const uint32_t* normal_im
                                         uint32_t image_width, uint32_t image_height, uint32_t x0, uint32_t x1,
                                         uint32_t y0, uint32_t y1, const float* Rt, size_t n,
                                         const q3dr_score_opts* opts, q3dr_result* result);
+
+/* ---- real-image down-weighting ----
+ *
+ * ViewpointPlannerData::updateWeightsWithRealViewpoints (viewpoint_planner_data.cpp:498-571) for n real images that
+ * share one depth camera (K, width x height = the depth map's size; group images by camera): every pixel is cast
+ * (remove_duplicates = false, viewpoint_raycast.cpp:166-219), and every hit pixel whose depth-map value is <= 0 or
+ * infinite lowers the weight of the voxel it hit, in scan order, image after image:
+ *     information = computeViewpointObservationScore(viewpoint, voxel, pixel)      (with the voxel's CURRENT weight)
+ *     weight      = max(0, weight - invalid_pixel_observation_factor * information)
+ * opts: ViewpointScore options + ranges (raycast_min_range is ignored like everywhere, Q1; the reference's default
+ * real_observed_voxels_raycast_max_range = FLT_MAX means unlimited, and so does any value >= 1e18 here).
+ * Normals: NodeObject::normal (mesh == NULL && normal_images == NULL: enable_opengl = false), the mesh at the pixel
+ * itself (mesh + ropts), or the caller's normal images (n x height x width ARGB32).  depth_maps: n x height x width
+ * floats, HOST.  The map's weights are updated in place (device and host copy); weights_out (nullable, n_leaves)
+ * receives them, n_updates (nullable) the number of (pixel, voxel) updates applied. */
+int q3dr_map_downweight_real_viewpoints(q3dr_map* map, const float K[4], uint32_t width, uint32_t height,
+                                        const float* Rt, const float* depth_maps, size_t n,
+                                        const q3dr_score_opts* opts, float invalid_pixel_observation_factor,
+                                        const q3dr_mesh* mesh, const q3dr_render_opts* ropts,
+                                        const uint32_t* normal_images, float* weights_out, uint64_t* n_updates);
 
 /* ---- one process, several GPUs: the map replicated in every GPU's HBM, the viewpoints of a
  * call sharded in contiguous slices, one host thread per GPU, results left per GPU (no merge copy).  For one process

@@ -106,6 +106,9 @@ def lib():
         C.c_void_p, fp, fp, fp, C.c_uint32, C.c_uint32, fp, C.c_size_t, C.POINTER(ScoreOpts), C.c_int, u32p, u32p, fp,
         C.POINTER(C.c_uint64),
     ]
+    L.orc_downweight_real_viewpoint.restype = C.c_uint64
+    L.orc_downweight_real_viewpoint.argtypes = [C.c_void_p, fp, fp, u32p, fp, C.c_uint32, C.c_uint32, fp, fp,
+                                                C.POINTER(ScoreOpts), C.c_float]
     L.orc_decode_normal.argtypes = [C.c_uint32, fp]
     L.orc_mesh_face_normals.argtypes = [fp, C.c_size_t, fp]
     L.orc_mesh_render_normals.argtypes = [fp, fp, C.c_size_t, fp, C.c_uint32, C.c_uint32, fp, C.c_float, C.c_float,
@@ -310,6 +313,18 @@ class OracleTree:
         assert k != C.c_size_t(-1).value
         return dict(leaf=leaf[:k].copy(), info=info[:k].copy(), pixel=pix[:k].copy(), dsq=dsq[:k].copy(),
                     hit_count=int(hc.value), total=float(tot.value))
+
+    def downweight_real_viewpoint(self, weights, normals, K, width, height, Rt, depth_map, factor: float,
+                                  opts: Optional[ScoreOpts] = None, normal_image=None):
+        """updateWeightsWithRealViewpoints for one image: returns (new weights, number of updates)."""
+        opts = opts or default_opts()
+        w = _f32(weights, (self.n,)).copy()
+        nr = _f32(normals, (self.n, 3))
+        d = _f32(depth_map, (height, width))
+        img = None if normal_image is None else np.ascontiguousarray(normal_image, dtype=np.uint32).reshape(height, width)
+        k = lib().orc_downweight_real_viewpoint(self._h, _f(w), _f(nr), None if img is None else _u(img), _f(_f32(K, (4,))),
+                                                width, height, _f(_f32(Rt).reshape(12)), _f(d), C.byref(opts), float(factor))
+        return w, int(k)
 
     def score_batch(self, weights, normals, K, width, height, Rt, opts: Optional[ScoreOpts] = None, threads: int = 1):
         opts = opts or default_opts()

@@ -794,6 +794,57 @@ size_t orc_score_viewpoint_image_normals(const orc_tree* t, const float* weights
   return n_out;
 }
 
+// ViewpointPlannerData::updateWeightsWithRealViewpoints for ONE real image (viewpoint_planner_data.cpp:498-571): every
+// pixel of the depth camera is cast, remove_duplicates = false, misses dropped (viewpoint_raycast.cpp:166-219; the
+// reference's removeInvalidRaycastHitVoxels is buggy, :287-303 -- the intended compaction is restated); then, in scan
+// order, every hit pixel whose depth-map value is <= 0 or infinite lowers the weight of the voxel it hit:
+//   information = computeViewpointObservationScore(viewpoint, voxel, pixel)   = (res * inc) * CURRENT weight
+//   weight      = max(0, weight - invalid_pixel_observation_factor * information)
+// weights (n_leaves) are updated in place; min_range is accepted and ignored (Q1); max_range >= FLT_MAX-ish means
+// unlimited like the reference's default.  normal_image (nullable): enable_opengl = true, the normal of the pixel itself
+// (static_cast<size_t>(image_coordinates), :535-538); otherwise the voxel normals.  Returns the number of updates.
+uint64_t orc_downweight_real_viewpoint(const orc_tree* t, float* weights, const float* normals,
+                                       const uint32_t* normal_image, const float K[4], uint32_t width, uint32_t height,
+                                       const float Rt[12], const float* depth_map, const orc_score_opts* opts,
+                                       float invalid_pixel_observation_factor) {
+  const Derived dv = derive(opts);
+  const float cam[3] = {Rt[3], Rt[7], Rt[11]};
+  uint64_t visits = 0, updates = 0;
+  // pass 1: the raycast results vector (all pixels, scan order, hits only)
+  struct PixelHit {
+    int32_t leaf;
+    uint32_t x, y;
+  };
+  std::vector<PixelHit> results;
+  for (uint32_t y = 0; y < height; ++y) {
+    for (uint32_t x = 0; x < width; ++x) {
+      Ray ray;
+      cameraRay(K, Rt, x, y, &ray);
+      Hit h;
+      if (treeIntersects(t, ray, opts->raycast_min_range, opts->raycast_max_range, &h, &visits)) {
+        results.push_back(PixelHit{t->nodes[h.node].leaf, x, y});
+      }
+    }
+  }
+  // pass 2: viewpoint_planner_data.cpp:551-568
+  for (const PixelHit& ir : results) {
+    const float depth = depth_map[(size_t)ir.y * width + ir.x];
+    if (depth <= 0 || std::isinf(depth)) {
+      float nrm_img[3];
+      const float* nrm = normals + 3 * (size_t)ir.leaf;
+      if (normal_image) {
+        decodeNormal(normal_image[(size_t)ir.y * width + ir.x], nrm_img);
+        nrm = nrm_img;
+      }
+      const float information = voxelInformation(t->leaf_boxes[ir.leaf], weights[ir.leaf], nrm, cam, K[0], width, opts, dv);
+      const float new_weight = std::max<float>(0, weights[ir.leaf] - invalid_pixel_observation_factor * information);
+      weights[ir.leaf] = new_weight;
+      ++updates;
+    }
+  }
+  return updates;
+}
+
 // order-independent 64-bit checksum of a voxel set: sum over the entries of splitmix64(leaf << 32 | pixel)
 static inline uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;

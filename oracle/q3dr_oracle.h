@@ -214,6 +214,14 @@ size_t orc_score_viewpoint_image_normals(const orc_tree* t, const float* weights
 
 /* orc_score_batch plus, per viewpoint, an order-independent checksum of its voxel set:
  * sum over the kept entries of splitmix64((uint64)leaf << 32 | first_pixel)  (mod 2^64). */
+/* updateWeightsWithRealViewpoints for one real image (viewpoint_planner_data.cpp:498-571): weights updated in place,
+ * normal_image nullable (enable_opengl = true: ARGB32 normal image of the pose, height x width).  Returns the number of
+ * weight updates (hit pixels with an invalid depth). */
+uint64_t orc_downweight_real_viewpoint(const orc_tree* t, float* weights, const float* normals,
+                                       const uint32_t* normal_image, const float K[4], uint32_t width, uint32_t height,
+                                       const float Rt[12], const float* depth_map, const orc_score_opts* opts,
+                                       float invalid_pixel_observation_factor);
+
 uint64_t orc_score_batch_checksum(const orc_tree* t, const float* weights, const float* normals,
                                   const float K[4], uint32_t width, uint32_t height,
                                   const float* Rt, size_t n_vp, const orc_score_opts* opts, int threads,

@@ -943,6 +943,29 @@ int q3dr_map_destroy(q3dr_map* m) {
   return Q3DR_OK;
 }
 
+}  // extern "C"
+
+// raycast2_kernel<kModePixels> of one viewpoint whose pose is already in device memory: per-pixel records into
+// m->d_pixels, on `s`, no synchronisation (q3dr_queries.cu: real-image down-weighting)
+int q3dr_detail::raycast_window_device(q3dr_map* m, const float K[4], const float* d_rt, uint32_t x0, uint32_t x1, uint32_t y0,
+                                       uint32_t y1, float max_range, cudaStream_t s) {
+  q3dr::RaycastParams rp;
+  fill_raycast_params(m, K, x0, x1, y0, y1, max_range, &rp);
+  const size_t npix = (size_t)rp.w * rp.h;
+  Q3DR_TRY(m->d_pixels.ensure(npix));
+  Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), s));
+  rp.rt = d_rt;
+  rp.total_tiles = rp.tiles_per_vp;
+  rp.pixels = m->d_pixels.p;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels],
+                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
+  Q3DR_CUDA(cudaGetLastError());
+  return Q3DR_OK;
+}
+
+extern "C" {
+
 int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint32_t x0, uint32_t x1, uint32_t y0,
                         uint32_t y1, float /*min_range*/, float max_range, q3dr_pixel_hit* out) {
   Q3DR_TRY(check_map(m));

@@ -282,6 +282,8 @@ struct NormalSource {
 
 namespace q3dr_detail {
 int check_map(const q3dr_map* m);
+int raycast_window_device(q3dr_map* m, const float K[4], const float* d_rt, uint32_t x0, uint32_t x1, uint32_t y0,
+                          uint32_t y1, float max_range, cudaStream_t s);
 // q3dr_exchange.cu: pushes entries [first_entry, first_entry + n_entries) of the chunk just packed (ready when `ready`
 // has fired) into this rank's slot on every peer; called by the scoring call for each finished chunk
 int exchange_push_chunk(q3dr_exchange* ex, cudaEvent_t ready, const int32_t* d_leaf, const float* d_info,

@@ -7,6 +7,9 @@
 #include "octree_kernels.cuh"
 #include "score_kernels.cuh"  // kLeafRecStride, kMaxChunkViewpoints, csr_offsets_kernel
 
+#include "downweight_kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
@@ -410,6 +413,119 @@ int q3dr_map_update_weights_from_grid(q3dr_map* m, const float grid_origin[3], f
   Q3DR_CUDA(cudaMemcpyAsync(m->h_weight.data(), d_w.p, m->n * sizeof(float), cudaMemcpyDeviceToHost, s));
   Q3DR_CUDA(cudaStreamSynchronize(s));
   if (weights_out) std::memcpy(weights_out, m->h_weight.data(), m->n * sizeof(float));
+  return Q3DR_OK;
+}
+
+// ---- real-image down-weighting (row N4) ----
+
+int q3dr_map_downweight_real_viewpoints(q3dr_map* m, const float K[4], uint32_t width, uint32_t height, const float* Rt,
+                                        const float* depth_maps, size_t n, const q3dr_score_opts* opts,
+                                        float invalid_pixel_observation_factor, const q3dr_mesh* mesh,
+                                        const q3dr_render_opts* ropts, const uint32_t* normal_images, float* weights_out,
+                                        uint64_t* n_updates) {
+  Q3DR_TRY(check_map(m));
+  if (!K || !opts || (n && (!Rt || !depth_maps))) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  if (width == 0 || height == 0 || (uint64_t)width * height >= 0xFFFFFFFFull) return fail(Q3DR_ERR_INVALID_ARG, "bad image size");
+  if (mesh && normal_images) return fail(Q3DR_ERR_INVALID_ARG, "give a mesh or normal images, not both");
+  if (mesh && (!ropts || !mesh->d_tris.p || mesh->device != m->device)) {
+    return fail(Q3DR_ERR_INVALID_ARG, "mesh without render options, or on another device than the map");
+  }
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = m->own_stream;
+  const uint32_t n_pix = width * height;
+  // the reference's default range is numeric_limits<float>::max(): the bound max_range^2 overflows to +inf, i.e. unlimited
+  const float max_range = (opts->raycast_max_range >= 1e18f) ? -1.0f : opts->raycast_max_range;
+  DevBuf<float> d_depth, d_rt, d_w;
+  DevBuf<uint32_t> d_img;
+  DevBuf<uint64_t> d_keys, d_sorted;
+  DevBuf<uint8_t> d_tmp;
+  DevBuf<unsigned long long> d_count;
+  struct Cleanup {
+    DevBuf<float>&a, &b, &c;
+    DevBuf<uint32_t>& d;
+    DevBuf<uint64_t>&e, &f;
+    DevBuf<uint8_t>& g;
+    DevBuf<unsigned long long>& h;
+    ~Cleanup() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); h.release(); }
+  } cleanup{d_depth, d_rt, d_w, d_img, d_keys, d_sorted, d_tmp, d_count};
+  Q3DR_TRY(d_depth.ensure(n_pix));
+  Q3DR_TRY(d_rt.ensure(12));
+  Q3DR_TRY(d_keys.ensure(n_pix));
+  Q3DR_TRY(d_sorted.ensure(n_pix));
+  Q3DR_TRY(d_count.ensure(1));
+  if (normal_images) Q3DR_TRY(d_img.ensure(n_pix));
+  size_t tmp_bytes = 0;
+  Q3DR_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys.p, d_sorted.p, (int)n_pix, 0, 64, s));
+  Q3DR_TRY(d_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
+  Q3DR_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), s));
+
+  const Derived dv = derive(*opts);
+  q3dr::ScoreParams2 sp;
+  std::memset(&sp, 0, sizeof(sp));
+  sp.fx = K[0];
+  sp.fy = K[1];
+  sp.cx = K[2];
+  sp.cy = K[3];
+  sp.image_width_f = (float)width;
+  sp.w = width;
+  sp.thr = dv.thr;
+  sp.kf = dv.kf;
+  sp.a_thr = dv.a_thr;
+  sp.ka = dv.ka;
+  sp.ignore_sign = opts->incidence_ignore_dot_product_sign;
+  sp.img_w = width;
+  sp.img_h = height;
+  q3dr::MeshDev mesh_dev{};
+  q3dr::RenderOptsDev ropts_dev{};
+  if (mesh) {
+    mesh_dev.nodes = mesh->d_nodes.p;
+    mesh_dev.tris = mesh->d_tris.p;
+    mesh_dev.normals = mesh->d_normals.p;
+    mesh_dev.n_tris = (uint32_t)mesh->n_tris;
+    mesh_dev.root_ref = mesh->root_ref;
+    mesh_dev.pad = mesh->pad;
+    ropts_dev.near_plane = ropts->near_plane;
+    ropts_dev.far_plane = ropts->far_plane;
+    ropts_dev.clear_argb = ropts->clear_argb;
+  }
+  q3dr::DownweightParams dp;
+  dp.leaf_rec = m->d_leaf_rec.p;
+  dp.rt = d_rt.p;
+  dp.normal_image = d_img.p;
+  dp.n_keys = n_pix;
+  dp.factor = invalid_pixel_observation_factor;
+  const unsigned blocks = (n_pix + 255) / 256;
+  for (size_t v = 0; v < n; ++v) {
+    // images follow each other (weights carry over); everything of one image is stream ordered, no host sync
+    Q3DR_CUDA(cudaMemcpyAsync(d_rt.p, Rt + 12 * v, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    Q3DR_CUDA(cudaMemcpyAsync(d_depth.p, depth_maps + v * (size_t)n_pix, n_pix * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (normal_images) {
+      Q3DR_CUDA(cudaMemcpyAsync(d_img.p, normal_images + v * (size_t)n_pix, n_pix * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    }
+    Q3DR_TRY(q3dr_detail::raycast_window_device(m, K, d_rt.p, 0, width, 0, height, max_range, s));
+    q3dr::dw_keys_kernel<<<blocks, 256, 0, s>>>(m->d_pixels.p, d_depth.p, n_pix, d_keys.p);
+    Q3DR_CUDA(cudaGetLastError());
+    Q3DR_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp.p, tmp_bytes, d_keys.p, d_sorted.p, (int)n_pix, 0, 64, s));
+    if (mesh) {
+      q3dr::dw_apply_kernel<q3dr::kNormalCode><<<blocks, 256, 0, s>>>(sp, dp, d_sorted.p, mesh_dev, ropts_dev, d_count.p);
+    } else if (normal_images) {
+      q3dr::dw_apply_kernel<q3dr::kNormalImage><<<blocks, 256, 0, s>>>(sp, dp, d_sorted.p, mesh_dev, ropts_dev, d_count.p);
+    } else {
+      q3dr::dw_apply_kernel<q3dr::kNormalVoxel><<<blocks, 256, 0, s>>>(sp, dp, d_sorted.p, mesh_dev, ropts_dev, d_count.p);
+    }
+    Q3DR_CUDA(cudaGetLastError());
+    // (pageable host sources: the copies above have been staged when cudaMemcpyAsync returns)
+  }
+  // the host copy of the weights follows (q3dr_map_reset re-uploads from it)
+  Q3DR_TRY(d_w.ensure(m->n));
+  q3dr::gather_weights_kernel<<<(unsigned)((m->n + 255) / 256), 256, 0, s>>>(m->d_leaf_rec.p, (uint32_t)m->n, d_w.p);
+  Q3DR_CUDA(cudaGetLastError());
+  Q3DR_CUDA(cudaMemcpyAsync(m->h_weight.data(), d_w.p, m->n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  unsigned long long count = 0;
+  Q3DR_CUDA(cudaMemcpyAsync(&count, d_count.p, sizeof(count), cudaMemcpyDeviceToHost, s));
+  Q3DR_CUDA(cudaStreamSynchronize(s));
+  if (weights_out) std::memcpy(weights_out, m->h_weight.data(), m->n * sizeof(float));
+  if (n_updates) *n_updates = (uint64_t)count;
   return Q3DR_OK;
 }
 

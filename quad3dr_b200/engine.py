@@ -186,6 +186,8 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_map_downweight_real_viewpoints.argtypes = [vp, fp, C.c_uint32, C.c_uint32, fp, fp, C.c_size_t, C.POINTER(ScoreOpts),
+                                                      C.c_float, vp, C.POINTER(RenderOpts), u32p, fp, C.POINTER(C.c_uint64)]
     L.q3dr_exchange_layout_of.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(ExchangeLayout)]
     L.q3dr_exchange_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.q3dr_exchange_destroy.argtypes = [vp]
@@ -581,6 +583,27 @@ class OccupancyMap:
             self._h, _fp(_f32(grid_origin, (3,))), float(grid_increment), dim.ctypes.data_as(C.POINTER(C.c_int32)), _fp(gw),
             float(lam), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(out)))
         return out
+
+    def downweight_real_viewpoints(self, K, width: int, height: int, Rt, depth_maps, factor: float,
+                                   opts: Optional[ScoreOpts] = None, mesh: Optional["NormalMesh"] = None,
+                                   ropts: Optional["RenderOpts"] = None, normal_images=None):
+        """ViewpointPlannerData::updateWeightsWithRealViewpoints for images sharing one depth camera: the map's weights
+        are lowered in place; returns (weights, number of updates)."""
+        K = _f32(K, (4,))
+        Rt = _f32(Rt).reshape(-1, 12)
+        n = Rt.shape[0]
+        d = _f32(depth_maps, (n, height, width))
+        opts = opts or default_opts()
+        img = None if normal_images is None else np.ascontiguousarray(normal_images, dtype=np.uint32).reshape(n, height, width)
+        if mesh is not None and ropts is None:
+            ropts = default_render_opts()
+        out = np.empty(self.n, dtype=np.float32)
+        cnt = C.c_uint64(0)
+        _check(load_library().q3dr_map_downweight_real_viewpoints(
+            self._h, _fp(K), width, height, _fp(Rt), _fp(d), n, C.byref(opts), float(factor),
+            mesh._h if mesh is not None else None, C.byref(ropts) if ropts is not None else None,
+            img.ctypes.data_as(C.POINTER(C.c_uint32)) if img is not None else None, _fp(out), C.byref(cnt)))
+        return out, int(cnt.value)
 
     def overlap_boxes(self, boxes) -> Tuple[np.ndarray, np.ndarray]:
         """bvh::Tree::intersects(bbox) for many boxes: CSR (offsets uint64 (n+1), leaf int32) of the overlapping
