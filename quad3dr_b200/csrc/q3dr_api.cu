@@ -39,6 +39,9 @@ void release_device(q3dr_map* m) {
   m->max_blocks = 0;
   m->d_depth.release();
   m->d_counter.release();
+  m->d_planes.release();
+  m->d_vp_flags.release();
+  m->d_vp_list.release();
   m->d_first_pix.release();
   m->d_bitmap.release();
   m->d_kept.release();
@@ -88,10 +91,13 @@ typedef void (*RaycastKernel)(const q3dr::RaycastParams);
 struct RayVariant {
   const char* name;
   int nr, tw;
-  RaycastKernel kernel[2];  // [MODE]
+  RaycastKernel kernel[2];   // [MODE], with the on-face check (any viewpoint)
+  RaycastKernel score_fast;  // kModeScore without the check: viewpoints whose centre lies on no box plane
 };
-#define Q3DR_VARIANT(NAME, NR, TW, PK)                                                   \
-  {NAME, NR, TW, {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK>}}
+#define Q3DR_VARIANT(NAME, NR, TW, PK)                                                                          \
+  {NAME, NR, TW,                                                                                                  \
+   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true>}, \
+   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false>}
 const RayVariant kRayVariants[] = {
     Q3DR_VARIANT("2x8x8", 2, 8, false),     // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 64 registers
     Q3DR_VARIANT("2x8x8p", 2, 8, true),     // 1: ... with FADD2 / FMUL2
@@ -120,6 +126,12 @@ int configure_kernel2(q3dr_map* m) {
     if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
     m->grid2_ctas[mode] = per_sm * m->sm_count;
   }
+  {
+    int per_sm = 0;
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.score_fast, q3dr::kThreadsPerCta, 0));
+    if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
+    m->grid2_ctas[q3dr::kModeScore] = std::min(m->grid2_ctas[q3dr::kModeScore], per_sm * m->sm_count);
+  }
   return Q3DR_OK;
 }
 
@@ -143,6 +155,23 @@ int upload_map(q3dr_map* m) {
   }
   Q3DR_TRY(m->d_depth.ensure(n));
   Q3DR_CUDA(cudaMemcpy(m->d_depth.p, m->h_depth.data(), n, cudaMemcpyHostToDevice));
+  {
+    // sorted distinct plane coordinates per axis (flag_viewpoints_kernel)
+    std::vector<float> all;
+    for (int a = 0; a < 3; ++a) {
+      std::vector<float> v(2 * n);
+      for (size_t k = 0; k < n; ++k) {
+        v[2 * k] = m->h_boxes[6 * k + a];
+        v[2 * k + 1] = m->h_boxes[6 * k + 3 + a];
+      }
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      m->n_planes[a] = (uint32_t)v.size();
+      all.insert(all.end(), v.begin(), v.end());
+    }
+    Q3DR_TRY(m->d_planes.ensure(std::max<size_t>(all.size(), 1)));
+    Q3DR_CUDA(cudaMemcpy(m->d_planes.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   Q3DR_TRY(m->d_counter.ensure(4));
   Q3DR_CUDA(cudaMemset(m->d_counter.p, 0, 4 * sizeof(uint32_t)));
   Q3DR_TRY(m->h_scalar.ensure(8));
@@ -171,6 +200,8 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
     m->fp_epoch = 0;
     m->fp_tagged_garbage = false;
     Q3DR_TRY(m->d_kept.ensure(slots));
+    Q3DR_TRY(m->d_vp_flags.ensure(slots));
+    Q3DR_TRY(m->d_vp_list.ensure(slots));
     m->slots = slots;
     m->leaf_stride = leaf_stride;
     m->word_stride = word_stride;
@@ -420,15 +451,25 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     }
     rp.rt = d_Rt + 12 * v0;
     rp.total_tiles = (uint32_t)(nb * rp.tiles_per_vp);
-    Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(uint32_t), stream));
+    rp.vp_flags = m->d_vp_flags.p;
+    rp.vp_list = m->d_vp_list.p;
+    rp.n_flagged = m->d_counter.p + 2;
+    Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, 3 * sizeof(uint32_t), stream));
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 0], stream));
     m->scratch_dirty = true;  // cleared when this chunk's scoring kernels have been issued
+    // viewpoints whose centre lies on a box plane go to the checking instantiation, everybody else to the fast one
+    q3dr::flag_viewpoints_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(
+        rp.rt, (uint32_t)nb, m->d_planes.p, m->d_planes.p + m->n_planes[0], m->d_planes.p + m->n_planes[0] + m->n_planes[1],
+        m->n_planes[0], m->n_planes[1], m->n_planes[2], m->d_vp_flags.p, m->d_vp_list.p, m->d_counter.p + 2);
+    Q3DR_CUDA(cudaGetLastError());
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore],
                                             ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-    variant_of(m).kernel[q3dr::kModeScore]<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
+    variant_of(m).score_fast<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
+    Q3DR_CUDA(cudaGetLastError());
+    variant_of(m).kernel[q3dr::kModeScore]<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);  // exits at once if none is flagged
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
-    st.kernel_launches += 1;
+    st.kernel_launches += 3;
     return Q3DR_OK;
   };
 

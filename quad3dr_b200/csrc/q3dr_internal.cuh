@@ -163,7 +163,11 @@ struct q3dr_map {
   DevBuf<float4> d_nodes;
   DevBuf<float4> d_leaf_rec;  // [n][4]: {min xyz, weight}, {max xyz, 0}, {normal xyz, 0}, pad (64-byte records)
   DevBuf<uint8_t> d_depth;
-  DevBuf<uint32_t> d_counter;
+  DevBuf<uint32_t> d_counter;           // [0] tiles of the main launch, [1] tiles of the checking launch, [2] flagged viewpoints
+  DevBuf<float> d_planes;               // sorted distinct box plane coordinates, x | y | z
+  uint32_t n_planes[3] = {0, 0, 0};
+  DevBuf<uint8_t> d_vp_flags;           // [slots] camera centre on a box plane (flag_viewpoints_kernel)
+  DevBuf<uint32_t> d_vp_list;           // [slots] the flagged viewpoints of the chunk
   // device: per-chunk scratch
   DevBuf<uint32_t> d_first_pix, d_bitmap, d_kept;
   DevBuf<uint32_t> d_seg_u32;  // [2][slots][n_segs]: hits, off

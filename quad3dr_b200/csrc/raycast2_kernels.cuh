@@ -73,7 +73,11 @@ __device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 
 // The reference's clamp of tmax at FLT_MAX is omitted: it can only bind when all three exit parameters overflow,
 // which a normalised direction (|inv| <= 2 on some axis) cannot produce over a map bounded by 1e18 -- a packet
 // precondition as well.  The exit parameter is kept as x' = min(exit, tU): "hit and still needed" is then entry < x'.
-template <int NR, bool kMixed, bool kPacked>
+//
+// kOnFace       : the packet's origin may lie exactly on a face plane of a box.  Only then can an exit parameter be
+//                 exactly 0 (below), where the reference's inside / outside distinction decides; such nodes are redone
+//                 with the literal box test.  flag_viewpoints_kernel sorts the viewpoints into the two instantiations.
+template <int NR, bool kMixed, bool kPacked, bool kOnFace>
 __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, float A, const Dir2 (&r)[NR], Best2 (&b)[NR],
                                                  const float4* __restrict__ nodes, uint32_t octant) {
   float stack_t[NR][kStackEntries];
@@ -157,8 +161,10 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
     }
     // exit parameter == 0 for some child of some ray (tU > 0, so x' == 0 says exactly that): the ray's origin lies
     // on a face plane of the box, where the reference's inside / outside distinction decides -- redo this node with
-    // the reference's full box test and express its verdict in the same form.  Rare.
-    {
+    // the reference's full box test and express its verdict in the same form.  An exit parameter is a product
+    // (plane - origin) * inv with |inv| >= 1 - 2^-22 (normalised direction), so it is 0 only if plane == origin: a
+    // viewpoint whose centre shares no coordinate with any box plane of the map never gets here (kOnFace = false).
+    if (kOnFace) {
       float mm = kInf;
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
@@ -339,7 +345,8 @@ struct PacketShape {
 
 // MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_rays_kernel).
 // NR rays per lane; resident CTAs per SM chosen so that the register file is used up: 4 x 64 or 2 x 128 registers.
-template <int MODE, int NR, int TW, bool kPacked>
+// kOnFace = false: viewpoints flagged in p.vp_flags are skipped (the kOnFace = true launch casts them, from p.vp_list).
+template <int MODE, int NR, int TW, bool kPacked, bool kOnFace>
 __global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_kernel(const RaycastParams p) {
   __shared__ uint32_t s_tile[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
@@ -349,15 +356,22 @@ __global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_ke
   constexpr int kRows = PacketShape<NR, TW>::kRowsPerSlab;
   constexpr int kTileH = PacketShape<NR, TW>::kTileH;
 
+  // the checking instantiation of a scoring launch works through the flagged viewpoints only (usually none)
+  const bool listed = kOnFace && (p.vp_list != nullptr);
+  const uint32_t total_tiles = listed ? __ldg(p.n_flagged) * p.tiles_per_vp : p.total_tiles;
+  uint32_t* counter = p.tile_counter + (listed ? 1 : 0);
+
   while (true) {
-    if (lane == 0) s_tile[warp] = atomicAdd(p.tile_counter, 1u);
+    if (lane == 0) s_tile[warp] = atomicAdd(counter, 1u);
     __syncwarp();
     const uint32_t tile = s_tile[warp];
     __syncwarp();
-    if (tile >= p.total_tiles) break;
+    if (tile >= total_tiles) break;
 
-    const uint32_t vp = tile / p.tiles_per_vp;
-    const uint32_t rem = tile - vp * p.tiles_per_vp;
+    const uint32_t slot = tile / p.tiles_per_vp;
+    const uint32_t vp = listed ? __ldg(p.vp_list + slot) : slot;
+    if (!kOnFace && p.vp_flags != nullptr && __ldg(p.vp_flags + vp) != 0) continue;
+    const uint32_t rem = tile - slot * p.tiles_per_vp;
     const uint32_t ty = rem / p.tiles_x;
     const uint32_t tx = rem - ty * p.tiles_x;
     const uint32_t px = tx * TW + (lane % TW);
@@ -429,9 +443,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_ke
       const bool anz = __any_sync(Q3DR_FULL_MASK, nza), apz = __any_sync(Q3DR_FULL_MASK, pza);
       if (!(anx && apx) && !(any_ && apy) && !(anz && apz)) {
         const uint32_t octant = (anx ? 1u : 0u) | (any_ ? 2u : 0u) | (anz ? 4u : 0u);
-        traverse_packetN<NR, false, kPacked>(ox, oy, oz, A, r, b, p.nodes, octant);
+        traverse_packetN<NR, false, kPacked, kOnFace>(ox, oy, oz, A, r, b, p.nodes, octant);
       } else {
-        traverse_packetN<NR, true, kPacked>(ox, oy, oz, A, r, b, p.nodes, 0u);
+        traverse_packetN<NR, true, kPacked, kOnFace>(ox, oy, oz, A, r, b, p.nodes, 0u);
       }
     } else {
       // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge
@@ -485,6 +499,36 @@ __global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_ke
       }
     }
   }
+}
+
+// Per viewpoint of a chunk: does the camera centre share a coordinate with a face plane of some box of the map?
+// planes[a] = the sorted distinct min / max coordinates of all leaf boxes on axis a (inner boxes are unions of leaf
+// boxes, so they add no planes).  Flagged viewpoints are listed for the checking instantiation of the raycast kernel.
+static __global__ void flag_viewpoints_kernel(const float* __restrict__ rt, uint32_t n_vp, const float* __restrict__ planes_x,
+                                              const float* __restrict__ planes_y, const float* __restrict__ planes_z,
+                                              uint32_t nx, uint32_t ny, uint32_t nz, uint8_t* __restrict__ flags,
+                                              uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vp) return;
+  const float o[3] = {rt[12 * (size_t)v + 3], rt[12 * (size_t)v + 7], rt[12 * (size_t)v + 11]};
+  const float* pl[3] = {planes_x, planes_y, planes_z};
+  const uint32_t np[3] = {nx, ny, nz};
+  bool on = false;
+  for (int a = 0; a < 3; ++a) {
+    uint32_t lo = 0, hi = np[a];  // first plane >= o[a]
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (pl[a][mid] < o[a]) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    on = on || (lo < np[a] && pl[a][lo] == o[a]);
+    on = on || !(o[a] == o[a]);  // NaN origin: let the checking path have it
+  }
+  flags[v] = on ? 1 : 0;
+  if (on) list[atomicAdd(count, 1u)] = v;
 }
 
 }  // namespace q3dr

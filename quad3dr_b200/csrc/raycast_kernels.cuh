@@ -58,6 +58,12 @@ struct RaycastParams {
   // (huge windows): pix_tag = 0, pix_limit = 0xFFFFFFFE and the table is kept at 0xFFFFFFFF between chunks.
   uint32_t pix_tag;
   uint32_t pix_limit;
+  // Viewpoints whose camera centre lies exactly on a face plane of some box of the map (flag_viewpoints_kernel) take
+  // the kernel instantiation that re-checks such nodes with the reference's literal box test; all others run without
+  // that check.  vp_flags[v] != 0: v is such a viewpoint.  The checking instantiation walks vp_list[0 .. *n_flagged).
+  const uint8_t* __restrict__ vp_flags;
+  const uint32_t* __restrict__ vp_list;
+  const uint32_t* __restrict__ n_flagged;
   // kModePixels / raycast_rays_kernel
   q3dr_pixel_hit* pixels;
   const uint8_t* __restrict__ leaf_depth;
