@@ -34,6 +34,9 @@
  *        ViewpointOffscreenRenderer::uploadPoissonMesh, drawPoissonMeshNormals, computePoissonMeshNormalVector
  *        viewpoint_planner/src/planner/viewpoint_offscreen_renderer.cpp:138-200,276-293,361-397,499-527 ;
  *        viewpoint_planner/src/shaders/triangles_normals.{v,f}.glsl
+ *   q3dr_octree_read / q3dr_octree_leaves
+ *        octomap::AbstractOcTree::read + the begin_tree() walk of generateBVHTree
+ *        viewpoint_planner/src/octree/occupancy_map.hxx:1123-1127 ; viewpoint_planner_data.cpp:820-838
  *   q3dr_map_downweight_real_viewpoints
  *        ViewpointPlannerData::updateWeightsWithRealViewpoints        viewpoint_planner_data.cpp:498-571
  *   q3dr_exchange_* / q3dr_multi_enable_gather
@@ -308,6 +311,36 @@ int q3dr_octree_leaves_to_boxes(const float* center, const float* size, const fl
                                 const uint32_t* observation_count, size_t n, const float bvh_bbox[6],
                                 float obstacle_free_height, float occupancy_threshold, uint32_t observation_threshold,
                                 int device, float* out_boxes, uint32_t* out_source, size_t* n_out);
+
+/* The host half of row N1: OctoMap's ".ot" stream -> the octree's leaves in begin_tree() order, ready for
+ * q3dr_octree_leaves_to_boxes.  Replaces octomap::AbstractOcTree::read (viewpoint_planner/src/octree/
+ * occupancy_map.hxx:1123-1127) + the begin_tree() walk of generateBVHTree (viewpoint_planner_data.cpp:820-838) for the
+ * purpose of feeding the engine; quad3dr_b200/csrc/octree_io.cpp states the format.  No device work. */
+typedef struct q3dr_octree q3dr_octree;
+
+enum q3dr_octree_payload {
+  Q3DR_OCTREE_AUTO = 0,      /* by the stream's id; for the reference's id, the node type that fits the stream */
+  Q3DR_OCTREE_OCCUPANCY = 1, /* OccupancyNode: float occupancy, uint32 observation_count */
+  Q3DR_OCTREE_AUGMENTED = 2, /* AugmentedOccupancyNode: ... + float weight + uint64 observation_count_sum */
+  Q3DR_OCTREE_LOGODDS = 3    /* stock octomap::OcTree: float log-odds */
+};
+
+typedef struct q3dr_octree_info {
+  char id[64];         /* tree type of the header, e.g. "Ait_OccupancyMap" */
+  double resolution;   /* metres, edge of a finest-level voxel */
+  uint64_t n_nodes;    /* "size" of the header = nodes in the stream */
+  uint64_t n_leaves;
+  uint32_t tree_depth; /* 16 */
+  uint32_t payload;    /* q3dr_octree_payload actually used */
+} q3dr_octree_info;
+
+int q3dr_octree_read(const char* path, uint32_t payload, q3dr_octree** out);
+int q3dr_octree_get_info(const q3dr_octree* octree, q3dr_octree_info* info);
+/* Leaves in begin_tree() order; any array may be NULL.  center: n x 3 (it.getCoordinate()), size (it.getSize()),
+ * weight: AugmentedOccupancyNode::weight (0 for the other payloads), depth: octree depth of the leaf. */
+int q3dr_octree_leaves(const q3dr_octree* octree, float* center, float* size, float* occupancy,
+                       uint32_t* observation_count, float* weight, uint32_t* depth);
+int q3dr_octree_destroy(q3dr_octree* octree);
 
 /* ViewpointPlannerData::updateWeights (viewpoint_planner_data.cpp:438-482,573-577) on the device: every grid cell
  * (centre grid_origin + grid_increment * (ix, iy, iz), edge grid_increment) writes

@@ -108,7 +108,7 @@ const RayVariant kRayVariants[] = {
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
-constexpr int kDefaultRayVariant = 0;
+constexpr int kDefaultRayVariant = 1;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar by 4-5 %, four rays per lane lose 2x
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
 
@@ -254,7 +254,10 @@ size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint6
 
 float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+    cudaGetLastError();  // (an event that was never recorded) -- statistics only, must not leak into the next call's checks
+    return 0.f;
+  }
   return ms;
 }
 
@@ -515,8 +518,10 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     return Q3DR_OK;
   };
 
+  std::vector<uint8_t> packed(n_chunks, 0);
   auto issue_pack = [&](size_t c) -> int {
     const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
+    packed[c] = 1;
     q3dr::PackParams2 pp;
     pp.offsets = m->d_offsets.p + v0;
     pp.blk_off = blk_off;
@@ -623,7 +628,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   for (size_t c = 0; c < n_chunks; ++c) {
     st.raycast_ms += elapsed_ms(m->ev_chunk[5 * c + 0], m->ev_chunk[5 * c + 1]);
     st.score_ms += elapsed_ms(m->ev_chunk[5 * c + 1], m->ev_chunk[5 * c + 2]);
-    st.score_ms += elapsed_ms(m->ev_chunk[5 * c + 3], m->ev_chunk[5 * c + 4]);
+    if (packed[c]) st.score_ms += elapsed_ms(m->ev_chunk[5 * c + 3], m->ev_chunk[5 * c + 4]);
   }
   // S(c) is bracketed by the end of R(c) and its own end event; R(c+1) is issued after that event, so the brackets
   // do not overlap

@@ -62,6 +62,16 @@ class _OverlapResult(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
 
 
+class OctreeInfo(C.Structure):
+    """q3dr_octree_info"""
+
+    _fields_ = [("id", C.c_char * 64), ("resolution", C.c_double), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64),
+                ("tree_depth", C.c_uint32), ("payload", C.c_uint32)]
+
+
+OCTREE_AUTO, OCTREE_OCCUPANCY, OCTREE_AUGMENTED, OCTREE_LOGODDS = 0, 1, 2, 3
+
+
 class ExchangeLayout(C.Structure):
     """q3dr_exchange_layout: byte offsets inside one receive buffer of the result exchange."""
 
@@ -186,6 +196,10 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_octree_read.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(vp)]
+    L.q3dr_octree_get_info.argtypes = [vp, C.POINTER(OctreeInfo)]
+    L.q3dr_octree_leaves.argtypes = [vp, fp, fp, fp, u32p, fp, u32p]
+    L.q3dr_octree_destroy.argtypes = [vp]
     L.q3dr_map_downweight_real_viewpoints.argtypes = [vp, fp, C.c_uint32, C.c_uint32, fp, fp, C.c_size_t, C.POINTER(ScoreOpts),
                                                       C.c_float, vp, C.POINTER(RenderOpts), u32p, fp, C.POINTER(C.c_uint64)]
     L.q3dr_exchange_layout_of.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(ExchangeLayout)]
@@ -305,6 +319,27 @@ def octree_leaves_to_boxes(center, size, occupancy, observation_count, bvh_bbox,
         float(obstacle_free_height), float(occupancy_threshold), int(observation_threshold), int(device),
         _fp(boxes), src.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(k)))
     return boxes[:k.value].copy(), src[:k.value].copy()
+
+
+def read_octree_leaves(path: str, payload: int = OCTREE_AUTO) -> dict:
+    """OctoMap ".ot" stream -> its leaves in begin_tree() order (host only): dict with info (OctreeInfo), center (n, 3),
+    size, occupancy, observation_count, weight, depth -- the inputs of octree_leaves_to_boxes."""
+    L = load_library()
+    h = C.c_void_p()
+    _check(L.q3dr_octree_read(os.fsencode(path), payload, C.byref(h)))
+    try:
+        info = OctreeInfo()
+        _check(L.q3dr_octree_get_info(h, C.byref(info)))
+        n = int(info.n_leaves)
+        out = dict(info=info, center=np.empty((n, 3), np.float32), size=np.empty(n, np.float32),
+                   occupancy=np.empty(n, np.float32), observation_count=np.empty(n, np.uint32),
+                   weight=np.empty(n, np.float32), depth=np.empty(n, np.uint32))
+        u = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        _check(L.q3dr_octree_leaves(h, _fp(out["center"]), _fp(out["size"]), _fp(out["occupancy"]),
+                                    u(out["observation_count"]), _fp(out["weight"]), u(out["depth"])))
+        return out
+    finally:
+        L.q3dr_octree_destroy(h)
 
 
 def voxel_indices(n: int) -> np.ndarray:
