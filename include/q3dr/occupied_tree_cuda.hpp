@@ -34,6 +34,7 @@
 #include <cstring>
 #include <iterator>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -63,14 +64,60 @@ template <typename NodeT>
 using VoxelWithInformationSet =
     std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash>;
 
+/// Recycles the arrays of VoxelSetBlocks whose views are all gone: a planner that scores batch after batch and drops
+/// the rejected candidates' sets would otherwise pay the page faults of a fresh 10^8-byte block for every batch.
+struct VoxelSetArrayPool {
+  struct Arrays {
+    std::unique_ptr<std::int32_t[]> leaf;
+    std::unique_ptr<float[]> information;
+    std::size_t capacity;
+  };
+  std::mutex mutex;
+  std::vector<Arrays> free_list;
+  // plain arrays, deliberately NOT value-initialised: the parallel copy that fills them is also their first touch
+  Arrays take(std::size_t n) {
+    {
+      std::lock_guard<std::mutex> lock(mutex);
+      for (std::size_t i = 0; i < free_list.size(); ++i) {
+        if (free_list[i].capacity >= n) {
+          Arrays a = std::move(free_list[i]);
+          free_list.erase(free_list.begin() + static_cast<std::ptrdiff_t>(i));
+          return a;
+        }
+      }
+    }
+    Arrays a;
+    a.capacity = n > 0 ? n : 1;
+    a.leaf.reset(new std::int32_t[a.capacity]);
+    a.information.reset(new float[a.capacity]);
+    return a;
+  }
+  void give_back(Arrays&& a) {
+    std::lock_guard<std::mutex> lock(mutex);
+    if (free_list.size() < 2) free_list.push_back(std::move(a));  // (more than two idle blocks are simply freed)
+  }
+};
+
 /// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.
 template <typename NodeT>
 struct VoxelSetBlock {
-  // plain arrays, deliberately NOT value-initialised: the parallel copy that fills them is also their first touch, so
-  // the page faults of a fresh 10^8-byte block are spread over all host threads instead of serialised in a resize()
+  VoxelSetBlock() : n_entries(0), nodes(nullptr), leaf_of(nullptr), tree(nullptr) {}
+  ~VoxelSetBlock() {
+    if (pool) {
+      VoxelSetArrayPool::Arrays a;
+      a.leaf = std::move(leaf);
+      a.information = std::move(information);
+      a.capacity = capacity;
+      pool->give_back(std::move(a));
+    }
+  }
+  VoxelSetBlock(const VoxelSetBlock&) = delete;
+  VoxelSetBlock& operator=(const VoxelSetBlock&) = delete;
   std::unique_ptr<std::int32_t[]> leaf;     // ascending leaf index inside every viewpoint's range
   std::unique_ptr<float[]> information;
   std::size_t n_entries;
+  std::size_t capacity;
+  std::shared_ptr<VoxelSetArrayPool> pool;
   std::vector<NodeT*> const* nodes;   // leaf index -> host node (owned by the OccupiedTreeCuda, which must outlive the views)
   std::unordered_map<const NodeT*, std::int32_t> const* (*leaf_of)(const void*);  // host node -> leaf index, built on first find()
   const void* tree;
@@ -565,7 +612,8 @@ class ViewpointRaycastCuda {
 
   /// viewpoint_raycast.h:28-31 (min_range is accepted and, like in the reference, never used by the query)
   ViewpointRaycastCuda(TreeType* bvh_tree, float min_range = 0, float max_range = 60)
-      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range), mesh_normals_(nullptr) {
+      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range), mesh_normals_(nullptr),
+        pool_(std::make_shared<VoxelSetArrayPool>()) {
     q3dr_score_opts_default(&opts_);
     opts_.raycast_min_range = min_range;
     opts_.raycast_max_range = max_range;
@@ -670,8 +718,11 @@ class ViewpointRaycastCuda {
     const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
     std::shared_ptr<VoxelSetBlock<NodeT> > block = std::make_shared<VoxelSetBlock<NodeT> >();
     const std::size_t ne = static_cast<std::size_t>(r.n_entries);
-    block->leaf.reset(new std::int32_t[ne > 0 ? ne : 1]);
-    block->information.reset(new float[ne > 0 ? ne : 1]);
+    VoxelSetArrayPool::Arrays arrays = pool_->take(ne);
+    block->leaf = std::move(arrays.leaf);
+    block->information = std::move(arrays.information);
+    block->capacity = arrays.capacity;
+    block->pool = pool_;
     block->n_entries = ne;
     block->nodes = &bvh_tree_->leafNodes();
     block->leaf_of = &TreeType::leafIndexTableOf;
@@ -735,6 +786,7 @@ class ViewpointRaycastCuda {
   float max_range_;
   q3dr_score_opts opts_;
   const PoissonMeshNormalsCuda* mesh_normals_;
+  std::shared_ptr<VoxelSetArrayPool> pool_;
 };
 
 /// One ViewpointPath::observed_voxel_map on the device plus the information sums the path search evaluates against

@@ -34,6 +34,8 @@
  *        ViewpointOffscreenRenderer::uploadPoissonMesh, drawPoissonMeshNormals, computePoissonMeshNormalVector
  *        viewpoint_planner/src/planner/viewpoint_offscreen_renderer.cpp:138-200,276-293,361-397,499-527 ;
  *        viewpoint_planner/src/shaders/triangles_normals.{v,f}.glsl
+ *   q3dr_generate_viewpoint_entries
+ *        ViewpointPlanner::tryToAddViewpointEntry, batched        viewpoint_planner_graph.cpp:542-655
  *   q3dr_octree_read / q3dr_octree_leaves
  *        octomap::AbstractOcTree::read + the begin_tree() walk of generateBVHTree
  *        viewpoint_planner/src/octree/occupancy_map.hxx:1123-1127 ; viewpoint_planner_data.cpp:820-838
@@ -298,6 +300,53 @@ int q3dr_overlap_boxes(q3dr_map* map, const float* boxes, size_t n, q3dr_overlap
  * bvh_bbox: ViewpointPlannerData::bvh_bbox_.  valid[i] = 1 / 0. */
 int q3dr_valid_object_positions(q3dr_map* map, const float* positions, size_t n, const float object_bbox[6],
                                 const float bvh_bbox[6], float obstacle_free_height, uint8_t* valid);
+
+/* ---- batched candidate generation ----
+ *
+ * ViewpointPlanner::tryToAddViewpointEntry (viewpoint_planner_graph.cpp:542-655) for n candidate poses IN ORDER, with
+ * the decisions of the reference's one-at-a-time loop: a candidate is accepted iff its position is valid
+ * (isValidObjectPosition), it is not too close to a viewpoint already in the graph -- the existing ones and the
+ * candidates accepted before it -- (k nearest neighbours, squared distance < 0.6 * exploration_step^2 and angular
+ * distance below the threshold, :549-583), it sees at least min_voxel_count voxels and min_information information
+ * (:599-613).  The expensive parts run batched on the GPU (one overlap query, one scoring call over all valid
+ * candidates); only the distance gate is sequential, on the host, with exact nearest neighbours (the reference asks
+ * FLANN, an approximate third-party index).  Poses: position (x, y, z) + image-to-world quaternion (w, x, y, z), what
+ * Pose::createFromImageToWorldTransformation takes (:664). */
+typedef struct q3dr_candidate_opts {
+  float object_bbox[6];                           /* drone_bbox_ relative to the position, min xyz max xyz */
+  float bvh_bbox[6];                              /* ViewpointPlannerData::bvh_bbox_ */
+  float obstacle_free_height;
+  uint32_t discard_dist_knn;                      /* viewpoint_discard_dist_knn, 10 */
+  float exploration_step;                         /* viewpoint_exploration_step, 3 */
+  float exploration_step_max;                     /* FLT_MAX */
+  int32_t exploration_dilation_squared;           /* 1 */
+  float exploration_dilation_start_bbox_distance; /* 0 */
+  float exploration_dilation_speed;               /* 2 */
+  float exploration_bbox[6];                      /* getExplorationBbox() */
+  float exploration_angular_dist_threshold_degrees; /* 30 */
+  uint32_t min_voxel_count;                       /* viewpoint_min_voxel_count, 100 */
+  float min_information;                          /* viewpoint_min_information, 10 */
+} q3dr_candidate_opts;
+
+enum q3dr_candidate_status {
+  Q3DR_CANDIDATE_ACCEPTED = 0,
+  Q3DR_CANDIDATE_INVALID_POSITION = 1,
+  Q3DR_CANDIDATE_TOO_CLOSE = 2,
+  Q3DR_CANDIDATE_TOO_FEW_VOXELS = 3,
+  Q3DR_CANDIDATE_TOO_LITTLE_INFORMATION = 4
+};
+
+void q3dr_candidate_opts_default(q3dr_candidate_opts* opts);
+
+/* status_out: n q3dr_candidate_status values.  result: CSR over all n candidates (host memory owned by the map, valid
+ * until the next scoring call): the voxel set and total of every candidate with a valid position, whatever its status
+ * (an invalid position owns an empty range); accepted candidates are the new ViewpointEntries. */
+int q3dr_generate_viewpoint_entries(q3dr_map* map, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1,
+                                    uint32_t y0, uint32_t y1, const float* candidate_positions,
+                                    const float* candidate_quaternions_wxyz, size_t n, const float* existing_positions,
+                                    const float* existing_quaternions_wxyz, size_t n_existing,
+                                    const q3dr_score_opts* opts, const q3dr_candidate_opts* candidate_opts,
+                                    uint8_t* status_out, q3dr_result* result);
 
 /* ---- occupancy octree -> BVH leaves, grid weights ---- */
 

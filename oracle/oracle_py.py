@@ -488,3 +488,90 @@ def mesh_cast_pixels(tri_vertices, tri_normals, K, width, height, Rt, xs, ys, ne
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+# ---- batched candidate generation (row N3): the reference's one-at-a-time loop, literally ----
+
+def _exploration_step(p, o) -> np.float32:
+    """ViewpointPlanner::computeExplorationStep (viewpoint_planner_graph.cpp:672-690), binary32 throughout"""
+    f = np.float32
+    step = f(o["exploration_step"])
+    bb = np.asarray(o["exploration_bbox"], dtype=np.float32)
+    p = np.asarray(p, dtype=np.float32)
+    outside = bool(np.any(p < bb[:3]) or np.any(p > bb[3:]))
+    if outside:
+        dist_sq = f(0)
+        for i in range(3):
+            if p[i] < bb[i] or p[i] > bb[3 + i]:
+                d = min(abs(f(p[i] - bb[i])), abs(f(p[i] - bb[3 + i])))
+                dist_sq = f(dist_sq + f(d * d))
+        dil = f(np.sqrt(dist_sq) - f(o["exploration_dilation_start_bbox_distance"]))
+        if dil > 0:
+            if o["exploration_dilation_squared"]:
+                step = f(step + f(f(f(o["exploration_dilation_speed"]) * dil) * dil))
+            else:
+                step = f(step + f(f(o["exploration_dilation_speed"]) * dil))
+    return min(step, f(o["exploration_step_max"]))
+
+
+def _angular_distance(a, b) -> np.float32:
+    """Eigen::QuaternionBase::angularDistance (3.3): 2 atan2(|vec(a conj(b))|, |w|); (w, x, y, z)"""
+    f = np.float32
+    a = [f(x) for x in a]
+    bw, bx, by, bz = f(b[0]), f(-b[1]), f(-b[2]), f(-b[3])
+    w = f(f(f(f(a[0] * bw) - f(a[1] * bx)) - f(a[2] * by)) - f(a[3] * bz))
+    x = f(f(f(f(a[0] * bx) + f(a[1] * bw)) + f(a[2] * bz)) - f(a[3] * by))
+    y = f(f(f(f(a[0] * by) + f(a[2] * bw)) + f(a[3] * bx)) - f(a[1] * bz))
+    z = f(f(f(f(a[0] * bz) + f(a[3] * bw)) + f(a[1] * by)) - f(a[2] * bx))
+    return f(f(2) * f(np.arctan2(f(np.sqrt(f(f(x * x) + f(f(y * y) + f(z * z))))), abs(w))))
+
+
+def generate_viewpoint_entries_sequential(tree: "OracleTree", weights, normals, K, width, height, cand_pos, cand_quat,
+                                          existing_pos, existing_quat, o: dict, opts: Optional[ScoreOpts] = None):
+    """tryToAddViewpointEntry (viewpoint_planner_graph.cpp:542-655) candidate after candidate: validity, distance gate
+    against the k nearest viewpoints accepted so far (exact neighbours, ascending squared distance), raycast + score
+    of THIS candidate, thresholds, add.  o: dict with the fields of q3dr_candidate_opts.  Returns (status, results)
+    where results[j] is the score_viewpoint dict of candidate j or None if it was never cast."""
+    f = np.float32
+    pos = [np.asarray(p, dtype=np.float32) for p in np.asarray(existing_pos, dtype=np.float32).reshape(-1, 3)]
+    quat = [np.asarray(q, dtype=np.float32) for q in np.asarray(existing_quat, dtype=np.float32).reshape(-1, 4)]
+    cand_pos = np.asarray(cand_pos, dtype=np.float32).reshape(-1, 3)
+    cand_quat = np.asarray(cand_quat, dtype=np.float32).reshape(-1, 4)
+    ang_thr = f(f(f(o["exploration_angular_dist_threshold_degrees"]) * f(np.pi)) / f(180.0))
+    status, results = [], []
+    for j in range(cand_pos.shape[0]):
+        p, q = cand_pos[j], cand_quat[j]
+        results.append(None)
+        if not tree.valid_object_position(p, o["object_bbox"], o["bvh_bbox"], o["obstacle_free_height"]):
+            status.append(1)
+            continue
+        step = _exploration_step(p, o)
+        discard = False
+        if pos:
+            P = np.stack(pos)
+            d = (P - p).astype(np.float32)
+            dsq = ((d[:, 0] * d[:, 0]).astype(np.float32) + (d[:, 1] * d[:, 1]).astype(np.float32)).astype(np.float32)
+            dsq = (dsq + (d[:, 2] * d[:, 2]).astype(np.float32)).astype(np.float32)
+            knn = np.argsort(dsq, kind="stable")[: int(o["discard_dist_knn"])]
+            for i in knn:
+                step = min(step, _exploration_step(pos[i], o))
+                thr = f(f(f(0.6) * step) * step)
+                if dsq[i] < thr and _angular_distance(q, quat[i]) < ang_thr:
+                    discard = True
+                    break
+        if discard:
+            status.append(2)
+            continue
+        rt = pose_to_rt(q, p)
+        r = tree.score_viewpoint(weights, normals, K, width, rt, height=height, opts=opts)
+        results[-1] = r
+        if len(r["leaf"]) < int(o["min_voxel_count"]):
+            status.append(3)
+            continue
+        if f(r["total"]) < f(o["min_information"]):
+            status.append(4)
+            continue
+        status.append(0)
+        pos.append(p)
+        quat.append(q)
+    return np.array(status, dtype=np.uint8), results

@@ -215,6 +215,10 @@ struct q3dr_map {
   DevBuf<uint8_t> d_q_tmp, d_q_valid;
   std::vector<uint64_t> h_q_offsets;
   std::vector<int32_t> h_q_leaf;
+  // q3dr_generate_viewpoint_entries: per-candidate CSR offsets / totals / hit counts (host)
+  std::vector<uint64_t> cand_offsets;
+  std::vector<float> cand_total;
+  std::vector<uint32_t> cand_hits;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
   cudaStream_t own_stream = nullptr;   // non-blocking; the host-buffer entry points work on it (they return synchronised),

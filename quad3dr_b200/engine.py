@@ -62,6 +62,30 @@ class _OverlapResult(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
 
 
+class CandidateOpts(C.Structure):
+    """q3dr_candidate_opts: the planner options tryToAddViewpointEntry reads"""
+
+    _fields_ = [("object_bbox", C.c_float * 6), ("bvh_bbox", C.c_float * 6), ("obstacle_free_height", C.c_float),
+                ("discard_dist_knn", C.c_uint32), ("exploration_step", C.c_float), ("exploration_step_max", C.c_float),
+                ("exploration_dilation_squared", C.c_int32), ("exploration_dilation_start_bbox_distance", C.c_float),
+                ("exploration_dilation_speed", C.c_float), ("exploration_bbox", C.c_float * 6),
+                ("exploration_angular_dist_threshold_degrees", C.c_float), ("min_voxel_count", C.c_uint32),
+                ("min_information", C.c_float)]
+
+
+CANDIDATE_ACCEPTED, CANDIDATE_INVALID_POSITION, CANDIDATE_TOO_CLOSE, CANDIDATE_TOO_FEW_VOXELS, CANDIDATE_TOO_LITTLE_INFORMATION = range(5)
+
+
+def default_candidate_opts(**kw) -> "CandidateOpts":
+    o = CandidateOpts()
+    load_library().q3dr_candidate_opts_default(C.byref(o))
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple, np.ndarray)):
+            v = (C.c_float * 6)(*[float(x) for x in v])
+        setattr(o, k, v)
+    return o
+
+
 class OctreeInfo(C.Structure):
     """q3dr_octree_info"""
 
@@ -196,6 +220,11 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_candidate_opts_default.argtypes = [C.POINTER(CandidateOpts)]
+    L.q3dr_candidate_opts_default.restype = None
+    L.q3dr_generate_viewpoint_entries.argtypes = ([vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [fp, fp, C.c_size_t, fp, fp, C.c_size_t,
+                                                  C.POINTER(ScoreOpts), C.POINTER(CandidateOpts), C.POINTER(C.c_uint8),
+                                                  C.POINTER(_Result)])
     L.q3dr_octree_read.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(vp)]
     L.q3dr_octree_get_info.argtypes = [vp, C.POINTER(OctreeInfo)]
     L.q3dr_octree_leaves.argtypes = [vp, fp, fp, fp, u32p, fp, u32p]
@@ -639,6 +668,23 @@ class OccupancyMap:
             mesh._h if mesh is not None else None, C.byref(ropts) if ropts is not None else None,
             img.ctypes.data_as(C.POINTER(C.c_uint32)) if img is not None else None, _fp(out), C.byref(cnt)))
         return out, int(cnt.value)
+
+    def generate_viewpoint_entries(self, K, image_width: int, window: Sequence[int], cand_pos, cand_quat, existing_pos,
+                                   existing_quat, copts: "CandidateOpts", opts: Optional[ScoreOpts] = None):
+        """tryToAddViewpointEntry for a batch of candidate poses in order: (status uint8 (n,), ScoreResult over all n)."""
+        K = _f32(K, (4,))
+        cp = _f32(cand_pos).reshape(-1, 3)
+        cq = _f32(cand_quat).reshape(-1, 4)
+        ep = _f32(existing_pos).reshape(-1, 3)
+        eq = _f32(existing_quat).reshape(-1, 4)
+        opts = opts or default_opts()
+        x0, x1, y0, y1 = window
+        status = np.empty(cp.shape[0], dtype=np.uint8)
+        r = _Result()
+        _check(load_library().q3dr_generate_viewpoint_entries(
+            self._h, _fp(K), image_width, x0, x1, y0, y1, _fp(cp), _fp(cq), cp.shape[0], _fp(ep), _fp(eq), ep.shape[0],
+            C.byref(opts), C.byref(copts), status.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(r)))
+        return status, ScoreResult(r, copy=True)
 
     def overlap_boxes(self, boxes) -> Tuple[np.ndarray, np.ndarray]:
         """bvh::Tree::intersects(bbox) for many boxes: CSR (offsets uint64 (n+1), leaf int32) of the overlapping
