@@ -94,17 +94,17 @@ struct RayVariant {
   RaycastKernel kernel[2];   // [MODE], with the on-face check (any viewpoint)
   RaycastKernel score_fast;  // kModeScore without the check: viewpoints whose centre lies on no box plane
 };
-#define Q3DR_VARIANT(NAME, NR, TW, PK)                                                                          \
+#define Q3DR_VARIANT(NAME, NR, TW, PK, MC)                                                                      \
   {NAME, NR, TW,                                                                                                  \
-   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true>}, \
-   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false>}
+   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC>}, \
+   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC>}
 const RayVariant kRayVariants[] = {
-    Q3DR_VARIANT("2x8x8", 2, 8, false),     // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 64 registers
-    Q3DR_VARIANT("2x8x8p", 2, 8, true),     // 1: ... with FADD2 / FMUL2
-    Q3DR_VARIANT("4x8x16", 4, 8, false),    // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
-    Q3DR_VARIANT("4x8x16p", 4, 8, true),    // 3
-    Q3DR_VARIANT("4x16x8", 4, 16, false),   // 4: four rays per lane, 16 x 8 pixel packets
-    Q3DR_VARIANT("4x16x8p", 4, 16, true),   // 5
+    Q3DR_VARIANT("2x8x8", 2, 8, false, 4),    // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 64 registers
+    Q3DR_VARIANT("2x8x8p", 2, 8, true, 4),    // 1: ... with FADD2 / FMUL2
+    Q3DR_VARIANT("4x8x16", 4, 8, false, 2),   // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
+    Q3DR_VARIANT("4x8x16p", 4, 8, true, 2),   // 3
+    Q3DR_VARIANT("2x8x8p/3", 2, 8, true, 3),  // 4: like 1 with 3 CTAs x 80 registers
+    Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3),  // 5: like 0 with 3 CTAs x 80 registers
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));

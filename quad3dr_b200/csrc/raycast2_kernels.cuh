@@ -207,21 +207,25 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
       for (int c = 0; c < 4; ++c) {
         if (todo & (1u << c)) {
           const int32_t li = (int32_t)(chv[c] & kPayloadMask);
+          // branch-free per lane: every lane evaluates dist_sq (lanes that cannot accept compute a value nobody reads),
+          // the accept decision is a predicate, the update a select -- no divergent path, nothing recomputed
           float d[NR];
           bool acc[NR];
           bool some = false;
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
             d[j] = dist_sq_at2(ox, oy, oz, r[j], t[j][c]);
-            acc[j] = (x[j][c] > t[j][c]) && (d[j] < b[j].dsq || (d[j] == b[j].dsq && li > b[j].leaf));
-            some = some || acc[j];
+            acc[j] = (x[j][c] > t[j][c]) & ((d[j] < b[j].dsq) | ((d[j] == b[j].dsq) & (li > b[j].leaf)));
+            some = some | acc[j];
           }
           if (__any_sync(Q3DR_FULL_MASK, some)) {
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-              if (acc[j]) {
-                b[j].dsq = d[j]; b[j].t = t[j][c]; b[j].leaf = li; b[j].tU = bound_after(t[j][c], A);
-              }
+              const float u = bound_after(t[j][c], A);
+              b[j].dsq = acc[j] ? d[j] : b[j].dsq;
+              b[j].t = acc[j] ? t[j][c] : b[j].t;
+              b[j].leaf = acc[j] ? li : b[j].leaf;
+              b[j].tU = acc[j] ? u : b[j].tU;
             }
             tightened = true;
           }
@@ -344,10 +348,11 @@ struct PacketShape {
 };
 
 // MODE: kModeScore or kModePixels (camera windows only; ray lists use raycast_rays_kernel).
-// NR rays per lane; resident CTAs per SM chosen so that the register file is used up: 4 x 64 or 2 x 128 registers.
+// NR rays per lane.
 // kOnFace = false: viewpoints flagged in p.vp_flags are skipped (the kOnFace = true launch casts them, from p.vp_list).
-template <int MODE, int NR, int TW, bool kPacked, bool kOnFace>
-__global__ void __launch_bounds__(kThreadsPerCta, (NR <= 2) ? 4 : 2) raycast2_kernel(const RaycastParams p) {
+// kMinCtas: resident CTAs per SM the register allocation is tuned for (4 x 64, 3 x 80 or 2 x 128 registers).
+template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas>
+__global__ void __launch_bounds__(kThreadsPerCta, kMinCtas) raycast2_kernel(const RaycastParams p) {
   __shared__ uint32_t s_tile[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
