@@ -249,41 +249,40 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
     // inner children
     uint32_t inner = any & ~leaf_mask;
     if (inner) {
+      uint32_t near_c = (uint32_t)__ffs((int)inner) - 1u;
       if (inner & (inner - 1u)) {
-        // more than one: nearest first; the others go on the stack, farthest first, with every ray's own entry
-        // parameter (+inf for rays that do not need the child)
+        // more than one: the nearest is entered now (warp minimum of the entry parameters of the rays that need the
+        // child); the others go on the stack with every ray's own entry parameter (+inf for rays that do not need the
+        // child), in slot order -- with static child indices, no sorting network: what order far siblings are popped
+        // in changes how early the bounds tighten, never the result
         const uint32_t kNone = 0xFFFFFFFFu;
-        uint32_t key[4];
+        uint32_t best_key = kNone;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          key[c] = kNone;
           if (inner & (1u << c)) {
             uint32_t k = kNone;
 #pragma unroll
             for (int j = 0; j < NR; ++j) k = min(k, (t[j][c] < x[j][c]) ? __float_as_uint(t[j][c]) : kNone);
-            key[c] = __reduce_min_sync(Q3DR_FULL_MASK, k);
-          }
-        }
-        while (inner & (inner - 1u)) {
-          uint32_t far = 0u, far_key = 0u;  // farthest remaining candidate (ties: higher slot)
-#pragma unroll
-          for (uint32_t c = 0; c < 4u; ++c) {
-            if (((inner >> c) & 1u) && key[c] >= far_key) {
-              far = c;
-              far_key = key[c];
+            k = __reduce_min_sync(Q3DR_FULL_MASK, k);
+            if (k < best_key) {
+              best_key = k;
+              near_c = (uint32_t)c;
             }
           }
-          inner &= ~(1u << far);
+        }
 #pragma unroll
-          for (int j = 0; j < NR; ++j) {
-            const float T = pick4f(far, t[j][0], t[j][1], t[j][2], t[j][3]), X = pick4f(far, x[j][0], x[j][1], x[j][2], x[j][3]);
-            stack_t[j][sp] = (T < X) ? T : kInf;  // tU only shrinks: an entry parameter >= tU now stays >= tU
+        for (int c = 3; c >= 0; --c) {
+          if ((inner & (1u << c)) && near_c != (uint32_t)c) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+              stack_t[j][sp] = (t[j][c] < x[j][c]) ? t[j][c] : kInf;  // tU only shrinks: an entry >= tU now stays >= tU
+            }
+            stack_n[sp] = chv[c] & kPayloadMask;
+            ++sp;
           }
-          stack_n[sp] = pick4(far, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
-          ++sp;
         }
       }
-      ref = pick4((uint32_t)__ffs((int)inner) - 1u, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
+      ref = pick4(near_c, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
       continue;
     }
     bool found = false;
