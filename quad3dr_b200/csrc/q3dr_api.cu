@@ -278,6 +278,8 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   p->tiles_x = (p->w + tile_w - 1) / tile_w;
   const uint32_t tiles_y = (p->h + tile_h - 1) / tile_h;
   p->tiles_per_vp = p->tiles_x * tiles_y;
+  p->inv_tiles_x = 1.0 / (double)p->tiles_x;
+  p->inv_tiles_per_vp = 1.0 / (double)p->tiles_per_vp;
   p->max_range = max_range;
   p->leaf_depth = m->d_depth.p;
   p->tile_counter = m->d_counter.p;

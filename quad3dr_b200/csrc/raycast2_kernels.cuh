@@ -321,9 +321,9 @@ __device__ __forceinline__ bool camera_dir2(const float* __restrict__ R /* 12 fl
     r.dy = d1;
     r.dz = d2;
   }
-  r.ix = __fdiv_rn(1.0f, r.dx);
-  r.iy = __fdiv_rn(1.0f, r.dy);
-  r.iz = __fdiv_rn(1.0f, r.dz);
+  r.ix = __frcp_rn(r.dx);  // the correctly rounded reciprocal IS 1.0f / x in binary32 (bvh.h:380 cwiseInverse)
+  r.iy = __frcp_rn(r.dy);
+  r.iz = __frcp_rn(r.dz);
   return n2 >= 1e-30f && n2 <= 1e30f;
 }
 
@@ -372,12 +372,25 @@ __global__ void __launch_bounds__(kThreadsPerCta, kMinCtas) raycast2_kernel(cons
     __syncwarp();
     if (tile >= total_tiles) break;
 
-    const uint32_t slot = tile / p.tiles_per_vp;
+    // tile -> (viewpoint slot, tile row, tile column): quotients through the reciprocals the host prepared (a double
+    // holds any 32-bit integer exactly; the truncated product is the quotient or one below it) instead of two integer
+    // divisions by run-time divisors per packet
+    uint32_t slot = (uint32_t)__double2uint_rz((double)tile * p.inv_tiles_per_vp);
+    if (slot * p.tiles_per_vp > tile) --slot;  // (only a divisor beyond 2^20 could make the estimate overshoot)
+    uint32_t rem = tile - slot * p.tiles_per_vp;
+    if (rem >= p.tiles_per_vp) {
+      rem -= p.tiles_per_vp;
+      ++slot;
+    }
     const uint32_t vp = listed ? __ldg(p.vp_list + slot) : slot;
     if (!kOnFace && p.vp_flags != nullptr && __ldg(p.vp_flags + vp) != 0) continue;
-    const uint32_t rem = tile - slot * p.tiles_per_vp;
-    const uint32_t ty = rem / p.tiles_x;
-    const uint32_t tx = rem - ty * p.tiles_x;
+    uint32_t ty = (uint32_t)__double2uint_rz((double)rem * p.inv_tiles_x);
+    if (ty * p.tiles_x > rem) --ty;
+    uint32_t tx = rem - ty * p.tiles_x;
+    if (tx >= p.tiles_x) {
+      tx -= p.tiles_x;
+      ++ty;
+    }
     const uint32_t px = tx * TW + (lane % TW);
     uint32_t py[NR];
     bool live[NR];

@@ -44,6 +44,7 @@ struct RaycastParams {
   float fx, fy, cx, cy;
   uint32_t x0, y0, w, h;  // window
   uint32_t tiles_x, tiles_per_vp;
+  double inv_tiles_x, inv_tiles_per_vp;  // 1.0 / the two above (raycast2_kernel's tile decoding)
   uint32_t total_tiles;
   float max_range;
   // kModeScore

@@ -74,7 +74,8 @@ def test_batch_equals_sequential_loop(knn, ang_deg):
         sc.oracle, sc.leaves.weight, sc.leaves.normal, cam.K, w, h, cand_pos, cand_quat, existing_pos, existing_quat, fields)
     assert np.array_equal(status, ref_status)
     counts = np.bincount(status, minlength=5)
-    assert counts[E.CANDIDATE_ACCEPTED] > 10 and counts[E.CANDIDATE_TOO_CLOSE] > 10, counts
+    # every kind of decision occurs in the batch (how often depends on the scene)
+    assert counts[E.CANDIDATE_ACCEPTED] > 10 and counts[E.CANDIDATE_TOO_CLOSE] > 3 and counts[E.CANDIDATE_INVALID_POSITION] > 3, counts
     assert counts[E.CANDIDATE_TOO_FEW_VOXELS] + counts[E.CANDIDATE_TOO_LITTLE_INFORMATION] > 0, counts
     assert res.n_viewpoints == n
     for j in range(n):
