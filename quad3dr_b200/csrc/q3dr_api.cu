@@ -90,21 +90,22 @@ int configure_rays_kernel(q3dr_map* m) {
 typedef void (*RaycastKernel)(const q3dr::RaycastParams);
 struct RayVariant {
   const char* name;
-  int nr, tw;
+  int nr, tw, warps;         // rays per lane, tile width, warps per CTA
   RaycastKernel kernel[2];   // [MODE], with the on-face check (any viewpoint)
   RaycastKernel score_fast;  // kModeScore without the check: viewpoints whose centre lies on no box plane
 };
-#define Q3DR_VARIANT(NAME, NR, TW, PK, MC)                                                                      \
-  {NAME, NR, TW,                                                                                                  \
-   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC>}, \
-   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC>}
+#define Q3DR_VARIANT(NAME, NR, TW, PK, MC, WP)                                                                  \
+  {NAME, NR, TW, WP,                                                                                              \
+   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC, WP>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC, WP>}, \
+   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC, WP>}
 const RayVariant kRayVariants[] = {
-    Q3DR_VARIANT("2x8x8", 2, 8, false, 4),    // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 64 registers
-    Q3DR_VARIANT("2x8x8p", 2, 8, true, 4),    // 1: ... with FADD2 / FMUL2
-    Q3DR_VARIANT("4x8x16", 4, 8, false, 2),   // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
-    Q3DR_VARIANT("4x8x16p", 4, 8, true, 2),   // 3
-    Q3DR_VARIANT("2x8x8p/3", 2, 8, true, 3),  // 4: like 1 with 3 CTAs x 80 registers
-    Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3),  // 5: like 0 with 3 CTAs x 80 registers
+    Q3DR_VARIANT("2x8x8", 2, 8, false, 4, 8),      // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 8 warps x 64 registers
+    Q3DR_VARIANT("2x8x8p", 2, 8, true, 4, 8),      // 1: ... with FADD2 / FMUL2
+    Q3DR_VARIANT("4x8x16", 4, 8, false, 2, 8),     // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
+    Q3DR_VARIANT("4x8x16p", 4, 8, true, 2, 8),     // 3
+    Q3DR_VARIANT("2x8x8p/3", 2, 8, true, 3, 8),    // 4: like 1 with 3 CTAs x 80 registers (no spills, 24 warps per SM)
+    Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3, 8),    // 5: like 0 with 3 CTAs x 80 registers
+    Q3DR_VARIANT("2x8x8p/7x4", 2, 8, true, 7, 4),  // 6: like 1 with 7 CTAs x 4 warps x 72 registers (28 warps per SM)
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
@@ -122,13 +123,13 @@ int configure_kernel2(q3dr_map* m) {
   const RayVariant& rv = variant_of(m);
   for (int mode = 0; mode < 2; ++mode) {
     int per_sm = 0;
-    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.kernel[mode], q3dr::kThreadsPerCta, 0));
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.kernel[mode], rv.warps * 32, 0));
     if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
     m->grid2_ctas[mode] = per_sm * m->sm_count;
   }
   {
     int per_sm = 0;
-    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.score_fast, q3dr::kThreadsPerCta, 0));
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.score_fast, rv.warps * 32, 0));
     if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
     m->grid2_ctas[q3dr::kModeScore] = std::min(m->grid2_ctas[q3dr::kModeScore], per_sm * m->sm_count);
   }
@@ -233,7 +234,7 @@ int ensure_scratch(q3dr_map* m, size_t slots, uint64_t cap) {
 
 size_t choose_chunk(const q3dr_map* m, uint32_t tiles_per_vp, size_t n_vp, uint64_t cap) {
   // enough packets in flight that the persistent grid's tail is small ...
-  const size_t resident_warps = (size_t)m->grid2_ctas[q3dr::kModeScore] * q3dr::kWarpsPerCta;
+  const size_t resident_warps = (size_t)m->grid2_ctas[q3dr::kModeScore] * (size_t)variant_of(m).warps;
   size_t want = (64 * resident_warps + tiles_per_vp - 1) / tiles_per_vp;  // ~64 packets per resident warp
   // ... and enough viewpoints per chunk to amortise the per-chunk host sync and the small scoring kernels, few enough
   // that the D2H copy of a finished chunk overlaps the next one (measured on C2: 150 / 296 / 500 / 1000 viewpoints per
@@ -467,11 +468,11 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
         rp.rt, (uint32_t)nb, m->d_planes.p, m->d_planes.p + m->n_planes[0], m->d_planes.p + m->n_planes[0] + m->n_planes[1],
         m->n_planes[0], m->n_planes[1], m->n_planes[2], m->d_vp_flags.p, m->d_vp_list.p, m->d_counter.p + 2);
     Q3DR_CUDA(cudaGetLastError());
-    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore],
-                                            ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-    variant_of(m).score_fast<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);
+    const int wpc = variant_of(m).warps;
+    const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
+    variant_of(m).score_fast<<<grid, wpc * 32, 0, stream>>>(rp);
     Q3DR_CUDA(cudaGetLastError());
-    variant_of(m).kernel[q3dr::kModeScore]<<<grid, q3dr::kThreadsPerCta, 0, stream>>>(rp);  // exits at once if none is flagged
+    variant_of(m).kernel[q3dr::kModeScore]<<<grid, wpc * 32, 0, stream>>>(rp);  // exits at once if none is flagged
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
     st.kernel_launches += 3;
@@ -1005,9 +1006,9 @@ int q3dr_detail::raycast_window_device(q3dr_map* m, const float K[4], const floa
   rp.rt = d_rt;
   rp.total_tiles = rp.tiles_per_vp;
   rp.pixels = m->d_pixels.p;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels],
-                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
-  variant_of(m).kernel[q3dr::kModePixels]<<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
+  const int wpc = variant_of(m).warps;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   return Q3DR_OK;
 }
@@ -1031,10 +1032,10 @@ int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint3
   rp.rt = m->d_rt.p;
   rp.total_tiles = rp.tiles_per_vp;
   rp.pixels = m->d_pixels.p;
-  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels],
-                                          ((uint64_t)rp.total_tiles + q3dr::kWarpsPerCta - 1) / q3dr::kWarpsPerCta);
+  const int wpc = variant_of(m).warps;
+  const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
   Q3DR_CUDA(cudaEventRecord(m->ev[0], s));
-  variant_of(m).kernel[q3dr::kModePixels]<<<grid, q3dr::kThreadsPerCta, 0, s>>>(rp);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaEventRecord(m->ev[1], s));
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, npix * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));

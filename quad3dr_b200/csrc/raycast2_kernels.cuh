@@ -350,9 +350,11 @@ struct PacketShape {
 // NR rays per lane.
 // kOnFace = false: viewpoints flagged in p.vp_flags are skipped (the kOnFace = true launch casts them, from p.vp_list).
 // kMinCtas: resident CTAs per SM the register allocation is tuned for (4 x 64, 3 x 80 or 2 x 128 registers).
-template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas>
-__global__ void __launch_bounds__(kThreadsPerCta, kMinCtas) raycast2_kernel(const RaycastParams p) {
-  __shared__ uint32_t s_tile[kWarpsPerCta];
+// kWarps: warps per CTA (warps never synchronise with each other; the CTA size only sets the register granularity:
+// 7 CTAs of 4 warps leave 72 registers per thread, between the 64 of 4 x 8 warps and the 80 of 3 x 8 warps).
+template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const RaycastParams p) {
+  __shared__ uint32_t s_tile[kWarps];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
