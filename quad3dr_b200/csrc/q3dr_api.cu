@@ -109,7 +109,7 @@ const RayVariant kRayVariants[] = {
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
-constexpr int kDefaultRayVariant = 1;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar by 4-5 %, four rays per lane lose 2x
+constexpr int kDefaultRayVariant = 6;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar by 5-9 %, 72 registers beat 64 and 80 by 1-3 %, four rays per lane lose 2x
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
 

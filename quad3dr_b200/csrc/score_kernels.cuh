@@ -287,9 +287,13 @@ static __global__ void __launch_bounds__(kSegThreads) score_blocks_kernel(const 
       pix[u] = 0;
       ra[u] = rb[u] = rc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid[u]) {
-        uint32_t* fp = p.first_pix + (size_t)vp[u] * p.leaf_stride + (uint32_t)leaf[u];
-        pix[u] = *fp & p.pix_mask;
-        if (p.reset_fp) *fp = kEmptyPixel;
+        if (NMODE == kNormalCode && !p.reset_fp) {
+          pix[u] = p.tmp_pix[at[u]];  // mesh_kept_normals_kernel already fetched the kept pixel: no second random read
+        } else {
+          uint32_t* fp = p.first_pix + (size_t)vp[u] * p.leaf_stride + (uint32_t)leaf[u];
+          pix[u] = *fp & p.pix_mask;
+          if (p.reset_fp) *fp = kEmptyPixel;
+        }
         const float4* rec = p.leaf_rec + kLeafRecStride * (size_t)leaf[u];
         ra[u] = __ldg(rec);
         rb[u] = __ldg(rec + 1);
@@ -377,6 +381,7 @@ static __global__ void __launch_bounds__(kSegThreads) mesh_kept_normals_kernel(c
     MeshRay r;
     mesh_camera_ray(m, p.fx, p.fy, p.cx, p.cy, p.img_w, p.img_h, p.x0 + px, p.y0 + py, r);
     p.tmp_code[at] = mesh_cast(mesh, ropts, r);
+    p.tmp_pix[at] = pix;  // score_blocks_kernel<kNormalCode> takes the kept pixel from here
   }
 }
 
