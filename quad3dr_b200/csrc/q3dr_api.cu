@@ -91,21 +91,24 @@ typedef void (*RaycastKernel)(const q3dr::RaycastParams);
 struct RayVariant {
   const char* name;
   int nr, tw, warps;         // rays per lane, tile width, warps per CTA
+  bool smem_top;             // top tree levels staged in shared memory (dynamic smem = top nodes x 128 bytes)
   RaycastKernel kernel[2];   // [MODE], with the on-face check (any viewpoint)
   RaycastKernel score_fast;  // kModeScore without the check: viewpoints whose centre lies on no box plane
 };
-#define Q3DR_VARIANT(NAME, NR, TW, PK, MC, WP)                                                                  \
-  {NAME, NR, TW, WP,                                                                                              \
-   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC, WP>, q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC, WP>}, \
-   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC, WP>}
+#define Q3DR_VARIANT(NAME, NR, TW, PK, MC, WP, ST)                                                              \
+  {NAME, NR, TW, WP, ST,                                                                                          \
+   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC, WP, ST>,                                        \
+    q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC, WP, ST>},                                      \
+   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC, WP, ST>}
 const RayVariant kRayVariants[] = {
-    Q3DR_VARIANT("2x8x8", 2, 8, false, 4, 8),      // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 8 warps x 64 registers
-    Q3DR_VARIANT("2x8x8p", 2, 8, true, 4, 8),      // 1: ... with FADD2 / FMUL2
-    Q3DR_VARIANT("4x8x16", 4, 8, false, 2, 8),     // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
-    Q3DR_VARIANT("4x8x16p", 4, 8, true, 2, 8),     // 3
-    Q3DR_VARIANT("2x8x8p/3", 2, 8, true, 3, 8),    // 4: like 1 with 3 CTAs x 80 registers (no spills, 24 warps per SM)
-    Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3, 8),    // 5: like 0 with 3 CTAs x 80 registers
-    Q3DR_VARIANT("2x8x8p/7x4", 2, 8, true, 7, 4),  // 6: like 1 with 7 CTAs x 4 warps x 72 registers (28 warps per SM)
+    Q3DR_VARIANT("2x8x8", 2, 8, false, 4, 8, false),       // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 8 warps x 64 registers
+    Q3DR_VARIANT("2x8x8p", 2, 8, true, 4, 8, false),       // 1: ... with FADD2 / FMUL2
+    Q3DR_VARIANT("4x8x16", 4, 8, false, 2, 8, false),      // 2: four rays per lane, 8 x 16 pixel packets, 2 CTAs x 128 registers
+    Q3DR_VARIANT("4x8x16p", 4, 8, true, 2, 8, false),      // 3
+    Q3DR_VARIANT("2x8x8p/3", 2, 8, true, 3, 8, false),     // 4: like 1 with 3 CTAs x 80 registers (no spills, 24 warps per SM)
+    Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3, 8, false),     // 5: like 0 with 3 CTAs x 80 registers
+    Q3DR_VARIANT("2x8x8p/7x4", 2, 8, true, 7, 4, false),   // 6: like 1 with 7 CTAs x 4 warps x 72 registers (28 warps per SM)
+    Q3DR_VARIANT("2x8x8p/7x4/smem", 2, 8, true, 7, 4, true),  // 7: like 6 with the top tree levels in shared memory
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
@@ -123,13 +126,13 @@ int configure_kernel2(q3dr_map* m) {
   const RayVariant& rv = variant_of(m);
   for (int mode = 0; mode < 2; ++mode) {
     int per_sm = 0;
-    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.kernel[mode], rv.warps * 32, 0));
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.kernel[mode], rv.warps * 32, rv.smem_top ? m->smem_bytes : 0));
     if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
     m->grid2_ctas[mode] = per_sm * m->sm_count;
   }
   {
     int per_sm = 0;
-    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.score_fast, rv.warps * 32, 0));
+    Q3DR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rv.score_fast, rv.warps * 32, rv.smem_top ? m->smem_bytes : 0));
     if (per_sm < 1) return fail(Q3DR_ERR_INTERNAL, "raycast2 kernel does not fit on an SM");
     m->grid2_ctas[q3dr::kModeScore] = std::min(m->grid2_ctas[q3dr::kModeScore], per_sm * m->sm_count);
   }
@@ -470,9 +473,10 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaGetLastError());
     const int wpc = variant_of(m).warps;
     const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
-    variant_of(m).score_fast<<<grid, wpc * 32, 0, stream>>>(rp);
+    const size_t dyn_smem = variant_of(m).smem_top ? m->smem_bytes : 0;
+    variant_of(m).score_fast<<<grid, wpc * 32, dyn_smem, stream>>>(rp);
     Q3DR_CUDA(cudaGetLastError());
-    variant_of(m).kernel[q3dr::kModeScore]<<<grid, wpc * 32, 0, stream>>>(rp);  // exits at once if none is flagged
+    variant_of(m).kernel[q3dr::kModeScore]<<<grid, wpc * 32, dyn_smem, stream>>>(rp);  // exits at once if none is flagged
     Q3DR_CUDA(cudaGetLastError());
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
     st.kernel_launches += 3;
@@ -1008,7 +1012,7 @@ int q3dr_detail::raycast_window_device(q3dr_map* m, const float K[4], const floa
   rp.pixels = m->d_pixels.p;
   const int wpc = variant_of(m).warps;
   const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
-  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, 0, s>>>(rp);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, variant_of(m).smem_top ? m->smem_bytes : 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   return Q3DR_OK;
 }
@@ -1035,7 +1039,7 @@ int q3dr_raycast_window(q3dr_map* m, const float K[4], const float Rt[12], uint3
   const int wpc = variant_of(m).warps;
   const int grid = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModePixels], ((uint64_t)rp.total_tiles + wpc - 1) / wpc);
   Q3DR_CUDA(cudaEventRecord(m->ev[0], s));
-  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, 0, s>>>(rp);
+  variant_of(m).kernel[q3dr::kModePixels]<<<grid, wpc * 32, variant_of(m).smem_top ? m->smem_bytes : 0, s>>>(rp);
   Q3DR_CUDA(cudaGetLastError());
   Q3DR_CUDA(cudaEventRecord(m->ev[1], s));
   Q3DR_CUDA(cudaMemcpyAsync(out, m->d_pixels.p, npix * sizeof(q3dr_pixel_hit), cudaMemcpyDeviceToHost, s));

@@ -77,9 +77,13 @@ __device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 
 // kOnFace       : the packet's origin may lie exactly on a face plane of a box.  Only then can an exit parameter be
 //                 exactly 0 (below), where the reference's inside / outside distinction decides; such nodes are redone
 //                 with the literal box test.  flag_viewpoints_kernel sorts the viewpoints into the two instantiations.
-template <int NR, bool kMixed, bool kPacked, bool kOnFace>
+// kSmemTop      : the first n_top nodes (the top levels, breadth-first) are read from the CTA's shared-memory copy
+//                 instead of L1 / L2 (north_star's "shared-memory staging of the top tree levels"; measured, not the
+//                 default: see DESIGN.md section 4).
+template <int NR, bool kMixed, bool kPacked, bool kOnFace, bool kSmemTop>
 __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, float A, const Dir2 (&r)[NR], Best2 (&b)[NR],
-                                                 const float4* __restrict__ nodes, uint32_t octant) {
+                                                 const float4* __restrict__ nodes, uint32_t octant,
+                                                 const float4* smem_top, uint32_t n_top) {
   float stack_t[NR][kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
@@ -100,9 +104,18 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
   }
   while (true) {
     const float4* np = nodes + (size_t)ref * 8u;
-    const float4 nrx = __ldg(np + nx), nry = __ldg(np + ny), nrz = __ldg(np + nz);
-    const float4 frx = __ldg(np + fx), fry = __ldg(np + fy), frz = __ldg(np + fz);
-    const uint4 ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+    float4 nrx, nry, nrz, frx, fry, frz;
+    uint4 ch;
+    if (kSmemTop && ref < n_top) {
+      const float4* sp4 = smem_top + ref * 8u;
+      nrx = sp4[nx]; nry = sp4[ny]; nrz = sp4[nz];
+      frx = sp4[fx]; fry = sp4[fy]; frz = sp4[fz];
+      ch = *reinterpret_cast<const uint4*>(sp4 + 6);
+    } else {
+      nrx = __ldg(np + nx); nry = __ldg(np + ny); nrz = __ldg(np + nz);
+      frx = __ldg(np + fx); fry = __ldg(np + fy); frz = __ldg(np + fz);
+      ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
+    }
     const uint32_t chv[4] = {ch.x, ch.y, ch.z, ch.w};
 
     float t[NR][4];  // entry parameter, [ray][child]
@@ -352,9 +365,14 @@ struct PacketShape {
 // kMinCtas: resident CTAs per SM the register allocation is tuned for (4 x 64, 3 x 80 or 2 x 128 registers).
 // kWarps: warps per CTA (warps never synchronise with each other; the CTA size only sets the register granularity:
 // 7 CTAs of 4 warps leave 72 registers per thread, between the 64 of 4 x 8 warps and the 80 of 3 x 8 warps).
-template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps>
+template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps, bool kSmemTop>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const RaycastParams p) {
+  extern __shared__ float4 smem_top[];  // kSmemTop: p.n_top nodes of 8 float4 (launch with that much dynamic smem)
   __shared__ uint32_t s_tile[kWarps];
+  if (kSmemTop) {
+    for (uint32_t i = threadIdx.x; i < p.n_top * 8u; i += blockDim.x) smem_top[i] = p.nodes[i];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
@@ -462,9 +480,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
       const bool anz = __any_sync(Q3DR_FULL_MASK, nza), apz = __any_sync(Q3DR_FULL_MASK, pza);
       if (!(anx && apx) && !(any_ && apy) && !(anz && apz)) {
         const uint32_t octant = (anx ? 1u : 0u) | (any_ ? 2u : 0u) | (anz ? 4u : 0u);
-        traverse_packetN<NR, false, kPacked, kOnFace>(ox, oy, oz, A, r, b, p.nodes, octant);
+        traverse_packetN<NR, false, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, octant, smem_top, p.n_top);
       } else {
-        traverse_packetN<NR, true, kPacked, kOnFace>(ox, oy, oz, A, r, b, p.nodes, 0u);
+        traverse_packetN<NR, true, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, 0u, smem_top, p.n_top);
       }
     } else {
       // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge
