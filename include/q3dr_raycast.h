@@ -181,6 +181,10 @@ int q3dr_map_update_weights(q3dr_map* map, const float* weights);
 int q3dr_map_update_normals(q3dr_map* map, const float* normals);
 int q3dr_map_get_info(const q3dr_map* map, q3dr_map_info* info);
 int q3dr_map_last_stats(const q3dr_map* map, q3dr_stats* stats);
+/* Debugging aid.  With Q3DR_GUARD=1 in the environment (read once, before the first allocation) every device buffer of
+ * a map is followed by 256 guard bytes of a known pattern; this call synchronises the device and reports how many
+ * buffers had their guard overwritten (a write past the end).  Without Q3DR_GUARD it fails with INVALID_ARG. */
+int q3dr_map_check_guards(q3dr_map* map, int* overwritten);
 /* Frees and re-uploads all device state (the reference's recovery after a CUDA error, bvh.h:443-449). */
 int q3dr_map_reset(q3dr_map* map);
 int q3dr_map_destroy(q3dr_map* map);

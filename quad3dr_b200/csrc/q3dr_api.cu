@@ -954,6 +954,18 @@ int q3dr_map_get_info(const q3dr_map* m, q3dr_map_info* info) {
   return Q3DR_OK;
 }
 
+int q3dr_map_check_guards(q3dr_map* m, int* overwritten) {
+  if (!m || !overwritten) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
+  *overwritten = 0;
+  if (!guards_enabled()) return fail(Q3DR_ERR_INVALID_ARG, "guards are off: set Q3DR_GUARD=1 before the library allocates");
+  Q3DR_CUDA(cudaSetDevice(m->device));
+  Q3DR_CUDA(cudaDeviceSynchronize());
+  const int bad = m->overwritten_guards();
+  if (bad < 0) return fail(Q3DR_ERR_CUDA, "guard words could not be read back");
+  *overwritten = bad;
+  return Q3DR_OK;
+}
+
 int q3dr_map_last_stats(const q3dr_map* m, q3dr_stats* stats) {
   if (!m || !stats) return fail(Q3DR_ERR_INVALID_ARG, "NULL argument");
   *stats = m->stats;

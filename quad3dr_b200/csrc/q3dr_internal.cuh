@@ -49,15 +49,45 @@ using q3dr_detail::fail;
     if (st__ != Q3DR_OK) return st__; \
   } while (0)
 
+// Guard words behind every device buffer (Q3DR_GUARD=1 in the environment): compute-sanitizer is closed on the GPU pool
+// this library is developed on, so writes past the end of a buffer are caught by our own means -- every DevBuf is
+// allocated with kGuardBytes of a known pattern behind it, and q3dr_map_check_guards() reads the patterns back.
+constexpr size_t kGuardBytes = 256;
+constexpr unsigned char kGuardPattern = 0xA5;
+inline bool guards_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("Q3DR_GUARD");
+    return e != nullptr && e[0] != '\0' && e[0] != '0';
+  }();
+  return on;
+}
+inline cudaError_t guarded_malloc(void** q, size_t bytes) {
+  if (!guards_enabled()) return cudaMalloc(q, bytes);
+  cudaError_t e = cudaMalloc(q, bytes + kGuardBytes);
+  if (e == cudaSuccess) e = cudaMemset(static_cast<char*>(*q) + bytes, kGuardPattern, kGuardBytes);
+  return e;
+}
+// 0 = intact (or guards off), 1 = overwritten, -1 = could not be read
+inline int guard_state(const void* p, size_t bytes) {
+  if (!guards_enabled() || p == nullptr) return 0;
+  unsigned char h[kGuardBytes];
+  if (cudaMemcpy(h, static_cast<const char*>(p) + bytes, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  for (size_t i = 0; i < kGuardBytes; ++i) {
+    if (h[i] != kGuardPattern) return 1;
+  }
+  return 0;
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;  // elements
+  int guard() const { return guard_state(p, cap * sizeof(T)); }
   int ensure(size_t n, bool keep = false, cudaStream_t s = 0) {
     if (n <= cap) return Q3DR_OK;
     size_t want = std::max(n, cap + cap / 2);
     T* q = nullptr;
-    Q3DR_CUDA(cudaMalloc(&q, want * sizeof(T)));
+    Q3DR_CUDA(guarded_malloc(reinterpret_cast<void**>(&q), want * sizeof(T)));
     if (keep && p && cap) {
       cudaError_t e = cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s);
       if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -77,7 +107,7 @@ struct DevBuf {
   int grow_deferred(size_t n, size_t used, cudaStream_t s, std::vector<void*>* retired) {
     if (n <= cap) return Q3DR_OK;
     T* q = nullptr;
-    Q3DR_CUDA(cudaMalloc(&q, n * sizeof(T)));
+    Q3DR_CUDA(guarded_malloc(reinterpret_cast<void**>(&q), n * sizeof(T)));
     if (p && used) {
       cudaError_t e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) {
@@ -249,6 +279,24 @@ struct q3dr_map {
   void free_retired() {
     for (void* q : retired) cudaFree(q);
     retired.clear();
+  }
+
+  // number of device buffers of this map whose guard words were overwritten (Q3DR_GUARD=1), or -1 on a read error
+  int overwritten_guards() const {
+    const int states[] = {d_nodes.guard(), d_leaf_rec.guard(), d_depth.guard(), d_counter.guard(), d_planes.guard(),
+                          d_vp_flags.guard(), d_vp_list.guard(), d_first_pix.guard(), d_bitmap.guard(), d_kept.guard(),
+                          d_seg_u32.guard(), d_blk_u32.guard(), d_seg_f64.guard(), t_leaf.guard(), t_info.guard(),
+                          t_dsq.guard(), t_pix.guard(), t_code.guard(), d_nimg.guard(), d_offsets.guard(), d_total.guard(),
+                          d_hit_count.guard(), r_leaf.guard(), r_info.guard(), r_dsq.guard(), r_pix.guard(), d_rt.guard(),
+                          d_ray_o.guard(), d_ray_d.guard(), d_pixels.guard(), d_dense.guard(), d_set_out.guard(),
+                          d_set_idx.guard(), d_set_part.guard(), d_q_boxes.guard(), d_q_counts.guard(), d_q_offsets.guard(),
+                          d_q_leaf.guard(), d_q_sorted.guard(), d_q_tmp.guard(), d_q_valid.guard()};
+    int bad = 0;
+    for (int st : states) {
+      if (st < 0) return -1;
+      bad += st;
+    }
+    return bad;
   }
 
   uint64_t device_bytes() const {

@@ -220,6 +220,7 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_map_check_guards.argtypes = [vp, C.POINTER(C.c_int)]
     L.q3dr_candidate_opts_default.argtypes = [C.POINTER(CandidateOpts)]
     L.q3dr_candidate_opts_default.restype = None
     L.q3dr_generate_viewpoint_entries.argtypes = ([vp, fp, C.c_uint32] + [C.c_uint32] * 4 + [fp, fp, C.c_size_t, fp, fp, C.c_size_t,
@@ -613,6 +614,12 @@ class OccupancyMap:
             )
         )
         return ScoreResult(r, copy=copy)
+
+    def check_guards(self) -> int:
+        """Q3DR_GUARD=1 only: number of device buffers with an overwritten guard (a write past the end)."""
+        n = C.c_int(0)
+        _check(load_library().q3dr_map_check_guards(self._h, C.byref(n)))
+        return int(n.value)
 
     def set_result_fields(self, first_pixel: bool = True, dist_sq: bool = True):
         """Which per-entry arrays scoring calls deliver besides (leaf, information); see q3dr_map_set_result_fields."""

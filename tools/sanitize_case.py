@@ -1,7 +1,10 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck): the smoke test plus a
 multi-chunk scoring call (several chunks share the dedup tables and the result pools), the compat entry points, the
 mesh-normal scoring pass, the set consumers and the real-image down-weighting.
-    compute-sanitizer --tool memcheck python tools/sanitize_case.py"""
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py
+compute-sanitizer is closed on the GPU pool this was developed on (profiles/r02_memcheck.log); the substitute is
+    Q3DR_GUARD=1 python tools/sanitize_case.py
+which puts guard words behind every device buffer of the map and checks them afterwards (tests/test_guards.py)."""
 import os
 import sys
 
@@ -47,4 +50,8 @@ gmap.overlap_boxes(np.array([[-1, -1, 0, 1, 1, 2]], dtype=np.float32))
 depth_maps = np.ones((2, h, w), dtype=np.float32)
 depth_maps[:, 10:40, 20:70] = 0
 gmap.downweight_real_viewpoints(cam.K, w, h, vps[:2], depth_maps, 0.5, mesh=mesh)
+if os.environ.get("Q3DR_GUARD", "") not in ("", "0"):
+    bad = gmap.check_guards()
+    assert bad == 0, f"{bad} device buffers were written past their end"
+    print("guard words behind all device buffers intact")
 print("sanitize case OK:", a.n_entries, "entries,", int(gmap.stats().chunks), "chunks in the last call")
