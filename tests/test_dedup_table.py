@@ -1,0 +1,98 @@
+"""The first-pixel table of the dedup is never reset between chunks: entries carry a tag that decreases from chunk to
+chunk (raycast2_kernels.cuh, score_device_impl).  These tests walk the corners of that scheme on the GPU:
+  * more than 1022 chunks on one map (the tag space wraps and the table is cleared once),
+  * windows beyond 2^22 pixels (untagged mode: the scoring pass resets what it read) and switching between the modes,
+  * result fields switched off and on again between calls.
+Every result must equal the oracle's / the first call's bit for bit."""
+import numpy as np
+import pytest
+
+from _common import bits, scene
+from quad3dr_b200 import engine as E
+from quad3dr_b200 import synth
+
+
+def _same(a, b):
+    return (a.n_entries == b.n_entries and np.array_equal(a.offsets, b.offsets) and np.array_equal(a.leaf, b.leaf)
+            and np.array_equal(a.first_pixel, b.first_pixel) and np.array_equal(bits(a.information), bits(b.information))
+            and np.array_equal(bits(a.dist_sq), bits(b.dist_sq)) and np.array_equal(bits(a.total), bits(b.total))
+            and np.array_equal(a.hit_count, b.hit_count))
+
+
+@pytest.mark.gpu
+def test_tag_space_wraps_without_a_trace(monkeypatch):
+    sc = scene("tiny")
+    gmap = E.OccupancyMap(sc.leaves.boxes, sc.leaves.weight, sc.leaves.normal, sc.depth)
+    w, h = 48, 36
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(sc.leaves, 6, config_id=81)
+    monkeypatch.setenv("Q3DR_CHUNK", "2")  # 3 chunks per call, different viewpoints share table slots over time
+    first = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps)
+    assert first.n_entries > 300
+    ref = [sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, cam.K, w, vps[v], height=h) for v in range(6)]
+    for v in range(6):
+        assert np.array_equal(first.viewpoint(v)["leaf"], ref[v]["leaf"]) and np.array_equal(first.viewpoint(v)["pixel"], ref[v]["pixel"])
+    # 400 calls x 3 chunks = 1200 chunks > 1022 tags; rotate the viewpoints so that slots see different images
+    for it in range(400):
+        k = it % 6
+        rolled = np.roll(vps, -k, axis=0)
+        res = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), rolled)
+        if it % 37 == 0 or 330 <= it <= 345:  # around the wrap (chunk 1022 falls into call 340) and spot checks
+            for v in range(6):
+                a, b = res.viewpoint(v), first.viewpoint((v + k) % 6)
+                assert np.array_equal(a["leaf"], b["leaf"]) and np.array_equal(a["pixel"], b["pixel"]), (it, v)
+                assert np.array_equal(bits(a["info"]), bits(b["info"])) and a["hit_count"] == b["hit_count"], (it, v)
+    assert _same(gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps), first)
+    gmap.close()
+
+
+@pytest.mark.gpu
+def test_untagged_mode_for_huge_windows_and_mode_switches():
+    sc = scene("tiny")
+    gmap = E.OccupancyMap(sc.leaves.boxes, sc.leaves.weight, sc.leaves.normal, sc.depth)
+    vps = synth.make_viewpoints(sc.leaves, 2, config_id=82)
+    small = synth.make_camera(64, 48)
+    big_w, big_h = 2304, 1856  # 4.28 M pixels > 2^22: pixel indices no longer fit under a tag
+    big = synth.make_camera(big_w, big_h)
+    a0 = gmap.score_viewpoints(small.K, 64, (0, 64, 0, 48), vps)
+    b0 = gmap.score_viewpoints(big.K, big_w, (0, big_w, 0, big_h), vps[:1])
+    a1 = gmap.score_viewpoints(small.K, 64, (0, 64, 0, 48), vps)
+    b1 = gmap.score_viewpoints(big.K, big_w, (0, big_w, 0, big_h), vps[:1])
+    assert _same(a0, a1) and _same(b0, b1)
+    # the huge window against the oracle (first pixels well beyond 2^22 occur)
+    ref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, big.K, big_w, vps[0], height=big_h)
+    got = b0.viewpoint(0)
+    assert np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(got["pixel"], ref["pixel"])
+    assert got["pixel"].max() >= (1 << 22)
+    assert abs(got["total"] - ref["total"]) <= 1e-5 * abs(ref["total"])
+    # a sub-window of the same huge image is tagged again (small pixel count): same voxels as the matching crop
+    sub = gmap.score_viewpoints(big.K, big_w, (1000, 1400, 800, 1100), vps[:1])
+    px = ref["pixel"]
+    assert sub.n_entries > 0
+    ref_sub = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, big.K, big_w, vps[0], window=(1000, 1400, 800, 1100), height=big_h)
+    assert np.array_equal(sub.viewpoint(0)["leaf"], ref_sub["leaf"]) and np.array_equal(sub.viewpoint(0)["pixel"], ref_sub["pixel"])
+    gmap.close()
+
+
+@pytest.mark.gpu
+def test_result_fields_off_and_on(monkeypatch):
+    sc = scene("small")
+    gmap = E.OccupancyMap(sc.leaves.boxes, sc.leaves.weight, sc.leaves.normal, sc.depth)
+    w, h = 96, 72
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(sc.leaves, 9, config_id=83)
+    monkeypatch.setenv("Q3DR_CHUNK", "4")
+    full = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps)
+    gmap.set_result_fields(first_pixel=False, dist_sq=False)
+    lean = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps)
+    assert lean.first_pixel.size == 0 and lean.dist_sq.size == 0
+    assert np.array_equal(lean.leaf, full.leaf) and np.array_equal(bits(lean.information), bits(full.information))
+    assert np.array_equal(lean.offsets, full.offsets) and np.array_equal(bits(lean.total), bits(full.total))
+    gmap.set_result_fields(first_pixel=True, dist_sq=False)
+    half = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps)
+    assert np.array_equal(half.first_pixel, full.first_pixel) and half.dist_sq.size == 0
+    gmap.set_result_fields(first_pixel=True, dist_sq=True)
+    assert _same(gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps), full)
+    with pytest.raises(E.Q3drError):
+        E._check(E.load_library().q3dr_map_set_result_fields(gmap._h, 8))
+    gmap.close()
