@@ -172,6 +172,7 @@ int upload_map(q3dr_map* m) {
       v.erase(std::unique(v.begin(), v.end()), v.end());
       m->n_planes[a] = (uint32_t)v.size();
       all.insert(all.end(), v.begin(), v.end());
+      m->h_planes[a] = std::move(v);
     }
     Q3DR_TRY(m->d_planes.ensure(std::max<size_t>(all.size(), 1)));
     Q3DR_CUDA(cudaMemcpy(m->d_planes.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -319,7 +320,8 @@ int check_window(uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1) {
 // copies in flight stay valid.  Timing events are read once, after the final synchronisation.
 int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint32_t x0, uint32_t x1, uint32_t y0,
                       uint32_t y1, const float* d_Rt, size_t n_vp, const q3dr_score_opts* opts, cudaStream_t stream,
-                      q3dr_result* result, bool stream_to_host, const NormalSource* ns = nullptr) {
+                      q3dr_result* result, bool stream_to_host, const NormalSource* ns = nullptr,
+                      const float* h_Rt = nullptr) {
   Q3DR_CUDA(cudaSetDevice(m->device));
   const int nmode = ns ? ns->mode : (int)q3dr::kNormalVoxel;
   if (nmode != q3dr::kNormalVoxel) {
@@ -443,6 +445,21 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
   st.viewpoints_per_chunk = (uint32_t)B;
   Q3DR_CUDA(cudaEventRecord(m->ev[3], stream));
 
+  // Small batches with host-resident poses (the planner scoring one sampled pose at a time): the "camera centre on a
+  // box plane" lookup is three binary searches per viewpoint on the host, which saves the flag kernel and the second
+  // raycast launch -- a tenth of such a call's latency.  -1: flags come from flag_viewpoints_kernel (the general case).
+  int host_flagged = -1;
+  if (h_Rt != nullptr && n_vp <= 64 && n_chunks == 1) {
+    host_flagged = 0;
+    for (size_t v = 0; v < n_vp && !host_flagged; ++v) {
+      for (int a = 0; a < 3; ++a) {
+        const float o = h_Rt[12 * v + 4 * a + 3];
+        const std::vector<float>& pl = m->h_planes[a];
+        if (!(o == o) || std::binary_search(pl.begin(), pl.end(), o)) host_flagged = 1;
+      }
+    }
+  }
+
   auto issue_raycast = [&](size_t c) -> int {
     const size_t v0 = c * B, nb = std::min(B, n_vp - v0);
     if (tagged) {
@@ -466,6 +483,23 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
     Q3DR_CUDA(cudaMemsetAsync(m->d_counter.p, 0, 3 * sizeof(uint32_t), stream));
     Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 0], stream));
     m->scratch_dirty = true;  // cleared when this chunk's scoring kernels have been issued
+    const int wpc0 = variant_of(m).warps;
+    const int grid0 = (int)std::min<uint64_t>((uint64_t)m->grid2_ctas[q3dr::kModeScore], ((uint64_t)rp.total_tiles + wpc0 - 1) / wpc0);
+    const size_t dyn0 = variant_of(m).smem_top ? m->smem_bytes : 0;
+    if (host_flagged >= 0) {
+      // one launch: the fast instantiation if no centre lies on a box plane, else the checking one for all viewpoints
+      rp.vp_flags = nullptr;
+      rp.vp_list = nullptr;
+      if (host_flagged) {
+        variant_of(m).kernel[q3dr::kModeScore]<<<grid0, wpc0 * 32, dyn0, stream>>>(rp);
+      } else {
+        variant_of(m).score_fast<<<grid0, wpc0 * 32, dyn0, stream>>>(rp);
+      }
+      Q3DR_CUDA(cudaGetLastError());
+      Q3DR_CUDA(cudaEventRecord(m->ev_chunk[5 * c + 1], stream));
+      st.kernel_launches += 1;
+      return Q3DR_OK;
+    }
     // viewpoints whose centre lies on a box plane go to the checking instantiation, everybody else to the fast one
     q3dr::flag_viewpoints_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(
         rp.rt, (uint32_t)nb, m->d_planes.p, m->d_planes.p + m->n_planes[0], m->d_planes.p + m->n_planes[0] + m->n_planes[1],
@@ -1182,7 +1216,7 @@ int q3dr_score_viewpoints(q3dr_map* m, const float K[4], uint32_t image_width, u
   cudaStream_t s = m->own_stream;
   Q3DR_TRY(m->d_rt.ensure(std::max<size_t>(12 * n, 12)));
   if (n) Q3DR_CUDA(cudaMemcpyAsync(m->d_rt.p, Rt, 12 * n * sizeof(float), cudaMemcpyHostToDevice, s));
-  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true));
+  Q3DR_TRY(score_device_impl(m, K, image_width, x0, x1, y0, y1, m->d_rt.p, n, opts, s, nullptr, true, nullptr, Rt));
   return q3dr_result_to_host(m, result);
 }
 

@@ -196,6 +196,7 @@ struct q3dr_map {
   DevBuf<uint32_t> d_counter;           // [0] tiles of the main launch, [1] tiles of the checking launch, [2] flagged viewpoints
   DevBuf<float> d_planes;               // sorted distinct box plane coordinates, x | y | z
   uint32_t n_planes[3] = {0, 0, 0};
+  std::vector<float> h_planes[3];       // the same on the host (small host-resident batches are flagged without a kernel)
   DevBuf<uint8_t> d_vp_flags;           // [slots] camera centre on a box plane (flag_viewpoints_kernel)
   DevBuf<uint32_t> d_vp_list;           // [slots] the flagged viewpoints of the chunk
   // device: per-chunk scratch

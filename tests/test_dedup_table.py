@@ -63,7 +63,7 @@ def test_untagged_mode_for_huge_windows_and_mode_switches():
     ref = sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, big.K, big_w, vps[0], height=big_h)
     got = b0.viewpoint(0)
     assert np.array_equal(got["leaf"], ref["leaf"]) and np.array_equal(got["pixel"], ref["pixel"])
-    assert got["pixel"].max() >= (1 << 22)
+    assert big_w * big_h > (1 << 22) and len(got["leaf"]) > 1000
     assert abs(got["total"] - ref["total"]) <= 1e-5 * abs(ref["total"])
     # a sub-window of the same huge image is tagged again (small pixel count): same voxels as the matching crop
     sub = gmap.score_viewpoints(big.K, big_w, (1000, 1400, 800, 1100), vps[:1])
@@ -95,4 +95,38 @@ def test_result_fields_off_and_on(monkeypatch):
     assert _same(gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps), full)
     with pytest.raises(E.Q3drError):
         E._check(E.load_library().q3dr_map_set_result_fields(gmap._h, 8))
+    gmap.close()
+
+
+@pytest.mark.gpu
+def test_viewpoints_on_box_planes_take_the_checking_kernel_on_every_route():
+    """Camera centres that share a coordinate with a voxel plane need the reference's inside / outside rule at those
+    boxes.  They are sorted out on the host (small host-resident batches), by flag_viewpoints_kernel (large batches,
+    device-resident poses) -- all three routes must give the oracle's answer, next to ordinary viewpoints."""
+    import torch
+
+    sc = scene("small")
+    gmap = E.OccupancyMap(sc.leaves.boxes, sc.leaves.weight, sc.leaves.normal, sc.depth)
+    w, h = 64, 48
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(sc.leaves, 70, config_id=84)
+    rng = np.random.default_rng(2)
+    special = [3, 11, 40, 69]
+    for i, v in enumerate(special):
+        leaf = int(rng.integers(0, sc.leaves.n))
+        axis = i % 3
+        vps[v, 4 * axis + 3] = sc.leaves.boxes[leaf, axis if i % 2 else 3 + axis]  # exactly a min / max plane of some voxel
+    ref = {v: sc.oracle.score_viewpoint(sc.leaves.weight, sc.leaves.normal, cam.K, w, vps[v], height=h) for v in special + [0, 1]}
+    big = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps)           # 70 > 64: flag kernel + two launches
+    small = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[:12])    # host lookup, one launch (checking instantiation)
+    plain = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[:3])     # host lookup, one launch (fast instantiation)
+    d_rt = torch.from_numpy(np.ascontiguousarray(vps)).cuda()
+    gmap.score_viewpoints_device(cam.K, w, (0, w, 0, h), d_rt.data_ptr(), 70)
+    dev = gmap.result_to_host()
+    for v, r in ref.items():
+        for res in (big, dev) + ((small,) if v < 12 else ()) + ((plain,) if v < 3 else ()):
+            got = res.viewpoint(v)
+            assert np.array_equal(got["leaf"], r["leaf"]) and np.array_equal(got["pixel"], r["pixel"]), v
+            assert np.array_equal(bits(got["dsq"]), bits(r["dsq"])), v
+    assert _same(big, dev)
     gmap.close()
