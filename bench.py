@@ -710,6 +710,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_multi(args):
+    """--mode multi: the path as the reference's single C++ process would drive it -- q3dr_multi_*: one process, one host
+    thread per GPU, map replicated, viewpoints sharded, host poses in, host CSR results out, and (exchange on) every GPU
+    holding all GPUs' results at the end of the call.  Wall clock around the C-ABI call."""
+    import torch
+
+    from quad3dr_b200 import engine as E
+
+    n_gpus = max(1, int(args.gpus))
+    if torch.cuda.device_count() < n_gpus:
+        raise SystemExit(f"bench.py --mode multi: {n_gpus} GPUs requested, {torch.cuda.device_count()} visible")
+    leaves, depth, cam, vps = build_inputs(args.workload, 0, 1, nvp=WORKLOADS[args.workload][1] * n_gpus)
+    nvp, w, h = vps.shape[0], cam.width, cam.height
+    multi = E.MultiGpuMap(leaves.boxes, leaves.weight, leaves.normal, depth, devices=list(range(n_gpus)))
+    multi.set_result_fields(first_pixel=False, dist_sq=False)
+    opts = E.default_opts()
+    window = (0, w, 0, h)
+    probe = multi.score_viewpoints(cam.K, w, window, vps, opts, copy=False)
+    per_gpu_vp = max(r.n_viewpoints for _, r in probe)
+    per_gpu_entries = max(r.n_entries for _, r in probe)
+    if n_gpus > 1 and os.environ.get("Q3DR_GATHER", "peer") == "peer":
+        multi.enable_gather(per_gpu_vp, int(per_gpu_entries * 1.25) + 4096)
+        gather_note = "q3dr_multi_enable_gather: per finished chunk copy-engine pushes into every GPU's HBM (peer access), completion flags"
+    else:
+        gather_note = "none: results stay per GPU in pinned host memory"
+    for _ in range(max(args.warmup, 3)):
+        multi.score_viewpoints(cam.K, w, window, vps, opts, copy=False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    flushes = [torch.empty(256 << 20, dtype=torch.uint8, device=torch.device("cuda", g)) for g in range(n_gpus)]
+    t_wall0 = time.time()
+    ms = 0.0
+    parts = None
+    for s_ in range(args.steps):
+        for f in flushes:
+            f.fill_(s_ & 0xFF)
+        for g in range(n_gpus):
+            torch.cuda.synchronize(g)
+        t0 = time.perf_counter()
+        parts = multi.score_viewpoints(cam.K, w, window, vps, opts, copy=False)
+        ms += (time.perf_counter() - t0) * 1e3
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    entries = sum(r.n_entries for _, r in parts)
+    verified = None
+    if n_gpus > 1 and gather_note.startswith("q3dr_multi_enable_gather"):
+        # every GPU's copy of every part against the part's own host result
+        from quad3dr_b200.dist import CudaArrayView
+
+        verified = True
+        for on in range(n_gpus):
+            for src, (_, ref) in enumerate(parts):
+                v = multi.gathered(on, src)
+                ok = v.n_viewpoints == ref.n_viewpoints and v.n_entries == ref.n_entries
+                if ok and ref.n_entries:
+                    dev = torch.device("cuda", on)
+                    leaf = torch.as_tensor(CudaArrayView(v.leaf, v.n_entries, "<i4"), device=dev).cpu().numpy()
+                    info = torch.as_tensor(CudaArrayView(v.information, v.n_entries, "<i4"), device=dev).cpu().numpy()
+                    ok = bool(np.array_equal(leaf, ref.leaf) and np.array_equal(info, ref.information.view(np.int32)))
+                verified = verified and ok
+    rays = nvp * w * h
+    ms_per_step = ms / args.steps
+    cfg = workload_config(args.workload, leaves, cam, nvp // n_gpus, n_gpus)
+    cfg["parallelism"] = f"one process, one host thread per GPU (q3dr_multi_*), viewpoint-sharded x{n_gpus}, map replicated"
+    cfg["timing"] = "wall clock around q3dr_multi_score_viewpoints (host poses in, host CSR results out), summed over steps"
+    cfg["gather"] = gather_note
+    cfg["normals"] = "per voxel (enable_opengl = false)"
+    line = {
+        "metric": METRIC, "value": rays / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "mode": "multi", "config": cfg,
+        "viewpoints_per_sec": nvp / (ms_per_step * 1e-3),
+        "e2e": {"value": rays / (ms_per_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nvp * 48,
+                "d2h_bytes_per_step": (nvp + n_gpus) * 8 + nvp * 8 + entries * 8, "ms_per_step": ms_per_step,
+                "note": "the timed call IS the host-buffer call: value == e2e in this mode"},
+        "gpu_launches": None, "clocks": clocks, "result_entries": int(entries), "gather_verified": verified,
+    }
+    multi.close()
+    emit(line)
+
+
 _REAL_STDOUT = None
 
 
@@ -745,13 +827,21 @@ def main():
     ap.add_argument("--no-north-star", dest="north_star", action="store_false",
                     help="skip the C3 block (10 M-leaf map) that accompanies the default C2 line")
     ap.add_argument("--no-shim", dest="shim", action="store_false", help="skip the e2e_shim block (C++ call surface)")
+    ap.add_argument("--mode", default="ranks", choices=["ranks", "multi"],
+                    help="ranks: one process per GPU (torchrun contract, the default); multi: ONE process drives all --gpus "
+                         "through q3dr_multi_* like the reference's C++ process would (launch with plain python)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not (args.impl == "ours" and args.gpus > 1 and world == 1):
+    if not (args.impl == "ours" and args.gpus > 1 and world == 1 and args.mode == "ranks"):
         _quiet_stdout()  # (the torchrun re-launch below passes its children's stdout through untouched)
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.mode == "multi":
+        if world > 1:
+            raise SystemExit("bench.py --mode multi is a single process: launch it with plain python, not torchrun")
+        run_multi(args)
         return
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU

@@ -112,6 +112,7 @@ const RayVariant kRayVariants[] = {
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
+constexpr uint32_t kDefaultTileRun = 1;
 constexpr int kDefaultRayVariant = 6;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar by 5-9 %, 72 registers beat 64 and 80 by 1-3 %, four rays per lane lose 2x
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
@@ -123,6 +124,8 @@ int configure_kernel2(q3dr_map* m) {
     if (v < 0 || v >= kNumRayVariants) return fail(Q3DR_ERR_INVALID_ARG, "Q3DR_RAY_VARIANT out of range");
     m->ray_variant = (int)v;
   }
+  m->tile_run = kDefaultTileRun;
+  if (const char* e = std::getenv("Q3DR_TILE_RUN")) m->tile_run = (uint32_t)std::min<long>(64, std::max<long>(1, std::strtol(e, nullptr, 10)));
   const RayVariant& rv = variant_of(m);
   for (int mode = 0; mode < 2; ++mode) {
     int per_sm = 0;
@@ -283,6 +286,7 @@ void fill_raycast_params(const q3dr_map* m, const float K[4], uint32_t x0, uint3
   p->tiles_x = (p->w + tile_w - 1) / tile_w;
   const uint32_t tiles_y = (p->h + tile_h - 1) / tile_h;
   p->tiles_per_vp = p->tiles_x * tiles_y;
+  p->tile_run = m->tile_run;
   p->inv_tiles_x = 1.0 / (double)p->tiles_x;
   p->inv_tiles_per_vp = 1.0 / (double)p->tiles_per_vp;
   p->max_range = max_range;

@@ -273,6 +273,7 @@ struct q3dr_map {
   q3dr_exchange* exchange = nullptr;   // pushes every finished chunk to the peers (q3dr_exchange_begin_step)
   int grid_rays_ctas = 0;
   int grid2_ctas[2] = {0, 0};
+  uint32_t tile_run = 1;               // consecutive tiles per warp and counter visit (Q3DR_TILE_RUN)
   int ray_variant = 0;                 // packet shape of the camera-window kernel (q3dr_api.cu: kRayVariants)
   size_t smem_bytes = 0;
   q3dr_stats stats{};

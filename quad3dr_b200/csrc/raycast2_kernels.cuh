@@ -368,13 +368,11 @@ struct PacketShape {
 template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps, bool kSmemTop>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const RaycastParams p) {
   extern __shared__ float4 smem_top[];  // kSmemTop: p.n_top nodes of 8 float4 (launch with that much dynamic smem)
-  __shared__ uint32_t s_tile[kWarps];
   if (kSmemTop) {
     for (uint32_t i = threadIdx.x; i < p.n_top * 8u; i += blockDim.x) smem_top[i] = p.nodes[i];
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
   const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
   const float kInf = __int_as_float(0x7F800000);
   constexpr int kRows = PacketShape<NR, TW>::kRowsPerSlab;
@@ -385,11 +383,18 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
   const uint32_t total_tiles = listed ? __ldg(p.n_flagged) * p.tiles_per_vp : p.total_tiles;
   uint32_t* counter = p.tile_counter + (listed ? 1 : 0);
 
+  // A warp takes RUNS of p.tile_run consecutive tiles (neighbouring packets of one image row): what the previous packet
+  // pulled into this SM's L1 -- the bottom of the tree around its pixels -- is what the next one walks first, and the
+  // tile counter sees one atomic per run.
+  uint32_t run_next = 0, run_end = 0;
   while (true) {
-    if (lane == 0) s_tile[warp] = atomicAdd(counter, 1u);
-    __syncwarp();
-    const uint32_t tile = s_tile[warp];
-    __syncwarp();
+    if (run_next == run_end) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(counter, p.tile_run);
+      run_next = __shfl_sync(Q3DR_FULL_MASK, base, 0);
+      run_end = run_next + p.tile_run;
+    }
+    const uint32_t tile = run_next++;
     if (tile >= total_tiles) break;
 
     // tile -> (viewpoint slot, tile row, tile column): quotients through the reciprocals the host prepared (a double

@@ -46,6 +46,7 @@ struct RaycastParams {
   uint32_t tiles_x, tiles_per_vp;
   double inv_tiles_x, inv_tiles_per_vp;  // 1.0 / the two above (raycast2_kernel's tile decoding)
   uint32_t total_tiles;
+  uint32_t tile_run;     // raycast2_kernel: consecutive tiles a warp takes per visit to the tile counter (>= 1)
   float max_range;
   // kModeScore
   uint32_t* first_pix;  // [slot][leaf_stride]

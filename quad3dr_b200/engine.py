@@ -952,6 +952,11 @@ class MultiGpuMap:
     def update_weights(self, weights):
         _check(load_library().q3dr_multi_update_weights(self._h, _fp(_f32(weights))))
 
+    def set_result_fields(self, first_pixel: bool = True, dist_sq: bool = True):
+        f = (RESULT_FIRST_PIXEL if first_pixel else 0) | (RESULT_DIST_SQ if dist_sq else 0)
+        for i in range(self.n_devices):
+            _check(load_library().q3dr_map_set_result_fields(load_library().q3dr_multi_map(self._h, i), f))
+
     def enable_gather(self, max_viewpoints_per_gpu: int, max_entries_per_gpu: int):
         """after this every score_viewpoints call leaves the results of ALL GPUs on every GPU (0, 0 switches it off)"""
         _check(load_library().q3dr_multi_enable_gather(self._h, max_viewpoints_per_gpu, max_entries_per_gpu))
@@ -962,8 +967,10 @@ class MultiGpuMap:
         _check(load_library().q3dr_multi_gathered(self._h, on, src, C.byref(r)))
         return DeviceResult(r)
 
-    def score_viewpoints(self, K, image_width: int, window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None):
-        """Returns [(first_viewpoint, ScoreResult)] per GPU; viewpoint v of part g is viewpoint first + v of the call."""
+    def score_viewpoints(self, K, image_width: int, window: Sequence[int], Rt, opts: Optional[ScoreOpts] = None,
+                         copy: bool = True):
+        """Returns [(first_viewpoint, ScoreResult)] per GPU; viewpoint v of part g is viewpoint first + v of the call.
+        copy=False: the arrays alias the maps' pinned host buffers (valid until the next call)."""
         K = _f32(K, (4,))
         Rt = np.ascontiguousarray(_f32(Rt).reshape(-1, 12))
         opts = opts or default_opts()
@@ -973,4 +980,4 @@ class MultiGpuMap:
             self._h, _fp(K), image_width, x0, x1, y0, y1, _fp(Rt), Rt.shape[0], C.byref(opts), C.byref(r)))
         first = np.ctypeslib.as_array(C.cast(r.first_viewpoint, C.POINTER(C.c_uint64)), shape=(r.n_parts + 1,)).copy()
         parts = C.cast(r.parts, C.POINTER(_Result))
-        return [(int(first[g]), ScoreResult(parts[g], copy=True)) for g in range(r.n_parts)]
+        return [(int(first[g]), ScoreResult(parts[g], copy=copy)) for g in range(r.n_parts)]

@@ -13,7 +13,7 @@ from quad3dr_b200 import engine as E
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "C2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,2,3,4,5").split(",")]
+variants = [v for v in os.environ.get("VARIANTS", "0,1,2,3,4,5").split(",")]  # "6" or "6:4" = variant 6 with Q3DR_TILE_RUN=4
 leaves, depth, cam, vps = B.build_inputs(workload, 0, 1)
 dev = torch.device("cuda", 0)
 d_rt = torch.from_numpy(vps).to(dev)
@@ -22,7 +22,12 @@ stream = torch.cuda.current_stream()
 ref = None
 out = []
 for v in variants:
-    os.environ["Q3DR_RAY_VARIANT"] = str(v)
+    vv, _, run = str(v).partition(":")
+    os.environ["Q3DR_RAY_VARIANT"] = vv
+    if run:
+        os.environ["Q3DR_TILE_RUN"] = run
+    else:
+        os.environ.pop("Q3DR_TILE_RUN", None)
     gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=0)
     opts = E.default_opts()
     win = (0, cam.width, 0, cam.height)
