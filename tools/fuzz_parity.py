@@ -96,6 +96,28 @@ while time.time() < t_end:
                   got["leaf"][bad[:8]], ref["leaf"][bad[:8]])
             sys.exit(1)
         rays += (x1 - x0) * (y1 - y0)
+    # a batch large enough for the device-side route (flag_viewpoints_kernel + fast launch + checking launch), cut into
+    # several chunks: every viewpoint against the oracle, poses on faces / corners / inside boxes mixed with ordinary ones
+    if scenes % 3 == 0:
+        nb = int(rng.integers(65, 90))
+        W, H = int(rng.integers(8, 40)), int(rng.integers(8, 30))
+        f = W * 10.0 ** rng.uniform(-0.5, 0.5)
+        K = np.array([f, f, W / 2 + rng.uniform(-2, 2), H / 2 + rng.uniform(-2, 2)], np.float32)
+        Rts = np.stack([random_pose(boxes) for _ in range(nb)])
+        max_range = float(rng.choice([-1.0, 60.0, 5.0]))
+        os.environ["Q3DR_CHUNK"] = str(int(rng.integers(7, 40)))
+        opts = dict(raycast_max_range=max_range, ignore_voxels_with_zero_information=int(rng.integers(0, 2)))
+        res = gmap.score_viewpoints(K, W, (0, W, 0, H), Rts, E.default_opts(**opts))
+        os.environ.pop("Q3DR_CHUNK", None)
+        for v in range(nb):
+            sref = oracle.score_viewpoint(w, nr, K, W, Rts[v], window=(0, W, 0, H), opts=O.default_opts(**opts))
+            g = res.viewpoint(v)
+            if not (np.array_equal(g["leaf"], sref["leaf"]) and np.array_equal(g["pixel"], sref["pixel"])
+                    and np.array_equal(bits(g["dsq"]), bits(sref["dsq"])) and g["hit_count"] == sref["hit_count"]):
+                np.savez("gpurun_out/fuzz_fail_batch.npz", boxes=boxes, w=w, nr=nr, K=K, Rt=Rts, v=v, max_range=max_range)
+                print("MISMATCH (batch) scene", scenes, "viewpoint", v, "of", nb)
+                sys.exit(1)
+        rays += nb * W * H
     # ray-list entry point (intersectsCuda): random rays, some axis-parallel, some starting on box planes
     m = 1500
     lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
