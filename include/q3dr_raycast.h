@@ -177,6 +177,8 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
  *         or NULL (=> the splitMedian depth implied by n and k). */
 int q3dr_map_create(const float* boxes, const float* weights, const float* normals, const uint32_t* depth,
                     size_t n, int device, q3dr_map** out);
+/* (Every scoring / raycast entry point returns with its stream synchronised and keeps no reference to a caller's stream
+ * afterwards, so updates and follow-up queries never race with work of an earlier call.) */
 int q3dr_map_update_weights(q3dr_map* map, const float* weights);
 int q3dr_map_update_normals(q3dr_map* map, const float* normals);
 int q3dr_map_get_info(const q3dr_map* map, q3dr_map_info* info);
