@@ -339,6 +339,23 @@ class OccupiedTreeCuda {
     check(q3dr_map_update_weights(map_, weights_left_to_right.data()));
   }
 
+  /// ViewpointPlannerData::updateWeightsWithRealViewpoints (viewpoint_planner_data.cpp:498-571) for real images that
+  /// share one depth camera: poses (Rt: n x 12, image-to-world [R|t] rows), depth maps (n x height x width, <= 0 or inf =
+  /// nothing reconstructed at that pixel).  Lowers the weights on the device and returns them (left-to-right leaf
+  /// order) so that the caller can write them back into NodeObject::weight and the octree, as the reference does.
+  std::vector<float> updateWeightsWithRealViewpoints(const float K[4], std::size_t width, std::size_t height,
+                                                     const std::vector<float>& Rt, const std::vector<float>& depth_maps,
+                                                     const q3dr_score_opts& opts, float invalid_pixel_observation_factor,
+                                                     std::uint64_t* n_updates = nullptr) {
+    requireMap();
+    std::vector<float> weights(nodes_.size());
+    check(q3dr_map_downweight_real_viewpoints(map_, K, static_cast<std::uint32_t>(width), static_cast<std::uint32_t>(height),
+                                              Rt.data(), depth_maps.data(), Rt.size() / 12, &opts,
+                                              invalid_pixel_observation_factor, nullptr, nullptr, nullptr, weights.data(),
+                                              n_updates));
+    return weights;
+  }
+
   std::size_t getNumOfLeafNodes() const { return nodes_.size(); }
   /// leaf index of a host node (the inverse of leafNode); -1 if the node is not a leaf of this tree
   std::int32_t leafIndex(const NodeT* node) const {

@@ -542,6 +542,44 @@ int main(int argc, char** argv) {
     }
   }
 
+  // updateWeightsWithRealViewpoints through the shim against the oracle's literal loop (must stay the LAST user of the
+  // tree's weights: it lowers them)
+  {
+    const std::size_t np = cam.w * cam.h;
+    std::vector<float> Rt, depth(2 * np, 3.0f);
+    for (int v = 0; v < 2; ++v)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) Rt.push_back(vps[v].p.T.m[r][c]);
+    for (std::size_t y = 10; y < 50; ++y)
+      for (std::size_t x = 20; x < 80; ++x) {
+        depth[y * cam.w + x] = 0.0f;
+        depth[np + y * cam.w + x] = (x % 3 == 0) ? -1.0f : 2.0f;
+      }
+    q3dr_score_opts so;
+    q3dr_score_opts_default(&so);
+    so.raycast_min_range = 5.0f;
+    so.raycast_max_range = 3.0e38f;  // the reference's default for this pass: unlimited
+    std::uint64_t n_updates = 0;
+    std::vector<float> lowered = tree.updateWeightsWithRealViewpoints(Kf, cam.w, cam.h, Rt, depth, so, 0.5f, &n_updates);
+    std::vector<float> ref_w = weights;
+    orc_score_opts ro = oo;
+    ro.raycast_min_range = 5.0f;
+    ro.raycast_max_range = -1.0f;
+    std::uint64_t ref_updates = 0;
+    for (int v = 0; v < 2; ++v) {
+      ref_updates += orc_downweight_real_viewpoint(oracle, ref_w.data(), normals.data(), nullptr, Kf, (uint32_t)cam.w, (uint32_t)cam.h,
+                                                   Rt.data() + 12 * v, depth.data() + v * np, &ro, 0.5f);
+    }
+    CHECK(n_updates == ref_updates && n_updates > 500);
+    std::size_t touched = 0;
+    for (std::size_t k = 0; k < n; ++k) {
+      CHECK(std::fabs(lowered[k] - ref_w[k]) <= 1e-5f * std::fabs(ref_w[k]) + 1e-30f);
+      if (ref_w[k] != weights[k]) ++touched;
+      if (ref_w[k] == weights[k]) CHECK(lowered[k] == weights[k]);
+    }
+    CHECK(touched > 100);
+  }
+
   // error convention: callers catch OccupiedTreeType::Error
   bool threw = false;
   try {
