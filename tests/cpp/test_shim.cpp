@@ -550,10 +550,10 @@ int main(int argc, char** argv) {
     for (int v = 0; v < 2; ++v)
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 4; ++c) Rt.push_back(vps[v].p.T.m[r][c]);
-    for (std::size_t y = 10; y < 50; ++y)
-      for (std::size_t x = 20; x < 80; ++x) {
-        depth[y * cam.w + x] = 0.0f;
-        depth[np + y * cam.w + x] = (x % 3 == 0) ? -1.0f : 2.0f;
+    for (std::size_t y = 0; y < cam.h; ++y)
+      for (std::size_t x = 0; x < cam.w; ++x) {
+        if ((x / 8 + y / 8) % 2 == 0) depth[y * cam.w + x] = 0.0f;               // image 0: a checkerboard of holes
+        depth[np + y * cam.w + x] = (x % 3 == 0) ? -1.0f : 2.0f;                 // image 1: every third column
       }
     q3dr_score_opts so;
     q3dr_score_opts_default(&so);
@@ -570,14 +570,16 @@ int main(int argc, char** argv) {
       ref_updates += orc_downweight_real_viewpoint(oracle, ref_w.data(), normals.data(), nullptr, Kf, (uint32_t)cam.w, (uint32_t)cam.h,
                                                    Rt.data() + 12 * v, depth.data() + v * np, &ro, 0.5f);
     }
-    CHECK(n_updates == ref_updates && n_updates > 500);
+    if (n_updates != ref_updates) std::fprintf(stderr, "down-weighting: %llu updates vs %llu in the oracle\n", (unsigned long long)n_updates, (unsigned long long)ref_updates);
+    CHECK(n_updates == ref_updates);
+    CHECK(n_updates > 100);
     std::size_t touched = 0;
     for (std::size_t k = 0; k < n; ++k) {
       CHECK(std::fabs(lowered[k] - ref_w[k]) <= 1e-5f * std::fabs(ref_w[k]) + 1e-30f);
       if (ref_w[k] != weights[k]) ++touched;
       if (ref_w[k] == weights[k]) CHECK(lowered[k] == weights[k]);
     }
-    CHECK(touched > 100);
+    CHECK(touched > 50);
   }
 
   // error convention: callers catch OccupiedTreeType::Error
