@@ -82,8 +82,8 @@ __device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 
 //                 default: see DESIGN.md section 4).
 template <int NR, bool kMixed, bool kPacked, bool kOnFace, bool kSmemTop>
 __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, float A, const Dir2 (&r)[NR], Best2 (&b)[NR],
-                                                 const float4* __restrict__ nodes, uint32_t octant,
-                                                 const float4* smem_top, uint32_t n_top) {
+                                                 const float4* __restrict__ nodes, const float4* __restrict__ nodes_v,
+                                                 uint32_t octant, const float4* smem_top, uint32_t n_top) {
   float stack_t[NR][kStackEntries];
   uint32_t stack_n[kStackEntries];
   int sp = 0;
@@ -102,6 +102,10 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
     iiy[j] = make_float2(r[j].iy, r[j].iy);
     iiz[j] = make_float2(r[j].iz, r[j].iz);
   }
+  // kPacked, two rays per lane: the directions of the lane's rays as pairs (leaf distances, below)
+  const float2 pox = make_float2(ox, ox), poy = make_float2(oy, oy), poz = make_float2(oz, oz);
+  const float2 ddx = make_float2(r[0].dx, r[NR - 1].dx), ddy = make_float2(r[0].dy, r[NR - 1].dy),
+               ddz = make_float2(r[0].dz, r[NR - 1].dz);
   while (true) {
     const float4* np = nodes + (size_t)ref * 8u;
     float4 nrx, nry, nrz, frx, fry, frz;
@@ -112,8 +116,11 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
       frx = sp4[fx]; fry = sp4[fy]; frz = sp4[fz];
       ch = *reinterpret_cast<const uint4*>(sp4 + 6);
     } else {
-      nrx = __ldg(np + nx); nry = __ldg(np + ny); nrz = __ldg(np + nz);
-      frx = __ldg(np + fx); fry = __ldg(np + fy); frz = __ldg(np + fz);
+      // plane rows through the lane-opaque base (vector address arithmetic, see the kernel), the child words through
+      // the plain one: everything the control flow depends on stays provably warp-uniform
+      const float4* nv = nodes_v + (size_t)ref * 8u;
+      nrx = __ldg(nv + nx); nry = __ldg(nv + ny); nrz = __ldg(nv + nz);
+      frx = __ldg(nv + fx); fry = __ldg(nv + fy); frz = __ldg(nv + fz);
       ch = __ldg(reinterpret_cast<const uint4*>(np + 6));
     }
     const uint32_t chv[4] = {ch.x, ch.y, ch.z, ch.w};
@@ -225,9 +232,27 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
           float d[NR];
           bool acc[NR];
           bool some = false;
+          if (kPacked && NR == 2) {
+            // the two rays of the lane side by side: the products and the differences with the packed instructions,
+            // the sums that consume a product with scalar adds -- the same nine roundings per ray as dist_sq_at2 in
+            // the same order.  (ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even under
+            // --fmad false, one rounding instead of two; a packed product feeding a scalar add.rn is left alone, and so
+            // is every add -> mul chain, which is all the slab test above has.  o - p is computed as o + (-p), the
+            // same IEEE operation.)
+            const float2 tt = make_float2(t[0][c], t[1][c]);
+            const float2 qx = __fmul2_rn(ddx, tt), qy = __fmul2_rn(ddy, tt), qz = __fmul2_rn(ddz, tt);
+            const float2 ex = __fadd2_rn(pox, make_float2(-__fadd_rn(ox, qx.x), -__fadd_rn(ox, qx.y)));
+            const float2 ey = __fadd2_rn(poy, make_float2(-__fadd_rn(oy, qy.x), -__fadd_rn(oy, qy.y)));
+            const float2 ez = __fadd2_rn(poz, make_float2(-__fadd_rn(oz, qz.x), -__fadd_rn(oz, qz.y)));
+            const float2 sx = __fmul2_rn(ex, ex), sy = __fmul2_rn(ey, ey), sz = __fmul2_rn(ez, ez);
+            d[0] = __fadd_rn(sx.x, __fadd_rn(sy.x, sz.x));
+            d[NR - 1] = __fadd_rn(sx.y, __fadd_rn(sy.y, sz.y));
+          } else {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) d[j] = dist_sq_at2(ox, oy, oz, r[j], t[j][c]);
+          }
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
-            d[j] = dist_sq_at2(ox, oy, oz, r[j], t[j][c]);
             acc[j] = (x[j][c] > t[j][c]) & ((d[j] < b[j].dsq) | ((d[j] == b[j].dsq) & (li > b[j].leaf)));
             some = some | acc[j];
           }
@@ -235,10 +260,12 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
               const float u = bound_after(t[j][c], A);
-              b[j].dsq = acc[j] ? d[j] : b[j].dsq;
-              b[j].t = acc[j] ? t[j][c] : b[j].t;
-              b[j].leaf = acc[j] ? li : b[j].leaf;
-              b[j].tU = acc[j] ? u : b[j].tU;
+              if (acc[j]) {
+                b[j].dsq = d[j];
+                b[j].t = t[j][c];
+                b[j].leaf = li;
+                b[j].tU = u;
+              }
             }
             tightened = true;
           }
@@ -262,7 +289,8 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
     // inner children
     uint32_t inner = any & ~leaf_mask;
     if (inner) {
-      uint32_t near_c = (uint32_t)__ffs((int)inner) - 1u;
+      uint32_t near_c = 0u;
+      uint32_t near_w = (inner & 1u) ? ch.x : (inner & 2u) ? ch.y : (inner & 4u) ? ch.z : ch.w;  // the only one, if so
       if (inner & (inner - 1u)) {
         // more than one: the nearest is entered now (warp minimum of the entry parameters of the rays that need the
         // child); the others go on the stack with every ray's own entry parameter (+inf for rays that do not need the
@@ -280,6 +308,7 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
             if (k < best_key) {
               best_key = k;
               near_c = (uint32_t)c;
+              near_w = chv[c];
             }
           }
         }
@@ -295,7 +324,7 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
           }
         }
       }
-      ref = pick4(near_c, ch.x, ch.y, ch.z, ch.w) & kPayloadMask;
+      ref = near_w & kPayloadMask;
       continue;
     }
     bool found = false;
@@ -304,7 +333,9 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
       bool need = false;
 #pragma unroll
       for (int j = 0; j < NR; ++j) need = need || (stack_t[j][sp] < b[j].tU);
-      const uint32_t n = stack_n[sp];
+      // the stack lives in per-thread local memory: say explicitly that every lane holds the same node reference, so
+      // that the branches that depend on node words are compiled as uniform branches (no convergence barriers)
+      const uint32_t n = __shfl_sync(Q3DR_FULL_MASK, stack_n[sp], 0);
       if (__any_sync(Q3DR_FULL_MASK, need)) {
         ref = n;
         found = true;
@@ -373,6 +404,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
+  // The node array through a base the compiler cannot prove warp-uniform (a lane-dependent zero is added): node
+  // references are uniform by construction, and with a provably uniform base the six row addresses of every node visit
+  // would be formed in the uniform datapath and copied into vector registers (four instructions per load instead of two).
+  uint32_t lane_zero;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_zero));
+  lane_zero = __umulhi(lane_zero, 0x04000000u);  // laneid < 32: always 0
+  const float4* const nodes_v = p.nodes + lane_zero;
   const float range_sq = (p.max_range > 0.0f) ? __fmul_rn(p.max_range, p.max_range) : FLT_MAX;
   const float kInf = __int_as_float(0x7F800000);
   constexpr int kRows = PacketShape<NR, TW>::kRowsPerSlab;
@@ -485,9 +523,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
       const bool anz = __any_sync(Q3DR_FULL_MASK, nza), apz = __any_sync(Q3DR_FULL_MASK, pza);
       if (!(anx && apx) && !(any_ && apy) && !(anz && apz)) {
         const uint32_t octant = (anx ? 1u : 0u) | (any_ ? 2u : 0u) | (anz ? 4u : 0u);
-        traverse_packetN<NR, false, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, octant, smem_top, p.n_top);
+        traverse_packetN<NR, false, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, nodes_v, octant, smem_top, p.n_top);
       } else {
-        traverse_packetN<NR, true, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, 0u, smem_top, p.n_top);
+        traverse_packetN<NR, true, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, nodes_v, 0u, smem_top, p.n_top);
       }
     } else {
       // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge
