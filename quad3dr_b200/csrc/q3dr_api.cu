@@ -109,11 +109,13 @@ const RayVariant kRayVariants[] = {
     Q3DR_VARIANT("2x8x8/3", 2, 8, false, 3, 8, false),     // 5: like 0 with 3 CTAs x 80 registers
     Q3DR_VARIANT("2x8x8p/7x4", 2, 8, true, 7, 4, false),   // 6: like 1 with 7 CTAs x 4 warps x 72 registers (28 warps per SM)
     Q3DR_VARIANT("2x8x8p/7x4/smem", 2, 8, true, 7, 4, true),  // 7: like 6 with the top tree levels in shared memory
+    Q3DR_VARIANT("2x8x8p/8x4", 2, 8, true, 8, 4, false),   // 8: like 1 in CTAs of 4 warps (8 CTAs x 4 warps x 64 registers)
+    Q3DR_VARIANT("2x8x8p/9x4", 2, 8, true, 9, 4, false),   // 9: 9 CTAs x 4 warps x 56 registers (36 warps per SM)
 };
 #undef Q3DR_VARIANT
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
 constexpr uint32_t kDefaultTileRun = 1;
-constexpr int kDefaultRayVariant = 6;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar by 5-9 %, 72 registers beat 64 and 80 by 1-3 %, four rays per lane lose 2x
+constexpr int kDefaultRayVariant = 8;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar, 32 warps per SM at 64 registers beat 28 at 72 and 36 at 56 by 5 %, four rays per lane lose 2x
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
 
