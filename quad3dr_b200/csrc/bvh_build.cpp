@@ -440,6 +440,7 @@ void fill_node(const BuildCtx& c, const Child ch[4], int cnt, uint32_t depth, ui
     if (n4->child[s] & kLeafFlag) leaf_mask |= 1u << s;
   }
   n4->child[0] |= leaf_mask << kLeafMaskShift;
+  n4->child[1] |= (axis & 3u) << kOrderAxisShift;
   n4->meta[0] = (uint32_t)cnt;
   n4->meta[1] = leaves;
   n4->meta[2] = depth;

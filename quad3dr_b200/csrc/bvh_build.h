@@ -27,6 +27,7 @@ constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kPayloadBits = 27;
 constexpr uint32_t kPayloadMask = (1u << kPayloadBits) - 1u;
 constexpr uint32_t kLeafMaskShift = kPayloadBits;
+constexpr uint32_t kOrderAxisShift = kPayloadBits;  // child[1], bits 27..28: the axis the four children are sorted along (ascending box centres)
 constexpr uint32_t kEmptyChild = kLeafFlag | kPayloadMask;
 constexpr uint32_t kNodeIndexMask = kPayloadMask;
 

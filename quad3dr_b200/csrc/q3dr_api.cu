@@ -95,11 +95,12 @@ struct RayVariant {
   RaycastKernel kernel[2];   // [MODE], with the on-face check (any viewpoint)
   RaycastKernel score_fast;  // kModeScore without the check: viewpoints whose centre lies on no box plane
 };
-#define Q3DR_VARIANT(NAME, NR, TW, PK, MC, WP, ST)                                                              \
+#define Q3DR_VARIANT_SO(NAME, NR, TW, PK, MC, WP, ST, SO)                                                      \
   {NAME, NR, TW, WP, ST,                                                                                          \
-   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC, WP, ST>,                                        \
-    q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC, WP, ST>},                                      \
-   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC, WP, ST>}
+   {q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, true, MC, WP, ST, SO>,                                    \
+    q3dr::raycast2_kernel<q3dr::kModePixels, NR, TW, PK, true, MC, WP, ST, SO>},                                  \
+   q3dr::raycast2_kernel<q3dr::kModeScore, NR, TW, PK, false, MC, WP, ST, SO>}
+#define Q3DR_VARIANT(NAME, NR, TW, PK, MC, WP, ST) Q3DR_VARIANT_SO(NAME, NR, TW, PK, MC, WP, ST, false)
 const RayVariant kRayVariants[] = {
     Q3DR_VARIANT("2x8x8", 2, 8, false, 4, 8, false),       // 0: two rays per lane, 8 x 8 pixel packets, 4 CTAs x 8 warps x 64 registers
     Q3DR_VARIANT("2x8x8p", 2, 8, true, 4, 8, false),       // 1: ... with FADD2 / FMUL2
@@ -111,11 +112,13 @@ const RayVariant kRayVariants[] = {
     Q3DR_VARIANT("2x8x8p/7x4/smem", 2, 8, true, 7, 4, true),  // 7: like 6 with the top tree levels in shared memory
     Q3DR_VARIANT("2x8x8p/8x4", 2, 8, true, 8, 4, false),   // 8: like 1 in CTAs of 4 warps (8 CTAs x 4 warps x 64 registers)
     Q3DR_VARIANT("2x8x8p/9x4", 2, 8, true, 9, 4, false),   // 9: 9 CTAs x 4 warps x 56 registers (36 warps per SM)
+    Q3DR_VARIANT_SO("2x8x8p/8x4/op", 2, 8, true, 8, 4, false, true),  // 10: like 8, far siblings stacked nearest-on-top
 };
 #undef Q3DR_VARIANT
+#undef Q3DR_VARIANT_SO
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
 constexpr uint32_t kDefaultTileRun = 1;
-constexpr int kDefaultRayVariant = 8;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar, 32 warps per SM at 64 registers beat 28 at 72 and 36 at 56 by 5 %, four rays per lane lose 2x
+constexpr int kDefaultRayVariant = 10;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar, 32 warps per SM at 64 registers beat 28 at 72 and 36 at 56 by 5 %, four rays per lane lose 2x
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
 
@@ -820,8 +823,8 @@ int q3dr_debug_flat_tree(const float* boxes, size_t n, int top_levels, uint64_t*
         uint32_t lm = 0;
         for (int q = 0; q < 4; ++q) lm |= ((nd.child[q] >> 31) & 1u) << q;
         if (((c >> q3dr::kLeafMaskShift) & 0xFu) != lm) return fail(Q3DR_ERR_INTERNAL, "leaf mask mismatch");
-        c &= q3dr::kLeafFlag | q3dr::kPayloadMask;
       }
+      c &= q3dr::kLeafFlag | q3dr::kPayloadMask;  // slot 0 carries the leaf mask, slot 1 the order axis
       if (c == q3dr::kEmptyChild) continue;
       const float* ref;
       if (c & q3dr::kLeafFlag) {

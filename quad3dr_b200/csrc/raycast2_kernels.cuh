@@ -77,10 +77,14 @@ __device__ __forceinline__ float bound_after(float t, float A) { return fmaf(t, 
 // kOnFace       : the packet's origin may lie exactly on a face plane of a box.  Only then can an exit parameter be
 //                 exactly 0 (below), where the reference's inside / outside distinction decides; such nodes are redone
 //                 with the literal box test.  flag_viewpoints_kernel sorts the viewpoints into the two instantiations.
+// kOrderedPush  : the far siblings of the entered child are stacked nearest-on-top (see the push) instead of always in
+//                 slot order.  (Rejected: visiting surviving children in the builder's slot order along the node's
+//                 order axis, with no reductions at all -- C2 17.7 -> 22.4 ms, C3 24.2 -> 35.5 ms,
+//                 profiles/r02_variants_static_order.jsonl: the nearest-first choice is worth far more than it costs.)
 // kSmemTop      : the first n_top nodes (the top levels, breadth-first) are read from the CTA's shared-memory copy
 //                 instead of L1 / L2 (north_star's "shared-memory staging of the top tree levels"; measured, not the
 //                 default: see DESIGN.md section 4).
-template <int NR, bool kMixed, bool kPacked, bool kOnFace, bool kSmemTop>
+template <int NR, bool kMixed, bool kPacked, bool kOnFace, bool kSmemTop, bool kOrderedPush>
 __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, float A, const Dir2 (&r)[NR], Best2 (&b)[NR],
                                                  const float4* __restrict__ nodes, const float4* __restrict__ nodes_v,
                                                  uint32_t octant, const float4* smem_top, uint32_t n_top) {
@@ -296,17 +300,19 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
       if (inner & (inner - 1u)) {
         // more than one: the nearest is entered now (warp minimum of the entry parameters of the rays that need the
         // child); the others go on the stack with every ray's own entry parameter (+inf for rays that do not need the
-        // child), in slot order -- with static child indices, no sorting network: what order far siblings are popped
-        // in changes how early the bounds tighten, never the result
+        // child).  What order far siblings are popped in changes how early the bounds tighten, never the result.
         const uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t key[4];
         uint32_t best_key = kNone;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          key[c] = kNone;
           if (inner & (1u << c)) {
             uint32_t k = kNone;
 #pragma unroll
             for (int j = 0; j < NR; ++j) k = min(k, (t[j][c] < x[j][c]) ? __float_as_uint(t[j][c]) : kNone);
             k = __reduce_min_sync(Q3DR_FULL_MASK, k);
+            key[c] = k;
             if (k < best_key) {
               best_key = k;
               near_c = (uint32_t)c;
@@ -314,17 +320,30 @@ __device__ __forceinline__ void traverse_packetN(float ox, float oy, float oz, f
             }
           }
         }
-#pragma unroll
-        for (int c = 3; c >= 0; --c) {
-          if ((inner & (1u << c)) && near_c != (uint32_t)c) {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) {
-              stack_t[j][sp] = (t[j][c] < x[j][c]) ? t[j][c] : kInf;  // tU only shrinks: an entry >= tU now stays >= tU
-            }
-            stack_n[sp] = chv[c] & kPayloadMask;
-            ++sp;
+#define Q3DR_PUSH_CHILD(C)                                                                                  \
+  if ((rest & (1u << (C))) != 0u) {                                                                         \
+    _Pragma("unroll") for (int j = 0; j < NR; ++j) {                                                        \
+      stack_t[j][sp] = (t[j][C] < x[j][C]) ? t[j][C] : kInf; /* tU only shrinks: an entry >= tU stays >= tU */ \
+    }                                                                                                       \
+    stack_n[sp] = chv[C] & kPayloadMask;                                                                    \
+    ++sp;                                                                                                   \
+  }
+        const uint32_t rest = inner & ~(1u << near_c);
+        if (kOrderedPush) {
+          // static child indices, no sorting network: the siblings go on the stack in slot order or in reverse slot
+          // order, whichever leaves the nearer of the two outermost ones on top (exact for two siblings)
+          const uint32_t lo_c = (uint32_t)__ffs((int)rest) - 1u, hi_c = 31u - (uint32_t)__clz((int)rest);
+          const uint32_t k_lo = (lo_c == 0u) ? key[0] : (lo_c == 1u) ? key[1] : (lo_c == 2u) ? key[2] : key[3];
+          const uint32_t k_hi = (hi_c == 0u) ? key[0] : (hi_c == 1u) ? key[1] : (hi_c == 2u) ? key[2] : key[3];
+          if (k_lo <= k_hi) {
+            Q3DR_PUSH_CHILD(3) Q3DR_PUSH_CHILD(2) Q3DR_PUSH_CHILD(1) Q3DR_PUSH_CHILD(0)
+          } else {
+            Q3DR_PUSH_CHILD(0) Q3DR_PUSH_CHILD(1) Q3DR_PUSH_CHILD(2) Q3DR_PUSH_CHILD(3)
           }
+        } else {
+          Q3DR_PUSH_CHILD(3) Q3DR_PUSH_CHILD(2) Q3DR_PUSH_CHILD(1) Q3DR_PUSH_CHILD(0)
         }
+#undef Q3DR_PUSH_CHILD
       }
       ref = near_w & kPayloadMask;
       continue;
@@ -398,7 +417,7 @@ struct PacketShape {
 // kMinCtas: resident CTAs per SM the register allocation is tuned for (4 x 64, 3 x 80 or 2 x 128 registers).
 // kWarps: warps per CTA (warps never synchronise with each other; the CTA size only sets the register granularity:
 // 7 CTAs of 4 warps leave 72 registers per thread, between the 64 of 4 x 8 warps and the 80 of 3 x 8 warps).
-template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps, bool kSmemTop>
+template <int MODE, int NR, int TW, bool kPacked, bool kOnFace, int kMinCtas, int kWarps, bool kSmemTop, bool kOrderedPush = false>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const RaycastParams p) {
   extern __shared__ float4 smem_top[];  // kSmemTop: p.n_top nodes of 8 float4 (launch with that much dynamic smem)
   if (kSmemTop) {
@@ -525,9 +544,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
       const bool anz = __any_sync(Q3DR_FULL_MASK, nza), apz = __any_sync(Q3DR_FULL_MASK, pza);
       if (!(anx && apx) && !(any_ && apy) && !(anz && apz)) {
         const uint32_t octant = (anx ? 1u : 0u) | (any_ ? 2u : 0u) | (anz ? 4u : 0u);
-        traverse_packetN<NR, false, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, nodes_v, octant, smem_top, p.n_top);
+        traverse_packetN<NR, false, kPacked, kOnFace, kSmemTop, kOrderedPush>(ox, oy, oz, A, r, b, p.nodes, nodes_v, octant, smem_top, p.n_top);
       } else {
-        traverse_packetN<NR, true, kPacked, kOnFace, kSmemTop>(ox, oy, oz, A, r, b, p.nodes, nodes_v, 0u, smem_top, p.n_top);
+        traverse_packetN<NR, true, kPacked, kOnFace, kSmemTop, kOrderedPush>(ox, oy, oz, A, r, b, p.nodes, nodes_v, 0u, smem_top, p.n_top);
       }
     } else {
       // some ray is exactly parallel to an axis, or the packet is outside the fast loops' proven domain (huge

@@ -455,7 +455,7 @@ __device__ __forceinline__ void traverse_packet_fast(const Ray& ray, PacketHit& 
     while (sp > 0) {
       --sp;
       const float d = stack_t[sp];
-      const uint32_t n = stack_n[sp];
+      const uint32_t n = __shfl_sync(Q3DR_FULL_MASK, stack_n[sp], 0);  // provably warp-uniform (see raycast2_kernels.cuh)
       if (__any_sync(Q3DR_FULL_MASK, d < best.tU)) {
         ref = n;
         found = true;

@@ -169,3 +169,18 @@ def test_voxel_indices_equal_the_reference_iterator_order(n):
     t = O.OracleTree(boxes)
     assert np.array_equal(t.dfs_order(), np.arange(n))
     assert np.array_equal(E.voxel_indices(n), t.voxel_index())
+
+
+def test_no_fused_packed_multiply_add_in_the_library():
+    """ptxas 12.9 contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even under --fmad false (one rounding instead
+    of the reference's two).  The kernels avoid that shape (raycast2_kernels.cuh: packed products, scalar sums); this
+    test makes a relapse visible without a GPU."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", E.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "FMUL2" in sass and "FADD2" in sass  # the packed path is really there ...
+    assert "FFMA2" not in sass  # ... and nothing of it was contracted
