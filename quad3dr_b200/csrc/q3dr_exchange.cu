@@ -2,12 +2,13 @@
 //
 // The path shards by viewpoint and needs no collective during compute; what remains is the
 // gather of the per-viewpoint hit lists and scores.  It is overlapped with the compute: the scoring call hands every
-// packed chunk to exchange_push_chunk, which enqueues copy-engine pushes (cudaMemcpyAsync into peer memory, side
-// stream) behind the chunk's "packed" event and returns at once; the SMs are already casting the next chunk.  The
-// raycast kernel is issue-bound and owns every register of every SM, so an SM-driven collective could not overlap
-// with it -- copy engines can.  Completion is signalled through memory: behind its data every rank pushes one 8-byte
-// flag per peer on the same stream (copies of one stream complete in order), and end_step waits for all flags with a
-// single-warp kernel on the caller's stream.  No NCCL call, no host barrier; works across processes (CUDA IPC) and
+// packed chunk to exchange_push_chunk, which enqueues copy-engine pushes (cudaMemcpyAsync into peer memory, one side
+// stream per target rank so that pushes to different peers run on different copy engines at once) behind the chunk's
+// "packed" event and returns at once; the SMs are already casting the next chunk.  The raycast kernel is issue-bound
+// and owns every register of every SM, so an SM-driven collective could not overlap with it -- copy engines can.
+// Completion is signalled through memory: behind its data every rank pushes one 8-byte flag per peer on that peer's
+// stream (copies of one stream complete in order), and end_step waits for all flags with a single-warp kernel on the
+// caller's stream.  No NCCL call, no host barrier; works across processes (CUDA IPC) and
 // across threads of one process (peer access).
 #include "q3dr_internal.cuh"
 
@@ -59,8 +60,8 @@ struct q3dr_exchange {
   char* base[2] = {nullptr, nullptr};                // this rank's receive buffers
   std::vector<char*> peer[2];                        // every rank's receive buffers as seen from this device
   std::vector<bool> opened[2];                       // mapped through CUDA IPC (to be closed)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_tail = nullptr;
+  std::vector<cudaStream_t> side;                    // one push stream per target rank: pushes to different peers overlap
+  cudaEvent_t ev_tail = nullptr;                     // "header and flag of this step are staged in device memory"
   SlotHeader* h_header = nullptr;                    // pinned staging [2]
   uint64_t* h_flag = nullptr;                        // pinned staging [2]
   char* d_stage = nullptr;                           // device staging [2] x {SlotHeader, flag}: peers are written D2D only
@@ -86,16 +87,19 @@ int exchange_push_chunk(q3dr_exchange* ex, cudaEvent_t ready, const int32_t* d_l
     return Q3DR_OK;
   }
   if (n_entries == 0) return Q3DR_OK;
-  cudaError_t e = cudaStreamWaitEvent(ex->side, ready, 0);
+  cudaError_t e = cudaSuccess;
   const uint64_t slot = (uint64_t)ex->rank * ex->lay.slot_bytes;
   for (uint32_t k = 0; k < ex->n_ranks && e == cudaSuccess; ++k) {
     const uint32_t p = (ex->rank + k) % ex->n_ranks;  // different ranks start with different targets
     char* dst = ex->peer[ex->cur][p] + slot;
-    e = cudaMemcpyAsync(dst + ex->lay.leaf_off + 4 * first_entry, d_leaf + first_entry, 4 * n_entries,
-                        cudaMemcpyDeviceToDevice, ex->side);
+    e = cudaStreamWaitEvent(ex->side[p], ready, 0);
+    if (e == cudaSuccess) {
+      e = cudaMemcpyAsync(dst + ex->lay.leaf_off + 4 * first_entry, d_leaf + first_entry, 4 * n_entries,
+                          cudaMemcpyDeviceToDevice, ex->side[p]);
+    }
     if (e == cudaSuccess) {
       e = cudaMemcpyAsync(dst + ex->lay.info_off + 4 * first_entry, d_info + first_entry, 4 * n_entries,
-                          cudaMemcpyDeviceToDevice, ex->side);
+                          cudaMemcpyDeviceToDevice, ex->side[p]);
     }
   }
   if (e != cudaSuccess) {
@@ -154,7 +158,8 @@ int q3dr_exchange_create(q3dr_map* map, uint32_t n_ranks, uint32_t rank, uint64_
     ex->opened[b].assign(n_ranks, false);
     if (e == cudaSuccess) ex->peer[b][rank] = ex->base[b];
   }
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ex->side, cudaStreamNonBlocking);
+  ex->side.assign(n_ranks, nullptr);
+  for (uint32_t p = 0; p < n_ranks && e == cudaSuccess; ++p) e = cudaStreamCreateWithFlags(&ex->side[p], cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->ev_tail, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc(&ex->h_header, 2 * sizeof(SlotHeader), cudaHostAllocDefault);
   if (e == cudaSuccess) e = cudaHostAlloc(&ex->h_flag, 2 * sizeof(uint64_t), cudaHostAllocDefault);
@@ -177,7 +182,9 @@ int q3dr_exchange_create(q3dr_map* map, uint32_t n_ranks, uint32_t rank, uint64_
 int q3dr_exchange_disconnect(q3dr_exchange* ex) {
   if (!ex) return Q3DR_OK;
   cudaSetDevice(ex->device);
-  if (ex->side) cudaStreamSynchronize(ex->side);
+  for (cudaStream_t st : ex->side) {
+    if (st) cudaStreamSynchronize(st);
+  }
   for (int b = 0; b < 2; ++b) {
     for (uint32_t p = 0; p < ex->peer[b].size(); ++p) {
       if (ex->opened[b][p] && ex->peer[b][p]) cudaIpcCloseMemHandle(ex->peer[b][p]);
@@ -198,7 +205,9 @@ int q3dr_exchange_destroy(q3dr_exchange* ex) {
   for (int b = 0; b < 2; ++b) {
     if (ex->base[b]) cudaFree(ex->base[b]);
   }
-  if (ex->side) cudaStreamDestroy(ex->side);
+  for (cudaStream_t st : ex->side) {
+    if (st) cudaStreamDestroy(st);
+  }
   if (ex->ev_tail) cudaEventDestroy(ex->ev_tail);
   if (ex->h_header) cudaFreeHost(ex->h_header);
   if (ex->h_flag) cudaFreeHost(ex->h_flag);
@@ -302,7 +311,7 @@ int q3dr_exchange_end_step(q3dr_exchange* ex, int local_status, void* stream_v) 
     failed = Q3DR_ERR_INTERNAL;
     why = "the scoring call of this step did not push all its entries";
   }
-  // headers + flag behind the data pushes, on the same side stream: a peer that sees the flag sees everything before
+  // headers + flags behind the data pushes
   const uint32_t b = ex->cur;
   SlotHeader* hh = ex->h_header + b;
   hh->n_viewpoints = failed ? 0 : nv;
@@ -312,26 +321,29 @@ int q3dr_exchange_end_step(q3dr_exchange* ex, int local_status, void* stream_v) 
   ex->h_flag[b] = (ex->step << 1) | (failed ? 1ull : 0ull);
   const uint64_t slot = (uint64_t)ex->rank * ex->lay.slot_bytes;
   char* stage = ex->d_stage + b * kAlign;  // {SlotHeader, flag} of this step in local device memory
-  cudaError_t e = cudaMemcpyAsync(stage, hh, sizeof(SlotHeader), cudaMemcpyHostToDevice, ex->side);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(stage + sizeof(SlotHeader), ex->h_flag + b, 8, cudaMemcpyHostToDevice, ex->side);
-  for (uint32_t k = 0; k < ex->n_ranks; ++k) {
+  cudaStream_t own = ex->side[ex->rank];
+  cudaError_t e = cudaMemcpyAsync(stage, hh, sizeof(SlotHeader), cudaMemcpyHostToDevice, own);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(stage + sizeof(SlotHeader), ex->h_flag + b, 8, cudaMemcpyHostToDevice, own);
+  if (e == cudaSuccess) e = cudaEventRecord(ex->ev_tail, own);
+  // per target rank, on that target's stream (behind the data pushes to it): offsets, totals, header, and the flag last --
+  // a peer that sees the flag sees everything this rank pushed to it before
+  for (uint32_t k = 0; k < ex->n_ranks && e == cudaSuccess; ++k) {
     const uint32_t p = (ex->rank + k) % ex->n_ranks;
     char* dst = ex->peer[b][p];
+    cudaStream_t st = ex->side[p];
+    if (p != ex->rank) e = cudaStreamWaitEvent(st, ex->ev_tail, 0);
     if (e == cudaSuccess && !failed && nv > 0) {
-      e = cudaMemcpyAsync(dst + slot + ex->lay.offsets_off, m->d_offsets.p, 8 * (nv + 1), cudaMemcpyDeviceToDevice, ex->side);
+      e = cudaMemcpyAsync(dst + slot + ex->lay.offsets_off, m->d_offsets.p, 8 * (nv + 1), cudaMemcpyDeviceToDevice, st);
       if (e == cudaSuccess) {
-        e = cudaMemcpyAsync(dst + slot + ex->lay.total_off, m->d_total.p, 4 * nv, cudaMemcpyDeviceToDevice, ex->side);
+        e = cudaMemcpyAsync(dst + slot + ex->lay.total_off, m->d_total.p, 4 * nv, cudaMemcpyDeviceToDevice, st);
       }
     }
     if (e == cudaSuccess) {
-      e = cudaMemcpyAsync(dst + slot + ex->lay.header_off, stage, sizeof(SlotHeader), cudaMemcpyDeviceToDevice, ex->side);
+      e = cudaMemcpyAsync(dst + slot + ex->lay.header_off, stage, sizeof(SlotHeader), cudaMemcpyDeviceToDevice, st);
     }
-  }
-  // flags last, in a second round: every header is on its way before any flag
-  for (uint32_t k = 0; k < ex->n_ranks && e == cudaSuccess; ++k) {
-    const uint32_t p = (ex->rank + k) % ex->n_ranks;
-    e = cudaMemcpyAsync(ex->peer[b][p] + ex->lay.flags_off + 8 * (uint64_t)ex->rank, stage + sizeof(SlotHeader), 8,
-                        cudaMemcpyDeviceToDevice, ex->side);
+    if (e == cudaSuccess) {
+      e = cudaMemcpyAsync(dst + ex->lay.flags_off + 8 * (uint64_t)ex->rank, stage + sizeof(SlotHeader), 8, cudaMemcpyDeviceToDevice, st);
+    }
   }
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -347,7 +359,7 @@ int q3dr_exchange_end_step(q3dr_exchange* ex, int local_status, void* stream_v) 
   Q3DR_CUDA(cudaMemcpy2DAsync(ex->h_all, sizeof(SlotHeader), ex->base[b] + ex->lay.header_off, ex->lay.slot_bytes, sizeof(SlotHeader),
                               ex->n_ranks, cudaMemcpyDeviceToHost, stream));
   Q3DR_CUDA(cudaStreamSynchronize(stream));
-  Q3DR_CUDA(cudaStreamSynchronize(ex->side));  // own pushes done: the map's pools may be reused by the next call
+  for (cudaStream_t st : ex->side) Q3DR_CUDA(cudaStreamSynchronize(st));  // own pushes done: the map's pools may be reused by the next call
   if (failed != Q3DR_OK) return fail(failed, "exchange: this rank failed: " + why);
   if (*ex->h_status == 2u) return fail(Q3DR_ERR_INTERNAL, "exchange: timed out waiting for the peers' completion flags");
   if (*ex->h_status == 1u) return fail(Q3DR_ERR_INTERNAL, "exchange: another rank reported a failure in this step");
