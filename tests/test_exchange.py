@@ -126,6 +126,67 @@ def test_two_ranks_exchange_their_results(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_four_ranks_exchange_over_per_target_streams(monkeypatch):
+    """Four ranks (host threads; devices round-robin over what the box has): every rank pushes to three peers and
+    itself on four different streams, several chunks per step, ragged slice sizes including an empty one."""
+    import torch
+
+    monkeypatch.setenv("Q3DR_CHUNK", "3")
+    monkeypatch.setenv("Q3DR_EXCHANGE_TIMEOUT_MS", "8000")
+    G = 4
+    n_dev = max(1, E.device_count())
+    devs = [r % n_dev for r in range(G)]
+    leaves = synth.map_small()
+    order, depth = E.splitmedian_order(leaves.boxes)
+    leaves = leaves.permuted(order)
+    w, h = 80, 60
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(leaves, 32, config_id=37)
+    slices = [vps[8 * r: 8 * r + 8] for r in range(G)]
+    maps = [E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=d) for d in devs]
+    exs = [E.Exchange(maps[r], G, r, 8, 8 * w * h) for r in range(G)]
+    E.Exchange.connect(exs)
+    own = [None] * G
+    errors = []
+
+    def rank_main(r, n_use, barrier):
+        try:
+            torch.cuda.set_device(devs[r])
+            stream = torch.cuda.Stream(device=devs[r])
+            d_rt = torch.from_numpy(np.ascontiguousarray(slices[r])).to(torch.device("cuda", devs[r]))
+            torch.cuda.synchronize(devs[r])
+            barrier.wait()
+            exs[r].begin_step()
+            maps[r].score_viewpoints_device(cam.K, w, (0, w, 0, h), d_rt.data_ptr(), n_use, stream=stream.cuda_stream)
+            exs[r].end_step(0, stream.cuda_stream)
+            own[r] = maps[r].result_to_host()
+        except Exception as e:  # noqa: BLE001 -- carried to the main thread
+            errors.append((r, e))
+
+    for step, n_use in enumerate([(8, 7, 8, 5), (0, 8, 3, 8), (8, 8, 8, 8)]):
+        barrier = threading.Barrier(G)
+        ts = [threading.Thread(target=rank_main, args=(r, n_use[r], barrier)) for r in range(G)]
+        [t.start() for t in ts]
+        [t.join(timeout=120) for t in ts]
+        assert not errors, errors
+        for on in range(G):
+            for src in range(G):
+                v = exs[on].view(src)
+                ref = own[src]
+                assert v.n_viewpoints == n_use[src] == ref.n_viewpoints and v.n_entries == ref.n_entries, (step, on, src)
+                if n_use[src] == 0:
+                    continue
+                assert np.array_equal(_dev_array(v.offsets, n_use[src] + 1, np.uint64, devs[on]), ref.offsets)
+                assert np.array_equal(_dev_array(v.total, n_use[src], np.uint32, devs[on]), ref.total.view(np.uint32))
+                assert np.array_equal(_dev_array(v.leaf, v.n_entries, np.int32, devs[on]), ref.leaf)
+                assert np.array_equal(_dev_array(v.information, v.n_entries, np.uint32, devs[on]), ref.information.view(np.uint32))
+    for ex in exs:
+        ex.close()
+    for m in maps:
+        m.close()
+
+
+@pytest.mark.gpu
 def test_multi_gather_leaves_all_parts_on_every_gpu():
     n_dev = E.device_count()
     devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
