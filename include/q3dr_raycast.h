@@ -525,7 +525,7 @@ int q3dr_multi_set_normal_mesh(q3dr_multi* multi, const float* tri_vertices, con
  * Every rank (one GPU each; ranks may be threads of one process or separate processes) owns a RECEIVE BUFFER in its
  * own HBM with one slot per source rank.  While a scoring call runs, every finished chunk of its CSR result is pushed
  * into this rank's slot on every rank by the copy engines (cudaMemcpyAsync into peer memory over NVLink / NVSwitch, on
- * a side stream, no SM involved) while the SMs cast the next chunk; q3dr_exchange_end_step pushes the per-viewpoint
+ * one side stream per target rank, no SM involved) while the SMs cast the next chunk; q3dr_exchange_end_step pushes the per-viewpoint
  * headers and a completion flag behind them and then waits -- on the device, in `stream` -- for the flags of all
  * ranks.  After it returns every rank holds the results of ALL ranks (the all-gather of the reference's single-GPU
  * result, viewpoint_planner_data.cpp:328-335 selects one device; here the candidate set is sharded).
@@ -565,7 +565,11 @@ int q3dr_exchange_connect(q3dr_exchange* const* all, uint32_t n_ranks);
 /* Arms the exchange: the next scoring call on the map pushes its chunks.  Call it on every rank, every step. */
 int q3dr_exchange_begin_step(q3dr_exchange* ex);
 /* local_status: status of this rank's scoring call; a non-zero value is forwarded so that all ranks fail together
- * instead of waiting for data that never comes.  stream: a cudaStream_t the wait is enqueued on (and synchronised). */
+ * instead of waiting for data that never comes.  stream: a cudaStream_t the wait is enqueued on (and synchronised).
+ * The wait is a small kernel polling the flags in this rank's HBM.  One rank per device is the supported deployment:
+ * ranks that SHARE a device (only the tests do that) must not make device-synchronising calls (cudaMalloc, cudaFree)
+ * while another rank of that device sits in end_step -- such a call waits for the polling kernel, which waits for
+ * the caller's flag. */
 int q3dr_exchange_end_step(q3dr_exchange* ex, int local_status, void* stream);
 /* Result of source rank `src` in this rank's receive buffer (DEVICE pointers; first_pixel, dist_sq, hit_count NULL). */
 int q3dr_exchange_view(const q3dr_exchange* ex, uint32_t src, q3dr_result* out);

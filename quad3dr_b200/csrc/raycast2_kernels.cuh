@@ -569,12 +569,17 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) raycast2_kernel(const R
       // merges the slabs and the other tiles of the viewpoint).
       uint32_t* fpv = p.first_pix + (size_t)vp * p.leaf_stride;
       uint32_t* bmv = p.bitmap + (size_t)vp * p.word_stride;
+      // the pixel coordinates are formed again from the lane index (read again, so that the compiler cannot keep the
+      // earlier values alive): three registers fewer across the traversal loop, which runs at the 64-register limit
+      uint32_t lane2;
+      asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane2));
+      const uint32_t px2 = tx * TW + (lane2 % TW);
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const int32_t leaf = b[j].leaf;
-        const uint32_t pix = py[j] * p.w + px;
+        const uint32_t pix = (ty * kTileH + (lane2 / TW) + kRows * j) * p.w + px2;
         const uint32_t grp = __match_any_sync(Q3DR_FULL_MASK, leaf);
-        const bool leader = (leaf >= 0) && ((__ffs(grp) - 1) == lane);
+        const bool leader = (leaf >= 0) && ((__ffs(grp) - 1) == (int)lane2);
         if (leader) {
           const uint32_t old = atomicMin(fpv + (uint32_t)leaf, p.pix_tag | pix);
           if (old > p.pix_limit) {  // nothing of THIS chunk was there yet: first toucher

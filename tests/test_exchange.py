@@ -53,6 +53,21 @@ def _dev_array(ptr, n, dt, device):
     return torch.as_tensor(CudaArrayView(ptr, n, typestr), device=torch.device("cuda", device)).cpu().numpy()
 
 
+def _warm_up(maps, slices, cam, w, h, devs):
+    """One plain scoring call per rank at the largest size of the test: the result pools are then grown, and no rank
+    calls cudaMalloc inside an exchange step.  Only needed because these tests put several ranks on ONE device: a
+    device-synchronising call of one rank would wait for the flag-wait kernel of another rank on the same device, which
+    waits for the first rank's flag (one rank per device, the supported deployment, has no such coupling)."""
+    import torch
+
+    for r, m in enumerate(maps):
+        torch.cuda.set_device(devs[r])
+        d_rt = torch.from_numpy(np.ascontiguousarray(slices[r])).to(torch.device("cuda", devs[r]))
+        m.score_viewpoints_device(cam.K, w, (0, w, 0, h), d_rt.data_ptr(), len(slices[r]))
+        m.result_to_host()
+        torch.cuda.synchronize(devs[r])
+
+
 @pytest.mark.gpu
 def test_two_ranks_exchange_their_results(monkeypatch):
     import torch
@@ -69,6 +84,7 @@ def test_two_ranks_exchange_their_results(monkeypatch):
     slices = [vps[:13], vps[13:]]
     maps = [E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=d) for d in devs]
     maps[1].set_result_fields(first_pixel=False, dist_sq=False)  # the exchange ships (leaf, information) either way
+    _warm_up(maps, slices, cam, w, h, devs)
     exs = [E.Exchange(maps[r], 2, r, 13, 13 * w * h) for r in range(2)]
     E.Exchange.connect(exs)
     own = [None, None]
@@ -144,6 +160,7 @@ def test_four_ranks_exchange_over_per_target_streams(monkeypatch):
     vps = synth.make_viewpoints(leaves, 32, config_id=37)
     slices = [vps[8 * r: 8 * r + 8] for r in range(G)]
     maps = [E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth, device=d) for d in devs]
+    _warm_up(maps, slices, cam, w, h, devs)
     exs = [E.Exchange(maps[r], G, r, 8, 8 * w * h) for r in range(G)]
     E.Exchange.connect(exs)
     own = [None] * G
