@@ -64,60 +64,21 @@ template <typename NodeT>
 using VoxelWithInformationSet =
     std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash>;
 
-/// Recycles the arrays of VoxelSetBlocks whose views are all gone: a planner that scores batch after batch and drops
-/// the rejected candidates' sets would otherwise pay the page faults of a fresh 10^8-byte block for every batch.
-struct VoxelSetArrayPool {
-  struct Arrays {
-    std::unique_ptr<std::int32_t[]> leaf;
-    std::unique_ptr<float[]> information;
-    std::size_t capacity;
-  };
-  std::mutex mutex;
-  std::vector<Arrays> free_list;
-  // plain arrays, deliberately NOT value-initialised: the parallel copy that fills them is also their first touch
-  Arrays take(std::size_t n) {
-    {
-      std::lock_guard<std::mutex> lock(mutex);
-      for (std::size_t i = 0; i < free_list.size(); ++i) {
-        if (free_list[i].capacity >= n) {
-          Arrays a = std::move(free_list[i]);
-          free_list.erase(free_list.begin() + static_cast<std::ptrdiff_t>(i));
-          return a;
-        }
-      }
-    }
-    Arrays a;
-    a.capacity = n > 0 ? n : 1;
-    a.leaf.reset(new std::int32_t[a.capacity]);
-    a.information.reset(new float[a.capacity]);
-    return a;
-  }
-  void give_back(Arrays&& a) {
-    std::lock_guard<std::mutex> lock(mutex);
-    if (free_list.size() < 2) free_list.push_back(std::move(a));  // (more than two idle blocks are simply freed)
-  }
-};
-
-/// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.
+/// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.  The two arrays are
+/// the engine's own pinned host arrays, handed over by q3dr_result_detach_host (no copy on the host); they go back to
+/// the library's pool when the last view is gone.
 template <typename NodeT>
 struct VoxelSetBlock {
-  VoxelSetBlock() : n_entries(0), nodes(nullptr), leaf_of(nullptr), tree(nullptr) {}
-  ~VoxelSetBlock() {
-    if (pool) {
-      VoxelSetArrayPool::Arrays a;
-      a.leaf = std::move(leaf);
-      a.information = std::move(information);
-      a.capacity = capacity;
-      pool->give_back(std::move(a));
-    }
+  VoxelSetBlock() : leaf(nullptr), information(nullptr), n_entries(0), nodes(nullptr), leaf_of(nullptr), tree(nullptr) {
+    std::memset(&host, 0, sizeof(host));
   }
+  ~VoxelSetBlock() { q3dr_host_block_release(&host); }
   VoxelSetBlock(const VoxelSetBlock&) = delete;
   VoxelSetBlock& operator=(const VoxelSetBlock&) = delete;
-  std::unique_ptr<std::int32_t[]> leaf;     // ascending leaf index inside every viewpoint's range
-  std::unique_ptr<float[]> information;
+  q3dr_host_block host;
+  const std::int32_t* leaf;     // ascending leaf index inside every viewpoint's range
+  const float* information;
   std::size_t n_entries;
-  std::size_t capacity;
-  std::shared_ptr<VoxelSetArrayPool> pool;
   std::vector<NodeT*> const* nodes;   // leaf index -> host node (owned by the OccupiedTreeCuda, which must outlive the views)
   std::unordered_map<const NodeT*, std::int32_t> const* (*leaf_of)(const void*);  // host node -> leaf index, built on first find()
   const void* tree;
@@ -194,18 +155,18 @@ class VoxelWithInformationSetView {
     const std::unordered_map<const NodeT*, std::int32_t>* table = block_->leaf_of(block_->tree);
     typename std::unordered_map<const NodeT*, std::int32_t>::const_iterator it = table->find(vi.voxel);
     if (it == table->end()) return end();
-    const std::int32_t* first = block_->leaf.get() + begin_;
-    const std::int32_t* last = block_->leaf.get() + end_;
+    const std::int32_t* first = block_->leaf + begin_;
+    const std::int32_t* last = block_->leaf + end_;
     const std::int32_t* p = std::lower_bound(first, last, it->second);
     if (p == last || *p != it->second) return end();
-    const std::size_t i = static_cast<std::size_t>(p - block_->leaf.get());
+    const std::size_t i = static_cast<std::size_t>(p - block_->leaf);
     return block_->information[i] == vi.information ? const_iterator(block_.get(), i) : end();
   }
   size_type count(const value_type& vi) const { return find(vi) == end() ? 0 : 1; }
 
   /// the engine's view of the set: ascending leaf indices and their informations
-  const std::int32_t* leafData() const { return block_ ? block_->leaf.get() + begin_ : nullptr; }
-  const float* informationData() const { return block_ ? block_->information.get() + begin_ : nullptr; }
+  const std::int32_t* leafData() const { return block_ ? block_->leaf + begin_ : nullptr; }
+  const float* informationData() const { return block_ ? block_->information + begin_ : nullptr; }
 
   /// the reference's own container (one hash-node allocation per voxel)
   VoxelWithInformationSet<NodeT> toUnorderedSet() const {
@@ -629,8 +590,7 @@ class ViewpointRaycastCuda {
 
   /// viewpoint_raycast.h:28-31 (min_range is accepted and, like in the reference, never used by the query)
   ViewpointRaycastCuda(TreeType* bvh_tree, float min_range = 0, float max_range = 60)
-      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range), mesh_normals_(nullptr),
-        pool_(std::make_shared<VoxelSetArrayPool>()) {
+      : bvh_tree_(bvh_tree), min_range_(min_range), max_range_(max_range), mesh_normals_(nullptr) {
     q3dr_score_opts_default(&opts_);
     opts_.raycast_min_range = min_range;
     opts_.raycast_max_range = max_range;
@@ -725,7 +685,7 @@ class ViewpointRaycastCuda {
     return out;
   }
 
-  /// Batched form returning views into one shared copy of the CSR result: no per-voxel work on the host at all.
+  /// Batched form returning views into the engine's own host arrays: no per-voxel work on the host at all.
   template <typename ViewpointT>
   std::vector<std::pair<VoxelSetView, float>> getRaycastHitVoxelsWithInformationScoreBatchView(
       const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end, std::size_t y_start,
@@ -734,26 +694,14 @@ class ViewpointRaycastCuda {
     if (viewpoints.empty()) return out;
     const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
     std::shared_ptr<VoxelSetBlock<NodeT> > block = std::make_shared<VoxelSetBlock<NodeT> >();
-    const std::size_t ne = static_cast<std::size_t>(r.n_entries);
-    VoxelSetArrayPool::Arrays arrays = pool_->take(ne);
-    block->leaf = std::move(arrays.leaf);
-    block->information = std::move(arrays.information);
-    block->capacity = arrays.capacity;
-    block->pool = pool_;
-    block->n_entries = ne;
+    // the map hands its two big host arrays over (it takes others for its next call): nothing is copied on the host
+    bvh_tree_->check(q3dr_result_detach_host(bvh_tree_->handle(), &block->host));
+    block->leaf = block->host.leaf;
+    block->information = block->host.information;
+    block->n_entries = static_cast<std::size_t>(r.n_entries);
     block->nodes = &bvh_tree_->leafNodes();
     block->leaf_of = &TreeType::leafIndexTableOf;
     block->tree = bvh_tree_;
-    // the map-owned host arrays are overwritten by the next scoring call: one parallel copy into the shared block
-    const std::ptrdiff_t pieces = static_cast<std::ptrdiff_t>((ne + kCopyPiece - 1) / kCopyPiece);
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-    for (std::ptrdiff_t p = 0; p < pieces; ++p) {
-      const std::size_t a = static_cast<std::size_t>(p) * kCopyPiece, n = std::min(kCopyPiece, ne - a);
-      std::memcpy(block->leaf.get() + a, r.leaf + a, n * sizeof(std::int32_t));
-      std::memcpy(block->information.get() + a, r.information + a, n * sizeof(float));
-    }
     for (std::size_t v = 0; v < viewpoints.size(); ++v) {
       out[v].first = VoxelSetView(block, static_cast<std::size_t>(r.offsets[v]), static_cast<std::size_t>(r.offsets[v + 1]));
       out[v].second = r.total[v];
@@ -762,8 +710,6 @@ class ViewpointRaycastCuda {
   }
 
  private:
-  static const std::size_t kCopyPiece = 1u << 20;
-
   /// the engine call behind both batch forms; only (leaf, information) travel back (8 bytes per voxel)
   template <typename ViewpointT>
   q3dr_result scoreBatch(const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end,
@@ -803,7 +749,6 @@ class ViewpointRaycastCuda {
   float max_range_;
   q3dr_score_opts opts_;
   const PoissonMeshNormalsCuda* mesh_normals_;
-  std::shared_ptr<VoxelSetArrayPool> pool_;
 };
 
 /// One ViewpointPath::observed_voxel_map on the device plus the information sums the path search evaluates against

@@ -66,7 +66,7 @@
 extern "C" {
 #endif
 
-#define Q3DR_ABI_VERSION 4
+#define Q3DR_ABI_VERSION 5
 
 enum q3dr_status {
   Q3DR_OK = 0,
@@ -116,6 +116,14 @@ typedef struct q3dr_result {
   const float* total;          /* n_viewpoints: sum of information (fp64 accumulate, rounded once) */
   const uint32_t* hit_count;   /* n_viewpoints: unique voxels hit before the information > 0 filter */
 } q3dr_result;
+
+/* The two large host arrays of a result (leaf, information) handed over to the caller, see q3dr_result_detach_host. */
+typedef struct q3dr_host_block {
+  int32_t* leaf;
+  float* information;
+  uint64_t n_entries; /* valid entries */
+  uint64_t capacity;  /* entries allocated */
+} q3dr_host_block;
 
 typedef struct q3dr_map_info {
   uint64_t n_leaves;
@@ -241,6 +249,16 @@ int q3dr_map_set_chunk_callback(q3dr_map* map, q3dr_chunk_callback cb, void* use
 /* Copies the device-resident result of the last q3dr_score_viewpoints_device call to host memory
  * owned by the map. */
 int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);
+
+/* Ownership hand-over of the host arrays `leaf` and `information` of the last result (after q3dr_score_viewpoints* with
+ * host buffers or q3dr_result_to_host): the map forgets the two pinned arrays -- they stay valid until
+ * q3dr_host_block_release, whatever is called on the map meanwhile, and may outlive it -- and takes others for its next
+ * call (released blocks are kept in a small process-wide pool, so a caller that keeps a few results alive and drops
+ * them again causes no further allocation).  The C++ shim's VoxelWithInformationSet views rest on this: the 8 bytes
+ * per voxel the device produced are never copied again on the host.  offsets / total / hit_count of the q3dr_result stay
+ * with the map (small).  Replaces the conversion loop of bvh.h:430,487 / viewpoint_planner_raycast.cpp:116-148. */
+int q3dr_result_detach_host(q3dr_map* map, q3dr_host_block* out);
+int q3dr_host_block_release(q3dr_host_block* block); /* block may be all zeros; it is zeroed on return */
 
 /* Which per-entry arrays the scoring calls on this map deliver besides (leaf, information).  The reference's facade
  * (getRaycastHitVoxelsWithInformationScore -> VoxelWithInformationSet, viewpoint_planner_raycast.cpp:116-148) consumes

@@ -18,6 +18,68 @@ std::string& last_error() {
 
 namespace {
 
+// Process-wide pool of released host blocks (pairs of pinned arrays, q3dr_result_detach_host): a caller that keeps a few
+// results alive and drops them again allocates pinned memory a few times in total, not once per call.
+struct HostPair {
+  int32_t* leaf = nullptr;
+  float* info = nullptr;
+  size_t cap = 0;
+};
+std::mutex& host_pool_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+std::vector<HostPair>& host_pool() {
+  static std::vector<HostPair> pool;
+  return pool;
+}
+constexpr size_t kHostPoolBlocks = 3;
+
+// the smallest pooled pair with cap >= n; with n == 0 the largest one
+bool host_pool_take(size_t n, HostPair* out) {
+  std::lock_guard<std::mutex> lock(host_pool_mutex());
+  std::vector<HostPair>& pool = host_pool();
+  int pick = -1;
+  for (size_t i = 0; i < pool.size(); ++i) {
+    if (pool[i].cap < n) continue;
+    if (pick < 0 || (n == 0 ? pool[i].cap > pool[(size_t)pick].cap : pool[i].cap < pool[(size_t)pick].cap)) pick = (int)i;
+  }
+  if (pick < 0) return false;
+  *out = pool[(size_t)pick];
+  pool.erase(pool.begin() + pick);
+  return true;
+}
+
+void host_pool_give(const HostPair& hp) {
+  HostPair drop;
+  {
+    std::lock_guard<std::mutex> lock(host_pool_mutex());
+    std::vector<HostPair>& pool = host_pool();
+    pool.push_back(hp);
+    if (pool.size() <= kHostPoolBlocks) return;
+    size_t smallest = 0;
+    for (size_t i = 1; i < pool.size(); ++i) {
+      if (pool[i].cap < pool[smallest].cap) smallest = i;
+    }
+    drop = pool[smallest];
+    pool.erase(pool.begin() + (std::ptrdiff_t)smallest);
+  }
+  if (drop.leaf) cudaFreeHost(drop.leaf);
+  if (drop.info) cudaFreeHost(drop.info);
+  cudaGetLastError();
+}
+
+// a map without host arrays for (leaf, information) -- they were detached -- takes a pooled pair that is large enough
+void adopt_pooled_host_pair(q3dr_map* m, size_t n) {
+  if (m->h_leaf.p != nullptr || m->h_info.p != nullptr) return;
+  HostPair hp;
+  if (!host_pool_take(n, &hp)) return;
+  m->h_leaf.p = hp.leaf;
+  m->h_leaf.cap = hp.cap;
+  m->h_info.p = hp.info;
+  m->h_info.cap = hp.cap;
+}
+
 void release_device(q3dr_map* m) {
   m->d_nodes.release();
   m->d_leaf_rec.release();
@@ -651,6 +713,7 @@ int score_device_impl(q3dr_map* m, const float K[4], uint32_t image_width, uint3
         Q3DR_CUDA(cudaStreamSynchronize(m->copy_stream));
         const double per_vp = (double)total_entries / (double)(v0 + nb);
         const size_t want = (size_t)std::max<double>((double)total_entries, per_vp * (double)n_vp * 1.15 + 4096.0);
+        adopt_pooled_host_pair(m, want);
         Q3DR_TRY(m->h_leaf.grow_keep(want, copied_entries));
         Q3DR_TRY(m->h_info.grow_keep(want, copied_entries));
       }
@@ -1180,6 +1243,7 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
   Q3DR_TRY(m->h_offsets.ensure(nv + 1));
   Q3DR_TRY(m->h_total.ensure(std::max<size_t>(nv, 1)));
   Q3DR_TRY(m->h_hit_count.ensure(std::max<size_t>(nv, 1)));
+  adopt_pooled_host_pair(m, std::max<size_t>(ne, 1));
   Q3DR_TRY(m->h_leaf.ensure(std::max<size_t>(ne, 1)));
   Q3DR_TRY(m->h_info.ensure(std::max<size_t>(ne, 1)));
   if (want_pix) Q3DR_TRY(m->h_pix.ensure(std::max<size_t>(ne, 1)));
@@ -1196,6 +1260,7 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
     if (want_dsq) Q3DR_CUDA(cudaMemcpyAsync(m->h_dsq.p, m->r_dsq.p, ne * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   Q3DR_CUDA(cudaStreamSynchronize(s));
+  m->host_result_valid = true;
   result->n_viewpoints = nv;
   result->n_entries = ne;
   result->offsets = m->h_offsets.p;
@@ -1205,6 +1270,43 @@ int q3dr_result_to_host(q3dr_map* m, q3dr_result* result) {
   result->dist_sq = want_dsq ? m->h_dsq.p : nullptr;
   result->total = m->h_total.p;
   result->hit_count = m->h_hit_count.p;
+  return Q3DR_OK;
+}
+
+int q3dr_result_detach_host(q3dr_map* m, q3dr_host_block* out) {
+  Q3DR_TRY(check_map(m));
+  if (!out) return fail(Q3DR_ERR_INVALID_ARG, "out is NULL");
+  std::memset(out, 0, sizeof(*out));
+  if (!m->host_result_valid || m->h_leaf.p == nullptr || m->h_info.p == nullptr) {
+    return fail(Q3DR_ERR_INVALID_ARG, "no host result to detach (q3dr_score_viewpoints or q3dr_result_to_host first)");
+  }
+  out->leaf = m->h_leaf.p;
+  out->information = m->h_info.p;
+  out->n_entries = m->last_n_entries;
+  out->capacity = std::min(m->h_leaf.cap, m->h_info.cap);
+  m->h_leaf.p = nullptr;
+  m->h_leaf.cap = 0;
+  m->h_info.p = nullptr;
+  m->h_info.cap = 0;
+  m->host_result_valid = false;
+  adopt_pooled_host_pair(m, 0);  // the largest released pair, if any: the next call then allocates nothing
+  return Q3DR_OK;
+}
+
+int q3dr_host_block_release(q3dr_host_block* block) {
+  if (!block) return Q3DR_OK;
+  if (block->leaf != nullptr && block->information != nullptr && block->capacity > 0) {
+    HostPair hp;
+    hp.leaf = block->leaf;
+    hp.info = block->information;
+    hp.cap = (size_t)block->capacity;
+    host_pool_give(hp);
+  } else {
+    if (block->leaf) cudaFreeHost(block->leaf);
+    if (block->information) cudaFreeHost(block->information);
+    cudaGetLastError();
+  }
+  std::memset(block, 0, sizeof(*block));
   return Q3DR_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -138,7 +139,7 @@ struct PinnedBuf {
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
-    Q3DR_CUDA(cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocDefault));
+    Q3DR_CUDA(cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocPortable));
     cap = want;
     return Q3DR_OK;
   }
@@ -147,7 +148,7 @@ struct PinnedBuf {
     if (n <= cap) return Q3DR_OK;
     size_t want = std::max(n, cap + cap / 2);
     T* q = nullptr;
-    Q3DR_CUDA(cudaHostAlloc(&q, want * sizeof(T), cudaHostAllocDefault));
+    Q3DR_CUDA(cudaHostAlloc(&q, want * sizeof(T), cudaHostAllocPortable));
     if (p && used) std::memcpy(q, p, used * sizeof(T));
     if (p) cudaFreeHost(p);
     p = q;

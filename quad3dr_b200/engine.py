@@ -58,6 +58,24 @@ class _Result(C.Structure):
     ]
 
 
+class HostBlock(C.Structure):
+    """q3dr_host_block: the (leaf, information) host arrays of a result after q3dr_result_detach_host"""
+
+    _fields_ = [("leaf", C.c_void_p), ("information", C.c_void_p), ("n_entries", C.c_uint64), ("capacity", C.c_uint64)]
+
+    def arrays(self):
+        """numpy views (no copy) of the valid entries; they die with release()"""
+        n = int(self.n_entries)
+        if n == 0:
+            return np.empty(0, np.int32), np.empty(0, np.float32)
+        leaf = np.ctypeslib.as_array(C.cast(self.leaf, C.POINTER(C.c_int32)), shape=(n,))
+        info = np.ctypeslib.as_array(C.cast(self.information, C.POINTER(C.c_float)), shape=(n,))
+        return leaf, info
+
+    def release(self):
+        _check(load_library().q3dr_host_block_release(C.byref(self)))
+
+
 class _OverlapResult(C.Structure):
     _fields_ = [("n_boxes", C.c_uint64), ("n_entries", C.c_uint64), ("offsets", C.c_void_p), ("leaf", C.c_void_p)]
 
@@ -220,6 +238,8 @@ def load_library() -> C.CDLL:
     L.q3dr_result_to_host.argtypes = [vp, C.POINTER(_Result)]
     L.q3dr_map_set_chunk_callback.argtypes = [vp, CHUNK_CALLBACK, vp]
     L.q3dr_map_set_result_fields.argtypes = [vp, C.c_uint32]
+    L.q3dr_result_detach_host.argtypes = [vp, C.POINTER(HostBlock)]
+    L.q3dr_host_block_release.argtypes = [C.POINTER(HostBlock)]
     L.q3dr_map_check_guards.argtypes = [vp, C.POINTER(C.c_int)]
     L.q3dr_candidate_opts_default.argtypes = [C.POINTER(CandidateOpts)]
     L.q3dr_candidate_opts_default.restype = None
@@ -718,6 +738,13 @@ class OccupancyMap:
         r = _Result()
         _check(load_library().q3dr_result_to_host(self._h, C.byref(r)))
         return ScoreResult(r, copy=copy)
+
+    def detach_host_result(self) -> HostBlock:
+        """Takes the (leaf, information) host arrays of the last result away from the map (q3dr_result_detach_host):
+        they stay valid until HostBlock.release(), whatever the map does next."""
+        hb = HostBlock()
+        _check(load_library().q3dr_result_detach_host(self._h, C.byref(hb)))
+        return hb
 
 
 def exchange_layout(n_ranks: int, max_viewpoints: int, max_entries: int) -> ExchangeLayout:

@@ -130,3 +130,52 @@ def test_viewpoints_on_box_planes_take_the_checking_kernel_on_every_route():
             assert np.array_equal(bits(got["dsq"]), bits(r["dsq"])), v
     assert _same(big, dev)
     gmap.close()
+
+
+@pytest.mark.gpu
+def test_detached_host_arrays_survive_later_calls_and_are_recycled():
+    """q3dr_result_detach_host: the shim's voxel-set views keep the engine's own host arrays instead of copying them."""
+    leaves = synth.map_small()
+    order, depth = E.splitmedian_order(leaves.boxes)
+    leaves = leaves.permuted(order)
+    w, h = 96, 72
+    cam = synth.make_camera(w, h)
+    vps = synth.make_viewpoints(leaves, 12, config_id=41)
+    gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth)
+    with pytest.raises(E.Q3drError):
+        gmap.detach_host_result()  # nothing scored yet
+    r1 = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[:7])
+    hb1 = gmap.detach_host_result()
+    leaf1, info1 = hb1.arrays()
+    assert hb1.n_entries == r1.n_entries and hb1.capacity >= hb1.n_entries
+    assert np.array_equal(leaf1, r1.leaf) and np.array_equal(info1.view(np.uint32), r1.information.view(np.uint32))
+    with pytest.raises(E.Q3drError):
+        gmap.detach_host_result()  # already gone
+    # the map scores something else: the detached arrays are not its buffers any more
+    r2 = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[5:])
+    assert r2.n_entries != r1.n_entries or not np.array_equal(r2.leaf, r1.leaf)
+    assert np.array_equal(leaf1, r1.leaf) and np.array_equal(info1.view(np.uint32), r1.information.view(np.uint32))
+    hb2 = gmap.detach_host_result()
+    assert hb2.leaf != hb1.leaf and hb2.information != hb1.information
+    leaf2, _ = hb2.arrays()
+    assert np.array_equal(leaf2, r2.leaf)
+    # a released block is what the map takes next (no fresh pinned allocation per call)
+    p1 = (hb1.leaf, hb1.information)
+    hb1.release()
+    assert hb1.leaf is None and hb1.capacity == 0
+    gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[:7])
+    hb3 = gmap.detach_host_result()
+    assert (hb3.leaf, hb3.information) == p1
+    leaf3, info3 = hb3.arrays()
+    assert np.array_equal(leaf3, r1.leaf) and np.array_equal(info3.view(np.uint32), r1.information.view(np.uint32))
+    # detaching works after the device-resident call + q3dr_result_to_host as well
+    import torch
+
+    d_rt = torch.from_numpy(np.ascontiguousarray(vps[:7])).cuda()
+    gmap.score_viewpoints_device(cam.K, w, (0, w, 0, h), d_rt.data_ptr(), 7)
+    r4 = gmap.result_to_host()
+    hb4 = gmap.detach_host_result()
+    assert np.array_equal(hb4.arrays()[0], r4.leaf) and np.array_equal(r4.leaf, r1.leaf)
+    for hb in (hb2, hb3, hb4):
+        hb.release()
+    gmap.close()

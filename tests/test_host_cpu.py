@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/q3dr_raycast.h but not exported"
-    assert lib.q3dr_abi_version() == 4
+    assert lib.q3dr_abi_version() == 5
 
 
 def test_struct_layouts_match_header():
@@ -40,6 +40,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(E.RenderOpts) == 12   # q3dr_render_opts
     assert ctypes.sizeof(E.MeshInfo) == 40     # q3dr_mesh_info
     assert ctypes.sizeof(E.ExchangeLayout) == 64  # q3dr_exchange_layout
+    assert ctypes.sizeof(E.HostBlock) == 32       # q3dr_host_block
 
 
 def test_score_opts_defaults_match_reference_defaults():
@@ -184,3 +185,11 @@ def test_no_fused_packed_multiply_add_in_the_library():
     sass = subprocess.run([cuobjdump, "-sass", E.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert "FMUL2" in sass and "FADD2" in sass  # the packed path is really there ...
     assert "FFMA2" not in sass  # ... and nothing of it was contracted
+
+
+def test_host_block_calls_without_a_gpu():
+    lib = E.load_library()
+    hb = E.HostBlock()
+    assert lib.q3dr_result_detach_host(None, ctypes.byref(hb)) == E.Q3DR_ERR_INVALID_ARG
+    assert lib.q3dr_host_block_release(None) == E.Q3DR_OK
+    assert lib.q3dr_host_block_release(ctypes.byref(hb)) == E.Q3DR_OK  # all zeros: nothing to do
