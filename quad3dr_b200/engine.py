@@ -697,8 +697,9 @@ class OccupancyMap:
         return out, int(cnt.value)
 
     def generate_viewpoint_entries(self, K, image_width: int, window: Sequence[int], cand_pos, cand_quat, existing_pos,
-                                   existing_quat, copts: "CandidateOpts", opts: Optional[ScoreOpts] = None):
-        """tryToAddViewpointEntry for a batch of candidate poses in order: (status uint8 (n,), ScoreResult over all n)."""
+                                   existing_quat, copts: "CandidateOpts", opts: Optional[ScoreOpts] = None, copy: bool = True):
+        """tryToAddViewpointEntry for a batch of candidate poses in order: (status uint8 (n,), ScoreResult over all n);
+        copy = False: the ScoreResult's arrays are views of the map's host buffers (valid until the next call)."""
         K = _f32(K, (4,))
         cp = _f32(cand_pos).reshape(-1, 3)
         cq = _f32(cand_quat).reshape(-1, 4)
@@ -711,7 +712,7 @@ class OccupancyMap:
         _check(load_library().q3dr_generate_viewpoint_entries(
             self._h, _fp(K), image_width, x0, x1, y0, y1, _fp(cp), _fp(cq), cp.shape[0], _fp(ep), _fp(eq), ep.shape[0],
             C.byref(opts), C.byref(copts), status.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(r)))
-        return status, ScoreResult(r, copy=True)
+        return status, ScoreResult(r, copy=copy)
 
     def overlap_boxes(self, boxes) -> Tuple[np.ndarray, np.ndarray]:
         """bvh::Tree::intersects(bbox) for many boxes: CSR (offsets uint64 (n+1), leaf int32) of the overlapping
