@@ -29,14 +29,18 @@
 #define Q3DR_OCCUPIED_TREE_CUDA_HPP_
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <deque>
+#include <exception>
 #include <iterator>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <utility>
@@ -60,9 +64,80 @@ struct VoxelWithInformation {
   };
 };
 
+/// Monotonic arena behind one voxel set: hash nodes and bucket arrays are carved out of a few large chunks and freeing
+/// is a no-op; the memory goes when the last container sharing the arena dies.  A scoring batch fills 10^7 hash nodes:
+/// with the default allocator their allocation (and later their release, one free() per voxel) costs several times
+/// what the GPU does.
+class SetArena {
+ public:
+  SetArena() : cur_(nullptr), left_(0), next_chunk_(4096) {}
+  SetArena(const SetArena&) = delete;
+  SetArena& operator=(const SetArena&) = delete;
+  /// makes room for `bytes` more without another chunk (called with the known size of a set before it is filled)
+  void reserve(std::size_t bytes) {
+    if (bytes > left_) add_chunk(bytes);
+  }
+  void* take(std::size_t bytes, std::size_t align) {
+    std::size_t pad = padding(align);
+    if (pad + bytes > left_) {
+      add_chunk(bytes + align);
+      pad = padding(align);
+    }
+    cur_ += pad;
+    void* p = cur_;
+    cur_ += bytes;
+    left_ -= pad + bytes;
+    return p;
+  }
+
+ private:
+  std::size_t padding(std::size_t align) const {
+    return (align - (reinterpret_cast<std::uintptr_t>(cur_) & (align - 1))) & (align - 1);
+  }
+  void add_chunk(std::size_t at_least) {
+    const std::size_t n = std::max(at_least, next_chunk_);
+    chunks_.emplace_back(new char[n]);
+    cur_ = chunks_.back().get();
+    left_ = n;
+    next_chunk_ = std::min<std::size_t>(2 * next_chunk_, std::size_t(1) << 20);
+  }
+  std::vector<std::unique_ptr<char[]> > chunks_;
+  char* cur_;
+  std::size_t left_, next_chunk_;
+};
+
+/// Standard allocator over a SetArena.  A moved or swapped container takes its arena along; a COPY gets an arena of its
+/// own (two copies may be filled by two threads).  Not thread-safe per arena, like the container it serves.
+template <typename T>
+class SetArenaAllocator {
+ public:
+  typedef T value_type;
+  typedef std::true_type propagate_on_container_move_assignment;
+  typedef std::true_type propagate_on_container_swap;
+  typedef std::false_type propagate_on_container_copy_assignment;
+  SetArenaAllocator() : arena_(std::make_shared<SetArena>()) {}
+  template <typename U>
+  SetArenaAllocator(const SetArenaAllocator<U>& o) : arena_(o.arena_ptr()) {}
+  SetArenaAllocator select_on_container_copy_construction() const { return SetArenaAllocator(); }
+  T* allocate(std::size_t n) { return static_cast<T*>(arena_->take(n * sizeof(T), alignof(T))); }
+  void deallocate(T*, std::size_t) {}
+  SetArena& arena() const { return *arena_; }
+  const std::shared_ptr<SetArena>& arena_ptr() const { return arena_; }
+  template <typename U>
+  bool operator==(const SetArenaAllocator<U>& o) const { return arena_ == o.arena_ptr(); }
+  template <typename U>
+  bool operator!=(const SetArenaAllocator<U>& o) const { return arena_ != o.arena_ptr(); }
+
+ private:
+  std::shared_ptr<SetArena> arena_;
+};
+
+/// The reference's container (planner/occupied_tree.h:91: std::unordered_set<VoxelWithInformation, VoxelHash>) with the
+/// arena allocator as its fourth template argument; everything a consumer does with the set is unchanged.
 template <typename NodeT>
 using VoxelWithInformationSet =
-    std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash>;
+    std::unordered_set<VoxelWithInformation<NodeT>, typename VoxelWithInformation<NodeT>::VoxelHash,
+                       std::equal_to<VoxelWithInformation<NodeT> >, SetArenaAllocator<VoxelWithInformation<NodeT> > >;
 
 /// The per-viewpoint voxel sets of one batched scoring call, CSR form, shared by the views below.  The two arrays are
 /// the engine's own pinned host arrays, handed over by q3dr_result_detach_host (no copy on the host); they go back to
@@ -660,28 +735,86 @@ class ViewpointRaycastCuda {
 
   /// Batched form: all candidates of one graph-building round in one call (one camera for all viewpoints), the
   /// reference's own container per viewpoint.  The sets are filled by all host threads (OpenMP over viewpoints, like the
-  /// reference's result conversion, bvh.h:430,487); for 10^3 viewpoints x 10^4 voxels this conversion, not the GPU, is
-  /// what the call costs -- consumers that only read the sets take ...BatchView below.
+  /// reference's result conversion, bvh.h:430,487) out of per-set arenas, and large batches are cut into pieces of
+  /// kSetBatchPiece viewpoints: a helper thread drives the engine through the pieces while this thread's team turns the
+  /// finished ones into sets -- the 10^7 hash-table insertions of a 10^3-viewpoint batch overlap with the GPU work.
+  /// Consumers that only read the sets take ...BatchView below (no host work per voxel at all).
   template <typename ViewpointT>
   std::vector<std::pair<VoxelSet, float>> getRaycastHitVoxelsWithInformationScoreBatch(
       const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end, std::size_t y_start,
       std::size_t y_end, bool ignore_voxels_with_zero_information = false) const {
     std::vector<std::pair<VoxelSet, float>> out(viewpoints.size());
     if (viewpoints.empty()) return out;
-    const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
-    const std::vector<NodeT*>& nodes = bvh_tree_->leafNodes();
-    const std::ptrdiff_t nv = static_cast<std::ptrdiff_t>(viewpoints.size());
-#ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 4)
-#endif
-    for (std::ptrdiff_t v = 0; v < nv; ++v) {
-      VoxelSet& set = out[static_cast<std::size_t>(v)].first;
-      set.reserve(static_cast<std::size_t>(r.offsets[v + 1] - r.offsets[v]));
-      for (std::uint64_t i = r.offsets[v]; i < r.offsets[v + 1]; ++i) {
-        set.insert(VoxelWithInformation<NodeT>(nodes[static_cast<std::size_t>(r.leaf[i])], r.information[i]));
-      }
-      out[static_cast<std::size_t>(v)].second = r.total[v];
+    const std::size_t n = viewpoints.size();
+    if (n <= kSetBatchPiece) {
+      const q3dr_result r = scoreBatch(viewpoints, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
+      fillSets(r.offsets, r.total, r.leaf, r.information, 0, n, &out);
+      return out;
     }
+    // producer: the engine calls, piece after piece; every piece's host arrays are detached from the map at once
+    struct Piece {
+      std::size_t first, count;
+      std::vector<std::uint64_t> offsets;
+      std::vector<float> total;
+      q3dr_host_block host;
+    };
+    std::mutex mutex;
+    std::condition_variable ready;
+    std::deque<std::shared_ptr<Piece> > queue;
+    bool done = false;
+    std::exception_ptr producer_error;
+    std::thread producer([&]() {
+      try {
+        for (std::size_t first = 0; first < n; first += kSetBatchPiece) {
+          const std::size_t count = std::min(kSetBatchPiece, n - first);
+          const std::vector<const ViewpointT*> sub(viewpoints.begin() + static_cast<std::ptrdiff_t>(first),
+                                                   viewpoints.begin() + static_cast<std::ptrdiff_t>(first + count));
+          const q3dr_result r = scoreBatch(sub, x_start, x_end, y_start, y_end, ignore_voxels_with_zero_information);
+          std::shared_ptr<Piece> p = std::make_shared<Piece>();
+          p->first = first;
+          p->count = count;
+          p->offsets.assign(r.offsets, r.offsets + count + 1);
+          p->total.assign(r.total, r.total + count);
+          std::memset(&p->host, 0, sizeof(p->host));
+          bvh_tree_->check(q3dr_result_detach_host(bvh_tree_->handle(), &p->host));
+          {
+            std::lock_guard<std::mutex> lock(mutex);
+            queue.push_back(p);
+          }
+          ready.notify_one();
+        }
+      } catch (...) {
+        producer_error = std::current_exception();
+      }
+      {
+        std::lock_guard<std::mutex> lock(mutex);
+        done = true;
+      }
+      ready.notify_one();
+    });
+    // consumer: this thread and its OpenMP team
+    std::exception_ptr consumer_error;
+    for (;;) {
+      std::shared_ptr<Piece> p;
+      {
+        std::unique_lock<std::mutex> lock(mutex);
+        ready.wait(lock, [&]() { return !queue.empty() || done; });
+        if (queue.empty()) break;
+        p = queue.front();
+        queue.pop_front();
+      }
+      if (!consumer_error) {
+        try {
+          fillSets(p->offsets.data(), p->total.data(), p->host.leaf, p->host.information, p->first, p->count, &out);
+        } catch (...) {
+          consumer_error = std::current_exception();
+        }
+      }
+      q3dr_host_block_release(&p->host);
+    }
+    producer.join();
+    if (producer_error) std::rethrow_exception(producer_error);
+    if (consumer_error) std::rethrow_exception(consumer_error);
     return out;
   }
 
@@ -710,6 +843,29 @@ class ViewpointRaycastCuda {
   }
 
  private:
+  static const std::size_t kSetBatchPiece = 256;
+
+  /// sets of viewpoints [first, first + count) of `out` from a CSR piece (offsets / total indexed from 0)
+  void fillSets(const std::uint64_t* offsets, const float* total, const std::int32_t* leaf, const float* information,
+                std::size_t first, std::size_t count, std::vector<std::pair<VoxelSet, float>>* out) const {
+    const std::vector<NodeT*>& nodes = bvh_tree_->leafNodes();
+    const std::ptrdiff_t nv = static_cast<std::ptrdiff_t>(count);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (std::ptrdiff_t v = 0; v < nv; ++v) {
+      VoxelSet& set = (*out)[first + static_cast<std::size_t>(v)].first;
+      const std::size_t k = static_cast<std::size_t>(offsets[v + 1] - offsets[v]);
+      // one arena chunk for the whole set: 32-byte hash nodes + the bucket array
+      set.get_allocator().arena().reserve(k * (sizeof(VoxelWithInformation<NodeT>) + 2 * sizeof(void*)) + 2 * k * sizeof(void*) + 256);
+      set.reserve(k);
+      for (std::uint64_t i = offsets[v]; i < offsets[v + 1]; ++i) {
+        set.insert(VoxelWithInformation<NodeT>(nodes[static_cast<std::size_t>(leaf[i])], information[i]));
+      }
+      (*out)[first + static_cast<std::size_t>(v)].second = total[v];
+    }
+  }
+
   /// the engine call behind both batch forms; only (leaf, information) travel back (8 bytes per voxel)
   template <typename ViewpointT>
   q3dr_result scoreBatch(const std::vector<const ViewpointT*>& viewpoints, std::size_t x_start, std::size_t x_end,

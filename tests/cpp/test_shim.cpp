@@ -532,6 +532,36 @@ int main(int argc, char** argv) {
         CHECK(other[v].first.size() <= again[v].first.size());
       }
     }
+    // a batch larger than one piece of the pipelined conversion (helper thread drives the engine, this thread's team
+    // fills the sets): every set equals the view of the same viewpoint, copies and moves of arena-backed sets behave
+    {
+      std::vector<const mock::Viewpoint*> big;
+      for (int rep = 0; rep < 210; ++rep)
+        for (const mock::Viewpoint& vp : vps) big.push_back(&vp);
+      CHECK(big.size() > 600);
+      auto sets_big = raycaster.getRaycastHitVoxelsWithInformationScoreBatch(big, 0, cam.w, 0, cam.h, true);
+      auto views_big = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(big, 0, cam.w, 0, cam.h, true);
+      CHECK(sets_big.size() == big.size() && views_big.size() == big.size());
+      std::size_t total_voxels = 0;
+      for (std::size_t v = 0; v < big.size(); ++v) {
+        CHECK(sets_big[v].second == views_big[v].second);
+        CHECK(sets_big[v].first.size() == views_big[v].first.size());
+        if (v % 37 == 0) CHECK(views_big[v].first.toUnorderedSet() == sets_big[v].first);
+        CHECK(sets_big[v].first == sets_big[v % vps.size()].first);  // the same viewpoint again
+        total_voxels += sets_big[v].first.size();
+      }
+      CHECK(total_voxels > 10000);
+      q3dr::VoxelWithInformationSet<mock::Node> copy = sets_big[3].first;  // a copy owns an arena of its own
+      q3dr::VoxelWithInformationSet<mock::Node> moved = std::move(sets_big[3].first);
+      CHECK(copy == moved && copy.size() == views_big[3].first.size());
+      sets_big.clear();  // the moved-from vector dies; copy and moved live on
+      CHECK(copy == moved);
+      copy.erase(copy.begin());
+      CHECK(copy.size() + 1 == moved.size());
+      copy.insert(*moved.begin());
+      copy.insert(*views_big[3].first.begin());
+      CHECK(copy.size() >= moved.size());
+    }
     // the set consumers take a view as well
     auto views = raycaster.getRaycastHitVoxelsWithInformationScoreBatchView(batch, 0, cam.w, 0, cam.h, true);
     auto sets = raycaster.getRaycastHitVoxelsWithInformationScoreBatch(batch, 0, cam.w, 0, cam.h, true);
