@@ -22,6 +22,15 @@ try:
     PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
+# instructions per ray of the committed ncu captures (profiles/traffic.json): the kernel is issue-bound, the issue
+# fraction is the one that means something; the byte model of SURVEY.md 8(d) is kept because C5 names it
+WI = {"1M": 52.5, "10M": 58.8}
+try:
+    _t = json.load(open(os.path.join(os.path.dirname(__file__), "..", "profiles", "traffic.json")))
+    WI = {"1M": _t["C2"]["warp_instructions_per_ray"], "10M": _t["C3"]["warp_instructions_per_ray"]}
+except Exception:
+    pass
+ISSUE_PEAK = 148 * 4 * 1.965e9
 plans = [("1M-leaf map (octree depth 14 class)", synth.map_1m, [1e6, 1e7, 1e8, 1e9, 1e10]),
          ("10M-leaf map (octree depth 16 class)", synth.map_10m, [1e7, 1e8, 1e9, 1e10])]
 if len(sys.argv) > 1 and sys.argv[1] == "--quick":
@@ -63,7 +72,8 @@ for name, mk, ray_counts in plans:
             rps = total_rays / (float(ms) * 1e-3)
             print(json.dumps({"map": name, "n_leaves": leaves.n, "n_gpus": world, "rays": total_rays, "viewpoints": nvp_total,
                               "ms": float(ms), "rays_per_sec": rps, "algorithmic_GBps_per_gpu": rps / world * b_ray / 1e9,
-                              "frac_of_measured_hbm_peak": rps / world * b_ray / 1e9 / PEAK, "bytes_per_ray": b_ray}), flush=True)
+                              "frac_of_measured_hbm_peak": rps / world * b_ray / 1e9 / PEAK, "bytes_per_ray": b_ray,
+                              "frac_of_issue_peak": rps / world * WI["1M" if leaves.n < 5_000_000 else "10M"] / ISSUE_PEAK}), flush=True)
     gmap.close()
     del gmap
 if dist is not None:
