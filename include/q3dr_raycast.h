@@ -259,6 +259,7 @@ int q3dr_result_to_host(q3dr_map* map, q3dr_result* result);
  * with the map (small).  Replaces the conversion loop of bvh.h:430,487 / viewpoint_planner_raycast.cpp:116-148. */
 int q3dr_result_detach_host(q3dr_map* map, q3dr_host_block* out);
 int q3dr_host_block_release(q3dr_host_block* block); /* block may be all zeros; it is zeroed on return */
+int q3dr_host_pool_trim(void); /* frees the released blocks the pool still holds (at most three); returns Q3DR_OK */
 
 /* Which per-entry arrays the scoring calls on this map deliver besides (leaf, information).  The reference's facade
  * (getRaycastHitVoxelsWithInformationScore -> VoxelWithInformationSet, viewpoint_planner_raycast.cpp:116-148) consumes

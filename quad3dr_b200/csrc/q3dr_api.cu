@@ -1310,6 +1310,20 @@ int q3dr_host_block_release(q3dr_host_block* block) {
   return Q3DR_OK;
 }
 
+int q3dr_host_pool_trim(void) {
+  std::vector<HostPair> drop;
+  {
+    std::lock_guard<std::mutex> lock(host_pool_mutex());
+    drop.swap(host_pool());
+  }
+  for (const HostPair& hp : drop) {
+    if (hp.leaf) cudaFreeHost(hp.leaf);
+    if (hp.info) cudaFreeHost(hp.info);
+  }
+  cudaGetLastError();
+  return Q3DR_OK;
+}
+
 int q3dr_map_set_result_fields(q3dr_map* m, uint32_t fields) {
   if (!m) return fail(Q3DR_ERR_INVALID_ARG, "map is NULL");
   if (fields & ~(uint32_t)(Q3DR_RESULT_FIRST_PIXEL | Q3DR_RESULT_DIST_SQ)) return fail(Q3DR_ERR_INVALID_ARG, "unknown result field");

@@ -193,3 +193,4 @@ def test_host_block_calls_without_a_gpu():
     assert lib.q3dr_result_detach_host(None, ctypes.byref(hb)) == E.Q3DR_ERR_INVALID_ARG
     assert lib.q3dr_host_block_release(None) == E.Q3DR_OK
     assert lib.q3dr_host_block_release(ctypes.byref(hb)) == E.Q3DR_OK  # all zeros: nothing to do
+    assert lib.q3dr_host_pool_trim() == E.Q3DR_OK  # empty pool
