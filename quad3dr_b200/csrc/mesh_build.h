@@ -1,4 +1,4 @@
-// mesh_build.h -- host-side median-split BVH over the triangles of a q3dr_mesh (see mesh_kernels.cuh for the
+// mesh_build.h -- host-side BVH (binned SAH, object median as the fallback) over the triangles of a q3dr_mesh (see mesh_kernels.cuh for the
 // traversal and q3dr_mesh.cu for the upload).
 #pragma once
 
@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -48,6 +49,12 @@ struct MeshBuilder {
   std::vector<float4> nodes;
   uint32_t depth = 0;
   float pad = 0.f;
+  bool use_sah = true;  // Q3DR_MESH_BUILD=median switches back to the object-median split (for measurements)
+
+  static float half_area(const Box3& b) {
+    const float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+    return dx * dy + dy * dz + dz * dx;
+  }
 
   Box3 padded(Box3 b) const {
     for (int i = 0; i < 3; ++i) {
@@ -76,11 +83,76 @@ struct MeshBuilder {
     int axis = 0;
     if (cmx[1] - cmn[1] > cmx[axis] - cmn[axis]) axis = 1;
     if (cmx[2] - cmn[2] > cmx[axis] - cmn[axis]) axis = 2;
-    const size_t mid = begin + cnt / 2;
-    std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end, [&](uint32_t a, uint32_t b) {
-      const float ca = centroid[3 * (size_t)a + axis], cb = centroid[3 * (size_t)b + axis];
-      return ca < cb || (ca == cb && a < b);
-    });
+    size_t mid = begin + cnt / 2;
+    bool split_done = false;
+    if (use_sah && cnt > 8) {
+      // binned surface-area heuristic over the three axes (16 bins of the centroid range): the cut with the least
+      // area(left) * count(left) + area(right) * count(right); the traversal's answer does not depend on the tree
+      // (mesh_kernels.cuh), so this only changes how many nodes a ray visits
+      constexpr int kBins = 16;
+      float best_cost = FLT_MAX;
+      int best_axis = -1, best_bin = -1;
+      for (int a = 0; a < 3; ++a) {
+        const float ext = cmx[a] - cmn[a];
+        if (!(ext > 0.0f)) continue;
+        const float scale = (float)kBins / ext;
+        Box3 bb[kBins];
+        uint32_t bc[kBins];
+        for (int k = 0; k < kBins; ++k) {
+          bb[k].reset();
+          bc[k] = 0;
+        }
+        for (size_t i = begin; i < end; ++i) {
+          const uint32_t t = order[i];
+          int k = (int)((centroid[3 * (size_t)t + a] - cmn[a]) * scale);
+          k = std::min(std::max(k, 0), kBins - 1);
+          bb[k].grow(tri_box[t]);
+          ++bc[k];
+        }
+        float right_area[kBins];
+        uint32_t right_cnt[kBins];
+        Box3 acc;
+        acc.reset();
+        uint32_t n_acc = 0;
+        for (int k = kBins - 1; k > 0; --k) {
+          if (bc[k]) acc.grow(bb[k]);
+          n_acc += bc[k];
+          right_area[k] = n_acc ? half_area(acc) : 0.0f;
+          right_cnt[k] = n_acc;
+        }
+        acc.reset();
+        n_acc = 0;
+        for (int k = 0; k < kBins - 1; ++k) {
+          if (bc[k]) acc.grow(bb[k]);
+          n_acc += bc[k];
+          if (n_acc == 0 || right_cnt[k + 1] == 0) continue;
+          const float cost = half_area(acc) * (float)n_acc + right_area[k + 1] * (float)right_cnt[k + 1];
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_axis = a;
+            best_bin = k;
+          }
+        }
+      }
+      if (best_axis >= 0) {
+        const float scale = (float)kBins / (cmx[best_axis] - cmn[best_axis]);
+        const float lo = cmn[best_axis];
+        auto it = std::stable_partition(order.begin() + begin, order.begin() + end, [&](uint32_t t) {
+          int k = (int)((centroid[3 * (size_t)t + best_axis] - lo) * scale);
+          k = std::min(std::max(k, 0), kBins - 1);
+          return k <= best_bin;
+        });
+        mid = (size_t)(it - order.begin());
+        split_done = mid > begin && mid < end;
+        if (!split_done) mid = begin + cnt / 2;
+      }
+    }
+    if (!split_done) {
+      std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end, [&](uint32_t a, uint32_t b) {
+        const float ca = centroid[3 * (size_t)a + axis], cb = centroid[3 * (size_t)b + axis];
+        return ca < cb || (ca == cb && a < b);
+      });
+    }
     const size_t me = nodes.size() / 4;
     nodes.resize(nodes.size() + 4);
     Box3 lb, rb;
@@ -114,6 +186,7 @@ struct MeshHost {
 inline void build_mesh_host(const float* tri_vertices, const float* tri_normals, size_t nf, MeshHost* out) {
   MeshBuilder b;
   b.v = tri_vertices;
+  if (const char* e = std::getenv("Q3DR_MESH_BUILD")) b.use_sah = std::strcmp(e, "median") != 0;
   b.tri_box.resize(nf);
   b.centroid.resize(3 * nf);
   b.order.resize(nf);
@@ -133,6 +206,14 @@ inline void build_mesh_host(const float* tri_vertices, const float* tri_normals,
   b.nodes.reserve(4 * (nf / 2 + 1));
   Box3 root_box;
   out->root_ref = b.build(0, nf, 0, &root_box);
+  if (b.use_sah && b.depth + 2 > (uint32_t)kMeshStack) {
+    // an adversarial triangle distribution made the SAH tree deeper than the traversal stack: the balanced tree instead
+    b.use_sah = false;
+    b.depth = 0;
+    b.nodes.clear();
+    for (size_t i = 0; i < nf; ++i) b.order[i] = (uint32_t)i;
+    out->root_ref = b.build(0, nf, 0, &root_box);
+  }
   out->depth = b.depth;
   out->pad = b.pad;
   out->nodes.swap(b.nodes);
