@@ -49,6 +49,7 @@ struct MeshBuilder {
   std::vector<float4> nodes;
   uint32_t depth = 0;
   float pad = 0.f;
+  static constexpr int kExactSweep = 32;
   bool use_sah = true;  // Q3DR_MESH_BUILD=median switches back to the object-median split (for measurements)
 
   static float half_area(const Box3& b) {
@@ -85,11 +86,49 @@ struct MeshBuilder {
     if (cmx[2] - cmn[2] > cmx[axis] - cmn[axis]) axis = 2;
     size_t mid = begin + cnt / 2;
     bool split_done = false;
-    if (use_sah && cnt > 8) {
-      // binned surface-area heuristic over the three axes (16 bins of the centroid range): the cut with the least
+    if (use_sah && cnt <= (size_t)kExactSweep) {
+      // small ranges: every cut position along every axis (sorted by centroid)
+      float best_cost = FLT_MAX;
+      int best_axis = -1;
+      size_t best_k = 0;
+      uint32_t tmp[kExactSweep];
+      float ra[kExactSweep];
+      for (int a = 0; a < 3; ++a) {
+        for (size_t i = 0; i < cnt; ++i) tmp[i] = order[begin + i];
+        std::sort(tmp, tmp + cnt, [&](uint32_t x, uint32_t y) {
+          const float cx = centroid[3 * (size_t)x + a], cy = centroid[3 * (size_t)y + a];
+          return cx < cy || (cx == cy && x < y);
+        });
+        Box3 acc;
+        acc.reset();
+        for (size_t i = cnt; i-- > 1;) {
+          acc.grow(tri_box[tmp[i]]);
+          ra[i] = half_area(acc);
+        }
+        acc.reset();
+        for (size_t k = 1; k < cnt; ++k) {  // left = first k
+          acc.grow(tri_box[tmp[k - 1]]);
+          const float cost = half_area(acc) * (float)k + ra[k] * (float)(cnt - k);
+          if (cost < best_cost) {
+            best_cost = cost;
+            best_axis = a;
+            best_k = k;
+          }
+        }
+      }
+      if (best_axis >= 0) {
+        std::sort(order.begin() + begin, order.begin() + end, [&](uint32_t x, uint32_t y) {
+          const float cx = centroid[3 * (size_t)x + best_axis], cy = centroid[3 * (size_t)y + best_axis];
+          return cx < cy || (cx == cy && x < y);
+        });
+        mid = begin + best_k;
+        split_done = true;
+      }
+    } else if (use_sah) {
+      // binned surface-area heuristic over the three axes (32 bins of the centroid range): the cut with the least
       // area(left) * count(left) + area(right) * count(right); the traversal's answer does not depend on the tree
       // (mesh_kernels.cuh), so this only changes how many nodes a ray visits
-      constexpr int kBins = 16;
+      constexpr int kBins = 32;
       float best_cost = FLT_MAX;
       int best_axis = -1, best_bin = -1;
       for (int a = 0; a < 3; ++a) {
