@@ -50,6 +50,7 @@ struct MeshBuilder {
   uint32_t depth = 0;
   float pad = 0.f;
   static constexpr int kExactSweep = 32;
+  size_t leaf_max = q3dr::kMeshLeafMaxTris;  // Q3DR_MESH_LEAF=1..4 (for measurements)
   bool use_sah = true;  // Q3DR_MESH_BUILD=median switches back to the object-median split (for measurements)
 
   static float half_area(const Box3& b) {
@@ -72,7 +73,7 @@ struct MeshBuilder {
     for (size_t i = begin; i < end; ++i) box.grow(tri_box[order[i]]);
     *box_out = box;
     const size_t cnt = end - begin;
-    if (cnt <= q3dr::kMeshLeafMaxTris) return ~(int32_t)((begin << 2) | (cnt - 1));
+    if (cnt <= leaf_max) return ~(int32_t)((begin << 2) | (cnt - 1));
     float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (size_t i = begin; i < end; ++i) {
       const float* c = &centroid[3 * (size_t)order[i]];
@@ -226,6 +227,7 @@ inline void build_mesh_host(const float* tri_vertices, const float* tri_normals,
   MeshBuilder b;
   b.v = tri_vertices;
   if (const char* e = std::getenv("Q3DR_MESH_BUILD")) b.use_sah = std::strcmp(e, "median") != 0;
+  if (const char* e = std::getenv("Q3DR_MESH_LEAF")) b.leaf_max = (size_t)std::min<long>(q3dr::kMeshLeafMaxTris, std::max<long>(1, std::strtol(e, nullptr, 10)));
   b.tri_box.resize(nf);
   b.centroid.resize(3 * nf);
   b.order.resize(nf);
