@@ -247,7 +247,9 @@ inline void build_mesh_host(const float* tri_vertices, const float* tri_normals,
   b.nodes.reserve(4 * (nf / 2 + 1));
   Box3 root_box;
   out->root_ref = b.build(0, nf, 0, &root_box);
-  if (b.use_sah && b.depth + 2 > (uint32_t)kMeshStack) {
+  uint32_t max_depth = (uint32_t)kMeshStack - 2;  // Q3DR_MESH_MAX_DEPTH lowers it (tests of the fallback below)
+  if (const char* e = std::getenv("Q3DR_MESH_MAX_DEPTH")) max_depth = std::min<uint32_t>(max_depth, (uint32_t)std::max<long>(1, std::strtol(e, nullptr, 10)));
+  if (b.use_sah && b.depth > max_depth) {
     // an adversarial triangle distribution made the SAH tree deeper than the traversal stack: the balanced tree instead
     b.use_sah = false;
     b.depth = 0;

@@ -196,6 +196,40 @@ def test_host_compiled_traversal_equals_brute_force_on_the_synthetic_mesh():
         assert (ref != CLEAR).mean() > 0.2
 
 
+def test_sah_tree_that_would_outgrow_the_stack_falls_back_to_the_balanced_tree(monkeypatch):
+    """Triangles spaced in a geometric progression make the surface-area heuristic build a lopsided tree (29 levels for
+    3000 triangles).  A tree deeper than the traversal stack allows (38 levels; lowered to 16 here through the
+    builder's test knob) must be replaced by the object-median tree, with the same answers."""
+    monkeypatch.setenv("Q3DR_MESH_MAX_DEPTH", "16")
+    lib = _harness()
+    nf = 3000
+    rng = np.random.default_rng(3)
+    x = (1.025 ** np.arange(nf)).astype(np.float64)
+    tv = np.zeros((nf, 3, 3))
+    tv[:, :, 0] = x[:, None] + rng.uniform(-0.1, 0.1, (nf, 3)) * x[:, None]
+    tv[:, :, 1] = rng.uniform(-1, 1, (nf, 3)) * x[:, None]
+    tv[:, :, 2] = 5.0 + rng.uniform(-1, 1, (nf, 3)) * x[:, None] * 0.2
+    tv = tv.astype(np.float32)
+    W, H = 64, 48
+    cam = synth.make_camera(W, H)
+    Rt = np.array([1, 0, 0, 0.3, 0, 1, 0, -0.2, 0, 0, 1, -1.0], np.float32)  # looks along +z
+    ys, xs = np.mgrid[0:H, 0:W]
+    xs, ys = xs.ravel().astype(np.uint32), ys.ravel().astype(np.uint32)
+    fp, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    out = np.empty(xs.shape[0], np.uint32)
+    depth = C.c_uint32(0)
+    tvc = np.ascontiguousarray(tv.reshape(-1, 9))
+    K = np.ascontiguousarray(cam.K, np.float32)
+    rc = lib.mesh_host_cast_pixels(tvc.ctypes.data_as(fp), None, nf, K.ctypes.data_as(fp), W, H, Rt.ctypes.data_as(fp),
+                                   0.5, 1e30, CLEAR, xs.ctypes.data_as(u32p), ys.ctypes.data_as(u32p), xs.shape[0],
+                                   out.ctypes.data_as(u32p), C.byref(depth), None)
+    assert rc == 0
+    assert depth.value <= 12  # ceil(log2(3000 / 4)) + slack: the balanced tree, not a chain of hundreds of levels
+    ref = O.mesh_cast_pixels(tv, O.mesh_face_normals(tv), cam.K, W, H, Rt, xs, ys, near=0.5, far=1e30)
+    assert np.array_equal(ref, out)
+    assert (ref != CLEAR).sum() > 50
+
+
 def test_host_compiled_traversal_equals_brute_force_on_adversarial_soups():
     lib = _harness()
     rng = np.random.default_rng(20261020)
