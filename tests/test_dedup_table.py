@@ -179,3 +179,8 @@ def test_detached_host_arrays_survive_later_calls_and_are_recycled():
     for hb in (hb2, hb3, hb4):
         hb.release()
     gmap.close()
+    assert E.load_library().q3dr_host_pool_trim() == E.Q3DR_OK  # the pooled blocks are freed; a later map allocates afresh
+    gmap = E.OccupancyMap(leaves.boxes, leaves.weight, leaves.normal, depth)
+    r5 = gmap.score_viewpoints(cam.K, w, (0, w, 0, h), vps[:7])
+    assert np.array_equal(r5.leaf, r1.leaf)
+    gmap.close()
