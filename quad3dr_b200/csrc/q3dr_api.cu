@@ -180,7 +180,7 @@ const RayVariant kRayVariants[] = {
 #undef Q3DR_VARIANT_SO
 constexpr int kNumRayVariants = (int)(sizeof(kRayVariants) / sizeof(kRayVariants[0]));
 constexpr uint32_t kDefaultTileRun = 1;
-constexpr int kDefaultRayVariant = 10;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar, 32 warps per SM at 64 registers beat 28 at 72 and 36 at 56 by 5 %, four rays per lane lose 2x
+constexpr int kDefaultRayVariant = 10;  // measured on C2 / C3 (profiles/r02_variants_*.jsonl): packed beats scalar, 32 warps per SM at 64 registers beat 28 at 72 and 36 at 56 by 5 %, ordered push gains 1 %, four rays per lane lose a third
 
 const RayVariant& variant_of(const q3dr_map* m) { return kRayVariants[m->ray_variant]; }
 
